@@ -1,0 +1,120 @@
+/*
+ * bfp_b200.h -- C ABI of libbfp_b200.so: the B200 (sm_100a) implementation of the
+ * block-floating-point quantise + N:M sparsify + BFP linear hot path of
+ * parsa-epfl/quantization-sparsity-interplay (src/transformers/bfp/bfp_ops.py).
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own: its operator
+ * API for this path *is* the Python module transformers.bfp.bfp_ops, so every entry
+ * point below names the reference function (file:line under
+ * /root/reference/src/transformers/bfp/) whose work it replaces; the Python mirror
+ * in quantization-sparsity-interplay_b200/bfp_ops.py binds them with ctypes
+ * (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all device pointers are caller-owned CUDA
+ *     device memory on the current device; `stream` is a cudaStream_t passed as void*.
+ *   - no allocation and no synchronisation inside the *_device entry points: work is
+ *     enqueued on `stream` and the call returns.  The *_host entry points take HOST
+ *     buffers, stage through internal pinned/device buffers and return when the
+ *     result is in the host output buffer.
+ *   - every call returns 0 on success, else a BFP_E_* code; bfp_last_error() gives
+ *     the message for the calling thread.  There is no CPU fallback: without a CUDA
+ *     device every compute call fails with BFP_E_CUDA.
+ *   - tensors are viewed as [rows, K] row-major contiguous: rows = product of the
+ *     leading dims, K = last dim.  Blocks (block_size) and N:M groups run along K and
+ *     never straddle rows; a ragged tail is treated as zero-padded
+ *     (bfp_ops.py:50-53, :79-82) and the padding is never written.
+ */
+#ifndef BFP_B200_H_
+#define BFP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BFP_B200_VERSION 100 /* 0.1.0 */
+
+/* element types of in/out tensors */
+enum { BFP_DT_F32 = 0, BFP_DT_F16 = 1, BFP_DT_BF16 = 2 };
+/* bfp_ops.py:16-18 rounding_modes: 'determ' / 'stoc' */
+enum { BFP_ROUND_NEAREST = 0, BFP_ROUND_STOCHASTIC = 1 };
+/* bfp_ops.py:141-149: first=='s' -> sparsify then quantise; anything else -> quantise then sparsify.
+ * QUANT_ONLY: sparsity flag off for this identifier; SPARSIFY_ONLY: sparsity_num_format=='fp32'. */
+enum { BFP_ORDER_QUANT_ONLY = 0, BFP_ORDER_SPARSIFY_QUANT = 1, BFP_ORDER_QUANT_SPARSIFY = 2, BFP_ORDER_SPARSIFY_ONLY = 3 };
+/* which torch.topk backend's tie-breaking the N:M mask reproduces (bfp_ops.py:84).
+ * TORCH_CUDA: the k smallest by (|v|, index) -- what the reference does with device='cuda' (measured on B200).
+ * TORCH_CPU : ATen's std::nth_element order; supported for N:M = 2:4 only. */
+enum { BFP_TIE_TORCH_CUDA = 0, BFP_TIE_TORCH_CPU = 1 };
+
+enum {
+    BFP_OK = 0,
+    BFP_E_ARG = 1,          /* invalid argument (the reference would assert / raise) */
+    BFP_E_UNSUPPORTED = 2,  /* valid in the reference but not implemented here */
+    BFP_E_CUDA = 3,         /* CUDA runtime error (including: no device) */
+    BFP_E_ALIGN = 4         /* pointer not aligned to the element size */
+};
+
+int bfp_version(void);
+const char* bfp_last_error(void);
+
+/* Number of kernels this library has launched since load (all threads); bench.py's gpu_launches. */
+uint64_t bfp_launch_count(void);
+
+/* Runtime knobs (also read once from the environment: BFP_STREAM_CTAS_PER_SM, BFP_FORCE_GENERIC, BFP_HOST_CHUNK_MB):
+ *   "stream_ctas_per_sm"  resident CTAs per SM the streaming quantiser sizes its grid for (default 8)
+ *   "force_generic"       1 = route every call through the generic (ragged-shape) kernel; for tests
+ *   "host_chunk_bytes"    input bytes per pipelined chunk of bfp_quantize_host (default 8 MiB) */
+int bfp_set_option(const char* name, int64_t value);
+
+/* sm count, compute capability, L2 bytes of the current device. */
+int bfp_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes);
+
+/*
+ * float_to_bfp_blocked (bfp_ops.py:124-149) for sparsity_num_format in {'bfp','fp32'} with
+ * sparsity_mode 'structured' -- ONE fused kernel: N:M magnitude mask (bfp_ops.py:73-91), shared block exponent
+ * ceil(log2(max|t|+eps)) (:29-33), mantissa rounding (:20-27) and clamp (:35-44), in the order `order`.
+ *
+ *   in_dtype   BFP_DT_*; out_dtype must equal in_dtype for BFP_ROUND_NEAREST and BFP_DT_F32 for
+ *              BFP_ROUND_STOCHASTIC (the reference's type promotion, bfp_ops.py:22-23).
+ *   block_size > 0, mant_bits in [0, 23] (number of magnitude bits m: HBFP8 -> 7).
+ *   rounding   BFP_ROUND_*; stochastic uniforms come from Philox4x32-10 keyed by `seed`, counter =
+ *              (flat element index / 4, offset): u = (word >> 8) * 2^-24.
+ *   N, M       keep N of every M along K (ignored for BFP_ORDER_QUANT_ONLY); 0 < N <= M <= 64.
+ *   out may alias in only when out_dtype == in_dtype and order == BFP_ORDER_QUANT_ONLY.
+ */
+int bfp_quantize(const void* in, void* out, int64_t rows, int64_t K, int in_dtype, int out_dtype, int block_size,
+                 int mant_bits, float eps, int rounding, uint64_t seed, uint64_t offset, int N, int M, int order,
+                 int tie_rule, void* stream);
+
+/* _structured_N_M_sparsity (bfp_ops.py:73-91) alone: = bfp_quantize(..., BFP_ORDER_SPARSIFY_ONLY). */
+int bfp_nm_sparsify(const void* in, void* out, int64_t rows, int64_t K, int dtype, int N, int M, int tie_rule,
+                    void* stream);
+
+/* get_exponent (bfp_ops.py:29-33): exp_out[rows, ceil(K/block_size)] fp32, in the arithmetic of `dtype`. */
+int bfp_block_exponent(const void* in, float* exp_out, int64_t rows, int64_t K, int dtype, int block_size, float eps,
+                       void* stream);
+
+/*
+ * The same operator through HOST buffers (what a caller holding CPU tensors sees): the tensor is split into row
+ * chunks; chunk i+1's host->device copy, chunk i's kernel and chunk i-1's device->host copy overlap on three
+ * streams.  host_in / host_out should be page-locked for full PCIe speed (pageable memory works, slower).
+ * Returns after host_out is complete.
+ */
+int bfp_quantize_host(const void* host_in, void* host_out, int64_t rows, int64_t K, int in_dtype, int out_dtype,
+                      int block_size, int mant_bits, float eps, int rounding, uint64_t seed, uint64_t offset, int N,
+                      int M, int order, int tie_rule);
+
+/* Frees the staging buffers bfp_quantize_host keeps between calls. */
+int bfp_host_staging_release(void);
+
+/* The 256-entry table behind BFP_TIE_TORCH_CPU for 2:4 (index = c0 + 4*c1 + 16*c2 + 64*c3 with
+ * c_i = #{j : |v_j| < |v_i|}; value = 4-bit drop mask, 0xff = unreachable).  Exposed for the tests. */
+int bfp_debug_cpu_tie_lut(uint8_t out[256]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BFP_B200_H_ */

@@ -1,0 +1,360 @@
+"""Host-side mirror of the reference operator module `transformers.bfp.bfp_ops`
+(/root/reference/src/transformers/bfp/bfp_ops.py): the same public names, argument lists, defaults and error
+behaviour, so the reference's patched OPT / LLaMA / ViT models (modeling_opt.py:42,162-176, modeling_llama.py:65,
+225-237,305-319, modeling_vit.py:41,168-215) run on it unchanged -- see `qsi_b200.install_as_reference_module()`.
+
+What differs is where the work happens: every quantise / sparsify call is ONE hand-written sm_100a kernel behind the
+C ABI (include/bfp_b200.h) instead of ~25 eager torch kernels.  torch is used here for device memory, streams and
+autograd plumbing only.  There is no CPU fallback: CPU tensors are processed on the GPU through the host-buffer entry
+point (bfp_quantize_host), and a missing library or GPU raises.
+
+Semantics kept from the reference (line numbers refer to the reference file):
+  * returns a new tensor of the input's shape; the fp32 format without sparsity returns the input object itself (:105-106,
+    :101-102); dtype = input dtype for 'determ', fp32 for 'stoc' on half inputs (:22-23)
+  * `first == 's'` sparsifies then quantises, ANY other value quantises then sparsifies (:141-149)
+  * `sparsity_num_format` selects the number format, `num_format` must be 'bfp' (:129-130)
+  * AssertionError / ValueError / NotImplementedError in the same places (:27, :62, :74, :100, :122, :129-130, :268, :287)
+  * `device` is advisory: the tensor's own device is used
+  * N:M ties follow the torch.topk backend the reference would have used for that tensor: torch-CUDA's rule (smallest
+    by (|v|, index)) for CUDA tensors, torch-CPU's rule for CPU tensors (2:4 only); override with BFP_TIE_RULE=cuda|cpu.
+"""
+import os
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+_DT = {torch.float32: _lib.DT_F32, torch.float16: _lib.DT_F16, torch.bfloat16: _lib.DT_BF16}
+
+
+class rounding_modes:
+    """bfp_ops.py:16-18"""
+    STOC, DETERM = 'stoc', 'determ'
+    modes = [STOC, DETERM]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Philox stream for stochastic rounding: key = torch's seed (so torch.manual_seed makes runs reproducible),
+# offset = number of stochastic calls made since that seed was first seen.
+# ---------------------------------------------------------------------------------------------------------------
+class _PhiloxState:
+    seed = None
+    calls = 0
+
+    @classmethod
+    def next(cls):
+        s = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+        if s != cls.seed:
+            cls.seed, cls.calls = s, 0
+        off = cls.calls
+        cls.calls += 1
+        return s, off
+
+
+def _tie_rule(t, N, M):
+    env = os.environ.get("BFP_TIE_RULE", "")
+    if env == "cuda":
+        return _lib.TIE_TORCH_CUDA
+    if env == "cpu":
+        return _lib.TIE_TORCH_CPU
+    if (not t.is_cuda) and N == 2 and M == 4:
+        return _lib.TIE_TORCH_CPU
+    return _lib.TIE_TORCH_CUDA
+
+
+def _rounding_code(rounding_mode):
+    if rounding_mode == rounding_modes.DETERM:
+        return _lib.ROUND_NEAREST
+    if rounding_mode == rounding_modes.STOC:
+        return _lib.ROUND_STOCHASTIC
+    raise NotImplementedError("Rounding mode %s is not implemented", rounding_mode)      # bfp_ops.py:27
+
+
+def _fused(t, order, block_size=0, mant_bits=0, epsilon=0.0, rounding_mode=rounding_modes.DETERM, N=0, M=0,
+           philox=None):
+    """One launch of the fused kernel on `t` viewed as [rows, K] (K = last dim).  Returns a new tensor."""
+    if t.dim() == 0:
+        raise IndexError("tuple index out of range")            # the reference indexes t.shape[-1]
+    if t.dtype not in _DT:
+        raise TypeError(f"bfp_b200 supports float32 / float16 / bfloat16 tensors, got {t.dtype}")
+    rounding = _rounding_code(rounding_mode) if order != _lib.ORDER_SPARSIFY_ONLY else _lib.ROUND_NEAREST
+    stoc = rounding == _lib.ROUND_STOCHASTIC
+    src = t.detach().contiguous()
+    out_dtype = torch.float32 if stoc else src.dtype
+    out = torch.empty(src.shape, dtype=out_dtype, device=src.device,
+                      pin_memory=(not src.is_cuda) and src.is_pinned())   # pinned in -> pinned out (full-speed D2H)
+    K = src.shape[-1]
+    rows = src.numel() // K if K else 0
+    if src.numel() == 0:
+        return out
+    seed, offset = (philox if philox is not None else _PhiloxState.next()) if stoc else (0, 0)
+    tie = _tie_rule(src, N, M)
+    L = _lib.lib()
+    if src.is_cuda:
+        with torch.cuda.device(src.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            rc = L.bfp_quantize(src.data_ptr(), out.data_ptr(), rows, K, _DT[src.dtype], _DT[out_dtype],
+                                int(block_size), int(mant_bits), float(epsilon), rounding, seed, offset, int(N), int(M),
+                                order, tie, stream)
+    else:
+        rc = L.bfp_quantize_host(src.data_ptr(), out.data_ptr(), rows, K, _DT[src.dtype], _DT[out_dtype],
+                                 int(block_size), int(mant_bits), float(epsilon), rounding, seed, offset, int(N), int(M),
+                                 order, tie)
+    _lib.check(rc)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bfp_ops.py:20-59: rounding, exponent, block conversion
+# ---------------------------------------------------------------------------------------------------------------
+def round_tensor(t, mode, device):
+    """bfp_ops.py:20-27.  Stand-alone helper (the fused kernel rounds in registers and never calls this)."""
+    if mode == rounding_modes.STOC:
+        sampled = torch.rand(t.shape, device=t.device) - 0.5
+        return sampled.add_(t).round()
+    elif mode == rounding_modes.DETERM:
+        return t.round()
+    raise NotImplementedError("Rounding mode %s is not implemented", mode)
+
+
+def get_exponent(t, epsilon):
+    """bfp_ops.py:29-33: per row of the 2-D [nblk, B] view, ceil(log2(max|t| + eps)) in t.dtype; shape [nblk, 1]."""
+    if t.dtype not in _DT:
+        raise TypeError(f"unsupported dtype {t.dtype}")
+    src = t.detach().contiguous()
+    nblk, B = src.shape
+    dev_src = src if src.is_cuda else src.cuda()
+    e = torch.empty((nblk, 1), dtype=torch.float32, device=dev_src.device)
+    if nblk and B:
+        with torch.cuda.device(dev_src.device):
+            _lib.check(_lib.lib().bfp_block_exponent(dev_src.data_ptr(), e.data_ptr(), nblk, B, _DT[src.dtype], B,
+                                                    float(epsilon), torch.cuda.current_stream().cuda_stream))
+    return e.to(device=t.device, dtype=t.dtype)
+
+
+def _convert_blocked_float_to_bfp(t, mant_bits, epsilon, rounding_mode, device):
+    """bfp_ops.py:35-44: t is the [nblk, B] view; every row is one block."""
+    return _fused(t, _lib.ORDER_QUANT_ONLY, block_size=t.shape[-1], mant_bits=mant_bits, epsilon=epsilon,
+                  rounding_mode=rounding_mode)
+
+
+def _no_sparsity_float_to_bfp(t, block_size, mant_bits, epsilon, rounding_mode, device):
+    """bfp_ops.py:46-59: blocks of block_size along the last dim (zero-padded tail, never straddling rows)."""
+    return _fused(t, _lib.ORDER_QUANT_ONLY, block_size=block_size, mant_bits=mant_bits, epsilon=epsilon,
+                  rounding_mode=rounding_mode)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bfp_ops.py:61-102: sparsity
+# ---------------------------------------------------------------------------------------------------------------
+def _unstructured_sparsity(t, device, sparsity_frac=0):
+    """bfp_ops.py:61-71: global magnitude pruning.  SURVEY.md section 8 row f1 ("next"): not built yet."""
+    assert (sparsity_frac > 0)
+    raise NotImplementedError("unstructured sparsity is not implemented in bfp_b200 yet (SURVEY.md section 8, row f1)")
+
+
+def _structured_N_M_sparsity(t, device, N=0, M=0):
+    """bfp_ops.py:73-91: zero the M-N smallest-magnitude entries of every group of M along the last dim."""
+    assert ((N > 0) and (M > 0) and (N <= M))
+    return _fused(t, _lib.ORDER_SPARSIFY_ONLY, N=N, M=M)
+
+
+def _sparsify(t, sparsity, sparsity_mode, device, N, M, sparsity_frac):
+    """bfp_ops.py:93-102"""
+    if sparsity == True:  # noqa: E712  (the reference compares with ==, so 1 counts as True)
+        if sparsity_mode == 'structured':
+            return _structured_N_M_sparsity(t, device, N, M)
+        elif sparsity_mode == 'unstructured':
+            return _unstructured_sparsity(t, device, sparsity_frac)
+        else:
+            raise ValueError(f'Unknown sparsity mode: {sparsity_mode} given as argument')
+    return t
+
+
+def _quantize(t, num_format, block_size, mant_bits, weight_mant_bits, sgd_update, epsilon, rounding_mode, device,
+              identifier):
+    """bfp_ops.py:104-122"""
+    if num_format == 'fp32':
+        return t
+    elif num_format == 'bfp':
+        if sgd_update:
+            mant_bits = weight_mant_bits
+        return _no_sparsity_float_to_bfp(t, block_size, mant_bits, epsilon, rounding_mode, device)
+    elif num_format == 'int':
+        raise NotImplementedError("the 'int' (SparseGPT per-channel) format is not implemented in bfp_b200 yet "
+                                  "(SURVEY.md section 8, row f2)")
+    raise ValueError(f'Unknown quantization format: {num_format} given as argument')
+
+
+def float_to_bfp_blocked(t, mant_bits, epsilon, rounding_mode, device, block_size,
+                         num_format, weight_mant_bits, in_sparsity, w_sparsity, grad_sparsity,
+                         sparsity_frac, N, M, sparsity_num_format, first, sparsity_mode, identifier='', sgd_update=False,
+                         mx_w_elem_format='', mx_a_elem_format='', scale_bits=0, bfloat=0):
+    """bfp_ops.py:124-149, the quantiser entry point.  Structured sparsity with the 'bfp' or 'fp32' format is ONE fused
+    kernel in either order; the remaining combinations compose the stand-alone functions exactly like the reference."""
+    assert (num_format == 'bfp')
+    assert (((sparsity_num_format == 'bfp') and (block_size > 0)) or (sparsity_num_format == 'fp32')
+            or (sparsity_num_format == 'int'))
+
+    sparsity = ((in_sparsity == True and identifier == 'in') or (w_sparsity == True and identifier == 'w')  # noqa: E712
+                or (grad_sparsity == True and identifier == 'grad'))                                        # noqa: E712
+
+    fusable = sparsity_num_format in ('bfp', 'fp32') and (not sparsity or sparsity_mode == 'structured')
+    if fusable:
+        if sparsity:
+            assert ((N > 0) and (M > 0) and (N <= M))                                   # bfp_ops.py:74
+        if sparsity_num_format == 'fp32':
+            return _fused(t, _lib.ORDER_SPARSIFY_ONLY, N=N, M=M) if sparsity else t
+        m = weight_mant_bits if sgd_update else mant_bits                               # bfp_ops.py:108-109
+        if not sparsity:
+            order = _lib.ORDER_QUANT_ONLY
+        else:
+            order = _lib.ORDER_SPARSIFY_QUANT if first == 's' else _lib.ORDER_QUANT_SPARSIFY
+        return _fused(t, order, block_size=block_size, mant_bits=m, epsilon=epsilon, rounding_mode=rounding_mode,
+                      N=N, M=M)
+
+    if first == 's':
+        sparse_t = _sparsify(t, sparsity, sparsity_mode, device, N, M, sparsity_frac)
+        return _quantize(sparse_t, sparsity_num_format, block_size, mant_bits, weight_mant_bits, sgd_update, epsilon,
+                         rounding_mode, device, identifier)
+    quant_t = _quantize(t, sparsity_num_format, block_size, mant_bits, weight_mant_bits, sgd_update, epsilon,
+                        rounding_mode, device, identifier)
+    return _sparsify(quant_t, sparsity, sparsity_mode, device, N, M, sparsity_frac)
+
+
+def float_to_bfp_tiled(t, **bfp_args):
+    """Name imported by the reference's bfp_optim.py:6 but missing from its bfp_ops.py;
+    called as float_to_bfp_tiled(p.data, sgd_update=True, **bfp_args)."""
+    return float_to_bfp_blocked(t, **bfp_args)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bfp_ops.py:151-200: operand pre-processing and the autograd wrappers
+# ---------------------------------------------------------------------------------------------------------------
+def MxM_pre_processing(x, w, transpose, **bfp_args):
+    """bfp_ops.py:151-155: both operands are blocked along the contraction dim."""
+    xq = float_to_bfp_blocked(x, **bfp_args, identifier='in')
+    if transpose == True:  # noqa: E712
+        wq = torch.transpose(float_to_bfp_blocked(torch.transpose(w, -1, -2), **bfp_args, identifier='w'), -1, -2)
+    else:
+        wq = float_to_bfp_blocked(w, **bfp_args, identifier='w')
+    return (xq, wq)
+
+
+def _get_op_name(name, epsilon, mant_bits, rounding_mode, **kwargs):
+    """bfp_ops.py:157-158"""
+    return '%s_BFP_%s_%d' % (name, rounding_mode, mant_bits)
+
+
+def _gen_bfp_op(op, name, bfp_args, transpose=False):
+    """bfp_ops.py:160-192: new_op(x, w, ...) = OutGrad(op(*QuantIn(x, w), ...)).
+    QuantIn: forward quantises both operands, backward is the straight-through identity (:168-170).
+    OutGrad: forward identity, backward quantises the output gradient with identifier='grad' (:180-182)."""
+    name = _get_op_name(name, **bfp_args)
+
+    class NewOpIn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, w):
+            return MxM_pre_processing(x, w, transpose, **bfp_args)
+
+        @staticmethod
+        def backward(ctx, grad_x, grad_w):
+            return (grad_x, grad_w)
+
+    NewOpIn.__name__ = name + '_In'
+
+    class NewOpOut(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, op_out):
+            return op_out.view_as(op_out)
+
+        @staticmethod
+        def backward(ctx, op_out_grad):
+            return float_to_bfp_blocked(op_out_grad, **bfp_args, identifier='grad')
+
+    NewOpOut.__name__ = name + '_Out'
+
+    def new_op(x, w, *args, **kwargs):
+        x, w = NewOpIn.apply(x, w)
+        out = op(x, w, *args, **kwargs)
+        return NewOpOut.apply(out)
+
+    new_op.__name__ = name
+    return new_op
+
+
+def _get_bfp_op(op, name, bfp_args, transpose=False):
+    """bfp_ops.py:194-200 (the reference's cache is a local dict, so every call generates a fresh op; same here)."""
+    return _gen_bfp_op(op, name, bfp_args, transpose)
+
+
+_BFP_ARG_DEFAULTS = (
+    ('num_format', 'fp32'), ('sparsity_num_format', 'fp32'), ('rounding_mode', 'stoc'), ('epsilon', 1e-8),
+    ('mant_bits', 0), ('block_size', 0), ('weight_mant_bits', 0), ('in_sparsity', False), ('w_sparsity', False),
+    ('grad_sparsity', False), ('N', 0), ('M', 0), ('first', 's'), ('sparsity_mode', 'unstructured'),
+    ('sparsity_frac', 0), ('mx_w_elem_format', ''), ('mx_a_elem_format', ''), ('bfloat', 16), ('scale_bits', 8),
+    ('device', 'cpu'),
+)
+
+
+def unpack_bfp_args(kwargs):
+    """bfp_ops.py:202-231: pops the 20 known keys (with the reference's defaults) out of `kwargs`, which is mutated;
+    unknown keys stay behind and are ignored by the callers."""
+    bfp_args = {}
+    for arg, default in _BFP_ARG_DEFAULTS:
+        bfp_args[arg] = kwargs.pop(arg) if arg in kwargs else default
+    return bfp_args
+
+
+def F_linear_bfp(**kwargs):
+    """bfp_ops.py:233-238"""
+    bfp_args = unpack_bfp_args(kwargs)
+    if bfp_args['num_format'] == 'bfp':
+        return _get_bfp_op(F.linear, 'linear', bfp_args)
+    return F.linear
+
+
+def F_matmul_bfp(**kwargs):
+    """bfp_ops.py:240-245"""
+    bfp_args = unpack_bfp_args(kwargs)
+    if bfp_args['num_format'] == 'bfp':
+        return _get_bfp_op(torch.matmul, 'matmul', bfp_args, True)
+    return torch.matmul
+
+
+class BFPConv2d(torch.nn.Conv2d):
+    """bfp_ops.py:247-268: input blocked along W, weight along kw; the convolution itself runs on the dequantised
+    operands (conv as im2col + BFP GEMM is "next")."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1,
+                 padding=0, dilation=1, groups=1, bias=True, **kwargs):
+        self.bfp_args = unpack_bfp_args(kwargs)
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias)
+        self.num_format = self.bfp_args['num_format']
+        self.conv_op = _get_bfp_op(F.conv2d, 'Conv2d', self.bfp_args)
+
+    def forward(self, input):
+        if self.num_format == 'fp32':
+            return F.conv2d(input, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+        elif self.num_format == 'bfp':
+            return self.conv_op(input, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+        raise NotImplementedError('NumFormat not implemented')
+
+
+class BFPLinear(torch.nn.Linear):
+    """bfp_ops.py:270-287: nn.Linear whose operands are BFP-quantised (activations id 'in', weights id 'w') on every
+    forward; parameters and state-dict are nn.Linear's.  The bias is never quantised."""
+
+    def __init__(self, in_features, out_features, bias=True, **kwargs):
+        self.bfp_args = unpack_bfp_args(kwargs)
+        super().__init__(in_features, out_features, bias)
+        self.num_format = self.bfp_args['num_format']
+        self.linear_op = _get_bfp_op(F.linear, 'linear', self.bfp_args)
+
+    def forward(self, input):
+        if self.num_format == 'fp32':
+            return F.linear(input, self.weight, self.bias)
+        elif self.num_format == 'bfp':
+            return self.linear_op(input, self.weight, self.bias)
+        raise NotImplementedError('NumFormat not implemented')

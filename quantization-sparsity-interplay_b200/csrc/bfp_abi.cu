@@ -1,0 +1,182 @@
+// bfp_abi.cu -- the extern "C" surface declared in include/bfp_b200.h: argument validation (mirroring the
+// reference's asserts / exceptions), error reporting, device bookkeeping.  No torch types, no allocation.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "bfp_internal.h"
+
+namespace bfp {
+
+static thread_local char t_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+int set_error(int code, const char* msg) {
+    snprintf(t_err, sizeof(t_err), "%s", msg ? msg : "");
+    return code;
+}
+int set_errorf(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return BFP_OK;
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+Tuning& tuning() {
+    static Tuning t = [] {
+        Tuning x;
+        if (const char* s = getenv("BFP_STREAM_CTAS_PER_SM")) x.stream_ctas_per_sm = atoi(s) > 0 ? atoi(s) : x.stream_ctas_per_sm;
+        if (const char* s = getenv("BFP_FORCE_GENERIC")) x.force_generic = atoi(s);
+        if (const char* s = getenv("BFP_HOST_CHUNK_MB")) x.host_chunk_bytes = (int64_t)(atoi(s) > 0 ? atoi(s) : 16) << 20;
+        return x;
+    }();
+    return t;
+}
+
+const DeviceInfo& device_info() {
+    static DeviceInfo cache[64];
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+        static DeviceInfo none;
+        return none;
+    }
+    std::lock_guard<std::mutex> lk(mu);
+    DeviceInfo& d = cache[dev];
+    if (d.device != dev) {
+        int v = 0;
+        cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+        cudaDeviceGetAttribute(&d.cc_minor, cudaDevAttrComputeCapabilityMinor, dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev);
+        d.l2_bytes = (size_t)v;
+        d.device = dev;
+    }
+    return d;
+}
+
+static int require_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return set_error(BFP_E_CUDA, "no CUDA device: libbfp_b200 has no CPU fallback");
+    }
+    const DeviceInfo& d = device_info();
+    if (d.cc_major != 10)
+        return set_errorf(BFP_E_CUDA, "device is sm_%d%d; libbfp_b200 is built for sm_100a only", d.cc_major, d.cc_minor);
+    return BFP_OK;
+}
+
+int validate_quant_args(const QuantArgs& a, bool /*device_pointers*/) {
+    if (a.rows < 0 || a.K < 0) return set_error(BFP_E_ARG, "negative shape");
+    if (a.in_dtype < 0 || a.in_dtype > 2 || a.out_dtype < 0 || a.out_dtype > 2) return set_error(BFP_E_ARG, "bad dtype");
+    if (a.order < 0 || a.order > 3) return set_error(BFP_E_ARG, "bad order");
+    if (a.rounding != BFP_ROUND_NEAREST && a.rounding != BFP_ROUND_STOCHASTIC)
+        return set_error(BFP_E_ARG, "Rounding mode is not implemented");                         // bfp_ops.py:27
+    const bool quant = a.order != BFP_ORDER_SPARSIFY_ONLY, sparse = a.order != BFP_ORDER_QUANT_ONLY;
+    if (quant) {
+        if (a.B <= 0) return set_error(BFP_E_ARG, "block_size must be > 0 for the bfp format");  // bfp_ops.py:130
+        if (a.m < 0 || a.m > 23) return set_error(BFP_E_ARG, "mant_bits must be in [0, 23]");
+    }
+    if (sparse) {
+        if (!(a.N > 0 && a.M > 0 && a.N <= a.M)) return set_error(BFP_E_ARG, "need 0 < N <= M");  // bfp_ops.py:74
+        if (a.M > 64) return set_error(BFP_E_UNSUPPORTED, "N:M groups larger than 64 are not supported");
+        if (a.tie != BFP_TIE_TORCH_CUDA && a.tie != BFP_TIE_TORCH_CPU) return set_error(BFP_E_ARG, "bad tie_rule");
+    }
+    const bool stoc = quant && a.rounding == BFP_ROUND_STOCHASTIC;
+    const int want_out = stoc ? BFP_DT_F32 : a.in_dtype;
+    if (a.out_dtype != want_out)
+        return set_error(BFP_E_ARG, "out_dtype must equal in_dtype for nearest rounding and be fp32 for stochastic rounding");
+    if (a.rows * a.K > 0) {
+        if (!a.in || !a.out) return set_error(BFP_E_ARG, "null pointer");
+        if (reinterpret_cast<uintptr_t>(a.in) % dtype_size(a.in_dtype) || reinterpret_cast<uintptr_t>(a.out) % dtype_size(a.out_dtype))
+            return set_error(BFP_E_ALIGN, "pointer not aligned to its element size");
+        if (a.in == a.out && !(a.order == BFP_ORDER_QUANT_ONLY && a.in_dtype == a.out_dtype))
+            return set_error(BFP_E_ARG, "in-place is only supported for quantise-only with equal dtypes");
+    }
+    return BFP_OK;
+}
+
+}  // namespace bfp
+
+using namespace bfp;
+
+extern "C" {
+
+int bfp_version(void) { return BFP_B200_VERSION; }
+const char* bfp_last_error(void) { return t_err; }
+uint64_t bfp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int bfp_set_option(const char* name, int64_t value) {
+    if (!name) return set_error(BFP_E_ARG, "null option name");
+    Tuning& t = tuning();
+    if (!strcmp(name, "stream_ctas_per_sm") && value > 0 && value <= 32) t.stream_ctas_per_sm = (int)value;
+    else if (!strcmp(name, "force_generic")) t.force_generic = value != 0;
+    else if (!strcmp(name, "host_chunk_bytes") && value >= 4096) t.host_chunk_bytes = value;
+    else return set_errorf(BFP_E_ARG, "unknown option or bad value: %s", name);
+    return BFP_OK;
+}
+
+int bfp_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return set_error(BFP_E_CUDA, "no CUDA device");
+    }
+    const DeviceInfo& d = device_info();
+    if (sm_count) *sm_count = d.sm_count;
+    if (cc_major) *cc_major = d.cc_major;
+    if (cc_minor) *cc_minor = d.cc_minor;
+    if (l2_bytes) *l2_bytes = d.l2_bytes;
+    return BFP_OK;
+}
+
+int bfp_quantize(const void* in, void* out, int64_t rows, int64_t K, int in_dtype, int out_dtype, int block_size,
+                 int mant_bits, float eps, int rounding, uint64_t seed, uint64_t offset, int N, int M, int order,
+                 int tie_rule, void* stream) {
+    QuantArgs a{in, out, rows, K, in_dtype, out_dtype, block_size, mant_bits, eps, rounding, seed, offset, N, M, order, tie_rule};
+    if (int rc = validate_quant_args(a, true)) return rc;
+    if (int rc = require_device()) return rc;
+    return quantize_device(a, static_cast<cudaStream_t>(stream));
+}
+
+int bfp_nm_sparsify(const void* in, void* out, int64_t rows, int64_t K, int dtype, int N, int M, int tie_rule, void* stream) {
+    return bfp_quantize(in, out, rows, K, dtype, dtype, 0, 0, 0.0f, BFP_ROUND_NEAREST, 0, 0, N, M, BFP_ORDER_SPARSIFY_ONLY,
+                        tie_rule, stream);
+}
+
+int bfp_block_exponent(const void* in, float* exp_out, int64_t rows, int64_t K, int dtype, int block_size, float eps, void* stream) {
+    if (rows < 0 || K < 0 || block_size <= 0 || dtype < 0 || dtype > 2) return set_error(BFP_E_ARG, "bad argument");
+    if (rows * K > 0 && (!in || !exp_out)) return set_error(BFP_E_ARG, "null pointer");
+    if (int rc = require_device()) return rc;
+    return block_exponent_device(in, exp_out, rows, K, dtype, block_size, eps, static_cast<cudaStream_t>(stream));
+}
+
+int bfp_quantize_host(const void* host_in, void* host_out, int64_t rows, int64_t K, int in_dtype, int out_dtype,
+                      int block_size, int mant_bits, float eps, int rounding, uint64_t seed, uint64_t offset, int N,
+                      int M, int order, int tie_rule) {
+    QuantArgs a{host_in, host_out, rows, K, in_dtype, out_dtype, block_size, mant_bits, eps, rounding, seed, offset, N, M, order, tie_rule};
+    if (int rc = validate_quant_args(a, false)) return rc;
+    if (int rc = require_device()) return rc;
+    return quantize_host(a);
+}
+
+int bfp_host_staging_release(void) { return host_staging_release(); }
+
+int bfp_debug_cpu_tie_lut(uint8_t out[256]) {
+    if (int rc = require_device()) return rc;
+    return debug_cpu_tie_lut(out);
+}
+
+}  // extern "C"

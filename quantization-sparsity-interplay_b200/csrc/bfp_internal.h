@@ -1,0 +1,51 @@
+// bfp_internal.h -- host-side glue shared by the translation units of libbfp_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bfp_b200.h"
+
+namespace bfp {
+
+struct DeviceInfo {
+    int device = -1;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    size_t l2_bytes = 0;
+};
+const DeviceInfo& device_info();          // of the current device (cached per device)
+
+struct Tuning {
+    int stream_ctas_per_sm = 8;           // resident CTAs of the stream kernel per SM (grid = sm_count * this)
+    int force_generic = 0;                // tests: route everything through the generic kernel
+    int64_t host_chunk_bytes = 8 << 20;   // bfp_quantize_host: input bytes per pipelined chunk
+};
+Tuning& tuning();
+
+int set_error(int code, const char* msg);         // records the thread's last error, returns code
+int set_errorf(int code, const char* fmt, ...);
+int check_launch(const char* what);               // cudaGetLastError() -> BFP_E_CUDA
+void count_launch();
+
+struct QuantArgs {
+    const void* in;
+    void* out;
+    int64_t rows, K;
+    int in_dtype, out_dtype;
+    int B, m;
+    float eps;
+    int rounding;
+    uint64_t seed, offset;
+    int N, M, order, tie;
+    int64_t index_base = 0;   // flat element index of in[0] within the whole tensor (Philox counter base; multiple of 8)
+};
+int validate_quant_args(const QuantArgs& a, bool device_pointers);
+int quantize_device(const QuantArgs& a, cudaStream_t st);
+int block_exponent_device(const void* in, float* e_out, int64_t rows, int64_t K, int dtype, int B, float eps, cudaStream_t st);
+int quantize_host(const QuantArgs& a);
+int host_staging_release();
+int debug_cpu_tie_lut(uint8_t out[256]);
+
+inline size_t dtype_size(int dt) { return dt == BFP_DT_F32 ? 4 : 2; }
+
+}  // namespace bfp

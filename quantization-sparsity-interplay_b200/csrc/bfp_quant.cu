@@ -1,0 +1,395 @@
+// bfp_quant.cu -- the fused BFP quantise + N:M sparsify kernels (fake-quant output) for sm_100a.
+//
+// Replaces, in one launch and one pass over HBM (read once, write once), what the reference does with ~25 eager torch
+// kernels: float_to_bfp_blocked (bfp_ops.py:124-149) = _structured_N_M_sparsity (:73-91) and
+// _no_sparsity_float_to_bfp (:46-59) in either order.
+//
+//  * stream kernel  -- the hot path.  Applies when K % block_size == 0, block_size is a power-of-two multiple of the
+//    128-bit vector (4 fp32 / 8 half elements), and the N:M group fits in one vector.  Then rows are irrelevant: the
+//    tensor is a flat sequence of vectors; lane l of a warp owns vector 32*w + l, a block is 2^j adjacent lanes,
+//    block max = butterfly of __shfl_xor, the N:M mask is lane-local.  HBM-bound: 8 B/element fp32, 4 B/element half.
+//  * generic kernel -- everything else (ragged K, odd block sizes, groups straddling vectors).  One thread per block
+//    (or per group), gather-style, no temporaries.  Correctness path for the ViT conv shapes; not tuned.
+#include <algorithm>
+
+#include "bfp_common.cuh"
+#include "bfp_internal.h"
+
+namespace bfp {
+
+// ---------------------------------------------------------------------------------------------------------------
+// 128-bit streaming loads / stores
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int DT> __device__ __forceinline__ void unpack_vec(const uint4& raw, float* v);
+template <> __device__ __forceinline__ void unpack_vec<BFP_DT_F32>(const uint4& raw, float* v) {
+    v[0] = __uint_as_float(raw.x); v[1] = __uint_as_float(raw.y); v[2] = __uint_as_float(raw.z); v[3] = __uint_as_float(raw.w);
+}
+template <> __device__ __forceinline__ void unpack_vec<BFP_DT_BF16>(const uint4& raw, float* v) {
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+template <> __device__ __forceinline__ void unpack_vec<BFP_DT_F16>(const uint4& raw, float* v) {
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+}
+template <int DT> __device__ __forceinline__ uint4 pack_vec(const float* v);   // 8 (half) or 4 (fp32) values -> 16 B
+template <> __device__ __forceinline__ uint4 pack_vec<BFP_DT_F32>(const float* v) {
+    return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+}
+template <> __device__ __forceinline__ uint4 pack_vec<BFP_DT_BF16>(const float* v) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<uint32_t*>(&h); }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+template <> __device__ __forceinline__ uint4 pack_vec<BFP_DT_F16>(const float* v) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<uint32_t*>(&h); }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// stream kernel
+// ---------------------------------------------------------------------------------------------------------------
+struct StreamParams {
+    const uint4* in;
+    uint4* out;
+    int64_t n_vec;          // number of 128-bit input vectors
+    int lanes_per_block;    // block_size / kVec, power of two in [1, 32]
+    int m;
+    float eps;
+    int kdrop;              // M - N
+    uint64_t seed, offset;
+    int64_t ctr_base;       // Philox counter of vector 0 (= flat element index / 4)
+};
+
+constexpr int kStreamThreads = 256;
+constexpr int kStreamUnroll = 4;
+
+// ORDER: BFP_ORDER_*.  M: group size held in-lane (0 = no sparsity).  STOC: stochastic rounding (fp32 output).
+template <int DT, int ORDER, int M, int TIE, bool STOC>
+__global__ void __launch_bounds__(kStreamThreads) quant_stream_kernel(const StreamParams p) {
+    using D = DType<DT>;
+    constexpr int V = D::kVec;
+    constexpr bool kQuant = ORDER != BFP_ORDER_SPARSIFY_ONLY;
+    constexpr bool kSparseFirst = ORDER == BFP_ORDER_SPARSIFY_QUANT || ORDER == BFP_ORDER_SPARSIFY_ONLY;
+    constexpr bool kSparseLast = ORDER == BFP_ORDER_QUANT_SPARSIFY;
+    constexpr int kOutVecs = (STOC && V == 8) ? 2 : 1;     // fp32 output of 8 half inputs = two 16-B stores
+
+    const int64_t tile_vecs = (int64_t)kStreamThreads * kStreamUnroll;
+    const int64_t n_tiles = (p.n_vec + tile_vecs - 1) / tile_vecs;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t base = tile * tile_vecs + threadIdx.x;
+        uint4 raw[kStreamUnroll];
+#pragma unroll
+        for (int u = 0; u < kStreamUnroll; ++u) {
+            const int64_t vi = base + (int64_t)u * kStreamThreads;
+            raw[u] = (vi < p.n_vec) ? ld_stream(p.in + vi) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < kStreamUnroll; ++u) {
+            const int64_t vi = base + (int64_t)u * kStreamThreads;
+            float v[V];
+            unpack_vec<DT>(raw[u], v);
+            if (M > 0 && kSparseFirst) {
+#pragma unroll
+                for (int g = 0; g < V / (M > 0 ? M : 1); ++g) nm_mask_group<(M > 0 ? M : 1), TIE>(v + g * M, p.kdrop);
+            }
+            if (kQuant) {
+                uint32_t amax = 0u;
+#pragma unroll
+                for (int i = 0; i < V; ++i) amax = max(amax, abs_bits(v[i]));
+                // butterfly over the lanes that share this block; every lane of the warp executes every shuffle
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1)
+                    if (off < p.lanes_per_block) amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+                const BlockScale sc = make_scale<DT>(amax, p.m, p.eps);
+                float un[V];
+                if (STOC) {
+#pragma unroll
+                    for (int q = 0; q < V / 4; ++q) {
+                        const uint4 r = philox4x32_10((uint64_t)(p.ctr_base + vi * (V / 4) + q), p.offset, p.seed);
+                        un[4 * q] = u01(r.x); un[4 * q + 1] = u01(r.y); un[4 * q + 2] = u01(r.z); un[4 * q + 3] = u01(r.w);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < V; ++i) v[i] = quant_elt<DT, STOC>(v[i], sc, STOC ? un[i] : 0.0f);
+            }
+            if (M > 0 && kSparseLast) {
+#pragma unroll
+                for (int g = 0; g < V / (M > 0 ? M : 1); ++g) nm_mask_group<(M > 0 ? M : 1), TIE>(v + g * M, p.kdrop);
+            }
+            if (vi < p.n_vec) {
+                if (kOutVecs == 1) {
+                    st_stream(p.out + vi, STOC ? pack_vec<BFP_DT_F32>(v) : pack_vec<DT>(v));
+                } else {
+                    st_stream(p.out + 2 * vi, pack_vec<BFP_DT_F32>(v));
+                    st_stream(p.out + 2 * vi + 1, pack_vec<BFP_DT_F32>(v + 4));
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// generic kernel: gather-style, any K / block_size / N:M.  unit = one block (orders q, s->q) or one group (s, q->s).
+// ---------------------------------------------------------------------------------------------------------------
+struct GenericParams {
+    const void* in;
+    void* out;
+    int64_t rows, K;
+    int B, m;
+    float eps;
+    int N, M, tie;
+    uint64_t seed, offset;
+    int64_t index_base;
+};
+
+template <int DT>
+__device__ __forceinline__ float ld_pad(const void* in, int64_t row, int64_t col, int64_t K) {
+    return (col < K) ? DType<DT>::load(in, row * K + col) : 0.0f;     // zero padding of F.pad (bfp_ops.py:52, :81)
+}
+
+// drop flag of element `col` under the N:M mask of `src(col)` (torch-CUDA rule, or CPU table for 2:4)
+template <class Src>
+__device__ __forceinline__ bool nm_dropped(const Src& src, int64_t col, int N, int M, int tie) {
+    const int64_t g0 = (col / M) * M;
+    const int i = (int)(col - g0);
+    const int kdrop = M - N;
+    if (tie == BFP_TIE_TORCH_CPU && M == 4 && kdrop == 2) {
+        uint32_t key[4];
+        for (int j = 0; j < 4; ++j) key[j] = abs_bits(src(g0 + j));
+        int idx = 0;
+        for (int a = 0; a < 4; ++a) { int c = 0; for (int b = 0; b < 4; ++b) c += (b != a) && (key[b] < key[a]); idx += c << (2 * a); }
+        return (c_cpu_tie_lut[idx] >> i) & 1u;
+    }
+    const uint32_t ki = abs_bits(src(col));
+    int rank = 0;
+    for (int j = 0; j < M; ++j) {
+        const uint32_t kj = abs_bits(src(g0 + j));
+        rank += (j < i) ? (kj <= ki) : ((j > i) ? (kj < ki) : 0);
+    }
+    return rank < kdrop;
+}
+
+template <int DT, int ORDER, bool STOC>
+__global__ void __launch_bounds__(128) quant_generic_kernel(const GenericParams p) {
+    using D = DType<DT>;
+    using DO = DType<STOC ? BFP_DT_F32 : DT>;
+    const int64_t nblk = (p.K + p.B - 1) / p.B;
+    const int64_t ngrp = (ORDER == BFP_ORDER_QUANT_ONLY) ? 0 : (p.K + p.M - 1) / p.M;
+    const bool per_group = (ORDER == BFP_ORDER_SPARSIFY_ONLY || ORDER == BFP_ORDER_QUANT_SPARSIFY);
+    const int64_t units = p.rows * (per_group ? ngrp : nblk);
+    for (int64_t unit = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; unit < units; unit += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = unit / (per_group ? ngrp : nblk);
+        const int64_t idx = unit % (per_group ? ngrp : nblk);
+        auto raw = [&](int64_t c) { return ld_pad<DT>(p.in, row, c, p.K); };
+        auto uni = [&](int64_t c) {
+            const uint64_t flat = (uint64_t)(p.index_base + row * p.K + c);
+            const uint4 r = philox4x32_10(flat >> 2, p.offset, p.seed);
+            const uint32_t w = (flat & 3) == 0 ? r.x : ((flat & 3) == 1 ? r.y : ((flat & 3) == 2 ? r.z : r.w));
+            return u01(w);
+        };
+        if (ORDER == BFP_ORDER_SPARSIFY_ONLY) {
+            for (int64_t c = idx * p.M; c < min(p.K, idx * p.M + p.M); ++c)
+                D::store(p.out, row * p.K + c, nm_dropped(raw, c, p.N, p.M, p.tie) ? 0.0f : raw(c));
+        } else if (ORDER == BFP_ORDER_QUANT_ONLY || ORDER == BFP_ORDER_SPARSIFY_QUANT) {
+            auto src = [&](int64_t c) {
+                const float t = raw(c);
+                if (ORDER == BFP_ORDER_SPARSIFY_QUANT) return (c < p.K && nm_dropped(raw, c, p.N, p.M, p.tie)) ? 0.0f : t;
+                return t;
+            };
+            const int64_t c0 = idx * p.B, c1 = min(p.K, c0 + p.B);
+            uint32_t amax = 0u;
+            for (int64_t c = c0; c < c1; ++c) amax = max(amax, abs_bits(src(c)));
+            const BlockScale sc = make_scale<DT>(amax, p.m, p.eps);
+            for (int64_t c = c0; c < c1; ++c)
+                DO::store(p.out, row * p.K + c, quant_elt<DT, STOC>(src(c), sc, STOC ? uni(c) : 0.0f));
+        } else {   // QUANT_SPARSIFY: quantise the group's elements (each with its own block's scale), then mask
+            float q[kMaxGroup];
+            const int64_t g0 = idx * p.M;
+            int64_t cur_blk = -1;
+            BlockScale sc = {};
+            for (int j = 0; j < p.M; ++j) {
+                const int64_t c = g0 + j;
+                if (c >= p.K) { q[j] = 0.0f; continue; }          // re-padded after the narrow: plain zeros
+                const int64_t b = c / p.B;
+                if (b != cur_blk) {
+                    cur_blk = b;
+                    uint32_t amax = 0u;
+                    for (int64_t cc = b * p.B; cc < min(p.K, b * p.B + p.B); ++cc) amax = max(amax, abs_bits(raw(cc)));
+                    sc = make_scale<DT>(amax, p.m, p.eps);
+                }
+                q[j] = quant_elt<DT, STOC>(raw(c), sc, STOC ? uni(c) : 0.0f);
+            }
+            auto qsrc = [&](int64_t c) { return q[c - g0]; };
+            for (int j = 0; j < p.M && g0 + j < p.K; ++j)
+                DO::store(p.out, row * p.K + g0 + j, nm_dropped(qsrc, g0 + j, p.N, p.M, p.tie) ? 0.0f : q[j]);
+        }
+    }
+}
+
+// get_exponent per block (bfp_ops.py:29-33), generic layout
+template <int DT>
+__global__ void __launch_bounds__(128) block_exponent_kernel(const void* in, float* e_out, int64_t rows, int64_t K, int B, float eps) {
+    const int64_t nblk = (K + B - 1) / B;
+    for (int64_t unit = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; unit < rows * nblk; unit += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = unit / nblk, kb = unit % nblk;
+        uint32_t amax = 0u;
+        for (int64_t c = kb * B; c < min(K, kb * B + B); ++c) amax = max(amax, abs_bits(DType<DT>::load(in, row * K + c)));
+        // m = 1 keeps make_scale on its fast path whenever possible; e does not depend on m
+        e_out[unit] = make_scale<DT>(amax, 1, eps).e;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host-side dispatch
+// ---------------------------------------------------------------------------------------------------------------
+static inline bool is_pow2(int64_t x) { return x > 0 && (x & (x - 1)) == 0; }
+
+template <int DT, int ORDER, int M, int TIE, bool STOC>
+static int launch_stream_t(const StreamParams& p, cudaStream_t st) {
+    const int64_t tile_vecs = (int64_t)kStreamThreads * kStreamUnroll;
+    const int64_t n_tiles = (p.n_vec + tile_vecs - 1) / tile_vecs;
+    if (n_tiles == 0) return BFP_OK;
+    const DeviceInfo& di = device_info();
+    const int64_t max_ctas = (int64_t)di.sm_count * tuning().stream_ctas_per_sm;
+    const int grid = (int)std::min<int64_t>(n_tiles, max_ctas);
+    quant_stream_kernel<DT, ORDER, M, TIE, STOC><<<grid, kStreamThreads, 0, st>>>(p);
+    count_launch();
+    return check_launch("quant_stream_kernel");
+}
+
+template <int DT, int ORDER, bool STOC>
+static int launch_stream_m(const StreamParams& p, int M, int tie, cudaStream_t st) {
+    constexpr int V = DType<DT>::kVec;
+    if (ORDER == BFP_ORDER_QUANT_ONLY) return launch_stream_t<DT, ORDER, 0, BFP_TIE_TORCH_CUDA, STOC>(p, st);
+    if (tie == BFP_TIE_TORCH_CPU) {
+        if (M == 4) return launch_stream_t<DT, ORDER, 4, BFP_TIE_TORCH_CPU, STOC>(p, st);
+        return set_error(BFP_E_UNSUPPORTED, "BFP_TIE_TORCH_CPU is implemented for N:M = 2:4 only");
+    }
+    switch (M) {
+    case 1: return launch_stream_t<DT, ORDER, 1, BFP_TIE_TORCH_CUDA, STOC>(p, st);
+    case 2: return launch_stream_t<DT, ORDER, 2, BFP_TIE_TORCH_CUDA, STOC>(p, st);
+    case 4: return launch_stream_t<DT, ORDER, 4, BFP_TIE_TORCH_CUDA, STOC>(p, st);
+    case 8: if (V == 8) return launch_stream_t<DT, ORDER, (V == 8 ? 8 : 4), BFP_TIE_TORCH_CUDA, STOC>(p, st);
+    }
+    return set_error(BFP_E_UNSUPPORTED, "internal: stream path called with unsupported M");
+}
+
+template <int DT, bool STOC>
+static int launch_stream_o(const StreamParams& p, int order, int M, int tie, cudaStream_t st) {
+    switch (order) {
+    case BFP_ORDER_QUANT_ONLY: return launch_stream_m<DT, BFP_ORDER_QUANT_ONLY, STOC>(p, M, tie, st);
+    case BFP_ORDER_SPARSIFY_QUANT: return launch_stream_m<DT, BFP_ORDER_SPARSIFY_QUANT, STOC>(p, M, tie, st);
+    case BFP_ORDER_QUANT_SPARSIFY: return launch_stream_m<DT, BFP_ORDER_QUANT_SPARSIFY, STOC>(p, M, tie, st);
+    case BFP_ORDER_SPARSIFY_ONLY:
+        if (STOC) break;
+        return launch_stream_m<DT, BFP_ORDER_SPARSIFY_ONLY, false>(p, M, tie, st);
+    }
+    return set_error(BFP_E_ARG, "bad order");
+}
+
+template <int DT, int ORDER, bool STOC>
+static int launch_generic_t(const GenericParams& p, cudaStream_t st) {
+    const bool per_group = (ORDER == BFP_ORDER_SPARSIFY_ONLY || ORDER == BFP_ORDER_QUANT_SPARSIFY);
+    const int64_t units = p.rows * (per_group ? (p.K + p.M - 1) / p.M : (p.K + p.B - 1) / p.B);
+    if (units == 0) return BFP_OK;
+    const int grid = (int)std::min<int64_t>((units + 127) / 128, (int64_t)device_info().sm_count * 16);
+    quant_generic_kernel<DT, ORDER, STOC><<<grid, 128, 0, st>>>(p);
+    count_launch();
+    return check_launch("quant_generic_kernel");
+}
+
+template <int DT, bool STOC>
+static int launch_generic_o(const GenericParams& p, int order, cudaStream_t st) {
+    switch (order) {
+    case BFP_ORDER_QUANT_ONLY: return launch_generic_t<DT, BFP_ORDER_QUANT_ONLY, STOC>(p, st);
+    case BFP_ORDER_SPARSIFY_QUANT: return launch_generic_t<DT, BFP_ORDER_SPARSIFY_QUANT, STOC>(p, st);
+    case BFP_ORDER_QUANT_SPARSIFY: return launch_generic_t<DT, BFP_ORDER_QUANT_SPARSIFY, STOC>(p, st);
+    case BFP_ORDER_SPARSIFY_ONLY:
+        if (STOC) break;
+        return launch_generic_t<DT, BFP_ORDER_SPARSIFY_ONLY, false>(p, st);
+    }
+    return set_error(BFP_E_ARG, "bad order");
+}
+
+template <int DT>
+static int quantize_dt(const QuantArgs& a, cudaStream_t st) {
+    constexpr int V = DType<DT>::kVec;
+    const bool stoc = a.rounding == BFP_ROUND_STOCHASTIC && a.order != BFP_ORDER_SPARSIFY_ONLY;
+    const bool sparse = a.order != BFP_ORDER_QUANT_ONLY;
+    const bool quant = a.order != BFP_ORDER_SPARSIFY_ONLY;
+    const int64_t numel = a.rows * a.K;
+    // stream-path eligibility
+    bool fast = (numel % V == 0) && (a.index_base % 4 == 0) && (reinterpret_cast<uintptr_t>(a.in) % 16 == 0) && (reinterpret_cast<uintptr_t>(a.out) % 16 == 0);
+    if (quant) fast = fast && is_pow2(a.B) && a.B >= V && a.B <= 32 * V && (a.K % a.B == 0);
+    if (sparse) fast = fast && is_pow2(a.M) && a.M <= V && (a.K % a.M == 0) && !(a.tie == BFP_TIE_TORCH_CPU && !(a.M == 4 && a.N == 2));
+    if (!quant) fast = fast && (a.K % V == 0 || true);      // groups never straddle vectors: M | V and M | K
+    if (tuning().force_generic) fast = false;
+    if (fast) {
+        StreamParams p;
+        p.in = static_cast<const uint4*>(a.in);
+        p.out = static_cast<uint4*>(a.out);
+        p.n_vec = numel / V;
+        p.lanes_per_block = quant ? a.B / V : 1;
+        p.m = a.m; p.eps = a.eps; p.kdrop = sparse ? a.M - a.N : 0;
+        p.seed = a.seed; p.offset = a.offset; p.ctr_base = a.index_base / 4;
+        return stoc ? launch_stream_o<DT, true>(p, a.order, a.M, a.tie, st) : launch_stream_o<DT, false>(p, a.order, a.M, a.tie, st);
+    }
+    if (sparse && a.tie == BFP_TIE_TORCH_CPU && !(a.M == 4 && a.N == 2))
+        return set_error(BFP_E_UNSUPPORTED, "BFP_TIE_TORCH_CPU is implemented for N:M = 2:4 only");
+    GenericParams g;
+    g.in = a.in; g.out = a.out; g.rows = a.rows; g.K = a.K; g.B = quant ? a.B : 1; g.m = a.m; g.eps = a.eps;
+    g.N = a.N; g.M = sparse ? a.M : 1; g.tie = a.tie; g.seed = a.seed; g.offset = a.offset; g.index_base = a.index_base;
+    return stoc ? launch_generic_o<DT, true>(g, a.order, st) : launch_generic_o<DT, false>(g, a.order, st);
+}
+
+int quantize_device(const QuantArgs& a, cudaStream_t st) {
+    switch (a.in_dtype) {
+    case BFP_DT_F32: return quantize_dt<BFP_DT_F32>(a, st);
+    case BFP_DT_F16: return quantize_dt<BFP_DT_F16>(a, st);
+    case BFP_DT_BF16: return quantize_dt<BFP_DT_BF16>(a, st);
+    }
+    return set_error(BFP_E_ARG, "bad dtype");
+}
+
+int block_exponent_device(const void* in, float* e_out, int64_t rows, int64_t K, int dtype, int B, float eps, cudaStream_t st) {
+    const int64_t units = rows * ((K + B - 1) / B);
+    if (units == 0) return BFP_OK;
+    const int grid = (int)std::min<int64_t>((units + 127) / 128, (int64_t)device_info().sm_count * 16);
+    switch (dtype) {
+    case BFP_DT_F32: block_exponent_kernel<BFP_DT_F32><<<grid, 128, 0, st>>>(in, e_out, rows, K, B, eps); break;
+    case BFP_DT_F16: block_exponent_kernel<BFP_DT_F16><<<grid, 128, 0, st>>>(in, e_out, rows, K, B, eps); break;
+    case BFP_DT_BF16: block_exponent_kernel<BFP_DT_BF16><<<grid, 128, 0, st>>>(in, e_out, rows, K, B, eps); break;
+    default: return set_error(BFP_E_ARG, "bad dtype");
+    }
+    count_launch();
+    return check_launch("block_exponent_kernel");
+}
+
+int debug_cpu_tie_lut(uint8_t out[256]) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, c_cpu_tie_lut, 256);
+    if (e != cudaSuccess) return set_error(BFP_E_CUDA, cudaGetErrorString(e));
+    return BFP_OK;
+}
+
+}  // namespace bfp

@@ -1,0 +1,336 @@
+"""GPU parity suite for the fused quantise + N:M kernels.  Everything goes through the reference-shaped Python API
+(qsi_b200.bfp_ops) -> ctypes -> C ABI (libbfp_b200.so); the oracle (oracle/) is only the checker.
+
+Bar: bit-exact for round-to-nearest values and for the sparsity masks (including the sign of zero); stochastic
+rounding is checked bit-exactly given the kernel's own Philox uniforms and statistically for unbiasedness.
+"""
+import itertools
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import _golden
+from _refload import load_reference, ref_args
+
+pytestmark = pytest.mark.gpu
+
+TORCH_DT = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from qsi_b200 import bfp_ops, _lib
+    _lib.lib()
+    return bfp_ops
+
+
+def _to_dev(a, dt):
+    from oracle import bfp_oracle as O
+    return O.to_torch(a, dt).cuda()
+
+
+def _np(t):
+    from oracle import bfp_oracle as O
+    return O.from_torch(t)
+
+
+def _run(ops, x, kind, m, B, N, M, rounding="determ"):
+    if kind == "q":
+        return ops._no_sparsity_float_to_bfp(x, B, m, 1e-8, rounding, "cuda")
+    if kind == "s":
+        return ops._structured_N_M_sparsity(x, "cuda", N, M)
+    args = ops.unpack_bfp_args(dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode=rounding, epsilon=1e-8,
+                                    mant_bits=m, block_size=B, w_sparsity=True, N=N, M=M,
+                                    first="s" if kind == "sq" else "q", sparsity_mode="structured", device="cuda"))
+    return ops.float_to_bfp_blocked(x, **args, identifier="w")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 1. golden fixtures recorded from the reference (torch-CUDA on a B200, and torch-CPU)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("device", ["cuda", "cpu"])
+@pytest.mark.parametrize("generic", [0, 1])
+def test_kernel_matches_reference_golden(ops, device, generic, monkeypatch):
+    from qsi_b200 import _lib
+    z = _golden.load(device)
+    if z is None:
+        pytest.skip(f"tests/golden/ref_{device}.npz not recorded")
+    monkeypatch.setenv("BFP_TIE_RULE", device)
+    _lib.set_option("force_generic", generic)
+    try:
+        n = 0
+        for c in _golden.quant_cases(z):
+            if device == "cpu" and c["kind"] != "q" and (c["N"], c["M"]) != (2, 4):
+                continue                       # torch-CPU's tie order is reproduced for 2:4 only
+            x = _to_dev(c["x"], c["dt"])
+            y = _run(ops, x, c["kind"], c["m"], c["B"], c["N"], c["M"])
+            out, odt = _np(y)
+            assert odt == c["odt"] and out.shape == c["y"].shape, c["key"]
+            assert _golden.mismatches(out, c["y"], odt) == 0, (c["key"], generic)
+            n += 1
+        assert n > 400
+    finally:
+        _lib.set_option("force_generic", 0)
+
+
+@pytest.mark.parametrize("device", ["cuda", "cpu"])
+def test_kernel_matches_reference_golden_exponent_and_ties(ops, device, monkeypatch):
+    z = _golden.load(device)
+    if z is None:
+        pytest.skip("not recorded")
+    monkeypatch.setenv("BFP_TIE_RULE", device)
+    for dt in ("f32", "f16", "bf16"):
+        x, _ = _golden.get(z, f"expb_in_{dt}")
+        e = ops.get_exponent(_to_dev(x, dt), 1e-8).float().cpu().numpy()
+        ref = z[f"expb_out_{dt}"]
+        assert ((e == ref) | (np.isnan(e) & np.isnan(ref))).all(), dt
+    x, _ = _golden.get(z, "tie_in")
+    for (N, M) in ((2, 4), (1, 4), (3, 4)):
+        if device == "cpu" and (N, M) != (2, 4):
+            continue
+        y, _ = _golden.get(z, f"tie_out_{N}:{M}")
+        out = ops._structured_N_M_sparsity(_to_dev(x, "f32"), "cuda", N, M).cpu().numpy()
+        assert _golden.mismatches(out, y, "f32") == 0, (N, M)
+
+
+def test_cpu_tie_table_on_device(ops):
+    from qsi_b200 import _lib
+    import ctypes, re
+    buf = (ctypes.c_uint8 * 256)()
+    _lib.check(_lib.lib().bfp_debug_cpu_tie_lut(ctypes.addressof(buf)))
+    txt = "\n".join(l for l in open(os.path.join(_lib.CSRC, "nm_cpu_tie_lut.inc")).read().splitlines() if not l.startswith("//"))
+    assert list(buf) == [int(v, 16) for v in re.findall(r"0x([0-9A-F]{2})", txt)]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 2. seeded random inputs vs the oracle: dtype x mant x block x order x N:M, aligned and ragged shapes
+# ---------------------------------------------------------------------------------------------------------------
+def _inputs(seed, shape, dtype, scale):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.randn(*shape, generator=g) * scale
+    flat = t.view(-1)
+    flat[torch.randint(0, flat.numel(), (max(1, flat.numel() // 40),), generator=g)] = 0.0
+    flat[torch.randint(0, flat.numel(), (max(1, flat.numel() // 200),), generator=g)] *= 30.0
+    return t.to(dtype)
+
+
+@pytest.mark.parametrize("dt", ["f32", "bf16", "f16"])
+@pytest.mark.parametrize("shape", [(256, 1024), (3, 5, 200), (37, 96), (6, 3, 16, 16), (5, 7), (1, 64)])
+def test_kernel_matches_oracle_sweep(ops, oracle, dt, shape):
+    for si, scale in enumerate((1.0, 0.02, 200.0)):
+        x = _inputs(11 * si + len(shape), shape, TORCH_DT[dt], scale)
+        xa, _ = _np(x)
+        xd = x.cuda()
+        for (m, B) in ((3, 16), (5, 32), (7, 64), (7, 16), (15, 64), (3, 128), (7, 48)):
+            y, _ = _np(ops._no_sparsity_float_to_bfp(xd, B, m, 1e-8, "determ", "cuda"))
+            o, _ = oracle.bfp_quantize(xa, B, m, dt=dt)
+            assert _golden.mismatches(y, o, dt) == 0, ("q", scale, m, B)
+            for (N, M), kind in itertools.product(((2, 4), (1, 4), (3, 4), (1, 2), (4, 8), (2, 8), (3, 5)), ("sq", "qs")):
+                if (m, B) not in ((3, 16), (7, 64), (5, 32)):
+                    continue
+                y, _ = _np(_run(ops, xd, kind, m, B, N, M))
+                o, _ = oracle.float_to_bfp_blocked(xa, m, B, kind, N=N, M=M, tie_rule="cuda", dt=dt)
+                assert _golden.mismatches(y, o, dt) == 0, (kind, scale, m, B, N, M)
+        for (N, M) in ((2, 4), (1, 4), (3, 4), (1, 2), (4, 8), (2, 8), (8, 16), (3, 5), (1, 1)):
+            y, _ = _np(ops._structured_N_M_sparsity(xd, "cuda", N, M))
+            o = oracle.nm_sparsify(xa, N, M, tie_rule="cuda", dt=dt)
+            assert _golden.mismatches(y, o, dt) == 0, ("s", scale, N, M)
+
+
+def test_special_values_match_oracle(ops, oracle):
+    """zeros, -0.0, denormals, huge values, Inf / NaN blocks (NaN compares equal to NaN)."""
+    x = torch.zeros(8, 128)
+    x[1] = torch.randn(128) * 1e-40
+    x[2] = torch.randn(128) * 3e38
+    x[3, 7] = float("inf")
+    x[4, 70] = float("nan")
+    x[5, ::2] = -0.0
+    x[6] = torch.randn(128)
+    x[6, 3] = -float("inf")
+    x[7] = torch.randn(128) * 1e-9
+    for dt in ("f32", "bf16", "f16"):
+        xt = x.to(TORCH_DT[dt])
+        xa, _ = _np(xt)
+        for kind, (m, B) in itertools.product(("q", "sq", "qs", "s"), ((7, 64), (3, 16))):
+            y, _ = _np(_run(ops, xt.cuda(), kind, m, B, 2, 4))
+            if kind == "s":
+                o = oracle.nm_sparsify(xa, 2, 4, dt=dt)
+            else:
+                o, _ = oracle.float_to_bfp_blocked(xa, m, B, kind, dt=dt)
+            assert _golden.mismatches(y, o, dt) == 0, (dt, kind, m, B)
+
+
+def test_known_answers_on_device(ops):
+    q = lambda v, m, B: ops._no_sparsity_float_to_bfp(torch.tensor([v], device="cuda"), B, m, 1e-8, "determ", "cuda")[0].cpu()
+    assert torch.equal(q([1.0, 0.99, -1.0, 0.5], 7, 4), torch.tensor([127 / 128, 127 / 128, -127 / 128, 0.5]))
+    y = q([-0.3, 0.3, 100.0, -100.0], 3, 4)
+    assert torch.equal(y, torch.tensor([-0.0, 0.0, 96.0, -96.0])) and torch.signbit(y).tolist() == [True, False, False, True]
+    s = ops._structured_N_M_sparsity(torch.tensor([[-1.0, 2.0, -3.0, 4.0]], device="cuda"), "cuda", 2, 4).cpu()
+    assert torch.equal(s, torch.tensor([[0.0, 0.0, -3.0, 4.0]]))
+    assert torch.isnan(ops._no_sparsity_float_to_bfp(torch.zeros(1, 8, device="cuda", dtype=torch.float16), 8, 7, 1e-8, "determ", "cuda")).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 3. live against the reference on torch-CUDA (baseline/_ref travels to the GPU box; skipped when absent)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", ["f32", "bf16", "f16"])
+def test_kernel_matches_live_reference_on_cuda(ops, dt):
+    ref = load_reference()
+    if ref is None:
+        pytest.skip("reference sources not present on this box")
+    for seed, (shape, scale) in enumerate(itertools.product([(512, 1024), (3, 5, 200), (6, 3, 16, 16)], [0.02, 1.0])):
+        x = _inputs(500 + seed, shape, TORCH_DT[dt], scale).cuda()
+        for (m, B), (N, M), first in itertools.product(((3, 16), (5, 32), (7, 64)), ((2, 4), (1, 4), (4, 8)), ("s", "q")):
+            args = ref_args(ref, mant_bits=m, block_size=B, first=first, N=N, M=M, device="cuda")
+            r = ref.float_to_bfp_blocked(x, **args, identifier="w")
+            y = _run(ops, x, "sq" if first == "s" else "qs", m, B, N, M)
+            assert y.dtype == r.dtype and y.shape == r.shape
+            assert _golden.mismatches(_np(y)[0], _np(r)[0], dt) == 0, (shape, scale, m, B, N, M, first)
+        r = ref._no_sparsity_float_to_bfp(x, 64, 7, 1e-8, "determ", "cuda")
+        assert _golden.mismatches(_np(ops._no_sparsity_float_to_bfp(x, 64, 7, 1e-8, "determ", "cuda"))[0], _np(r)[0], dt) == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 4. stochastic rounding: bit-exact given the kernel's Philox stream, unbiased, fp32 output for half inputs
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", ["f32", "bf16", "f16"])
+@pytest.mark.parametrize("shape", [(64, 512), (9, 100)])
+def test_stochastic_rounding_bit_exact_given_philox(ops, oracle, dt, shape):
+    from qsi_b200 import _lib
+    x = _inputs(77, shape, TORCH_DT[dt], 1.0)
+    xa, _ = _np(x)
+    xd = x.cuda()
+    for (m, B), (seed, off) in itertools.product(((3, 16), (7, 64)), ((1234, 0), (2 ** 40 + 17, 5))):
+        u = oracle.philox_uniforms(x.numel(), seed, off).reshape(x.shape)
+        for kind, order in (("q", _lib.ORDER_QUANT_ONLY), ("sq", _lib.ORDER_SPARSIFY_QUANT), ("qs", _lib.ORDER_QUANT_SPARSIFY)):
+            y = ops._fused(xd, order, block_size=B, mant_bits=m, epsilon=1e-8, rounding_mode="stoc", N=2, M=4, philox=(seed, off))
+            assert y.dtype == torch.float32                    # type promotion of the reference (bfp_ops.py:22-23)
+            o, odt = oracle.float_to_bfp_blocked(xa, m, B, kind, rounding_mode="stoc", rand_u=u, dt=dt)
+            assert odt == "f32" and _golden.mismatches(y.cpu().numpy(), o, "f32") == 0, (kind, m, B, seed)
+
+
+def test_stochastic_rounding_statistics(ops):
+    torch.manual_seed(3)
+    n = 1 << 18
+    x = torch.full((n, 8), 0.3, device="cuda")
+    x[:, 0] = 1.0
+    y = ops._no_sparsity_float_to_bfp(x, 8, 3, 1e-8, "stoc", "cuda")
+    vals = torch.unique(y[:, 1:]).cpu().tolist()
+    assert set(vals) <= {0.25, 0.375}
+    assert abs(y[:, 1:].double().mean().item() - 0.3) < 5 * 0.0625 / np.sqrt(7 * n)
+    assert (y[:, 0] == 0.875).all()
+    y2 = ops._no_sparsity_float_to_bfp(x, 8, 3, 1e-8, "stoc", "cuda")
+    assert not torch.equal(y, y2)                              # successive calls advance the Philox offset
+    # error distribution: for uniform inputs the rounding error is ~U(-delta, delta) triangular with mean 0
+    w = torch.rand(1 << 20, device="cuda") * 0.9
+    w[::64] = 1.0
+    yq = ops._no_sparsity_float_to_bfp(w.view(-1, 64), 64, 7, 1e-8, "stoc", "cuda").view(-1)
+    err = (yq - w)[w < 0.95].double()
+    delta = 2.0 ** -7
+    assert abs(err.mean().item()) < 5 * delta / np.sqrt(err.numel())
+    assert err.abs().max().item() < delta
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 5. host-buffer entry point and full-size properties
+# ---------------------------------------------------------------------------------------------------------------
+def test_host_buffer_path_equals_device_path(ops):
+    from qsi_b200 import _lib
+    x = _inputs(5, (1000, 1024), torch.float32, 0.02)
+    _lib.set_option("host_chunk_bytes", 1 << 20)             # force several pipelined chunks
+    try:
+        for kind, rounding in itertools.product(("q", "sq", "qs", "s"), ("determ",)):
+            y_host = _run(ops, x.pin_memory(), kind, 7, 64, 2, 4)
+            y_page = _run(ops, x, kind, 7, 64, 2, 4)
+            assert not y_host.is_cuda
+            monkey = os.environ.get("BFP_TIE_RULE")
+            os.environ["BFP_TIE_RULE"] = "cpu"               # CPU tensors default to the torch-CPU 2:4 tie order
+            try:
+                y_dev = _run(ops, x.cuda(), kind, 7, 64, 2, 4).cpu()
+            finally:
+                if monkey is None:
+                    del os.environ["BFP_TIE_RULE"]
+                else:
+                    os.environ["BFP_TIE_RULE"] = monkey
+            assert _golden.mismatches(y_host.numpy(), y_dev.numpy(), "f32") == 0, kind
+            assert _golden.mismatches(y_page.numpy(), y_dev.numpy(), "f32") == 0, kind
+        # stochastic: chunking must not change the Philox stream
+        a = ops._fused(x.pin_memory(), _lib.ORDER_QUANT_ONLY, block_size=64, mant_bits=7, epsilon=1e-8, rounding_mode="stoc", philox=(9, 1))
+        b = ops._fused(x.cuda(), _lib.ORDER_QUANT_ONLY, block_size=64, mant_bits=7, epsilon=1e-8, rounding_mode="stoc", philox=(9, 1)).cpu()
+        assert torch.equal(a, b)
+    finally:
+        _lib.set_option("host_chunk_bytes", 8 << 20)
+        _lib.lib().bfp_host_staging_release()
+
+
+@pytest.mark.parametrize("shape", [(4096, 4096), (4096, 11008)])
+def test_full_size_properties(ops, oracle, shape):
+    """BASELINE config 2 shapes: oracle on a row sample, chunk invariance, N:M structure, idempotence of the mask."""
+    g = torch.Generator(device="cuda").manual_seed(0)
+    w = torch.randn(*shape, device="cuda", generator=g) * 0.02
+    rows = torch.randint(0, shape[0], (48,), generator=torch.Generator().manual_seed(1)).tolist()
+    for (m, B), kind in itertools.product(((3, 16), (5, 32), (7, 64)), ("sq", "qs")):
+        y = _run(ops, w, kind, m, B, 2, 4)
+        # (a) bit-exact against the oracle on sampled rows
+        xa = w[rows].cpu().numpy()
+        o, _ = oracle.float_to_bfp_blocked(xa, m, B, kind)
+        assert _golden.mismatches(y[rows].cpu().numpy(), o, "f32") == 0, (kind, m, B)
+        # (b) row-chunk invariance
+        parts = torch.cat([_run(ops, c, kind, m, B, 2, 4) for c in w.chunk(8, dim=0)], dim=0)
+        assert torch.equal(parts.view(torch.int32), y.view(torch.int32))
+        # (c) at least 2 zeros in every group of 4; kept values lie on the block grid
+        assert int((y.view(-1, 4) == 0).sum(dim=1).min()) >= 2
+        # (d) the mask is idempotent
+        assert torch.equal(ops._structured_N_M_sparsity(y, "cuda", 2, 4), y)
+    # bf16 / fp16 at full size against the oracle on the row sample
+    for dt in ("bf16", "f16"):
+        wt = w.to(TORCH_DT[dt])
+        y = _run(ops, wt, "sq", 7, 64, 2, 4)
+        o, _ = oracle.float_to_bfp_blocked(_np(wt[rows])[0], 7, 64, "sq", dt=dt)
+        assert _golden.mismatches(_np(y[rows])[0], o, dt) == 0
+
+
+def test_api_conventions_on_device(ops):
+    x = torch.randn(4, 6, 64, device="cuda")
+    xt = x.transpose(0, 1)                                     # non-contiguous input
+    args = ops.unpack_bfp_args(dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", mant_bits=7,
+                                    block_size=64, w_sparsity=True, N=2, M=4, first="s", sparsity_mode="structured"))
+    y = ops.float_to_bfp_blocked(xt, **args, identifier="w")
+    assert y.shape == xt.shape and y.data_ptr() != xt.data_ptr()
+    assert torch.equal(y, ops.float_to_bfp_blocked(xt.contiguous(), **args, identifier="w"))
+    y_in = ops.float_to_bfp_blocked(x, **args, identifier="in")      # activations are not sparsified
+    assert torch.equal(y_in, ops._no_sparsity_float_to_bfp(x, 64, 7, 1e-8, "determ", "cuda"))
+    assert ops.float_to_bfp_blocked(torch.empty(0, 64, device="cuda"), **args, identifier="w").shape == (0, 64)
+    with pytest.raises(NotImplementedError):
+        ops.float_to_bfp_blocked(x, **dict(args, sparsity_mode="unstructured", sparsity_frac=0.5), identifier="w")
+
+
+def test_bfp_linear_module_matches_oracle(ops, oracle):
+    """BFPLinear / F_matmul_bfp forward + STE backward (bfp_ops.py:160-192, 270-287)."""
+    torch.manual_seed(0)
+    kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=7,
+              block_size=64, w_sparsity=True, N=2, M=4, first="s", sparsity_mode="structured", device="cuda")
+    lin = ops.BFPLinear(256, 96, bias=True, **dict(kw)).cuda()
+    x = torch.randn(3, 20, 256, device="cuda", requires_grad=True)
+    y = lin(x)
+    xq, _ = oracle.bfp_quantize(x.detach().cpu().numpy(), 64, 7)
+    wq, _ = oracle.float_to_bfp_blocked(lin.weight.detach().cpu().numpy(), 7, 64, "sq")
+    ref = oracle.linear(xq, wq, lin.bias.detach().cpu().numpy())
+    rel = np.linalg.norm(y.detach().cpu().numpy() - ref) / np.linalg.norm(ref)
+    assert rel <= 1e-5, rel                                      # north_star GEMM tolerance
+    y.sum().backward()
+    # STE: dL/dx = Q_grad(1) @ W_q ; the all-ones gradient is exactly representable, so Q_grad is the identity here
+    gx = torch.from_numpy(wq).cuda().sum(dim=0).expand_as(x)
+    assert torch.allclose(x.grad, gx, rtol=1e-5, atol=1e-6)
+    assert lin.weight.grad is not None and lin.weight.grad.shape == lin.weight.shape
+    mm = ops.F_matmul_bfp(**dict(kw))
+    a = torch.randn(2, 4, 16, 64, device="cuda")
+    b = torch.randn(2, 4, 64, 32, device="cuda")
+    out = mm(a, b)
+    aq, _ = oracle.bfp_quantize(a.cpu().numpy(), 64, 7)
+    bq, _ = oracle.float_to_bfp_blocked(b.transpose(-1, -2).contiguous().cpu().numpy(), 7, 64, "sq")
+    ref = np.matmul(aq.astype(np.float64), np.swapaxes(bq, -1, -2).astype(np.float64))
+    assert np.linalg.norm(out.cpu().numpy() - ref) / np.linalg.norm(ref) <= 1e-5
