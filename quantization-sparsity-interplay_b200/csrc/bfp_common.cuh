@@ -79,12 +79,29 @@ __device__ __forceinline__ float u01(uint32_t w) { return (float)(w >> 8) * 5.96
 // block scale: everything derived from the block's max |t|   (bfp_ops.py:29-33, :38-39)
 // ---------------------------------------------------------------------------------------------------------------
 struct BlockScale {
-    float inv;     // 2^-(e-m)            fast path
+    float inv;     // 2^-(e-m)                       fast path only
     float delta;   // 2^(e-m)  (interval, bfp_ops.py:38)
-    float vmax;    // 2^e - interval (max_v, bfp_ops.py:39); fast path: = qmax * delta
+    float vmax;    // fast path: 2^m - 1 (clamp on the integer grid); slow path: 2^e - interval (max_v, bfp_ops.py:39)
     float e;       // block exponent as torch holds it (float in the tensor dtype)
     bool fast;
 };
+
+// Literal evaluation of bfp_ops.py:33,38-39, rounding through the dtype after every op.  Rare blocks only (all-zero,
+// denormal scale, overflow, Inf/NaN, mant_bits outside the exact range), so it is kept out of line.
+// returns (delta, vmax, e)
+template <int DT>
+__device__ __noinline__ float3 make_scale_slow(float s, int m) {
+    using D = DType<DT>;
+    const float ef = ceilf(D::rnd(log2f(s)));
+    const float p = D::rnd(ef - (float)m);
+    const float delta = D::rnd(powf(2.0f, p));
+    const float vmax = D::rnd(D::rnd(powf(2.0f, ef)) - delta);
+    return make_float3(delta, vmax, ef);
+}
+
+// ceil(log2f(s)) for the few fp32 values whose mantissa is within 128 ulp of a power of two (out of line: log2f is
+// ~20 instructions and this branch is taken for ~1.5e-5 of the blocks).
+__device__ __noinline__ int exponent_near_pow2(float s) { return (int)ceilf(log2f(s)); }
 
 template <int DT>
 __device__ __forceinline__ BlockScale make_scale(uint32_t amax_bits, int m, float eps) {
@@ -97,48 +114,51 @@ __device__ __forceinline__ BlockScale make_scale(uint32_t amax_bits, int m, floa
     bool ok = (k >= D::kMinExp) && (k < D::kMaxExp) && (m >= 1) && (m <= D::kMaxMant);
     int e = 0;
     if (ok) {
-        if (DT == BFP_DT_F32 && (sb & 0x7fffffu) > 128u) {
-            // log2f(s) lies at least 128*1.44*2^-23 above k: no 1-ulp log2f can round it down to k
+        if (DT == BFP_DT_F32) {
+            // mantissa > 128 ulp above 2^k: log2f(s) >= k + 128*1.44*2^-23, which no 1-ulp log2f can round down to k
             // (fp32 spacing near |k| <= 127 is at most 2^-17), so ceil(log2f(s)) = k + 1 without evaluating it.
-            e = k + 1;
+            e = ((sb & 0x7fffffu) > 128u) ? k + 1 : exponent_near_pow2(s);
         } else {
-            e = (int)ceilf(D::rnd(log2f(s)));             // bfp_ops.py:33  .log2().ceil()
+            e = (int)ceilf(D::rnd(log2f(s)));             // bfp_ops.py:33  .log2().ceil(), log2 rounded to the dtype
         }
         ok = (e - m >= D::kMinScaleExp) && (e <= D::kMaxExp) && (e >= D::kMinExp);
     }
-    sc.fast = ok;
     if (ok) {
         const int p = e - m;                              // in [-126, 125]: both 2^p and 2^-p are normal floats
         sc.delta = __uint_as_float((uint32_t)(p + 127) << 23);
         sc.inv = __uint_as_float((uint32_t)(127 - p) << 23);
-        sc.vmax = (float)((1 << m) - 1);                  // fast path clamps on the integer grid: |q| <= 2^m - 1
+        sc.vmax = (float)((1 << m) - 1);
         sc.e = (float)e;
+        sc.fast = true;
     } else {
-        // literal evaluation, rounding through the dtype after every op (all-zero fp16 block -> NaN, inf -> NaN, ...)
-        const float ef = ceilf(D::rnd(log2f(s)));
-        const float p = D::rnd(ef - (float)m);
-        sc.delta = D::rnd(powf(2.0f, p));
-        sc.vmax = D::rnd(D::rnd(powf(2.0f, ef)) - sc.delta);
-        sc.inv = 0.0f;
-        sc.e = ef;
+        const float3 r = make_scale_slow<DT>(s, m);
+        sc.delta = r.x; sc.vmax = r.y; sc.e = r.z; sc.inv = 0.0f; sc.fast = false;
     }
     return sc;
 }
 
-// one element: bfp_ops.py:40-44.  STOC: u is the element's uniform in [0,1).
+// one element, fast path: bfp_ops.py:40-44 with every product exact.  STOC: u is the element's uniform in [0,1).
+template <bool STOC>
+__device__ __forceinline__ float quant_elt_fast(float t, const BlockScale& sc, float u) {
+    const float x = t * sc.inv;                                   // exact (power-of-two scale)
+    const float r = STOC ? rintf((u - 0.5f) + x) : rintf(x);      // bfp_ops.py:22-25
+    return fminf(fmaxf(r, -sc.vmax), sc.vmax) * sc.delta;         // clamp on the grid, exact product
+}
+
+// one element, literal evaluation (out of line; see make_scale_slow)
+template <int DT, bool STOC>
+__device__ __noinline__ float quant_elt_slow(float t, float delta, float vmax, float u) {
+    using D = DType<DT>;
+    const float x = D::rnd(t / delta);
+    float y;
+    if (STOC) y = rintf((u - 0.5f) + x) * delta;                  // fp32 from here on (type promotion)
+    else y = D::rnd(rintf(x) * delta);
+    return t_min(t_max(y, -vmax), vmax);
+}
+
 template <int DT, bool STOC>
 __device__ __forceinline__ float quant_elt(float t, const BlockScale& sc, float u) {
-    using D = DType<DT>;
-    if (sc.fast) {
-        const float x = t * sc.inv;                                   // exact (power-of-two scale)
-        const float r = STOC ? rintf((u - 0.5f) + x) : rintf(x);      // bfp_ops.py:22-25
-        return fminf(fmaxf(r, -sc.vmax), sc.vmax) * sc.delta;         // clamp on the grid, exact product
-    }
-    const float x = D::rnd(t / sc.delta);
-    float y;
-    if (STOC) y = rintf((u - 0.5f) + x) * sc.delta;                   // fp32 from here on (type promotion)
-    else y = D::rnd(rintf(x) * sc.delta);
-    return t_min(t_max(y, -sc.vmax), sc.vmax);
+    return sc.fast ? quant_elt_fast<STOC>(t, sc, u) : quant_elt_slow<DT, STOC>(t, sc.delta, sc.vmax, u);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -148,6 +168,50 @@ __device__ __forceinline__ float quant_elt(float t, const BlockScale& sc, float 
 static __constant__ uint8_t c_cpu_tie_lut[256] = {
 #include "nm_cpu_tie_lut.inc"
 };
+
+// rank < K for a rank that is the number of true predicates among (a, b, c)
+template <int K> __device__ __forceinline__ bool fewer_than(bool a, bool b, bool c) {
+    if (K == 1) return !(a | b | c);
+    if (K == 2) return !((a & b) | (a & c) | (b & c));
+    return !(a & b & c);
+}
+
+// M = 4 with compile-time KDROP, torch-CUDA rule: element i is dropped iff fewer than KDROP elements precede it in
+// (|v|, index) order.  6 compares + 4 predicate LUTs + 4 selects.
+template <int KDROP>
+__device__ __forceinline__ void nm_mask4(float* v) {
+    const uint32_t k0 = abs_bits(v[0]), k1 = abs_bits(v[1]), k2 = abs_bits(v[2]), k3 = abs_bits(v[3]);
+    if (KDROP == 2) {
+        // c_ij = (k_i <= k_j), i < j.  j > i precedes i iff !c_ij; j < i precedes i iff c_ji.  With K = 2,
+        // "fewer than 2 of (a,b,c)" = !maj(a,b,c), and !maj(!a,!b,!c) = maj(a,b,c):
+        //   drop0 = maj(c01, c02, c03)   drop1 = maj(!c01, c12, c13)   drop2 = maj(!c02, !c12, c23)   drop3 = maj(!c03, !c13, !c23)
+        // written on predicate registers so ptxas emits one PLOP3 per majority.
+        asm("{\n\t"
+            ".reg .pred c01, c02, c03, c12, c13, c23, n01, n02, n03, n12, n13, n23, t0, t1, t2, d;\n\t"
+            "setp.le.u32 c01, %4, %5;\n\t setp.le.u32 c02, %4, %6;\n\t setp.le.u32 c03, %4, %7;\n\t"
+            "setp.le.u32 c12, %5, %6;\n\t setp.le.u32 c13, %5, %7;\n\t setp.le.u32 c23, %6, %7;\n\t"
+            "not.pred n01, c01;\n\t not.pred n02, c02;\n\t not.pred n03, c03;\n\t"
+            "not.pred n12, c12;\n\t not.pred n13, c13;\n\t not.pred n23, c23;\n\t"
+            "and.pred t0, c01, c02;\n\t and.pred t1, c01, c03;\n\t and.pred t2, c02, c03;\n\t"
+            "or.pred d, t0, t1;\n\t or.pred d, d, t2;\n\t selp.f32 %0, 0f00000000, %0, d;\n\t"
+            "and.pred t0, n01, c12;\n\t and.pred t1, n01, c13;\n\t and.pred t2, c12, c13;\n\t"
+            "or.pred d, t0, t1;\n\t or.pred d, d, t2;\n\t selp.f32 %1, 0f00000000, %1, d;\n\t"
+            "and.pred t0, n02, n12;\n\t and.pred t1, n02, c23;\n\t and.pred t2, n12, c23;\n\t"
+            "or.pred d, t0, t1;\n\t or.pred d, d, t2;\n\t selp.f32 %2, 0f00000000, %2, d;\n\t"
+            "and.pred t0, n03, n13;\n\t and.pred t1, n03, n23;\n\t and.pred t2, n13, n23;\n\t"
+            "or.pred d, t0, t1;\n\t or.pred d, d, t2;\n\t selp.f32 %3, 0f00000000, %3, d;\n\t"
+            "}"
+            : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3])
+            : "r"(k0), "r"(k1), "r"(k2), "r"(k3));
+        return;
+    }
+    const bool c01 = k0 <= k1, c02 = k0 <= k2, c03 = k0 <= k3, c12 = k1 <= k2, c13 = k1 <= k3, c23 = k2 <= k3;
+    const bool d0 = fewer_than<KDROP>(!c01, !c02, !c03);   // j > 0 precedes 0 iff key_j <  key_0
+    const bool d1 = fewer_than<KDROP>(c01, !c12, !c13);    // 0 precedes 1     iff key_0 <= key_1
+    const bool d2 = fewer_than<KDROP>(c02, c12, !c23);
+    const bool d3 = fewer_than<KDROP>(c03, c13, c23);
+    v[0] = d0 ? 0.0f : v[0]; v[1] = d1 ? 0.0f : v[1]; v[2] = d2 ? 0.0f : v[2]; v[3] = d3 ? 0.0f : v[3];
+}
 
 template <int M, int TIE>
 __device__ __forceinline__ void nm_mask_group(float* v, int kdrop) {

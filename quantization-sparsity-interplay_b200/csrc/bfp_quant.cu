@@ -83,8 +83,20 @@ struct StreamParams {
 constexpr int kStreamThreads = 256;
 constexpr int kStreamUnroll = 4;
 
-// ORDER: BFP_ORDER_*.  M: group size held in-lane (0 = no sparsity).  STOC: stochastic rounding (fp32 output).
-template <int DT, int ORDER, int M, int TIE, bool STOC>
+// ORDER: BFP_ORDER_*.  M: group size held in-lane (0 = no sparsity).  KD: compile-time M-N for M == 4 (0 = use the
+// runtime p.kdrop).  STOC: stochastic rounding (fp32 output).
+template <int M, int KD, int TIE, int V>
+__device__ __forceinline__ void mask_vec(float* v, int kdrop) {
+    if (M == 0) return;
+    constexpr int MM = M > 0 ? M : 1;
+#pragma unroll
+    for (int g = 0; g < V / MM; ++g) {
+        if (M == 4 && KD > 0 && TIE == BFP_TIE_TORCH_CUDA) nm_mask4<(KD > 0 ? KD : 1)>(v + g * MM);
+        else nm_mask_group<MM, TIE>(v + g * MM, kdrop);
+    }
+}
+
+template <int DT, int ORDER, int M, int KD, int TIE, bool STOC>
 __global__ void __launch_bounds__(kStreamThreads) quant_stream_kernel(const StreamParams p) {
     using D = DType<DT>;
     constexpr int V = D::kVec;
@@ -92,57 +104,67 @@ __global__ void __launch_bounds__(kStreamThreads) quant_stream_kernel(const Stre
     constexpr bool kSparseFirst = ORDER == BFP_ORDER_SPARSIFY_QUANT || ORDER == BFP_ORDER_SPARSIFY_ONLY;
     constexpr bool kSparseLast = ORDER == BFP_ORDER_QUANT_SPARSIFY;
     constexpr int kOutVecs = (STOC && V == 8) ? 2 : 1;     // fp32 output of 8 half inputs = two 16-B stores
+    constexpr int kTileVecs = kStreamThreads * kStreamUnroll;
 
-    const int64_t tile_vecs = (int64_t)kStreamThreads * kStreamUnroll;
-    const int64_t n_tiles = (p.n_vec + tile_vecs - 1) / tile_vecs;
+    const int64_t n_tiles = (p.n_vec + kTileVecs - 1) / kTileVecs;
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t base = tile * tile_vecs + threadIdx.x;
+        const int64_t tile_base = tile * kTileVecs;
+        const int rem = (int)min((int64_t)kTileVecs, p.n_vec - tile_base);   // vectors of this tile that exist
+        const uint4* src = p.in + tile_base;
         uint4 raw[kStreamUnroll];
 #pragma unroll
         for (int u = 0; u < kStreamUnroll; ++u) {
-            const int64_t vi = base + (int64_t)u * kStreamThreads;
-            raw[u] = (vi < p.n_vec) ? ld_stream(p.in + vi) : make_uint4(0u, 0u, 0u, 0u);
+            const int li = (int)threadIdx.x + u * kStreamThreads;
+            raw[u] = (li < rem) ? ld_stream(src + li) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
         for (int u = 0; u < kStreamUnroll; ++u) {
-            const int64_t vi = base + (int64_t)u * kStreamThreads;
+            const int li = (int)threadIdx.x + u * kStreamThreads;
             float v[V];
             unpack_vec<DT>(raw[u], v);
-            if (M > 0 && kSparseFirst) {
-#pragma unroll
-                for (int g = 0; g < V / (M > 0 ? M : 1); ++g) nm_mask_group<(M > 0 ? M : 1), TIE>(v + g * M, p.kdrop);
-            }
-            if (kQuant) {
-                uint32_t amax = 0u;
+            uint32_t amax = 0u;
+            if (kQuant && kSparseFirst) {
+                // the block max always survives an N:M mask with N >= 1, so max over the unmasked keys is the
+                // masked block's max (SURVEY.md appendix A.4 i)
 #pragma unroll
                 for (int i = 0; i < V; ++i) amax = max(amax, abs_bits(v[i]));
+            }
+            if (kSparseFirst) mask_vec<M, KD, TIE, V>(v, p.kdrop);
+            if (kQuant) {
+                if (!kSparseFirst) {
+#pragma unroll
+                    for (int i = 0; i < V; ++i) amax = max(amax, abs_bits(v[i]));
+                }
                 // butterfly over the lanes that share this block; every lane of the warp executes every shuffle
 #pragma unroll
                 for (int off = 1; off < 32; off <<= 1)
                     if (off < p.lanes_per_block) amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, off));
                 const BlockScale sc = make_scale<DT>(amax, p.m, p.eps);
-                float un[V];
+                float un[STOC ? V : 1];
                 if (STOC) {
 #pragma unroll
                     for (int q = 0; q < V / 4; ++q) {
-                        const uint4 r = philox4x32_10((uint64_t)(p.ctr_base + vi * (V / 4) + q), p.offset, p.seed);
+                        const uint4 r = philox4x32_10((uint64_t)(p.ctr_base + (tile_base + li) * (V / 4) + q), p.offset, p.seed);
                         un[4 * q] = u01(r.x); un[4 * q + 1] = u01(r.y); un[4 * q + 2] = u01(r.z); un[4 * q + 3] = u01(r.w);
                     }
                 }
+                if (sc.fast) {                                 // one branch per vector, uniform across the block's lanes
 #pragma unroll
-                for (int i = 0; i < V; ++i) v[i] = quant_elt<DT, STOC>(v[i], sc, STOC ? un[i] : 0.0f);
-            }
-            if (M > 0 && kSparseLast) {
-#pragma unroll
-                for (int g = 0; g < V / (M > 0 ? M : 1); ++g) nm_mask_group<(M > 0 ? M : 1), TIE>(v + g * M, p.kdrop);
-            }
-            if (vi < p.n_vec) {
-                if (kOutVecs == 1) {
-                    st_stream(p.out + vi, STOC ? pack_vec<BFP_DT_F32>(v) : pack_vec<DT>(v));
+                    for (int i = 0; i < V; ++i) v[i] = quant_elt_fast<STOC>(v[i], sc, STOC ? un[i] : 0.0f);
                 } else {
-                    st_stream(p.out + 2 * vi, pack_vec<BFP_DT_F32>(v));
-                    st_stream(p.out + 2 * vi + 1, pack_vec<BFP_DT_F32>(v + 4));
+#pragma unroll
+                    for (int i = 0; i < V; ++i) v[i] = quant_elt_slow<DT, STOC>(v[i], sc.delta, sc.vmax, STOC ? un[i] : 0.0f);
+                }
+            }
+            if (kSparseLast) mask_vec<M, KD, TIE, V>(v, p.kdrop);
+            if (li < rem) {
+                uint4* dst = p.out + (tile_base + li) * kOutVecs;
+                if (kOutVecs == 1) {
+                    st_stream(dst, STOC ? pack_vec<BFP_DT_F32>(v) : pack_vec<DT>(v));
+                } else {
+                    st_stream(dst, pack_vec<BFP_DT_F32>(v));
+                    st_stream(dst + 1, pack_vec<BFP_DT_F32>(v + 4));
                 }
             }
         }
@@ -265,7 +287,7 @@ __global__ void __launch_bounds__(128) block_exponent_kernel(const void* in, flo
 // ---------------------------------------------------------------------------------------------------------------
 static inline bool is_pow2(int64_t x) { return x > 0 && (x & (x - 1)) == 0; }
 
-template <int DT, int ORDER, int M, int TIE, bool STOC>
+template <int DT, int ORDER, int M, int KD, int TIE, bool STOC>
 static int launch_stream_t(const StreamParams& p, cudaStream_t st) {
     const int64_t tile_vecs = (int64_t)kStreamThreads * kStreamUnroll;
     const int64_t n_tiles = (p.n_vec + tile_vecs - 1) / tile_vecs;
@@ -273,7 +295,7 @@ static int launch_stream_t(const StreamParams& p, cudaStream_t st) {
     const DeviceInfo& di = device_info();
     const int64_t max_ctas = (int64_t)di.sm_count * tuning().stream_ctas_per_sm;
     const int grid = (int)std::min<int64_t>(n_tiles, max_ctas);
-    quant_stream_kernel<DT, ORDER, M, TIE, STOC><<<grid, kStreamThreads, 0, st>>>(p);
+    quant_stream_kernel<DT, ORDER, M, KD, TIE, STOC><<<grid, kStreamThreads, 0, st>>>(p);
     count_launch();
     return check_launch("quant_stream_kernel");
 }
@@ -281,16 +303,23 @@ static int launch_stream_t(const StreamParams& p, cudaStream_t st) {
 template <int DT, int ORDER, bool STOC>
 static int launch_stream_m(const StreamParams& p, int M, int tie, cudaStream_t st) {
     constexpr int V = DType<DT>::kVec;
-    if (ORDER == BFP_ORDER_QUANT_ONLY) return launch_stream_t<DT, ORDER, 0, BFP_TIE_TORCH_CUDA, STOC>(p, st);
+    if (ORDER == BFP_ORDER_QUANT_ONLY) return launch_stream_t<DT, ORDER, 0, 0, BFP_TIE_TORCH_CUDA, STOC>(p, st);
     if (tie == BFP_TIE_TORCH_CPU) {
-        if (M == 4) return launch_stream_t<DT, ORDER, 4, BFP_TIE_TORCH_CPU, STOC>(p, st);
+        if (M == 4 && p.kdrop == 2) return launch_stream_t<DT, ORDER, 4, 0, BFP_TIE_TORCH_CPU, STOC>(p, st);
         return set_error(BFP_E_UNSUPPORTED, "BFP_TIE_TORCH_CPU is implemented for N:M = 2:4 only");
     }
     switch (M) {
-    case 1: return launch_stream_t<DT, ORDER, 1, BFP_TIE_TORCH_CUDA, STOC>(p, st);
-    case 2: return launch_stream_t<DT, ORDER, 2, BFP_TIE_TORCH_CUDA, STOC>(p, st);
-    case 4: return launch_stream_t<DT, ORDER, 4, BFP_TIE_TORCH_CUDA, STOC>(p, st);
-    case 8: if (V == 8) return launch_stream_t<DT, ORDER, (V == 8 ? 8 : 4), BFP_TIE_TORCH_CUDA, STOC>(p, st);
+    case 1: return launch_stream_t<DT, ORDER, 1, 0, BFP_TIE_TORCH_CUDA, STOC>(p, st);
+    case 2: return launch_stream_t<DT, ORDER, 2, 0, BFP_TIE_TORCH_CUDA, STOC>(p, st);
+    case 4:
+        switch (p.kdrop) {
+        case 0: return launch_stream_t<DT, ORDER, 1, 0, BFP_TIE_TORCH_CUDA, STOC>(p, st);   // 4:4 keeps everything
+        case 1: return launch_stream_t<DT, ORDER, 4, 1, BFP_TIE_TORCH_CUDA, STOC>(p, st);
+        case 2: return launch_stream_t<DT, ORDER, 4, 2, BFP_TIE_TORCH_CUDA, STOC>(p, st);
+        case 3: return launch_stream_t<DT, ORDER, 4, 3, BFP_TIE_TORCH_CUDA, STOC>(p, st);
+        }
+        break;
+    case 8: if (V == 8) return launch_stream_t<DT, ORDER, (V == 8 ? 8 : 4), 0, BFP_TIE_TORCH_CUDA, STOC>(p, st);
     }
     return set_error(BFP_E_UNSUPPORTED, "internal: stream path called with unsupported M");
 }
