@@ -110,6 +110,39 @@ int bfp_quantize_host(const void* host_in, void* host_out, int64_t rows, int64_t
 /* Frees the staging buffers bfp_quantize_host keeps between calls. */
 int bfp_host_staging_release(void);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Packed BFP operands and the tensor-core BFP linear (replaces the F.linear on dequantised tensors of
+ * bfp_ops.py:187-190 / BFPLinear.forward :278-287).
+ *
+ * Packed layout of a [rows, K] tensor quantised with (block_size B, mant_bits m <= 7):
+ *   mant    int8 [rows, Kp]            Kp = K rounded up to 16; integer mantissas q, |q| <= 2^m - 1; columns >= K zero
+ *   scale_t fp32 [nkb_pad, rows_pad]   block-major: scale_t[kb][row] = 2^(e - m) (the block's interval); value = q*scale
+ *                                      nkb_pad = ceil(Kp / 128) * (128 / B); rows_pad = rows rounded up to 256;
+ *                                      padding entries must be 0.  NaN marks a block the packed form cannot represent
+ *                                      (the reference yields NaN or leaves the normal range there).
+ * bfp_packed_layout fills the three sizes.  mant / scale_t must be 16-byte aligned; when Kp != K or padding exists the
+ * caller zero-fills the buffers before packing.
+ */
+int bfp_packed_layout(int64_t rows, int64_t K, int block_size, int64_t* Kp, int64_t* rows_pad, int64_t* nkb_pad);
+
+/* float_to_bfp_blocked (bfp_ops.py:124-149) straight into the packed form: same arguments as bfp_quantize (orders
+ * QUANT_ONLY / SPARSIFY_QUANT / QUANT_SPARSIFY; N:M ties follow BFP_TIE_TORCH_CUDA).
+ * Contract: bfp_unpack(bfp_quantize_pack(x)) == bfp_quantize(x) bit for bit, except that -0.0 unpacks as +0.0. */
+int bfp_quantize_pack(const void* in, int8_t* mant, float* scale_t, int64_t rows, int64_t K, int in_dtype,
+                      int block_size, int mant_bits, float eps, int rounding, uint64_t seed, uint64_t offset, int N,
+                      int M, int order, void* stream);
+
+/* packed -> fp32 [rows, K] */
+int bfp_unpack(const int8_t* mant, const float* scale_t, float* out, int64_t rows, int64_t K, int block_size,
+               void* stream);
+
+/* out[T, N] (fp32) = A_packed[T, K] . B_packed[N, K]^T + bias[N]:
+ *   out[t,n] = bias[n] + sum_kb a_scale_t[kb][t] * b_scale_t[kb][n] * sum_{k in kb} a_mant[t,k] * b_mant[n,k]
+ * tcgen05.mma.kind::i8 with int32 TMEM accumulators per BFP block, fp32 rescale + accumulation in registers.
+ * Both operands must be packed with the same block_size (32, 64 or 128) and the layout above; bias may be NULL. */
+int bfp_gemm_i8(const int8_t* a_mant, const float* a_scale_t, const int8_t* b_mant, const float* b_scale_t,
+                const float* bias, float* out, int64_t T, int64_t N, int64_t K, int block_size, void* stream);
+
 /* The 256-entry table behind BFP_TIE_TORCH_CPU for 2:4 (index = c0 + 4*c1 + 16*c2 + 64*c3 with
  * c_i = #{j : |v_j| < |v_i|}; value = 4-bit drop mask, 0xff = unreachable).  Exposed for the tests. */
 int bfp_debug_cpu_tie_lut(uint8_t out[256]);

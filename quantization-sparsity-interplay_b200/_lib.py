@@ -47,6 +47,10 @@ SIGNATURES = {
     "bfp_quantize_host": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _i32, _u64, _u64, _i32, _i32, _i32, _i32]),
     "bfp_host_staging_release": (_i32, []),
     "bfp_debug_cpu_tie_lut": (_i32, [_vp]),
+    "bfp_packed_layout": (_i32, [_i64, _i64, _i32] + [ctypes.POINTER(_i64)] * 3),
+    "bfp_quantize_pack": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _i32, _u64, _u64, _i32, _i32, _i32, _vp]),
+    "bfp_unpack": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _vp]),
+    "bfp_gemm_i8": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp]),
 }
 
 
@@ -77,3 +81,10 @@ def launch_count():
 
 def set_option(name, value):
     check(lib().bfp_set_option(name.encode(), int(value)))
+
+
+def packed_layout(rows, K, block_size):
+    """(Kp, rows_pad, nkb_pad) of the packed form of a [rows, K] tensor (include/bfp_b200.h)."""
+    kp, rp, nk = _i64(), _i64(), _i64()
+    check(lib().bfp_packed_layout(int(rows), int(K), int(block_size), ctypes.byref(kp), ctypes.byref(rp), ctypes.byref(nk)))
+    return kp.value, rp.value, nk.value

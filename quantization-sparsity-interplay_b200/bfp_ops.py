@@ -230,6 +230,104 @@ def float_to_bfp_tiled(t, **bfp_args):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# Packed operands + tensor-core BFP linear (new: the reference only ever holds dequantised floats).
+# ---------------------------------------------------------------------------------------------------------------
+class PackedBFP:
+    """A [rows, K] tensor in the packed BFP operand format of include/bfp_b200.h: int8 mantissas [rows, Kp] and the
+    block-major fp32 scale table [nkb_pad, rows_pad] (scale = 2^(e - m))."""
+    __slots__ = ("mant", "scale_t", "shape", "rows", "K", "block_size", "mant_bits")
+
+    def __init__(self, mant, scale_t, shape, block_size, mant_bits):
+        self.mant, self.scale_t, self.shape = mant, scale_t, tuple(shape)
+        self.K = self.shape[-1]
+        self.rows = mant.shape[0]
+        self.block_size, self.mant_bits = block_size, mant_bits
+
+
+def _order_for(bfp_args, identifier):
+    sparsity = ((bfp_args['in_sparsity'] == True and identifier == 'in') or (bfp_args['w_sparsity'] == True and identifier == 'w')  # noqa: E712
+                or (bfp_args['grad_sparsity'] == True and identifier == 'grad'))                                                  # noqa: E712
+    if not sparsity:
+        return _lib.ORDER_QUANT_ONLY
+    return _lib.ORDER_SPARSIFY_QUANT if bfp_args['first'] == 's' else _lib.ORDER_QUANT_SPARSIFY
+
+
+def pack_bfp(t, identifier='', philox=None, **bfp_args):
+    """float_to_bfp_blocked (bfp_ops.py:124-149) straight into the packed form (one fused kernel).  Needs the 'bfp' format,
+    structured (or no) sparsity and mant_bits <= 7.  unpack_bfp(pack_bfp(x)) == float_to_bfp_blocked(x) up to the sign of
+    zero; N:M ties follow the torch-CUDA rule."""
+    assert (bfp_args['num_format'] == 'bfp') and (bfp_args['sparsity_num_format'] == 'bfp') and (bfp_args['block_size'] > 0)
+    order = _order_for(bfp_args, identifier)
+    if order != _lib.ORDER_QUANT_ONLY and bfp_args['sparsity_mode'] != 'structured':
+        raise NotImplementedError("packed operands support structured N:M sparsity only")
+    if not t.is_cuda:
+        raise ValueError("pack_bfp needs a CUDA tensor")
+    if t.dtype not in _DT:
+        raise TypeError(f"unsupported dtype {t.dtype}")
+    src = t.detach().contiguous()
+    K = src.shape[-1]
+    rows = src.numel() // K if K else 0
+    B, m = int(bfp_args['block_size']), int(bfp_args['mant_bits'])
+    Kp, rows_pad, nkb_pad = _lib.packed_layout(rows, K, B)
+    nkb = -(-K // B)
+    alloc_m = torch.empty if Kp == K else torch.zeros
+    alloc_s = torch.empty if (rows_pad == rows and nkb_pad == nkb) else torch.zeros
+    mant = alloc_m((rows, Kp), dtype=torch.int8, device=src.device)
+    scale_t = alloc_s((nkb_pad, rows_pad), dtype=torch.float32, device=src.device)
+    rounding = _rounding_code(bfp_args['rounding_mode'])
+    seed, offset = (philox if philox is not None else _PhiloxState.next()) if rounding == _lib.ROUND_STOCHASTIC else (0, 0)
+    if rows and K:
+        with torch.cuda.device(src.device):
+            _lib.check(_lib.lib().bfp_quantize_pack(src.data_ptr(), mant.data_ptr(), scale_t.data_ptr(), rows, K, _DT[src.dtype], B, m,
+                                                    float(bfp_args['epsilon']), rounding, seed, offset, int(bfp_args['N']),
+                                                    int(bfp_args['M']), order, torch.cuda.current_stream().cuda_stream))
+    return PackedBFP(mant, scale_t, src.shape, B, m)
+
+
+def unpack_bfp(p):
+    """packed -> fp32 tensor of the original shape."""
+    out = torch.empty(p.shape, dtype=torch.float32, device=p.mant.device)
+    if out.numel():
+        with torch.cuda.device(out.device):
+            _lib.check(_lib.lib().bfp_unpack(p.mant.data_ptr(), p.scale_t.data_ptr(), out.data_ptr(), p.rows, p.K, p.block_size,
+                                             torch.cuda.current_stream().cuda_stream))
+    return out
+
+
+def bfp_linear_packed(xp, wp, bias=None):
+    """y[..., n] = sum_k x[..., k] w[n, k] + bias[n] on packed operands: tcgen05 int8 MMA per BFP block, fp32 rescale
+    (include/bfp_b200.h bfp_gemm_i8).  Returns fp32 of shape xp.shape[:-1] + (N,)."""
+    assert xp.K == wp.K and xp.block_size == wp.block_size
+    N = wp.rows
+    out = torch.empty(xp.shape[:-1] + (N,), dtype=torch.float32, device=xp.mant.device)
+    b = None
+    if bias is not None:
+        b = bias.detach().to(dtype=torch.float32).contiguous()
+    if out.numel():
+        with torch.cuda.device(out.device):
+            _lib.check(_lib.lib().bfp_gemm_i8(xp.mant.data_ptr(), xp.scale_t.data_ptr(), wp.mant.data_ptr(), wp.scale_t.data_ptr(),
+                                              b.data_ptr() if b is not None else None, out.data_ptr(), xp.rows, N, xp.K,
+                                              xp.block_size, torch.cuda.current_stream().cuda_stream))
+    return out
+
+
+def _tensor_core_eligible(x, w, bfp_args):
+    """The packed tensor-core path computes the same function as quantise + F.linear (fp32 accumulate order aside); it is
+    taken for inference on CUDA fp32 tensors when the configuration has a packed form."""
+    if os.environ.get("BFP_LINEAR_PATH", "tc") != "tc":
+        return False
+    if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad):
+        return False
+    return (x.is_cuda and w.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32
+            and bfp_args['num_format'] == 'bfp' and bfp_args['sparsity_num_format'] == 'bfp'
+            and 1 <= bfp_args['mant_bits'] <= 7 and bfp_args['block_size'] in (32, 64, 128)
+            and not (bfp_args['in_sparsity'] == True)                                                # noqa: E712
+            and (bfp_args['w_sparsity'] != True or (bfp_args['sparsity_mode'] == 'structured'      # noqa: E712
+                                                    and 0 < bfp_args['N'] <= bfp_args['M'] <= 64
+                                                    and (bfp_args['first'] == 's' or bfp_args['block_size'] % bfp_args['M'] == 0))))
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # bfp_ops.py:151-200: operand pre-processing and the autograd wrappers
 # ---------------------------------------------------------------------------------------------------------------
 def MxM_pre_processing(x, w, transpose, **bfp_args):
@@ -351,10 +449,22 @@ class BFPLinear(torch.nn.Linear):
         super().__init__(in_features, out_features, bias)
         self.num_format = self.bfp_args['num_format']
         self.linear_op = _get_bfp_op(F.linear, 'linear', self.bfp_args)
+        self._packed_w = None          # (key, PackedBFP): the weight is re-packed only when it changes
+
+    def _packed_weight(self):
+        w = self.weight
+        key = (w.data_ptr(), w._version, tuple(w.shape), w.device)
+        if self._packed_w is None or self._packed_w[0] != key:
+            self._packed_w = (key, pack_bfp(w, identifier='w', **self.bfp_args))
+        return self._packed_w[1]
 
     def forward(self, input):
         if self.num_format == 'fp32':
             return F.linear(input, self.weight, self.bias)
         elif self.num_format == 'bfp':
+            if (self.bfp_args['rounding_mode'] == rounding_modes.DETERM
+                    and _tensor_core_eligible(input, self.weight, self.bfp_args)):
+                # inference fast path: pack activations on the fly, cached packed weight, tcgen05 int8 BFP GEMM
+                return bfp_linear_packed(pack_bfp(input, identifier='in', **self.bfp_args), self._packed_weight(), self.bias)
             return self.linear_op(input, self.weight, self.bias)
         raise NotImplementedError('NumFormat not implemented')

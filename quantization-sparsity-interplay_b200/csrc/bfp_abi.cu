@@ -1,5 +1,6 @@
 // bfp_abi.cu -- the extern "C" surface declared in include/bfp_b200.h: argument validation (mirroring the
 // reference's asserts / exceptions), error reporting, device bookkeeping.  No torch types, no allocation.
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -173,6 +174,43 @@ int bfp_quantize_host(const void* host_in, void* host_out, int64_t rows, int64_t
 }
 
 int bfp_host_staging_release(void) { return host_staging_release(); }
+
+int bfp_packed_layout(int64_t rows, int64_t K, int block_size, int64_t* Kp, int64_t* rows_pad, int64_t* nkb_pad) {
+    if (rows < 0 || K < 0 || block_size <= 0) return set_error(BFP_E_ARG, "bad argument");
+    if (Kp) *Kp = packed_kp(K);
+    if (rows_pad) *rows_pad = packed_rows_pad(rows);
+    if (nkb_pad) *nkb_pad = std::max<int64_t>(packed_nkb_pad(K, block_size), (K + block_size - 1) / block_size);
+    return BFP_OK;
+}
+
+int bfp_quantize_pack(const void* in, int8_t* mant, float* scale_t, int64_t rows, int64_t K, int in_dtype, int block_size,
+                      int mant_bits, float eps, int rounding, uint64_t seed, uint64_t offset, int N, int M, int order, void* stream) {
+    const int out_dt = rounding == BFP_ROUND_STOCHASTIC ? BFP_DT_F32 : in_dtype;
+    QuantArgs a{in, mant, rows, K, in_dtype, out_dt, block_size, mant_bits, eps, rounding, seed, offset, N, M, order, BFP_TIE_TORCH_CUDA};
+    if (order == BFP_ORDER_SPARSIFY_ONLY) return set_error(BFP_E_ARG, "packing needs a quantising order");
+    if (int rc = validate_quant_args(a, true)) return rc;
+    if (mant_bits < 1 || mant_bits > 7) return set_error(BFP_E_UNSUPPORTED, "packed mantissas are int8: mant_bits must be in [1, 7]");
+    if (rows * K > 0 && !scale_t) return set_error(BFP_E_ARG, "null pointer");
+    if (reinterpret_cast<uintptr_t>(scale_t) % 4) return set_error(BFP_E_ALIGN, "scale_t not aligned");
+    if (int rc = require_device()) return rc;
+    return pack_device(a, mant, scale_t, packed_kp(K), packed_rows_pad(rows), static_cast<cudaStream_t>(stream));
+}
+
+int bfp_unpack(const int8_t* mant, const float* scale_t, float* out, int64_t rows, int64_t K, int block_size, void* stream) {
+    if (rows < 0 || K < 0 || block_size <= 0) return set_error(BFP_E_ARG, "bad argument");
+    if (rows * K > 0 && (!mant || !scale_t || !out)) return set_error(BFP_E_ARG, "null pointer");
+    if (int rc = require_device()) return rc;
+    return unpack_device(mant, scale_t, out, rows, K, packed_kp(K), packed_rows_pad(rows), block_size, static_cast<cudaStream_t>(stream));
+}
+
+int bfp_gemm_i8(const int8_t* a_mant, const float* a_scale_t, const int8_t* b_mant, const float* b_scale_t, const float* bias,
+                float* out, int64_t T, int64_t N, int64_t K, int block_size, void* stream) {
+    if (T < 0 || N < 0 || K <= 0 || block_size <= 0) return set_error(BFP_E_ARG, "bad argument");
+    if (T * N > 0 && (!a_mant || !a_scale_t || !b_mant || !b_scale_t || !out)) return set_error(BFP_E_ARG, "null pointer");
+    if (int rc = require_device()) return rc;
+    return gemm_i8_device(a_mant, a_scale_t, packed_rows_pad(T), b_mant, b_scale_t, packed_rows_pad(N), bias, out, T, N, packed_kp(K),
+                          block_size, static_cast<cudaStream_t>(stream));
+}
 
 int bfp_debug_cpu_tie_lut(uint8_t out[256]) {
     if (int rc = require_device()) return rc;

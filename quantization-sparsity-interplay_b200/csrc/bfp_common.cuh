@@ -101,7 +101,7 @@ __device__ __noinline__ float3 make_scale_slow(float s, int m) {
 
 // ceil(log2f(s)) for the few fp32 values whose mantissa is within 128 ulp of a power of two (out of line: log2f is
 // ~20 instructions and this branch is taken for ~1.5e-5 of the blocks).
-__device__ __noinline__ int exponent_near_pow2(float s) { return (int)ceilf(log2f(s)); }
+static __device__ __noinline__ int exponent_near_pow2(float s) { return (int)ceilf(log2f(s)); }
 
 template <int DT>
 __device__ __forceinline__ BlockScale make_scale(uint32_t amax_bits, int m, float eps) {

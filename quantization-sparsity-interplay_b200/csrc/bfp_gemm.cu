@@ -1,0 +1,359 @@
+// bfp_gemm.cu -- the BFP linear contraction on 5th-gen tensor cores (tcgen05, sm_100a).
+//
+// Replaces the reference's dequantise-then-fp32-GEMM (bfp_ops.py:187-190: F.linear on fake-quantised tensors) by an
+// exact restatement on PACKED operands:
+//     y[t,n] = bias[n] + sum_kb  sa[kb][t] * sb[kb][n] * ( sum_{k in kb} qa[t,k] * qb[n,k] )
+// The inner sums are exact integers (tcgen05.mma.kind::i8, int32 accumulators in TMEM), the scales are exact powers of
+// two; only the outer fp32 accumulation over K/B blocks rounds.
+//
+// Kernel shape (one persistent CTA per SM, 384 threads, warp-specialised):
+//   warp 0      TMA producer: per 128-byte K slab, one 2-D tensor copy each of the A tile [128 x 128 B] and the B tile
+//               [256 x 128 B] (SWIZZLE_128B) plus 1-D bulk copies of the slab's block scales, all landing on one mbarrier.
+//   warp 1      MMA issuer (one elected lane): 128x256x32 tcgen05.mma.kind::i8 per instruction; every BFP block starts
+//               a fresh accumulator (enable-input-d = 0) in one of TWO 256-column TMEM buffers and is committed to an
+//               mbarrier, so block kb+1 multiplies while block kb is rescaled.
+//   warp 2      TMEM allocator (512 columns).
+//   warps 4-11  epilogue: tcgen05.ld the int32 tile (warp w reads TMEM lanes 32*(w%4).., 128 columns per warp), convert,
+//               FMA with sa[t]*sb[n] into 128 fp32 registers per thread; after the last block add bias and store.
+// Barriers: full/empty per smem stage (empty = MMA commit + 8 epilogue warps, because the scales live in the stage),
+//           tmem_full/tmem_empty per accumulator buffer.
+#include <cuda.h>
+#include <cstdio>
+
+#include <algorithm>
+#include <mutex>
+
+#include "bfp_internal.h"
+
+namespace bfp {
+
+namespace gemm {
+
+constexpr int BM = 128, BN = 256, BKB = 128;           // tile: rows of A, rows of B, K bytes per stage (int8: 128 k)
+constexpr int UMMA_K = 32;                             // k per tcgen05.mma.kind::i8
+constexpr int kStages = 4;
+constexpr int kMaxBlocksPerStage = 4;                  // B >= 32
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 128 + kEpiWarps * 32;         // 384
+constexpr int kTmemCols = 512;
+
+constexpr int kSmemA = BM * BKB;                       // 16 KB
+constexpr int kSmemB = BN * BKB;                       // 32 KB
+constexpr int kSmemScaleA = kMaxBlocksPerStage * BM * 4;   // 2 KB
+constexpr int kSmemScaleB = kMaxBlocksPerStage * BN * 4;   // 4 KB
+constexpr int kStageBytes = kSmemA + kSmemB + kSmemScaleA + kSmemScaleB;   // 55296 (multiple of 1024)
+constexpr int kSmemBarriers = 1024;
+constexpr int kSmemTotal = kStages * kStageBytes + kSmemBarriers + 1024;   // + alignment slack
+
+struct Params {
+    const float* scale_a;       // [nkb_pad][lda_s]
+    const float* scale_b;       // [nkb_pad][ldb_s]
+    const float* bias;          // [N] or nullptr
+    float* out;                 // [T][N]
+    int64_t lda_s, ldb_s;
+    int T, N, K;                // K = padded mant row length (multiple of 16)
+    int blocks_per_stage;       // 128 / B
+    int mmas_per_block;         // B / 32
+    int num_k_stages;           // ceil(K / 128)
+    int tiles_m, tiles_n;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: a protocol bug must surface as a trap, not as a hung GPU box
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+        if (spin > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 r;\n\telect.sync r|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(addr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// start address >> 4 | LBO (ignored for swizzled K-major) = 1 | SBO = 1024 B (8 rows x 128 B) | version 1 | layout 2
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (InstrDescriptor): D = S32, A = B = signed int8, both K-major, N >> 3, M >> 4
+constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct Barriers {
+    uint64_t full[kStages];
+    uint64_t empty[kStages];
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+bfp_gemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    Barriers* bars = reinterpret_cast<Barriers*>(smem + kStages * kStageBytes);
+    auto stage_a = [&](int s) { return smem + s * kStageBytes; };
+    auto stage_b = [&](int s) { return smem + s * kStageBytes + kSmemA; };
+    auto stage_sa = [&](int s) { return reinterpret_cast<float*>(smem + s * kStageBytes + kSmemA + kSmemB); };
+    auto stage_sb = [&](int s) { return reinterpret_cast<float*>(smem + s * kStageBytes + kSmemA + kSmemB + kSmemScaleA); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = p.tiles_m * p.tiles_n;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1 + kEpiWarps); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], kEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    const uint32_t scale_bytes_a = (uint32_t)p.blocks_per_stage * BM * 4, scale_bytes_b = (uint32_t)p.blocks_per_stage * BN * 4;
+    const uint32_t stage_tx = kSmemA + kSmemB + scale_bytes_a + scale_bytes_b;
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;       // consecutive CTAs share the B tile
+                for (int ks = 0; ks < p.num_k_stages; ++ks) {
+                    mbar_wait(&bars->empty[stage], phase ^ 1);
+                    mbar_expect_tx(&bars->full[stage], stage_tx);
+                    tma_load_2d(stage_a(stage), &map_a, &bars->full[stage], ks * BKB, tm * BM);
+                    tma_load_2d(stage_b(stage), &map_b, &bars->full[stage], ks * BKB, tn * BN);
+                    for (int b = 0; b < p.blocks_per_stage; ++b) {
+                        const int64_t kb = (int64_t)ks * p.blocks_per_stage + b;
+                        bulk_load(stage_sa(stage) + b * BM, p.scale_a + kb * p.lda_s + (int64_t)tm * BM, BM * 4, &bars->full[stage]);
+                        bulk_load(stage_sb(stage) + b * BN, p.scale_b + kb * p.ldb_s + (int64_t)tn * BN, BN * 4, &bars->full[stage]);
+                    }
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =======================================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int buf = 0; uint32_t buf_phase[2] = {0, 0};
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int ks = 0; ks < p.num_k_stages; ++ks) {
+                    mbar_wait(&bars->full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = make_smem_desc(smem_u32(stage_a(stage)));
+                    const uint64_t db = make_smem_desc(smem_u32(stage_b(stage)));
+                    int mma = 0;
+                    for (int b = 0; b < p.blocks_per_stage; ++b) {
+                        mbar_wait(&bars->tmem_empty[buf], buf_phase[buf] ^ 1);     // epilogue drained this accumulator
+                        tc_fence_after();
+                        const uint32_t d = tmem_base + (uint32_t)buf * BN;
+                        for (int i = 0; i < p.mmas_per_block; ++i, ++mma) {
+                            // advance both descriptors by 32 bytes of K inside the 128-byte swizzle atom (+2 in 16-B units)
+                            mma_i8(d, da + (uint64_t)(mma * (UMMA_K >> 4)), db + (uint64_t)(mma * (UMMA_K >> 4)), kIdescI8, i > 0);
+                        }
+                        tc_commit(&bars->tmem_full[buf]);                          // accumulator of this BFP block is complete
+                        buf_phase[buf] ^= 1;
+                        buf ^= 1;
+                    }
+                    tc_commit(&bars->empty[stage]);                                // smem slab consumed by the tensor core
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================================== epilogue =========================================
+        const int ew = warp - 4;                    // 0..7
+        const int q = warp & 3;                     // TMEM lane quarter this warp may access
+        const int half = ew >> 2;                   // which 128 accumulator columns
+        const int row_in_tile = q * 32 + lane;
+        int stage = 0; uint32_t phase = 0;
+        int buf = 0; uint32_t buf_phase[2] = {0, 0};
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
+            float acc[128];
+#pragma unroll
+            for (int i = 0; i < 128; ++i) acc[i] = 0.0f;
+            for (int ks = 0; ks < p.num_k_stages; ++ks) {
+                mbar_wait(&bars->full[stage], phase);                              // scales of this slab have landed
+                for (int b = 0; b < p.blocks_per_stage; ++b) {
+                    const float sa = stage_sa(stage)[b * BM + row_in_tile];
+                    const float4* sb4 = reinterpret_cast<const float4*>(stage_sb(stage) + b * BN + half * 128);
+                    mbar_wait(&bars->tmem_full[buf], buf_phase[buf]);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * 128);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        uint32_t r[16];
+                        tmem_ld16(taddr + c * 16, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 s = sb4[c * 4 + (j >> 2)];
+                            acc[c * 16 + j + 0] = __fmaf_rn((float)(int)r[j + 0], sa * s.x, acc[c * 16 + j + 0]);
+                            acc[c * 16 + j + 1] = __fmaf_rn((float)(int)r[j + 1], sa * s.y, acc[c * 16 + j + 1]);
+                            acc[c * 16 + j + 2] = __fmaf_rn((float)(int)r[j + 2], sa * s.z, acc[c * 16 + j + 2]);
+                            acc[c * 16 + j + 3] = __fmaf_rn((float)(int)r[j + 3], sa * s.w, acc[c * 16 + j + 3]);
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
+                    buf_phase[buf] ^= 1;
+                    buf ^= 1;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->empty[stage]);                   // done with this slab's scales
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+            // bias + store: thread owns row t, 128 consecutive columns
+            const int t = tm * BM + row_in_tile;
+            const int n0 = tn * BN + half * 128;
+            if (t < p.T) {
+                float* dst = p.out + (int64_t)t * p.N + n0;
+                const bool vec_ok = (p.N % 4 == 0) && (n0 + 128 <= p.N);
+                if (vec_ok) {
+#pragma unroll
+                    for (int j = 0; j < 128; j += 4) {
+                        float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                        if (p.bias) {
+                            const float4 bv = *reinterpret_cast<const float4*>(p.bias + n0 + j);
+                            o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                        }
+                        *reinterpret_cast<float4*>(dst + j) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 128; ++j)
+                        if (n0 + j < p.N) dst[j] = acc[j] + (p.bias ? p.bias[n0 + j] : 0.0f);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t kbytes, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return set_error(BFP_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)kbytes, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kbytes};
+    cuuint32_t box[2] = {(cuuint32_t)BKB, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_errorf(BFP_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return BFP_OK;
+}
+
+}  // namespace gemm
+
+int gemm_i8_device(const int8_t* a_mant, const float* a_scale_t, int64_t lda_s, const int8_t* b_mant, const float* b_scale_t,
+                   int64_t ldb_s, const float* bias, float* out, int64_t T, int64_t N, int64_t Kp, int block_size, cudaStream_t st) {
+    using namespace gemm;
+    if (T == 0 || N == 0) return BFP_OK;
+    if (block_size < 32 || block_size > 128 || (block_size & (block_size - 1)))
+        return set_error(BFP_E_UNSUPPORTED, "bfp_gemm_i8 supports block_size 32, 64, 128 (one MMA is 32 deep)");
+    if (Kp % 16 != 0 || Kp <= 0) return set_error(BFP_E_ARG, "packed K must be a positive multiple of 16");
+    if (T > INT32_MAX || N > INT32_MAX || Kp > INT32_MAX) return set_error(BFP_E_ARG, "dimension too large");
+    if (reinterpret_cast<uintptr_t>(a_mant) % 16 || reinterpret_cast<uintptr_t>(b_mant) % 16 ||
+        reinterpret_cast<uintptr_t>(a_scale_t) % 16 || reinterpret_cast<uintptr_t>(b_scale_t) % 16 || lda_s % 4 || ldb_s % 4)
+        return set_error(BFP_E_ALIGN, "packed operands must be 16-byte aligned");
+    Params p;
+    p.scale_a = a_scale_t; p.scale_b = b_scale_t; p.bias = bias; p.out = out; p.lda_s = lda_s; p.ldb_s = ldb_s;
+    p.T = (int)T; p.N = (int)N; p.K = (int)Kp;
+    p.blocks_per_stage = BKB / block_size; p.mmas_per_block = block_size / UMMA_K;
+    p.num_k_stages = (int)((Kp + BKB - 1) / BKB);
+    p.tiles_m = (int)((T + BM - 1) / BM); p.tiles_n = (int)((N + BN - 1) / BN);
+    if ((int64_t)p.tiles_m * BM > lda_s || (int64_t)p.tiles_n * BN > ldb_s)
+        return set_error(BFP_E_ARG, "scale arrays must be padded to the tile size (rows_pad multiple of 256)");
+    CUtensorMap map_a, map_b;
+    if (int rc = make_map(&map_a, a_mant, T, Kp, BM)) return rc;
+    if (int rc = make_map(&map_b, b_mant, N, Kp, BN)) return rc;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(bfp_gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal); });
+    if (attr_err != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+    const int grid = std::min(p.tiles_m * p.tiles_n, device_info().sm_count);
+    bfp_gemm_i8_kernel<<<grid, kThreads, kSmemTotal, st>>>(map_a, map_b, p);
+    count_launch();
+    return check_launch("bfp_gemm_i8_kernel");
+}
+
+}  // namespace bfp

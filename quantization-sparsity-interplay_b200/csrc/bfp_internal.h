@@ -45,6 +45,16 @@ int block_exponent_device(const void* in, float* e_out, int64_t rows, int64_t K,
 int quantize_host(const QuantArgs& a);
 int host_staging_release();
 int debug_cpu_tie_lut(uint8_t out[256]);
+int pack_device(const QuantArgs& a, int8_t* mant, float* scale_t, int64_t Kp, int64_t rows_pad, cudaStream_t st);
+int unpack_device(const int8_t* mant, const float* scale_t, float* out, int64_t rows, int64_t K, int64_t Kp, int64_t rows_pad, int B,
+                  cudaStream_t st);
+int gemm_i8_device(const int8_t* a_mant, const float* a_scale_t, int64_t lda_s, const int8_t* b_mant, const float* b_scale_t,
+                   int64_t ldb_s, const float* bias, float* out, int64_t T, int64_t N, int64_t Kp, int block_size, cudaStream_t st);
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+inline int64_t packed_kp(int64_t K) { return round_up(K, 16); }
+inline int64_t packed_rows_pad(int64_t rows) { return round_up(rows, 256); }
+inline int64_t packed_nkb_pad(int64_t K, int B) { return round_up(packed_kp(K), 128) / 128 * (B <= 128 ? 128 / B : 1) ; }
 
 inline size_t dtype_size(int dt) { return dt == BFP_DT_F32 ? 4 : 2; }
 

@@ -1,0 +1,168 @@
+"""GPU parity suite for the packed BFP operands and the tcgen05 int8 BFP GEMM (C ABI: bfp_quantize_pack, bfp_unpack,
+bfp_gemm_i8).  Tolerance (north_star): relative error <= 1e-5 against the reference's dequantise-then-matmul; the
+integer part of the contraction is exact, so with unit scales the result must be bit-exact."""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available()
+    from qsi_b200 import bfp_ops, _lib
+    _lib.lib()
+    return bfp_ops
+
+
+def _make_packed(ops, q, scale, B, m=7):
+    """q: int8 [rows, K] tensor, scale: fp32 [rows, nkb] -> PackedBFP in the documented layout."""
+    from qsi_b200 import _lib
+    rows, K = q.shape
+    Kp, rows_pad, nkb_pad = _lib.packed_layout(rows, K, B)
+    mant = torch.zeros(rows, Kp, dtype=torch.int8, device="cuda")
+    mant[:, :K] = q
+    st = torch.zeros(nkb_pad, rows_pad, dtype=torch.float32, device="cuda")
+    st[: scale.shape[1], :rows] = scale.t()
+    return ops.PackedBFP(mant, st, (rows, K), B, m)
+
+
+def _ref(qa, sa, qb, sb, B, bias=None):
+    a = qa.double() * sa.double().repeat_interleave(B, dim=1)[:, : qa.shape[1]]
+    b = qb.double() * sb.double().repeat_interleave(B, dim=1)[:, : qb.shape[1]]
+    y = a @ b.t()
+    return y if bias is None else y + bias.double()
+
+
+@pytest.mark.parametrize("B", [64, 32, 128])
+@pytest.mark.parametrize("shape", [(128, 256, 128), (256, 512, 512), (200, 300, 384), (1, 8, 64 * 5), (4096, 768, 1024)])
+def test_gemm_unit_scales_is_exact_integer_matmul(ops, B, shape):
+    T, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(T + N + K + B)
+    qa = torch.randint(-127, 128, (T, K), generator=g, device="cuda", dtype=torch.int32).to(torch.int8)
+    qb = torch.randint(-127, 128, (N, K), generator=g, device="cuda", dtype=torch.int32).to(torch.int8)
+    nkb = -(-K // B)
+    sa = torch.ones(T, nkb, device="cuda")
+    sb = torch.ones(N, nkb, device="cuda")
+    y = ops.bfp_linear_packed(_make_packed(ops, qa, sa, B), _make_packed(ops, qb, sb, B))
+    ref = _ref(qa, sa, qb, sb, B)
+    if K * 127 * 127 < 2 ** 24:
+        assert torch.equal(y.double(), ref)
+    else:
+        assert (y.double() - ref).abs().max() <= ref.abs().max() * 2 ** -22
+
+
+@pytest.mark.parametrize("B", [64, 32, 128])
+@pytest.mark.parametrize("shape", [(256, 512, 512), (200, 300, 384), (130, 260, 200), (512, 1024, 2048)])
+def test_gemm_power_of_two_scales_and_bias(ops, B, shape):
+    T, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(7 * T + N + K + B)
+    qa = torch.randint(-127, 128, (T, K), generator=g, device="cuda", dtype=torch.int32).to(torch.int8)
+    qb = torch.randint(-127, 128, (N, K), generator=g, device="cuda", dtype=torch.int32).to(torch.int8)
+    nkb = -(-K // B)
+    sa = torch.exp2(torch.randint(-12, 4, (T, nkb), generator=g, device="cuda").float())
+    sb = torch.exp2(torch.randint(-14, -6, (N, nkb), generator=g, device="cuda").float())
+    bias = torch.randn(N, generator=g, device="cuda")
+    y = ops.bfp_linear_packed(_make_packed(ops, qa, sa, B), _make_packed(ops, qb, sb, B), bias)
+    ref = _ref(qa, sa, qb, sb, B, bias)
+    rel = ((y.double() - ref).norm() / ref.norm()).item()
+    assert rel <= 1e-6, rel
+    assert ((y.double() - ref).abs() <= 1e-5 * ref.abs() + 1e-6 * ref.abs().mean()).all()
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
+def test_pack_unpack_round_trip_equals_fake_quant(ops, dt):
+    """Contract of the packed layout: unpack(pack(x)) == float_to_bfp_blocked(x) (torch.equal: -0.0 unpacks as +0.0)."""
+    from qsi_b200 import _lib
+    for shape, (m, B), first, sparse in itertools.product([(256, 1024), (37, 96), (3, 5, 200), (130, 70)], [(7, 64), (3, 32), (5, 128), (7, 16)],
+                                                           ["s", "q"], [True, False]):
+        g = torch.Generator().manual_seed(len(shape) * 100 + m + B)
+        x = (torch.randn(*shape, generator=g) * 0.05).to(dt).cuda()
+        x.view(-1)[::37] = 0
+        args = ops.unpack_bfp_args(dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=m,
+                                        block_size=B, w_sparsity=sparse, N=2, M=4, first=first, sparsity_mode="structured", device="cuda"))
+        fq = ops.float_to_bfp_blocked(x, **args, identifier="w").float()
+        for generic in (0, 1):
+            _lib.set_option("force_generic", generic)
+            try:
+                p = ops.pack_bfp(x, identifier="w", **args)
+            finally:
+                _lib.set_option("force_generic", 0)
+            assert p.mant.abs().max().item() <= 2 ** m - 1
+            assert torch.equal(ops.unpack_bfp(p), fq), (shape, m, B, first, sparse, generic)
+    # stochastic packing draws the same Philox stream as the fake-quant kernel
+    x = torch.randn(64, 512, device="cuda")
+    a = ops.unpack_bfp_args(dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="stoc", mant_bits=7, block_size=64))
+    p = ops.pack_bfp(x, identifier="in", philox=(5, 3), **a)
+    fq = ops._fused(x, _lib.ORDER_QUANT_ONLY, block_size=64, mant_bits=7, epsilon=1e-8, rounding_mode="stoc", philox=(5, 3))
+    assert torch.equal(ops.unpack_bfp(p), fq)
+
+
+def test_unrepresentable_blocks_become_nan_rows(ops):
+    x = torch.randn(4, 128, device="cuda")
+    x[1, 5] = float("inf")
+    x[2, 70] = float("nan")
+    a = ops.unpack_bfp_args(dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", mant_bits=7, block_size=64))
+    p = ops.pack_bfp(x, identifier="in", **a)
+    w = ops.pack_bfp(torch.randn(8, 128, device="cuda"), identifier="w", **a)
+    y = ops.bfp_linear_packed(p, w)
+    ref = ops.float_to_bfp_blocked(x, **a, identifier="in") @ ops.float_to_bfp_blocked(torch.zeros(8, 128, device="cuda"), **a, identifier="w").t()
+    assert torch.isnan(y[1]).all() and torch.isnan(y[2]).all() and torch.isfinite(y[0]).all() and torch.isfinite(y[3]).all()
+    assert torch.isnan(ref[1]).all() and torch.isnan(ref[2]).all()          # the reference arithmetic NaNs the same rows
+
+
+@pytest.mark.parametrize("first", ["s", "q"])
+@pytest.mark.parametrize("mB", [(7, 64), (5, 32), (3, 128)])
+def test_bfplinear_tensor_core_path_matches_oracle(ops, oracle, first, mB, monkeypatch):
+    m, B = mB
+    kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=m, block_size=B,
+              w_sparsity=True, N=2, M=4, first=first, sparsity_mode="structured", device="cuda")
+    torch.manual_seed(1)
+    lin = ops.BFPLinear(512, 384, bias=True, **dict(kw)).cuda()
+    x = torch.randn(3, 70, 512, device="cuda")
+    x[0, 0, 3] = 25.0
+    with torch.no_grad():
+        y_tc = lin(x)
+        monkeypatch.setenv("BFP_LINEAR_PATH", "fakequant")
+        y_fq = lin(x)
+        monkeypatch.setenv("BFP_LINEAR_PATH", "tc")
+    xq, _ = oracle.bfp_quantize(x.cpu().numpy(), B, m)
+    wq, _ = oracle.float_to_bfp_blocked(lin.weight.detach().cpu().numpy(), m, B, "sq" if first == "s" else "qs", tie_rule="cuda")
+    ref = oracle.linear(xq, wq, lin.bias.detach().cpu().numpy())
+    for y in (y_tc, y_fq):
+        rel = np.linalg.norm(y.cpu().numpy() - ref) / np.linalg.norm(ref)
+        assert rel <= 1e-5, rel
+    # weight pack is cached until the weight changes
+    k0 = lin._packed_w[0]
+    with torch.no_grad():
+        lin(x)
+        assert lin._packed_w[0] == k0
+        lin.weight.mul_(2.0)
+        y2 = lin(x)
+    assert lin._packed_w[0] != k0
+    assert torch.allclose(y2 - lin.bias, 2 * (y_tc - lin.bias), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("NK", [(4096, 4096), (11008, 4096), (4096, 11008)])
+def test_gemm_llama7b_shapes_full_size(ops, NK):
+    """BASELINE LLaMA-7B shapes, T = 4096 tokens: parity against fp64 matmul of the dequantised operands."""
+    N, K = NK
+    T = 4096
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(T, K, device="cuda", generator=g)
+    x[::97, ::53] *= 20.0
+    w = torch.randn(N, K, device="cuda", generator=g) * 0.02
+    a = ops.unpack_bfp_args(dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", mant_bits=7, block_size=64,
+                                 w_sparsity=True, N=2, M=4, first="s", sparsity_mode="structured", device="cuda"))
+    xp, wp = ops.pack_bfp(x, identifier="in", **a), ops.pack_bfp(w, identifier="w", **a)
+    y = ops.bfp_linear_packed(xp, wp)
+    rows = torch.arange(0, T, 61, device="cuda")
+    ref = ops.unpack_bfp(xp)[rows].double() @ ops.unpack_bfp(wp).double().t()
+    rel = ((y[rows].double() - ref).norm() / ref.norm()).item()
+    assert rel <= 1e-5, rel
+    # linearity in the activations' block scales: doubling x doubles y exactly (power-of-two scaling commutes with BFP)
+    y2 = ops.bfp_linear_packed(ops.pack_bfp(2 * x, identifier="in", **a), wp)
+    assert torch.equal(y2, 2 * y)
