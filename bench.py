@@ -244,6 +244,44 @@ def main():
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
 
+    # secondary metric of BASELINE.json: BFP GEMM TOPS at the LLaMA-7B shapes (T = 4096 tokens, HBFP8 B=64, 2:4 s->q weights)
+    gemm = None
+    try:
+        gargs = bfp_ops.unpack_bfp_args(dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8,
+                                             mant_bits=7, block_size=64, w_sparsity=True, N=N_, M=M_, first="s",
+                                             sparsity_mode="structured", device="cuda"))
+        per_shape, ops_total, ms_sum = [], 0.0, 0.0
+        for (T, Nn, Kk) in ((4096, 4096, 4096), (4096, 11008, 4096), (4096, 4096, 11008)):
+            xg = torch.randn(T, Kk, device=dev, generator=g)
+            wg = torch.randn(Nn, Kk, device=dev, generator=g) * 0.02
+            xp, wp = bfp_ops.pack_bfp(xg, identifier="in", **gargs), bfp_ops.pack_bfp(wg, identifier="w", **gargs)
+            og = torch.empty(T, Nn, device=dev)
+
+            def grun():
+                rc = L.bfp_gemm_i8(xp.mant.data_ptr(), xp.scale_t.data_ptr(), wp.mant.data_ptr(), wp.scale_t.data_ptr(), None,
+                                   og.data_ptr(), T, Nn, Kk, 64, stream)
+                if rc:
+                    _lib.check(rc)
+            for _ in range(3):
+                grun()
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(10):
+                grun()
+            g1.record()
+            torch.cuda.synchronize()
+            ms = g0.elapsed_time(g1) / 10
+            per_shape.append({"T": T, "N": Nn, "K": Kk, "ms": ms, "tops": 2.0 * T * Nn * Kk / ms / 1e9})
+            ops_total += 2.0 * T * Nn * Kk
+            ms_sum += ms
+            del xg, wg, xp, wp, og
+        tops = ops_total / ms_sum / 1e9
+        gemm = {"kernel": "bfp_gemm_i8_kernel (tcgen05.mma.kind::i8, per-block fp32 rescale)", "tops": tops, "unit": "TOPS (2*T*N*K int8 ops)",
+                "frac_of_nominal_int8_4500": tops / 4500.0, "block": 64, "mant_bits": 7, "per_shape": per_shape}
+    except Exception as e:          # the headline metric must survive a GEMM problem; report it instead of hiding it
+        gemm = {"error": repr(e)[:300]}
+
     # e2e: the same sweep through the public API on pinned HOST tensors (H2D + kernel + D2H per call, inside the timing)
     e2e_steps = a.e2e_steps or min(a.steps, 5)
     host_in = {s: (torch.randn(*s, generator=torch.Generator().manual_seed(7)) * 0.02).pin_memory() for s in SHAPES}
@@ -293,6 +331,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": "bfp_ops.float_to_bfp_blocked(pinned CPU tensor) -> bfp_quantize_host", "check": chk},
         "cpu_baseline": cpu,
+        "gemm": gemm,
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
