@@ -143,6 +143,18 @@ int bfp_unpack(const int8_t* mant, const float* scale_t, float* out, int64_t row
 int bfp_gemm_i8(const int8_t* a_mant, const float* a_scale_t, const int8_t* b_mant, const float* b_scale_t,
                 const float* bias, float* out, int64_t T, int64_t N, int64_t K, int block_size, void* stream);
 
+/* Exact bf16 variant of the BFP linear.  For mant_bits <= 8 the dequantised value q * 2^(e-m) is exactly representable in
+ * bf16, so the operands carry their block scales in their exponents and the contraction needs no per-block rescale:
+ *   bfp_quantize_pack_bf16: float_to_bfp_blocked straight to bf16 [rows, Kp], Kp = K rounded up to 8 (caller zero-fills
+ *                           the buffer when Kp != K); unrepresentable blocks become NaN.  Any block_size (also 16).
+ *   bfp_gemm_bf16:          out[T,N] (fp32) = A[T,K] . B[N,K]^T + bias, tcgen05.mma.kind::f16 with fp32 TMEM accumulators.
+ * Same result contract as bfp_gemm_i8 (exact products, fp32 accumulation order differs). */
+int bfp_quantize_pack_bf16(const void* in, void* out_bf16, int64_t rows, int64_t K, int in_dtype, int block_size,
+                           int mant_bits, float eps, int rounding, uint64_t seed, uint64_t offset, int N, int M,
+                           int order, void* stream);
+int bfp_gemm_bf16(const void* a_bf16, const void* b_bf16, const float* bias, float* out, int64_t T, int64_t N, int64_t K,
+                  void* stream);
+
 /* The 256-entry table behind BFP_TIE_TORCH_CPU for 2:4 (index = c0 + 4*c1 + 16*c2 + 64*c3 with
  * c_i = #{j : |v_j| < |v_i|}; value = 4-bit drop mask, 0xff = unreachable).  Exposed for the tests. */
 int bfp_debug_cpu_tie_lut(uint8_t out[256]);

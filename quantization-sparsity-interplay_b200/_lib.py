@@ -50,6 +50,8 @@ SIGNATURES = {
     "bfp_packed_layout": (_i32, [_i64, _i64, _i32] + [ctypes.POINTER(_i64)] * 3),
     "bfp_quantize_pack": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _i32, _u64, _u64, _i32, _i32, _i32, _vp]),
     "bfp_unpack": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _vp]),
+    "bfp_quantize_pack_bf16": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _i32, _u64, _u64, _i32, _i32, _i32, _vp]),
+    "bfp_gemm_bf16": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "bfp_gemm_i8": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp]),
 }
 

@@ -311,6 +311,64 @@ def bfp_linear_packed(xp, wp, bias=None):
     return out
 
 
+def pack_bfp_bf16(t, identifier='', philox=None, **bfp_args):
+    """float_to_bfp_blocked straight to a dequantised bf16 [rows, Kp] operand (Kp = K rounded up to 8).  Exact for
+    mant_bits <= 8: q * 2^(e-m) has at most 8 significant bits.  Any block size."""
+    assert (bfp_args['num_format'] == 'bfp') and (bfp_args['sparsity_num_format'] == 'bfp') and (bfp_args['block_size'] > 0)
+    order = _order_for(bfp_args, identifier)
+    if order != _lib.ORDER_QUANT_ONLY and bfp_args['sparsity_mode'] != 'structured':
+        raise NotImplementedError("packed operands support structured N:M sparsity only")
+    if not t.is_cuda:
+        raise ValueError("pack_bfp_bf16 needs a CUDA tensor")
+    src = t.detach().contiguous()
+    K = src.shape[-1]
+    rows = src.numel() // K if K else 0
+    Kp = -(-K // 8) * 8
+    out = (torch.empty if Kp == K else torch.zeros)((rows, Kp), dtype=torch.bfloat16, device=src.device)
+    rounding = _rounding_code(bfp_args['rounding_mode'])
+    seed, offset = (philox if philox is not None else _PhiloxState.next()) if rounding == _lib.ROUND_STOCHASTIC else (0, 0)
+    if rows and K:
+        with torch.cuda.device(src.device):
+            _lib.check(_lib.lib().bfp_quantize_pack_bf16(src.data_ptr(), out.data_ptr(), rows, K, _DT[src.dtype],
+                                                         int(bfp_args['block_size']), int(bfp_args['mant_bits']), float(bfp_args['epsilon']),
+                                                         rounding, seed, offset, int(bfp_args['N']), int(bfp_args['M']), order,
+                                                         torch.cuda.current_stream().cuda_stream))
+    return out
+
+
+def bfp_linear_bf16(xb, wb, bias=None, out_shape=None):
+    """y = x w^T + bias on exact-bf16 BFP operands (include/bfp_b200.h bfp_gemm_bf16): tcgen05.mma.kind::f16, fp32 TMEM
+    accumulation, no per-block rescale.  xb [T, Kp], wb [N, Kp] bf16."""
+    T, Kp = xb.shape
+    N = wb.shape[0]
+    assert wb.shape[1] == Kp and xb.dtype == torch.bfloat16 and wb.dtype == torch.bfloat16
+    out = torch.empty((T, N), dtype=torch.float32, device=xb.device)
+    b = bias.detach().to(dtype=torch.float32).contiguous() if bias is not None else None
+    if out.numel():
+        with torch.cuda.device(out.device):
+            _lib.check(_lib.lib().bfp_gemm_bf16(xb.data_ptr(), wb.data_ptr(), b.data_ptr() if b is not None else None, out.data_ptr(),
+                                                T, N, Kp, torch.cuda.current_stream().cuda_stream))
+    return out.view(out_shape) if out_shape is not None else out
+
+
+def _tensor_core_kind(x, w, bfp_args):
+    """Which tensor-core contraction serves this configuration: 'bf16' (exact-bf16 operands, MMA-bound, any block size,
+    mant_bits <= 8), 'i8' (int8 mantissas + per-block rescale, block 32/64/128, mant_bits <= 7) or None (fake-quant +
+    library GEMM, the reference's own structure).  BFP_GEMM_KIND=bf16|i8 picks between the first two (default bf16: it is
+    the faster of the two for every block size <= 64)."""
+    if not _tensor_core_eligible(x, w, dict(bfp_args, block_size=64 if bfp_args['block_size'] > 0 else 0, mant_bits=min(bfp_args['mant_bits'], 7))):
+        return None
+    B, m = bfp_args['block_size'], bfp_args['mant_bits']
+    want = os.environ.get("BFP_GEMM_KIND", "bf16")
+    i8_ok = B in (32, 64, 128) and 1 <= m <= 7
+    bf16_ok = 1 <= m <= 8 and B >= 4 and (B & (B - 1)) == 0
+    if want == "i8" and i8_ok:
+        return 'i8'
+    if bf16_ok:
+        return 'bf16'
+    return 'i8' if i8_ok else None
+
+
 def _tensor_core_eligible(x, w, bfp_args):
     """The packed tensor-core path computes the same function as quantise + F.linear (fp32 accumulate order aside); it is
     taken for inference on CUDA fp32 tensors when the configuration has a packed form."""
@@ -449,22 +507,26 @@ class BFPLinear(torch.nn.Linear):
         super().__init__(in_features, out_features, bias)
         self.num_format = self.bfp_args['num_format']
         self.linear_op = _get_bfp_op(F.linear, 'linear', self.bfp_args)
-        self._packed_w = None          # (key, PackedBFP): the weight is re-packed only when it changes
+        self._packed_w = None          # (key, packed weight): the weight is re-packed only when it changes
 
-    def _packed_weight(self):
+    def _packed_weight(self, kind):
         w = self.weight
-        key = (w.data_ptr(), w._version, tuple(w.shape), w.device)
+        key = (kind, w.data_ptr(), w._version, tuple(w.shape), w.device)
         if self._packed_w is None or self._packed_w[0] != key:
-            self._packed_w = (key, pack_bfp(w, identifier='w', **self.bfp_args))
+            pack = pack_bfp if kind == 'i8' else pack_bfp_bf16
+            self._packed_w = (key, pack(w, identifier='w', **self.bfp_args))
         return self._packed_w[1]
 
     def forward(self, input):
         if self.num_format == 'fp32':
             return F.linear(input, self.weight, self.bias)
         elif self.num_format == 'bfp':
-            if (self.bfp_args['rounding_mode'] == rounding_modes.DETERM
-                    and _tensor_core_eligible(input, self.weight, self.bfp_args)):
+            kind = _tensor_core_kind(input, self.weight, self.bfp_args) if self.bfp_args['rounding_mode'] == rounding_modes.DETERM else None
+            if kind == 'i8':
                 # inference fast path: pack activations on the fly, cached packed weight, tcgen05 int8 BFP GEMM
-                return bfp_linear_packed(pack_bfp(input, identifier='in', **self.bfp_args), self._packed_weight(), self.bias)
+                return bfp_linear_packed(pack_bfp(input, identifier='in', **self.bfp_args), self._packed_weight(kind), self.bias)
+            if kind == 'bf16':
+                return bfp_linear_bf16(pack_bfp_bf16(input, identifier='in', **self.bfp_args), self._packed_weight(kind), self.bias,
+                                       out_shape=tuple(input.shape[:-1]) + (self.out_features,))
             return self.linear_op(input, self.weight, self.bias)
         raise NotImplementedError('NumFormat not implemented')

@@ -196,6 +196,25 @@ int bfp_quantize_pack(const void* in, int8_t* mant, float* scale_t, int64_t rows
     return pack_device(a, mant, scale_t, packed_kp(K), packed_rows_pad(rows), static_cast<cudaStream_t>(stream));
 }
 
+int bfp_quantize_pack_bf16(const void* in, void* out_bf16, int64_t rows, int64_t K, int in_dtype, int block_size, int mant_bits,
+                           float eps, int rounding, uint64_t seed, uint64_t offset, int N, int M, int order, void* stream) {
+    const int out_dt = rounding == BFP_ROUND_STOCHASTIC ? BFP_DT_F32 : in_dtype;
+    QuantArgs a{in, out_bf16, rows, K, in_dtype, out_dt, block_size, mant_bits, eps, rounding, seed, offset, N, M, order, BFP_TIE_TORCH_CUDA};
+    if (order == BFP_ORDER_SPARSIFY_ONLY) return set_error(BFP_E_ARG, "packing needs a quantising order");
+    if (int rc = validate_quant_args(a, true)) return rc;
+    if (mant_bits < 1 || mant_bits > 8) return set_error(BFP_E_UNSUPPORTED, "bf16 operands are exact for mant_bits in [1, 8] only");
+    if (reinterpret_cast<uintptr_t>(out_bf16) % 16) return set_error(BFP_E_ALIGN, "out_bf16 must be 16-byte aligned");
+    if (int rc = require_device()) return rc;
+    return pack_bf16_device(a, out_bf16, round_up(K, 8), static_cast<cudaStream_t>(stream));
+}
+
+int bfp_gemm_bf16(const void* a_bf16, const void* b_bf16, const float* bias, float* out, int64_t T, int64_t N, int64_t K, void* stream) {
+    if (T < 0 || N < 0 || K <= 0) return set_error(BFP_E_ARG, "bad argument");
+    if (T * N > 0 && (!a_bf16 || !b_bf16 || !out)) return set_error(BFP_E_ARG, "null pointer");
+    if (int rc = require_device()) return rc;
+    return gemm_bf16_device(a_bf16, b_bf16, bias, out, T, N, round_up(K, 8), static_cast<cudaStream_t>(stream));
+}
+
 int bfp_unpack(const int8_t* mant, const float* scale_t, float* out, int64_t rows, int64_t K, int block_size, void* stream) {
     if (rows < 0 || K < 0 || block_size <= 0) return set_error(BFP_E_ARG, "bad argument");
     if (rows * K > 0 && (!mant || !scale_t || !out)) return set_error(BFP_E_ARG, "null pointer");

@@ -292,6 +292,160 @@ bfp_gemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
 }
 
+// ================================================================================================================
+// Exact bf16 path.  For mant_bits <= 8 the dequantised value q * 2^(e-m) is exactly representable in bf16 (q has at most
+// 8 significant bits, the power of two only moves the exponent), so products are exact in the tensor core and the only
+// rounding is the fp32 accumulation -- the same contract as the int8 path, but with NO per-block rescale: the scales
+// ride in the operands' exponents.  MMA-bound for every block size (including B = 16, which kind::i8 cannot express).
+// Same tile / smem-byte geometry as the int8 kernel: stage = A[128 x 128 B] + B[256 x 128 B], 64 bf16 of K per stage,
+// four 128x256x16 tcgen05.mma.kind::f16 per stage; accumulators ping-pong between two TMEM buffers ACROSS TILES so the
+// epilogue of tile i overlaps the main loop of tile i+1.
+// ================================================================================================================
+constexpr int kStagesBf16 = 4;
+constexpr int kStageBytesBf16 = kSmemA + kSmemB;                               // 48 KB
+constexpr int kSmemTotalBf16 = kStagesBf16 * kStageBytesBf16 + kSmemBarriers + 1024;
+// D = F32 (1 << 4), A = B = BF16 (1 << 7, 1 << 10), K-major, N >> 3, M >> 4
+constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct ParamsBf16 {
+    const float* bias;
+    float* out;
+    int T, N;
+    int num_k_stages;           // ceil(K / 64)
+    int tiles_m, tiles_n;
+};
+
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+struct BarriersBf16 {
+    uint64_t full[kStagesBf16];
+    uint64_t empty[kStagesBf16];
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ParamsBf16 p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    BarriersBf16* bars = reinterpret_cast<BarriersBf16*>(smem + kStagesBf16 * kStageBytesBf16);
+    auto stage_a = [&](int s) { return smem + s * kStageBytesBf16; };
+    auto stage_b = [&](int s) { return smem + s * kStageBytesBf16 + kSmemA; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = p.tiles_m * p.tiles_n;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStagesBf16; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], kEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
+                for (int ks = 0; ks < p.num_k_stages; ++ks) {
+                    mbar_wait(&bars->empty[stage], phase ^ 1);
+                    mbar_expect_tx(&bars->full[stage], kStageBytesBf16);
+                    tma_load_2d(stage_a(stage), &map_a, &bars->full[stage], ks * 64, tm * BM);
+                    tma_load_2d(stage_b(stage), &map_b, &bars->full[stage], ks * 64, tn * BN);
+                    if (++stage == kStagesBf16) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int buf = 0; uint32_t buf_phase[2] = {0, 0};
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&bars->tmem_empty[buf], buf_phase[buf] ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)buf * BN;
+                for (int ks = 0; ks < p.num_k_stages; ++ks) {
+                    mbar_wait(&bars->full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = make_smem_desc(smem_u32(stage_a(stage)));
+                    const uint64_t db = make_smem_desc(smem_u32(stage_b(stage)));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)         // 16 bf16 = 32 bytes of K per MMA: +2 in 16-byte units
+                        mma_bf16(d, da + (uint64_t)(i * 2), db + (uint64_t)(i * 2), kIdescBf16, (ks | i) != 0);
+                    tc_commit(&bars->empty[stage]);
+                    if (++stage == kStagesBf16) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&bars->tmem_full[buf]);
+                buf_phase[buf] ^= 1;
+                buf ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        const int ew = warp - 4, q = warp & 3, half = ew >> 2;
+        const int row_in_tile = q * 32 + lane;
+        int buf = 0; uint32_t buf_phase[2] = {0, 0};
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
+            mbar_wait(&bars->tmem_full[buf], buf_phase[buf]);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * 128);
+            const int t = tm * BM + row_in_tile;
+            const int n0 = tn * BN + half * 128;
+            float* dst = p.out + (int64_t)t * p.N + n0;
+            const bool vec_ok = (p.N % 4 == 0) && (n0 + 128 <= p.N);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint32_t r[16];
+                tmem_ld16(taddr + c * 16, r);
+                tmem_ld_wait();
+                if (t < p.T) {
+                    if (vec_ok) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                            if (p.bias) {
+                                const float4 bv = *reinterpret_cast<const float4*>(p.bias + n0 + c * 16 + j);
+                                o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                            }
+                            *reinterpret_cast<float4*>(dst + c * 16 + j) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (n0 + c * 16 + j < p.N) dst[c * 16 + j] = __uint_as_float(r[j]) + (p.bias ? p.bias[n0 + c * 16 + j] : 0.0f);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
+            buf_phase[buf] ^= 1;
+            buf ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+}
+
 // ---- host side -------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -308,14 +462,14 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t kbytes, int box_rows) {
+static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t kbytes, int box_rows, bool bf16 = false) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return set_error(BFP_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-    cuuint64_t dims[2] = {(cuuint64_t)kbytes, (cuuint64_t)rows};
+    cuuint64_t dims[2] = {(cuuint64_t)(bf16 ? kbytes / 2 : kbytes), (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)kbytes};
-    cuuint32_t box[2] = {(cuuint32_t)BKB, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)(bf16 ? BKB / 2 : BKB), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+    CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_errorf(BFP_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -346,14 +500,35 @@ int gemm_i8_device(const int8_t* a_mant, const float* a_scale_t, int64_t lda_s, 
     CUtensorMap map_a, map_b;
     if (int rc = make_map(&map_a, a_mant, T, Kp, BM)) return rc;
     if (int rc = make_map(&map_b, b_mant, N, Kp, BN)) return rc;
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(bfp_gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal); });
+    const cudaError_t attr_err = cudaFuncSetAttribute(bfp_gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     if (attr_err != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
     const int grid = std::min(p.tiles_m * p.tiles_n, device_info().sm_count);
     bfp_gemm_i8_kernel<<<grid, kThreads, kSmemTotal, st>>>(map_a, map_b, p);
     count_launch();
     return check_launch("bfp_gemm_i8_kernel");
+}
+
+int gemm_bf16_device(const void* a_bf16, const void* b_bf16, const float* bias, float* out, int64_t T, int64_t N, int64_t Kp,
+                     cudaStream_t st) {
+    using namespace gemm;
+    if (T == 0 || N == 0) return BFP_OK;
+    if (Kp % 8 != 0 || Kp <= 0) return set_error(BFP_E_ARG, "bf16 operand K must be a positive multiple of 8");
+    if (T > INT32_MAX || N > INT32_MAX || Kp > INT32_MAX) return set_error(BFP_E_ARG, "dimension too large");
+    if (reinterpret_cast<uintptr_t>(a_bf16) % 16 || reinterpret_cast<uintptr_t>(b_bf16) % 16)
+        return set_error(BFP_E_ALIGN, "bf16 operands must be 16-byte aligned");
+    ParamsBf16 p;
+    p.bias = bias; p.out = out; p.T = (int)T; p.N = (int)N;
+    p.num_k_stages = (int)((Kp + 63) / 64);
+    p.tiles_m = (int)((T + BM - 1) / BM); p.tiles_n = (int)((N + BN - 1) / BN);
+    CUtensorMap map_a, map_b;
+    if (int rc = make_map(&map_a, a_bf16, T, Kp * 2, BM, true)) return rc;
+    if (int rc = make_map(&map_b, b_bf16, N, Kp * 2, BN, true)) return rc;
+    cudaError_t e = cudaFuncSetAttribute(bfp_gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalBf16);
+    if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    const int grid = std::min(p.tiles_m * p.tiles_n, device_info().sm_count);
+    bfp_gemm_bf16_kernel<<<grid, kThreads, kSmemTotalBf16, st>>>(map_a, map_b, p);
+    count_launch();
+    return check_launch("bfp_gemm_bf16_kernel");
 }
 
 }  // namespace bfp

@@ -51,6 +51,10 @@ int unpack_device(const int8_t* mant, const float* scale_t, float* out, int64_t 
 int gemm_i8_device(const int8_t* a_mant, const float* a_scale_t, int64_t lda_s, const int8_t* b_mant, const float* b_scale_t,
                    int64_t ldb_s, const float* bias, float* out, int64_t T, int64_t N, int64_t Kp, int block_size, cudaStream_t st);
 
+int pack_bf16_device(const QuantArgs& a, void* out_bf16, int64_t Kp, cudaStream_t st);
+int gemm_bf16_device(const void* a_bf16, const void* b_bf16, const float* bias, float* out, int64_t T, int64_t N, int64_t Kp,
+                     cudaStream_t st);
+
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline int64_t packed_kp(int64_t K) { return round_up(K, 16); }
 inline int64_t packed_rows_pad(int64_t rows) { return round_up(rows, 256); }

@@ -41,7 +41,9 @@ __device__ __forceinline__ uint32_t pack4_s8(const float* q) {
 
 // stream path: same lane mapping as quant_stream_kernel (bfp_quant.cu); requires K % B == 0 so rows never matter for
 // the mantissas (Kp == K) and a block's (row, kb) follows from its flat index.
-template <int DT, int ORDER, int M, int KD, bool STOC>
+// FMT: 0 = int8 mantissas + block-major fp32 scale table; 1 = dequantised bf16 (exact for m <= 8: q has <= 8 significant
+// bits and 2^(e-m) only moves the exponent), the operand format of the exact bf16 tensor-core GEMM.
+template <int DT, int ORDER, int M, int KD, bool STOC, int FMT>
 __global__ void __launch_bounds__(kStreamThreads) pack_stream_kernel(const PackParams p) {
     using D = DType<DT>;
     constexpr int V = D::kVec;
@@ -95,7 +97,20 @@ __global__ void __launch_bounds__(kStreamThreads) pack_stream_kernel(const PackP
                 for (int i = 0; i < V; ++i) q[i] = 0.0f;
             }
             if (kSparseLast) mask_vec<M, KD, BFP_TIE_TORCH_CUDA, V>(q, p.kdrop);   // same order as masking q * delta
-            if (li < rem) {
+            if (FMT == 1) {
+                if (li < rem) {
+                    const float d = sc.fast ? sc.delta : __int_as_float(0x7fc00000);
+                    uint32_t w[V / 2];
+#pragma unroll
+                    for (int i = 0; i < V / 2; ++i) {
+                        __nv_bfloat162 h = __floats2bfloat162_rn(q[2 * i] * d, q[2 * i + 1] * d);
+                        w[i] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                    uint16_t* dst = reinterpret_cast<uint16_t*>(p.mant) + vi * V;
+                    if (V == 4) *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
+                    else *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[V / 2 - 2], w[V / 2 - 1]);
+                }
+            } else if (li < rem) {
                 if (V == 4) {
                     *reinterpret_cast<uint32_t*>(p.mant + vi * 4) = pack4_s8(q);
                 } else {
@@ -123,7 +138,7 @@ struct PackGenericParams {
     uint64_t seed, offset;
 };
 
-template <int DT, int ORDER, bool STOC>
+template <int DT, int ORDER, bool STOC, int FMT>
 __global__ void __launch_bounds__(128) pack_generic_kernel(const PackGenericParams p) {
     const int64_t nkb = (p.K + p.B - 1) / p.B;
     for (int64_t unit = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; unit < p.rows * nkb; unit += (int64_t)gridDim.x * blockDim.x) {
@@ -144,7 +159,12 @@ __global__ void __launch_bounds__(128) pack_generic_kernel(const PackGenericPara
         uint32_t amax = 0u;
         for (int64_t c = c0; c < c1; ++c) amax = max(amax, abs_bits(src(c)));
         const BlockScale sc = make_scale<DT>(amax, p.m, p.eps);
-        p.scale_t[kb * p.rows_pad + row] = sc.fast ? sc.delta : __int_as_float(0x7fc00000);
+        const float dq = sc.fast ? sc.delta : __int_as_float(0x7fc00000);
+        if (FMT == 0) p.scale_t[kb * p.rows_pad + row] = dq;
+        auto put = [&](int64_t c, float qv) {
+            if (FMT == 0) p.mant[row * p.Kp + c] = (int8_t)__float2int_rn(qv);
+            else reinterpret_cast<__nv_bfloat16*>(p.mant)[row * p.Kp + c] = __float2bfloat16_rn(qv * dq);
+        };
         auto qof = [&](int64_t c) {
             if (!sc.fast || c >= c1) return 0.0f;
             const float x = src(c) * sc.inv;
@@ -157,10 +177,10 @@ __global__ void __launch_bounds__(128) pack_generic_kernel(const PackGenericPara
                 for (int j = 0; j < p.M; ++j) q[j] = qof(g0 + j);
                 auto qsrc = [&](int64_t c) { return q[c - g0]; };
                 for (int j = 0; j < p.M && g0 + j < c1; ++j)
-                    p.mant[row * p.Kp + g0 + j] = (int8_t)__float2int_rn(nm_dropped(qsrc, g0 + j, p.N, p.M, BFP_TIE_TORCH_CUDA) ? 0.0f : q[j]);
+                    put(g0 + j, nm_dropped(qsrc, g0 + j, p.N, p.M, BFP_TIE_TORCH_CUDA) ? 0.0f : q[j]);
             }
         } else {
-            for (int64_t c = c0; c < c1; ++c) p.mant[row * p.Kp + c] = (int8_t)__float2int_rn(qof(c));
+            for (int64_t c = c0; c < c1; ++c) put(c, qof(c));
         }
     }
 }
@@ -175,24 +195,24 @@ __global__ void __launch_bounds__(256) unpack_kernel(const int8_t* mant, const f
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-template <int DT, int ORDER, bool STOC>
+template <int DT, int ORDER, bool STOC, int FMT>
 static int launch_pack_stream(const PackParams& p, bool sparse, cudaStream_t st) {
     const int64_t n_tiles = (p.n_vec + kStreamThreads * kStreamUnroll - 1) / (kStreamThreads * kStreamUnroll);
     const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)device_info().sm_count * tuning().stream_ctas_per_sm);
-    if (sparse) pack_stream_kernel<DT, ORDER, 4, 2, STOC><<<grid, kStreamThreads, 0, st>>>(p);
-    else pack_stream_kernel<DT, BFP_ORDER_QUANT_ONLY, 0, 0, STOC><<<grid, kStreamThreads, 0, st>>>(p);
+    if (sparse) pack_stream_kernel<DT, ORDER, 4, 2, STOC, FMT><<<grid, kStreamThreads, 0, st>>>(p);
+    else pack_stream_kernel<DT, BFP_ORDER_QUANT_ONLY, 0, 0, STOC, FMT><<<grid, kStreamThreads, 0, st>>>(p);
     count_launch();
     return check_launch("pack_stream_kernel");
 }
 
-template <int DT, bool STOC>
+template <int DT, bool STOC, int FMT>
 static int pack_dt(const QuantArgs& a, int8_t* mant, float* scale_t, int64_t Kp, int64_t rows_pad, cudaStream_t st) {
     constexpr int V = DType<DT>::kVec;
     const bool sparse = a.order != BFP_ORDER_QUANT_ONLY;
     const int64_t numel = a.rows * a.K, nkb = (a.K + a.B - 1) / a.B;
     if (numel == 0) return BFP_OK;
     bool fast = (a.K % a.B == 0) && (a.B & (a.B - 1)) == 0 && a.B >= V && a.B <= 32 * V && Kp == a.K &&
-                reinterpret_cast<uintptr_t>(a.in) % 16 == 0 && reinterpret_cast<uintptr_t>(mant) % 8 == 0 &&
+                reinterpret_cast<uintptr_t>(a.in) % 16 == 0 && reinterpret_cast<uintptr_t>(mant) % 16 == 0 &&
                 a.rows * nkb < (int64_t)1 << 32 && !tuning().force_generic;
     if (sparse) fast = fast && a.M == 4 && a.N == 2;
     if (fast) {
@@ -201,9 +221,9 @@ static int pack_dt(const QuantArgs& a, int8_t* mant, float* scale_t, int64_t Kp,
         p.rows_pad = rows_pad; p.nkb = (uint32_t)nkb; p.lanes_per_block = a.B / V; p.lpb_shift = __builtin_ctz(a.B / V);
         p.m = a.m; p.eps = a.eps; p.kdrop = sparse ? a.M - a.N : 0; p.seed = a.seed; p.offset = a.offset;
         switch (a.order) {
-        case BFP_ORDER_QUANT_ONLY: return launch_pack_stream<DT, BFP_ORDER_QUANT_ONLY, STOC>(p, false, st);
-        case BFP_ORDER_SPARSIFY_QUANT: return launch_pack_stream<DT, BFP_ORDER_SPARSIFY_QUANT, STOC>(p, true, st);
-        case BFP_ORDER_QUANT_SPARSIFY: return launch_pack_stream<DT, BFP_ORDER_QUANT_SPARSIFY, STOC>(p, true, st);
+        case BFP_ORDER_QUANT_ONLY: return launch_pack_stream<DT, BFP_ORDER_QUANT_ONLY, STOC, FMT>(p, false, st);
+        case BFP_ORDER_SPARSIFY_QUANT: return launch_pack_stream<DT, BFP_ORDER_SPARSIFY_QUANT, STOC, FMT>(p, true, st);
+        case BFP_ORDER_QUANT_SPARSIFY: return launch_pack_stream<DT, BFP_ORDER_QUANT_SPARSIFY, STOC, FMT>(p, true, st);
         }
         return set_error(BFP_E_ARG, "bad order");
     }
@@ -215,23 +235,32 @@ static int pack_dt(const QuantArgs& a, int8_t* mant, float* scale_t, int64_t Kp,
     const int64_t units = a.rows * nkb;
     const int grid = (int)std::min<int64_t>((units + 127) / 128, (int64_t)device_info().sm_count * 16);
     switch (a.order) {
-    case BFP_ORDER_QUANT_ONLY: pack_generic_kernel<DT, BFP_ORDER_QUANT_ONLY, STOC><<<grid, 128, 0, st>>>(g); break;
-    case BFP_ORDER_SPARSIFY_QUANT: pack_generic_kernel<DT, BFP_ORDER_SPARSIFY_QUANT, STOC><<<grid, 128, 0, st>>>(g); break;
-    case BFP_ORDER_QUANT_SPARSIFY: pack_generic_kernel<DT, BFP_ORDER_QUANT_SPARSIFY, STOC><<<grid, 128, 0, st>>>(g); break;
+    case BFP_ORDER_QUANT_ONLY: pack_generic_kernel<DT, BFP_ORDER_QUANT_ONLY, STOC, FMT><<<grid, 128, 0, st>>>(g); break;
+    case BFP_ORDER_SPARSIFY_QUANT: pack_generic_kernel<DT, BFP_ORDER_SPARSIFY_QUANT, STOC, FMT><<<grid, 128, 0, st>>>(g); break;
+    case BFP_ORDER_QUANT_SPARSIFY: pack_generic_kernel<DT, BFP_ORDER_QUANT_SPARSIFY, STOC, FMT><<<grid, 128, 0, st>>>(g); break;
     default: return set_error(BFP_E_ARG, "bad order");
     }
     count_launch();
     return check_launch("pack_generic_kernel");
 }
 
-int pack_device(const QuantArgs& a, int8_t* mant, float* scale_t, int64_t Kp, int64_t rows_pad, cudaStream_t st) {
+template <int FMT>
+static int pack_fmt(const QuantArgs& a, int8_t* mant, float* scale_t, int64_t Kp, int64_t rows_pad, cudaStream_t st) {
     const bool stoc = a.rounding == BFP_ROUND_STOCHASTIC;
     switch (a.in_dtype) {
-    case BFP_DT_F32: return stoc ? pack_dt<BFP_DT_F32, true>(a, mant, scale_t, Kp, rows_pad, st) : pack_dt<BFP_DT_F32, false>(a, mant, scale_t, Kp, rows_pad, st);
-    case BFP_DT_F16: return stoc ? pack_dt<BFP_DT_F16, true>(a, mant, scale_t, Kp, rows_pad, st) : pack_dt<BFP_DT_F16, false>(a, mant, scale_t, Kp, rows_pad, st);
-    case BFP_DT_BF16: return stoc ? pack_dt<BFP_DT_BF16, true>(a, mant, scale_t, Kp, rows_pad, st) : pack_dt<BFP_DT_BF16, false>(a, mant, scale_t, Kp, rows_pad, st);
+    case BFP_DT_F32: return stoc ? pack_dt<BFP_DT_F32, true, FMT>(a, mant, scale_t, Kp, rows_pad, st) : pack_dt<BFP_DT_F32, false, FMT>(a, mant, scale_t, Kp, rows_pad, st);
+    case BFP_DT_F16: return stoc ? pack_dt<BFP_DT_F16, true, FMT>(a, mant, scale_t, Kp, rows_pad, st) : pack_dt<BFP_DT_F16, false, FMT>(a, mant, scale_t, Kp, rows_pad, st);
+    case BFP_DT_BF16: return stoc ? pack_dt<BFP_DT_BF16, true, FMT>(a, mant, scale_t, Kp, rows_pad, st) : pack_dt<BFP_DT_BF16, false, FMT>(a, mant, scale_t, Kp, rows_pad, st);
     }
     return set_error(BFP_E_ARG, "bad dtype");
+}
+
+int pack_device(const QuantArgs& a, int8_t* mant, float* scale_t, int64_t Kp, int64_t rows_pad, cudaStream_t st) {
+    return pack_fmt<0>(a, mant, scale_t, Kp, rows_pad, st);
+}
+// dequantised bf16 [rows, Kp] (Kp = K rounded up to 8 elements)
+int pack_bf16_device(const QuantArgs& a, void* out_bf16, int64_t Kp, cudaStream_t st) {
+    return pack_fmt<1>(a, static_cast<int8_t*>(out_bf16), nullptr, Kp, 0, st);
 }
 
 int unpack_device(const int8_t* mant, const float* scale_t, float* out, int64_t rows, int64_t K, int64_t Kp, int64_t rows_pad, int B,

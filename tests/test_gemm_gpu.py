@@ -114,10 +114,48 @@ def test_unrepresentable_blocks_become_nan_rows(ops):
     assert torch.isnan(ref[1]).all() and torch.isnan(ref[2]).all()          # the reference arithmetic NaNs the same rows
 
 
+@pytest.mark.parametrize("shape", [(128, 256, 64), (256, 512, 512), (200, 300, 384), (1, 8, 72), (4096, 768, 1024), (130, 260, 200)])
+def test_gemm_bf16_exact_products(ops, shape):
+    """kind::f16 path: small-integer bf16 operands -> the fp32 result is the exact integer matmul."""
+    T, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(T * 3 + N + K)
+    a = torch.randint(-15, 16, (T, K), generator=g, device="cuda").float()
+    b = torch.randint(-15, 16, (N, K), generator=g, device="cuda").float()
+    Kp = -(-K // 8) * 8
+    ab = torch.zeros(T, Kp, dtype=torch.bfloat16, device="cuda"); ab[:, :K] = a
+    bb = torch.zeros(N, Kp, dtype=torch.bfloat16, device="cuda"); bb[:, :K] = b
+    bias = torch.randint(-5, 6, (N,), generator=g, device="cuda").float()
+    y = ops.bfp_linear_bf16(ab, bb, bias)
+    assert torch.equal(y.double(), a.double() @ b.double().t() + bias.double())
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
+def test_pack_bf16_equals_fake_quant(ops, dt):
+    """bf16 operand = float_to_bfp_blocked(x) exactly (m <= 8), for every block size including 16."""
+    from qsi_b200 import _lib
+    for shape, (m, B), first, sparse in itertools.product([(256, 1024), (37, 96), (3, 5, 200), (130, 72)], [(7, 64), (3, 16), (5, 32), (8, 128)],
+                                                           ["s", "q"], [True, False]):
+        g = torch.Generator().manual_seed(len(shape) * 10 + m + B)
+        x = (torch.randn(*shape, generator=g) * 0.05).to(dt).cuda()
+        args = ops.unpack_bfp_args(dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=m,
+                                        block_size=B, w_sparsity=sparse, N=2, M=4, first=first, sparsity_mode="structured", device="cuda"))
+        fq = ops.float_to_bfp_blocked(x, **args, identifier="w").float().reshape(-1, shape[-1])
+        for generic in (0, 1):
+            _lib.set_option("force_generic", generic)
+            try:
+                pb = ops.pack_bfp_bf16(x, identifier="w", **args)
+            finally:
+                _lib.set_option("force_generic", 0)
+            assert torch.equal(pb[:, : shape[-1]].float(), fq), (shape, m, B, first, sparse, generic)
+            assert (pb[:, shape[-1]:] == 0).all()
+
+
+@pytest.mark.parametrize("kind", ["bf16", "i8"])
 @pytest.mark.parametrize("first", ["s", "q"])
-@pytest.mark.parametrize("mB", [(7, 64), (5, 32), (3, 128)])
-def test_bfplinear_tensor_core_path_matches_oracle(ops, oracle, first, mB, monkeypatch):
+@pytest.mark.parametrize("mB", [(7, 64), (5, 32), (3, 128), (3, 16)])
+def test_bfplinear_tensor_core_path_matches_oracle(ops, oracle, first, mB, kind, monkeypatch):
     m, B = mB
+    monkeypatch.setenv("BFP_GEMM_KIND", kind)
     kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=m, block_size=B,
               w_sparsity=True, N=2, M=4, first=first, sparsity_mode="structured", device="cuda")
     torch.manual_seed(1)
@@ -135,8 +173,11 @@ def test_bfplinear_tensor_core_path_matches_oracle(ops, oracle, first, mB, monke
     for y in (y_tc, y_fq):
         rel = np.linalg.norm(y.cpu().numpy() - ref) / np.linalg.norm(ref)
         assert rel <= 1e-5, rel
+    if B == 16 and kind == "i8":
+        return                                   # one int8 MMA is 32 deep: B = 16 is served by the bf16 kind
     # weight pack is cached until the weight changes
     k0 = lin._packed_w[0]
+    assert k0[0] == kind
     with torch.no_grad():
         lin(x)
         assert lin._packed_w[0] == k0
@@ -166,3 +207,7 @@ def test_gemm_llama7b_shapes_full_size(ops, NK):
     # linearity in the activations' block scales: doubling x doubles y exactly (power-of-two scaling commutes with BFP)
     y2 = ops.bfp_linear_packed(ops.pack_bfp(2 * x, identifier="in", **a), wp)
     assert torch.equal(y2, 2 * y)
+    # the exact-bf16 kind computes the same function (only the fp32 summation order differs)
+    yb = ops.bfp_linear_bf16(ops.pack_bfp_bf16(x, identifier="in", **a), ops.pack_bfp_bf16(w, identifier="w", **a))
+    assert ((yb[rows].double() - ref).norm() / ref.norm()).item() <= 1e-5
+    assert ((yb - y).norm() / y.norm()).item() <= 2e-6

@@ -26,6 +26,18 @@ for (T, N, K) in sum((SH[s] for s in a.shapes.split(",")), []):
         e1.record(); torch.cuda.synchronize(); ms_pack = e0.elapsed_time(e1) / a.iters
         tops = 2.0 * T * N * K / ms / 1e9
         res.append(dict(T=T, N=N, K=K, B=B, gemm_ms=ms, tops=tops, pack_x_ms=ms_pack))
+        if B == 64:
+            xb, wb = ops.pack_bfp_bf16(x, identifier="in", **kw), ops.pack_bfp_bf16(w, identifier="w", **kw)
+            runb = lambda: _lib.check(L.bfp_gemm_bf16(xb.data_ptr(), wb.data_ptr(), None, out.data_ptr(), T, N, K, st))
+            for _ in range(3): runb()
+            torch.cuda.synchronize(); e0.record()
+            for _ in range(a.iters): runb()
+            e1.record(); torch.cuda.synchronize(); msb = e0.elapsed_time(e1) / a.iters
+            e0.record()
+            for _ in range(a.iters): ops.pack_bfp_bf16(x, identifier="in", **kw)
+            e1.record(); torch.cuda.synchronize(); msbp = e0.elapsed_time(e1) / a.iters
+            print(f"T={T} N={N} K={K} exact-bf16 kind: gemm {msb:.3f} ms = {2.0*T*N*K/msb/1e9:.0f} TOPS; pack x {msbp*1e3:.1f} us", flush=True)
+            res.append(dict(T=T, N=N, K=K, kind="bf16", gemm_ms=msb, tops=2.0 * T * N * K / msb / 1e9, pack_x_ms=msbp))
         print(f"T={T} N={N} K={K} B={B}: gemm {ms:.3f} ms = {tops:.0f} TOPS ({100*tops/4500:.1f}% of 4500 nominal int8); pack x {ms_pack*1e3:.1f} us", flush=True)
     # yardsticks
     xq = ops.unpack_bfp(xp); wq = ops.unpack_bfp(wp)
