@@ -69,3 +69,56 @@ def sum_over_ranks(x, device=None):
     t = torch.tensor([float(x)], dtype=torch.float64, device=device if device is not None else "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Column-parallel BFP linear (SURVEY.md section 8e): W[N_out, K] is split by rows of N_out into contiguous shards.
+# Blocks and N:M groups run along K, so a shard quantises exactly as the same rows of the full matrix do; x is
+# replicated and quantised redundantly; rank g computes y_g = x W_g^T [T, N_out/G]; ONE all-gather assembles y.
+# ---------------------------------------------------------------------------------------------------------------
+def column_shard(n_out, rank, world):
+    """[lo, hi) rows of N_out owned by `rank` (contiguous, sizes differ by at most one)."""
+    base, rem = divmod(n_out, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class ColumnParallelBFPLinear(torch.nn.Module):
+    """Drop-in for BFPLinear(in_features, out_features) on `world` GPUs: each rank holds rows column_shard(out_features)
+    of the weight (and bias) in a local BFPLinear and the forward all-gathers the output slices."""
+
+    def __init__(self, in_features, out_features, bias=True, group=None, **bfp_kwargs):
+        super().__init__()
+        from .bfp_ops import BFPLinear
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.in_features, self.out_features = in_features, out_features
+        self.lo, self.hi = column_shard(out_features, self.rank, self.world)
+        self.local = BFPLinear(in_features, self.hi - self.lo, bias=bias, **bfp_kwargs)
+
+    @torch.no_grad()
+    def load_full(self, weight, bias=None):
+        """Copies this rank's shard out of the full [N_out, K] weight (and [N_out] bias)."""
+        self.local.weight.copy_(weight[self.lo:self.hi])
+        if bias is not None and self.local.bias is not None:
+            self.local.bias.copy_(bias[self.lo:self.hi])
+        return self
+
+    def forward(self, x):
+        y = self.local(x)                                           # [..., N_local]
+        if self.world == 1:
+            return y
+        lead = y.shape[:-1]
+        y2 = y.reshape(-1, y.shape[-1]).contiguous()
+        sizes = [column_shard(self.out_features, r, self.world) for r in range(self.world)]
+        equal = len({hi - lo for lo, hi in sizes}) == 1
+        if equal and y2.is_cuda:
+            buf = torch.empty((self.world,) + tuple(y2.shape), dtype=y2.dtype, device=y2.device)
+            dist.all_gather_into_tensor(buf, y2, group=self.group)  # NCCL over NVLink: [G, T, N/G]
+            out = buf.permute(1, 0, 2).reshape(y2.shape[0], self.out_features)
+        else:
+            parts = [torch.empty((y2.shape[0], hi - lo), dtype=y2.dtype, device=y2.device) for lo, hi in sizes]
+            dist.all_gather(parts, y2, group=self.group)
+            out = torch.cat(parts, dim=1)
+        return out.reshape(lead + (self.out_features,))

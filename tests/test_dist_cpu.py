@@ -62,3 +62,32 @@ def test_single_process_defaults():
     assert qd.max_over_ranks(3.5) == 3.5 and qd.sum_over_ranks(2) == 2.0
     assert qd.shard_by_layer(qd.model_tensors("llama-7b"), 0, 1) == qd.model_tensors("llama-7b")
     assert len(qd.model_tensors("opt-66b")) == 384
+
+
+def _cp_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import qsi_b200  # noqa: F401
+    from qsi_b200 import dist as qd
+    qd.init("gloo")
+    torch.manual_seed(0)                                   # same full weight / input on every rank
+    w, b, x = torch.randn(10, 16), torch.randn(10), torch.randn(3, 4, 16)
+    # num_format='fp32' keeps the quantiser out (no GPU here): this checks sharding + gather against the full linear
+    cp = qd.ColumnParallelBFPLinear(16, 10, bias=True, num_format="fp32").load_full(w, b)
+    y = cp(x)
+    q.put((rank, (cp.lo, cp.hi), torch.allclose(y, torch.nn.functional.linear(x, w, b), atol=1e-6), tuple(y.shape)))
+    dist.destroy_process_group()
+
+
+def test_column_parallel_linear_gathers_the_full_output():
+    world, port = 3, _free_port()                          # 10 rows over 3 ranks: uneven shards 4/3/3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_cp_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1] for r in res] == [(0, 4), (4, 7), (7, 10)]
+    assert all(r[2] and r[3] == (3, 4, 10) for r in res)
