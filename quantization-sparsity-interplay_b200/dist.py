@@ -112,13 +112,17 @@ class ColumnParallelBFPLinear(torch.nn.Module):
         lead = y.shape[:-1]
         y2 = y.reshape(-1, y.shape[-1]).contiguous()
         sizes = [column_shard(self.out_features, r, self.world) for r in range(self.world)]
-        equal = len({hi - lo for lo, hi in sizes}) == 1
-        if equal and y2.is_cuda:
-            buf = torch.empty((self.world,) + tuple(y2.shape), dtype=y2.dtype, device=y2.device)
+        wmax = max(hi - lo for lo, hi in sizes)
+        equal = all(hi - lo == wmax for lo, hi in sizes)
+        if not equal:                                               # collectives want equal shapes: pad the narrow shards
+            y2 = torch.nn.functional.pad(y2, (0, wmax - y2.shape[1]))
+        buf = torch.empty((self.world,) + tuple(y2.shape), dtype=y2.dtype, device=y2.device)
+        if y2.is_cuda:
             dist.all_gather_into_tensor(buf, y2, group=self.group)  # NCCL over NVLink: [G, T, N/G]
+        else:
+            dist.all_gather(list(buf.unbind(0)), y2, group=self.group)
+        if equal:
             out = buf.permute(1, 0, 2).reshape(y2.shape[0], self.out_features)
         else:
-            parts = [torch.empty((y2.shape[0], hi - lo), dtype=y2.dtype, device=y2.device) for lo, hi in sizes]
-            dist.all_gather(parts, y2, group=self.group)
-            out = torch.cat(parts, dim=1)
+            out = torch.cat([buf[r, :, : hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=1)
         return out.reshape(lead + (self.out_features,))
