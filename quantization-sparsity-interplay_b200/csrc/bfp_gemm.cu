@@ -33,8 +33,14 @@ constexpr int BM = 128, BN = 256, BKB = 128;           // tile: rows of A, rows 
 constexpr int UMMA_K = 32;                             // k per tcgen05.mma.kind::i8
 constexpr int kStages = 4;
 constexpr int kMaxBlocksPerStage = 4;                  // B >= 32
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 8;                           // bf16 kernel: the epilogue runs once per tile
 constexpr int kThreads = 128 + kEpiWarps * 32;         // 384
+constexpr int kEpiWarpsI8 = 8;                         // int8 kernel: 8 or 16 epilogue warps (16 measured ~6 % slower: the
+constexpr int kThreadsI8 = 128 + kEpiWarpsI8 * 32;     // rescale is pipe-throughput-bound, not latency-bound)
+constexpr int kColsI8 = BN / (kEpiWarpsI8 / 4);        // accumulator columns per epilogue thread: 128 (or 64)
+// Registers: the CTA's launch allocation is the pool setmaxnreg can redistribute (an .inc beyond it blocks forever):
+//   384 threads x 168 = 64512 >= 128 x 80 + 256 x 208 = 63488;   640 threads x 96 = 61440 >= 128 x 40 + 512 x 104 = 58368.
+constexpr int kRegDecI8 = kEpiWarpsI8 == 8 ? 80 : 40, kRegIncI8 = kEpiWarpsI8 == 8 ? 208 : 104;
 constexpr int kTmemCols = 512;
 
 constexpr int kSmemA = BM * BKB;                       // 16 KB
@@ -70,18 +76,28 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// bounded wait: a protocol bug must surface as a trap, not as a hung GPU box
+// bounded wait: a protocol bug must surface as a trap within ~2 s, not as a hung GPU box
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
+    uint64_t t0 = 0;
     for (uint32_t spin = 0;; ++spin) {
         uint32_t done;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+            : "=r"(done) : "r"(addr), "r"(parity), "r"(20000u) : "memory");      // suspend-time hint (ns)
         if (done) return;
-        if (spin > (1u << 26)) __trap();
+        if ((spin & 1023u) == 1023u) {
+            const uint64_t now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) __trap();
+        }
     }
 }
 __device__ __forceinline__ bool elect_one() {
@@ -117,6 +133,65 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t* r) {
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(addr));
 }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+// packed fp32x2 arithmetic (sm_100): one issue slot for two lanes of the epilogue's rescale
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(uint64_t v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ void fma2_acc(uint64_t& acc, uint64_t a, uint64_t b) {      // acc += a * b, in place (no register moves)
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// int32 -> fp32 for |v| < 2^22 without the (slow) conversion pipe: bit pattern of (v + 1.5 * 2^23) as a float is
+// 0x4B400000 + v, so one integer add per value and one packed fp32 subtract per pair; exact.
+__device__ __forceinline__ uint64_t cvt2_s32(uint32_t a, uint32_t b) {
+    uint64_t m;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(m) : "r"(a + 0x4B400000u), "r"(b + 0x4B400000u));
+    return add2(m, 0xCB400000CB400000ull);              // (-12582912.0f, -12582912.0f)
+}
+// acc (f32x2) += float(a, b) * w for two int32 accumulator values (I2FP: 64 lanes/clk/SM, tools/microbench/pipe_rates.cu)
+__device__ __forceinline__ void rescale_pair_xu(uint64_t& acc, uint32_t a, uint32_t b, uint64_t w) {
+    asm("{\n\t.reg .f32 fa, fb;\n\t.reg .b64 f;\n\t"
+        "cvt.rn.f32.s32 fa, %1;\n\tcvt.rn.f32.s32 fb, %2;\n\t"
+        "mov.b64 f, {fa, fb};\n\t"
+        "fma.rn.f32x2 %0, f, %3, %0;\n\t}"
+        : "+l"(acc) : "r"(a), "r"(b), "l"(w));
+}
+// the same with the conversion on the integer + FMA pipes: for |v| < 2^22 the bits of float(v + 1.5 * 2^23) are
+// 0x4B400000 + v, so float(v) = as_float(v + 0x4B400000) - 12582912.0f exactly (|block sums| <= 128 * 127^2 < 2^22).
+// Measured slower than I2FP here (the integer adds land on the same half-rate pipe); kept for reference.
+__device__ __forceinline__ void rescale_pair_magic(uint64_t& acc, uint32_t a, uint32_t b, uint64_t w) {
+    asm("{\n\t.reg .b64 m, f;\n\t"
+        "mov.b64 m, {%1, %2};\n\t"
+        "add.rn.f32x2 f, m, %4;\n\t"
+        "fma.rn.f32x2 %0, f, %3, %0;\n\t}"
+        : "+l"(acc) : "r"(a + 0x4B400000u), "r"(b + 0x4B400000u), "l"(w), "l"(0xCB400000CB400000ull));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
@@ -135,7 +210,7 @@ struct Barriers {
     uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsI8, 1)
 bfp_gemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -149,8 +224,8 @@ bfp_gemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const int num_tiles = p.tiles_m * p.tiles_n;
 
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1 + kEpiWarps); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], kEpiWarps); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1 + kEpiWarpsI8); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], kEpiWarpsI8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -167,6 +242,7 @@ bfp_gemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegDecI8));
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -187,9 +263,10 @@ bfp_gemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =======================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegDecI8));
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            int buf = 0; uint32_t buf_phase[2] = {0, 0};
+            int buf = 0; uint32_t buf_phases = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 for (int ks = 0; ks < p.num_k_stages; ++ks) {
                     mbar_wait(&bars->full[stage], phase);
@@ -198,7 +275,7 @@ bfp_gemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     const uint64_t db = make_smem_desc(smem_u32(stage_b(stage)));
                     int mma = 0;
                     for (int b = 0; b < p.blocks_per_stage; ++b) {
-                        mbar_wait(&bars->tmem_empty[buf], buf_phase[buf] ^ 1);     // epilogue drained this accumulator
+                        mbar_wait(&bars->tmem_empty[buf], ((buf_phases >> buf) & 1u) ^ 1u);   // epilogue drained this accumulator
                         tc_fence_after();
                         const uint32_t d = tmem_base + (uint32_t)buf * BN;
                         for (int i = 0; i < p.mmas_per_block; ++i, ++mma) {
@@ -206,7 +283,7 @@ bfp_gemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                             mma_i8(d, da + (uint64_t)(mma * (UMMA_K >> 4)), db + (uint64_t)(mma * (UMMA_K >> 4)), kIdescI8, i > 0);
                         }
                         tc_commit(&bars->tmem_full[buf]);                          // accumulator of this BFP block is complete
-                        buf_phase[buf] ^= 1;
+                        buf_phases ^= 1u << buf;
                         buf ^= 1;
                     }
                     tc_commit(&bars->empty[stage]);                                // smem slab consumed by the tensor core
@@ -214,60 +291,77 @@ bfp_gemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegDecI8));        // warps 2, 3: same warpgroup as the producer / issuer
+    } else {
         // ===================================== epilogue =========================================
-        const int ew = warp - 4;                    // 0..7
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegIncI8));
+        const int ew = warp - 4;                    // 0..kEpiWarpsI8-1
         const int q = warp & 3;                     // TMEM lane quarter this warp may access
-        const int half = ew >> 2;                   // which 128 accumulator columns
+        const int cg = ew >> 2;                     // which kColsI8 accumulator columns
         const int row_in_tile = q * 32 + lane;
         int stage = 0; uint32_t phase = 0;
-        int buf = 0; uint32_t buf_phase[2] = {0, 0};
+        int buf = 0; uint32_t buf_phases = 0;       // bit b = parity of accumulator buffer b
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
-            float acc[128];
+            uint64_t acc2[kColsI8 / 2];             // fp32 accumulators as f32x2 pairs
 #pragma unroll
-            for (int i = 0; i < 128; ++i) acc[i] = 0.0f;
+            for (int i = 0; i < kColsI8 / 2; ++i) acc2[i] = 0ull;
             for (int ks = 0; ks < p.num_k_stages; ++ks) {
                 mbar_wait(&bars->full[stage], phase);                              // scales of this slab have landed
                 for (int b = 0; b < p.blocks_per_stage; ++b) {
-                    const float sa = stage_sa(stage)[b * BM + row_in_tile];
-                    const float4* sb4 = reinterpret_cast<const float4*>(stage_sb(stage) + b * BN + half * 128);
-                    mbar_wait(&bars->tmem_full[buf], buf_phase[buf]);
+                    const float sa = lds32(smem_u32(stage_sa(stage) + b * BM + row_in_tile));
+                    const uint64_t sa2 = pack2(sa, sa);
+                    const uint32_t sb_addr = smem_u32(stage_sb(stage) + b * BN + cg * kColsI8);
+                    mbar_wait(&bars->tmem_full[buf], (buf_phases >> buf) & 1u);
                     tc_fence_after();
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * 128);
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cg * kColsI8);
+                    // software pipeline: the load of chunk c+1 is in flight while chunk c is rescaled
+                    uint32_t r0[16], r1[16];
+                    tmem_ld16(taddr, r0);
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        uint32_t r[16];
-                        tmem_ld16(taddr + c * 16, r);
+                    for (int c = 0; c < kColsI8 / 16; c += 2) {
                         tmem_ld_wait();
+                        tmem_ld16(taddr + (c + 1) * 16, r1);
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
-                            const float4 s = sb4[c * 4 + (j >> 2)];
-                            acc[c * 16 + j + 0] = __fmaf_rn((float)(int)r[j + 0], sa * s.x, acc[c * 16 + j + 0]);
-                            acc[c * 16 + j + 1] = __fmaf_rn((float)(int)r[j + 1], sa * s.y, acc[c * 16 + j + 1]);
-                            acc[c * 16 + j + 2] = __fmaf_rn((float)(int)r[j + 2], sa * s.z, acc[c * 16 + j + 2]);
-                            acc[c * 16 + j + 3] = __fmaf_rn((float)(int)r[j + 3], sa * s.w, acc[c * 16 + j + 3]);
+                            const float4 sv = lds128(sb_addr + (c * 4 + (j >> 2)) * 16);
+                            const uint64_t w01 = mul2(sa2, pack2(sv.x, sv.y)), w23 = mul2(sa2, pack2(sv.z, sv.w));
+                            rescale_pair_xu(acc2[c * 8 + (j >> 1)], r0[j], r0[j + 1], w01);
+                            rescale_pair_xu(acc2[c * 8 + (j >> 1) + 1], r0[j + 2], r0[j + 3], w23);
+                        }
+                        tmem_ld_wait();
+                        if (c + 2 < kColsI8 / 16) tmem_ld16(taddr + (c + 2) * 16, r0);
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 sv = lds128(sb_addr + ((c + 1) * 4 + (j >> 2)) * 16);
+                            const uint64_t w01 = mul2(sa2, pack2(sv.x, sv.y)), w23 = mul2(sa2, pack2(sv.z, sv.w));
+                            rescale_pair_xu(acc2[(c + 1) * 8 + (j >> 1)], r1[j], r1[j + 1], w01);
+                            rescale_pair_xu(acc2[(c + 1) * 8 + (j >> 1) + 1], r1[j + 2], r1[j + 3], w23);
                         }
                     }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
-                    buf_phase[buf] ^= 1;
+                    buf_phases ^= 1u << buf;
                     buf ^= 1;
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->empty[stage]);                   // done with this slab's scales
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
-            // bias + store: thread owns row t, 128 consecutive columns
+            float acc[kColsI8];
+#pragma unroll
+            for (int i = 0; i < kColsI8 / 2; ++i) { const float2 v = unpack2(acc2[i]); acc[2 * i] = v.x; acc[2 * i + 1] = v.y; }
+            // bias + store: thread owns row t, kColsI8 consecutive columns
             const int t = tm * BM + row_in_tile;
-            const int n0 = tn * BN + half * 128;
+            const int n0 = tn * BN + cg * kColsI8;
             if (t < p.T) {
                 float* dst = p.out + (int64_t)t * p.N + n0;
-                const bool vec_ok = (p.N % 4 == 0) && (n0 + 128 <= p.N);
+                const bool vec_ok = (p.N % 4 == 0) && (n0 + kColsI8 <= p.N);
                 if (vec_ok) {
 #pragma unroll
-                    for (int j = 0; j < 128; j += 4) {
+                    for (int j = 0; j < kColsI8; j += 4) {
                         float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
                         if (p.bias) {
                             const float4 bv = *reinterpret_cast<const float4*>(p.bias + n0 + j);
@@ -277,7 +371,7 @@ bfp_gemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 128; ++j)
+                    for (int j = 0; j < kColsI8; ++j)
                         if (n0 + j < p.N) dst[j] = acc[j] + (p.bias ? p.bias[n0 + j] : 0.0f);
                 }
             }
@@ -503,7 +597,7 @@ int gemm_i8_device(const int8_t* a_mant, const float* a_scale_t, int64_t lda_s, 
     const cudaError_t attr_err = cudaFuncSetAttribute(bfp_gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     if (attr_err != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
     const int grid = std::min(p.tiles_m * p.tiles_n, device_info().sm_count);
-    bfp_gemm_i8_kernel<<<grid, kThreads, kSmemTotal, st>>>(map_a, map_b, p);
+    bfp_gemm_i8_kernel<<<grid, kThreadsI8, kSmemTotal, st>>>(map_a, map_b, p);
     count_launch();
     return check_launch("bfp_gemm_i8_kernel");
 }

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "../../include/bfp_b200.h"
 
 namespace bfp {
@@ -59,6 +61,19 @@ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline int64_t packed_kp(int64_t K) { return round_up(K, 16); }
 inline int64_t packed_rows_pad(int64_t rows) { return round_up(rows, 256); }
 inline int64_t packed_nkb_pad(int64_t K, int B) { return round_up(packed_kp(K), 128) / 128 * (B <= 128 ? 128 / B : 1) ; }
+
+// Persistent grid of the streaming kernels: exactly the number of CTAs that are resident at once (SMs x occupancy of
+// that kernel instantiation, capped by the stream_ctas_per_sm knob), tiles dealt round-robin, so the tail is at most one
+// 16 KB tile per CTA instead of a partial second wave of whole CTAs.
+template <class Kernel>
+inline int kernel_occupancy(Kernel kernel, int threads) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, 0) != cudaSuccess || occ < 1) occ = 4;
+    return occ;
+}
+inline int stream_grid(int occ, int64_t n_tiles) {
+    return (int)std::min<int64_t>(n_tiles, (int64_t)device_info().sm_count * std::min(occ, tuning().stream_ctas_per_sm));
+}
 
 inline size_t dtype_size(int dt) { return dt == BFP_DT_F32 ? 4 : 2; }
 

@@ -198,7 +198,9 @@ __global__ void __launch_bounds__(256) unpack_kernel(const int8_t* mant, const f
 template <int DT, int ORDER, bool STOC, int FMT>
 static int launch_pack_stream(const PackParams& p, bool sparse, cudaStream_t st) {
     const int64_t n_tiles = (p.n_vec + kStreamThreads * kStreamUnroll - 1) / (kStreamThreads * kStreamUnroll);
-    const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)device_info().sm_count * tuning().stream_ctas_per_sm);
+    static const int occ_s = kernel_occupancy(pack_stream_kernel<DT, ORDER, 4, 2, STOC, FMT>, kStreamThreads);
+    static const int occ_d = kernel_occupancy(pack_stream_kernel<DT, BFP_ORDER_QUANT_ONLY, 0, 0, STOC, FMT>, kStreamThreads);
+    const int grid = stream_grid(sparse ? occ_s : occ_d, n_tiles);
     if (sparse) pack_stream_kernel<DT, ORDER, 4, 2, STOC, FMT><<<grid, kStreamThreads, 0, st>>>(p);
     else pack_stream_kernel<DT, BFP_ORDER_QUANT_ONLY, 0, 0, STOC, FMT><<<grid, kStreamThreads, 0, st>>>(p);
     count_launch();

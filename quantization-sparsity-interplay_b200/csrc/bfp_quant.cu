@@ -204,8 +204,9 @@ static int launch_stream_t(const StreamParams& p, cudaStream_t st) {
     const int64_t n_tiles = (p.n_vec + tile_vecs - 1) / tile_vecs;
     if (n_tiles == 0) return BFP_OK;
     const DeviceInfo& di = device_info();
-    const int64_t max_ctas = (int64_t)di.sm_count * tuning().stream_ctas_per_sm;
-    const int grid = (int)std::min<int64_t>(n_tiles, max_ctas);
+    static const int occ = kernel_occupancy(quant_stream_kernel<DT, ORDER, M, KD, TIE, STOC>, kStreamThreads);
+    const int grid = stream_grid(occ, n_tiles);
+    (void)di;
     quant_stream_kernel<DT, ORDER, M, KD, TIE, STOC><<<grid, kStreamThreads, 0, st>>>(p);
     count_launch();
     return check_launch("quant_stream_kernel");
