@@ -66,7 +66,8 @@ uint64_t bfp_launch_count(void);
 /* Runtime knobs (also read once from the environment: BFP_STREAM_CTAS_PER_SM, BFP_FORCE_GENERIC, BFP_HOST_CHUNK_MB):
  *   "stream_ctas_per_sm"  resident CTAs per SM the streaming quantiser sizes its grid for (default 8)
  *   "force_generic"       1 = route every call through the generic (ragged-shape) kernel; for tests
- *   "host_chunk_bytes"    input bytes per pipelined chunk of bfp_quantize_host (default 8 MiB) */
+ *   "host_chunk_bytes"    input bytes per pipelined chunk of bfp_quantize_host (default 8 MiB)
+ *   "gemm_bf16_tile_n"    0 = bfp_gemm_bf16 uses its 128x256 tile (128x128 when N <= 128); 128 / 256 forces one */
 int bfp_set_option(const char* name, int64_t value);
 
 /* sm count, compute capability, L2 bytes of the current device. */

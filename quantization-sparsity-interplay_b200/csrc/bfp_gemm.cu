@@ -395,11 +395,16 @@ bfp_gemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 // four 128x256x16 tcgen05.mma.kind::f16 per stage; accumulators ping-pong between two TMEM buffers ACROSS TILES so the
 // epilogue of tile i overlaps the main loop of tile i+1.
 // ================================================================================================================
-constexpr int kStagesBf16 = 4;
-constexpr int kStageBytesBf16 = kSmemA + kSmemB;                               // 48 KB
-constexpr int kSmemTotalBf16 = kStagesBf16 * kStageBytesBf16 + kSmemBarriers + 1024;
-// D = F32 (1 << 4), A = B = BF16 (1 << 7, 1 << 10), K-major, N >> 3, M >> 4
-constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// Two tile widths: 128x256 (4 stages of 48 KB, the default) and 128x128 (6 stages of 32 KB; for N <= 128 or forced with
+// bfp_set_option("gemm_bf16_tile_n", 128)).
+template <int TBN> struct Bf16Cfg {
+    static constexpr int kStages = TBN == 256 ? 4 : 6;
+    static constexpr int kStageBytes = kSmemA + TBN * BKB;
+    static constexpr int kSmemTotal = kStages * kStageBytes + kSmemBarriers + 1024;
+    // D = F32 (1 << 4), A = B = BF16 (1 << 7, 1 << 10), K-major, N >> 3, M >> 4
+    static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    static constexpr int kColsPerThread = TBN / 2;          // 8 epilogue warps: 4 lane quarters x 2 column halves
+};
 
 struct ParamsBf16 {
     const float* bias;
@@ -418,17 +423,20 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint6
 }
 
 struct BarriersBf16 {
-    uint64_t full[kStagesBf16];
-    uint64_t empty[kStagesBf16];
+    uint64_t full[6];
+    uint64_t empty[6];
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
     uint32_t tmem_base;
 };
 
+template <int TBN>
 __global__ void __launch_bounds__(kThreads, 1)
 bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ParamsBf16 p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    using C = Bf16Cfg<TBN>;
+    constexpr int kStagesBf16 = C::kStages, kStageBytesBf16 = C::kStageBytes, kCols = C::kColsPerThread;
     BarriersBf16* bars = reinterpret_cast<BarriersBf16*>(smem + kStagesBf16 * kStageBytesBf16);
     auto stage_a = [&](int s) { return smem + s * kStageBytesBf16; };
     auto stage_b = [&](int s) { return smem + s * kStageBytesBf16 + kSmemA; };
@@ -459,7 +467,7 @@ bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     mbar_wait(&bars->empty[stage], phase ^ 1);
                     mbar_expect_tx(&bars->full[stage], kStageBytesBf16);
                     tma_load_2d(stage_a(stage), &map_a, &bars->full[stage], ks * 64, tm * BM);
-                    tma_load_2d(stage_b(stage), &map_b, &bars->full[stage], ks * 64, tn * BN);
+                    tma_load_2d(stage_b(stage), &map_b, &bars->full[stage], ks * 64, tn * TBN);
                     if (++stage == kStagesBf16) { stage = 0; phase ^= 1; }
                 }
             }
@@ -471,7 +479,7 @@ bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 mbar_wait(&bars->tmem_empty[buf], buf_phase[buf] ^ 1);
                 tc_fence_after();
-                const uint32_t d = tmem_base + (uint32_t)buf * BN;
+                const uint32_t d = tmem_base + (uint32_t)buf * TBN;
                 for (int ks = 0; ks < p.num_k_stages; ++ks) {
                     mbar_wait(&bars->full[stage], phase);
                     tc_fence_after();
@@ -479,7 +487,7 @@ bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     const uint64_t db = make_smem_desc(smem_u32(stage_b(stage)));
 #pragma unroll
                     for (int i = 0; i < 4; ++i)         // 16 bf16 = 32 bytes of K per MMA: +2 in 16-byte units
-                        mma_bf16(d, da + (uint64_t)(i * 2), db + (uint64_t)(i * 2), kIdescBf16, (ks | i) != 0);
+                        mma_bf16(d, da + (uint64_t)(i * 2), db + (uint64_t)(i * 2), C::kIdesc, (ks | i) != 0);
                     tc_commit(&bars->empty[stage]);
                     if (++stage == kStagesBf16) { stage = 0; phase ^= 1; }
                 }
@@ -496,13 +504,13 @@ bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
             mbar_wait(&bars->tmem_full[buf], buf_phase[buf]);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * 128);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TBN + half * kCols);
             const int t = tm * BM + row_in_tile;
-            const int n0 = tn * BN + half * 128;
+            const int n0 = tn * TBN + half * kCols;
             float* dst = p.out + (int64_t)t * p.N + n0;
-            const bool vec_ok = (p.N % 4 == 0) && (n0 + 128 <= p.N);
+            const bool vec_ok = (p.N % 4 == 0) && (n0 + kCols <= p.N);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < kCols / 16; ++c) {
                 uint32_t r[16];
                 tmem_ld16(taddr + c * 16, r);
                 tmem_ld_wait();
@@ -613,14 +621,28 @@ int gemm_bf16_device(const void* a_bf16, const void* b_bf16, const float* bias, 
     ParamsBf16 p;
     p.bias = bias; p.out = out; p.T = (int)T; p.N = (int)N;
     p.num_k_stages = (int)((Kp + 63) / 64);
-    p.tiles_m = (int)((T + BM - 1) / BM); p.tiles_n = (int)((N + BN - 1) / BN);
+    p.tiles_m = (int)((T + BM - 1) / BM);
+    // tile width: 128x256 unless N fits a narrow tile.  (Measured on B200, profiles/r01_gemm_bench_v3_tiles.log: the
+    // 128x128 tile is operand-feed-bound at ~1.05 PFLOP/s and loses to 128x256 (1.24-1.45) even where its wave
+    // efficiency is better, e.g. 4096x4096: 6.92 vs 3.46 waves.)
+    const int sms = std::max(1, device_info().sm_count);
+    int tbn = N <= 128 ? 128 : 256;
+    if (tuning().gemm_bf16_tile_n == 128 || tuning().gemm_bf16_tile_n == 256) tbn = tuning().gemm_bf16_tile_n;
+    p.tiles_n = (int)((N + tbn - 1) / tbn);
     CUtensorMap map_a, map_b;
     if (int rc = make_map(&map_a, a_bf16, T, Kp * 2, BM, true)) return rc;
-    if (int rc = make_map(&map_b, b_bf16, N, Kp * 2, BN, true)) return rc;
-    cudaError_t e = cudaFuncSetAttribute(bfp_gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotalBf16);
-    if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    const int grid = std::min(p.tiles_m * p.tiles_n, device_info().sm_count);
-    bfp_gemm_bf16_kernel<<<grid, kThreads, kSmemTotalBf16, st>>>(map_a, map_b, p);
+    if (int rc = make_map(&map_b, b_bf16, N, Kp * 2, tbn, true)) return rc;
+    const int grid = std::min(p.tiles_m * p.tiles_n, sms);
+    cudaError_t e;
+    if (tbn == 256) {
+        e = cudaFuncSetAttribute(bfp_gemm_bf16_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bf16Cfg<256>::kSmemTotal);
+        if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        bfp_gemm_bf16_kernel<256><<<grid, kThreads, Bf16Cfg<256>::kSmemTotal, st>>>(map_a, map_b, p);
+    } else {
+        e = cudaFuncSetAttribute(bfp_gemm_bf16_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bf16Cfg<128>::kSmemTotal);
+        if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        bfp_gemm_bf16_kernel<128><<<grid, kThreads, Bf16Cfg<128>::kSmemTotal, st>>>(map_a, map_b, p);
+    }
     count_launch();
     return check_launch("bfp_gemm_bf16_kernel");
 }

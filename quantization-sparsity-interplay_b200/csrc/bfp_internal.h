@@ -20,7 +20,8 @@ const DeviceInfo& device_info();          // of the current device (cached per d
 struct Tuning {
     int stream_ctas_per_sm = 8;           // resident CTAs of the stream kernel per SM (grid = sm_count * this)
     int force_generic = 0;                // tests: route everything through the generic kernel
-    int64_t host_chunk_bytes = 8 << 20;   // bfp_quantize_host: input bytes per pipelined chunk
+    int64_t host_chunk_bytes = 8 << 20;
+    int gemm_bf16_tile_n = 0;             // 0 = default tile (128x256); 128 or 256 forces the width  // bfp_quantize_host: input bytes per pipelined chunk
 };
 Tuning& tuning();
 

@@ -125,8 +125,15 @@ def test_gemm_bf16_exact_products(ops, shape):
     ab = torch.zeros(T, Kp, dtype=torch.bfloat16, device="cuda"); ab[:, :K] = a
     bb = torch.zeros(N, Kp, dtype=torch.bfloat16, device="cuda"); bb[:, :K] = b
     bias = torch.randint(-5, 6, (N,), generator=g, device="cuda").float()
-    y = ops.bfp_linear_bf16(ab, bb, bias)
-    assert torch.equal(y.double(), a.double() @ b.double().t() + bias.double())
+    from qsi_b200 import _lib
+    ref = a.double() @ b.double().t() + bias.double()
+    for tile_n in (0, 128, 256):                      # auto, and both tile widths forced
+        _lib.set_option("gemm_bf16_tile_n", tile_n)
+        try:
+            y = ops.bfp_linear_bf16(ab, bb, bias)
+        finally:
+            _lib.set_option("gemm_bf16_tile_n", 0)
+        assert torch.equal(y.double(), ref), tile_n
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])

@@ -37,6 +37,15 @@ for (T, N, K) in sum((SH[s] for s in a.shapes.split(",")), []):
             for _ in range(a.iters): ops.pack_bfp_bf16(x, identifier="in", **kw)
             e1.record(); torch.cuda.synchronize(); msbp = e0.elapsed_time(e1) / a.iters
             print(f"T={T} N={N} K={K} exact-bf16 kind: gemm {msb:.3f} ms = {2.0*T*N*K/msb/1e9:.0f} TOPS; pack x {msbp*1e3:.1f} us", flush=True)
+            for tn in (128, 256):
+                _lib.set_option("gemm_bf16_tile_n", tn)
+                for _ in range(3): runb()
+                torch.cuda.synchronize(); e0.record()
+                for _ in range(a.iters): runb()
+                e1.record(); torch.cuda.synchronize(); mst = e0.elapsed_time(e1) / a.iters
+                print(f"    tile 128x{tn}: {mst:.3f} ms = {2.0*T*N*K/mst/1e9:.0f} TOPS", flush=True)
+                res.append(dict(T=T, N=N, K=K, kind="bf16", tile_n=tn, gemm_ms=mst, tops=2.0 * T * N * K / mst / 1e9))
+            _lib.set_option("gemm_bf16_tile_n", 0)
             res.append(dict(T=T, N=N, K=K, kind="bf16", gemm_ms=msb, tops=2.0 * T * N * K / msb / 1e9, pack_x_ms=msbp))
         print(f"T={T} N={N} K={K} B={B}: gemm {ms:.3f} ms = {tops:.0f} TOPS ({100*tops/4500:.1f}% of 4500 nominal int8); pack x {ms_pack*1e3:.1f} us", flush=True)
     # yardsticks
