@@ -94,6 +94,15 @@ int bfp_quantize(const void* in, void* out, int64_t rows, int64_t K, int in_dtyp
 int bfp_nm_sparsify(const void* in, void* out, int64_t rows, int64_t K, int dtype, int N, int M, int tie_rule,
                     void* stream);
 
+/* _unstructured_sparsity (bfp_ops.py:61-71): global magnitude pruning of the whole tensor viewed as one row.  Zeroes the
+ * k entries torch.topk(|t|, k, largest=False) returns on torch-CUDA: every entry strictly below the k-th smallest
+ * magnitude, and of the entries equal to it the first ones in index order; NaN counts as largest.
+ * k = int(numel * sparsity_frac) is computed by the caller (bfp_ops.py:66).  `workspace` is caller-owned device scratch of
+ * bfp_unstructured_workspace_bytes() bytes (no allocation inside).  out may alias in. */
+size_t bfp_unstructured_workspace_bytes(void);
+int bfp_unstructured_sparsify(const void* in, void* out, int64_t numel, int dtype, uint64_t k, void* workspace,
+                              void* stream);
+
 /* get_exponent (bfp_ops.py:29-33): exp_out[rows, ceil(K/block_size)] fp32, in the arithmetic of `dtype`. */
 int bfp_block_exponent(const void* in, float* exp_out, int64_t rows, int64_t K, int dtype, int block_size, float eps,
                        void* stream);

@@ -85,6 +85,8 @@ static inline void store_elt(void *p, int dt, int64_t i, float v) {
     else ((uint16_t *)p)[i] = f32_to_bf16(v);
 }
 
+static inline uint32_t order_key(float absv);
+
 /* torch.max / torch.min (binary, elementwise): NaN in either operand propagates. */
 static inline float t_max(float a, float b) { if (a != a) return a; if (b != b) return b; return a > b ? a : b; }
 static inline float t_min(float a, float b) { if (a != a) return a; if (b != b) return b; return a < b ? a : b; }
@@ -257,6 +259,30 @@ int oracle_nm_sparsify(const void *in, void *out, int64_t rows, int64_t K, int d
         }
         free(v); free(idx); free(drop);
     }
+    return 0;
+}
+
+/* ---- unstructured (global) magnitude sparsity ------------------------------------
+ * bfp_ops.py:61-71 _unstructured_sparsity: view(1, -1), topk(|t|, k = int(numel*frac), largest=False), dropped -> +0.0.
+ * torch-CUDA tie order (the only one restated: torch-CPU's nth_element order on a 16 M-element slice is not a contract
+ * anyone can rely on): the k smallest by (|v|, index).  k is passed in (the caller evaluates int(numel*frac) in double
+ * precision exactly as Python does).
+ */
+typedef struct { uint32_t key; int64_t idx; } kv_t;
+static int kv_cmp(const void *a, const void *b) {
+    const kv_t *x = (const kv_t *)a, *y = (const kv_t *)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx);
+}
+int oracle_unstructured_sparsify(const void *in, void *out, int64_t n, int dt, int64_t k) {
+    if (k < 0) return 1;
+    if (k > n) k = n;
+    kv_t *kv = (kv_t *)malloc(sizeof(kv_t) * (size_t)(n > 0 ? n : 1));
+    for (int64_t i = 0; i < n; ++i) { kv[i].key = order_key(fabsf(load_elt(in, dt, i))); kv[i].idx = i; }
+    qsort(kv, (size_t)n, sizeof(kv_t), kv_cmp);
+    for (int64_t i = 0; i < n; ++i) store_elt(out, dt, i, load_elt(in, dt, i));
+    for (int64_t j = 0; j < k; ++j) store_elt(out, dt, kv[j].idx, 0.0f);
+    free(kv);
     return 0;
 }
 

@@ -149,9 +149,24 @@ def _no_sparsity_float_to_bfp(t, block_size, mant_bits, epsilon, rounding_mode, 
 # bfp_ops.py:61-102: sparsity
 # ---------------------------------------------------------------------------------------------------------------
 def _unstructured_sparsity(t, device, sparsity_frac=0):
-    """bfp_ops.py:61-71: global magnitude pruning.  SURVEY.md section 8 row f1 ("next"): not built yet."""
+    """bfp_ops.py:61-71: global magnitude pruning -- the k = int(numel * frac) smallest |t| of the whole tensor become
+    +0.0 (ties at the threshold in index order, like torch-CUDA's topk).  Multi-pass radix select on the GPU
+    (csrc/bfp_unstructured.cu); CPU tensors are staged through the GPU."""
     assert (sparsity_frac > 0)
-    raise NotImplementedError("unstructured sparsity is not implemented in bfp_b200 yet (SURVEY.md section 8, row f1)")
+    if t.dtype not in _DT:
+        raise TypeError(f"bfp_b200 supports float32 / float16 / bfloat16 tensors, got {t.dtype}")
+    src = t.detach().contiguous()
+    n = src.numel()
+    k = int(n * sparsity_frac)                                   # bfp_ops.py:66
+    dev_src = src if src.is_cuda else src.cuda()
+    out = torch.empty_like(dev_src)
+    if n:
+        L = _lib.lib()
+        with torch.cuda.device(dev_src.device):
+            ws = torch.empty(L.bfp_unstructured_workspace_bytes() // 8 + 1, dtype=torch.int64, device=dev_src.device)
+            _lib.check(L.bfp_unstructured_sparsify(dev_src.data_ptr(), out.data_ptr(), n, _DT[src.dtype], k, ws.data_ptr(),
+                                                   torch.cuda.current_stream().cuda_stream))
+    return out if src.is_cuda else out.cpu()
 
 
 def _structured_N_M_sparsity(t, device, N=0, M=0):

@@ -158,6 +158,16 @@ int bfp_nm_sparsify(const void* in, void* out, int64_t rows, int64_t K, int dtyp
                         tie_rule, stream);
 }
 
+size_t bfp_unstructured_workspace_bytes(void) { return unstructured_workspace_bytes(); }
+
+int bfp_unstructured_sparsify(const void* in, void* out, int64_t numel, int dtype, uint64_t k, void* workspace, void* stream) {
+    if (numel < 0 || dtype < 0 || dtype > 2) return set_error(BFP_E_ARG, "bad argument");
+    if (numel > 0 && (!in || !out || !workspace)) return set_error(BFP_E_ARG, "null pointer");
+    if (reinterpret_cast<uintptr_t>(workspace) % 8) return set_error(BFP_E_ALIGN, "workspace must be 8-byte aligned");
+    if (int rc = require_device()) return rc;
+    return unstructured_device(in, out, numel, dtype, k, workspace, static_cast<cudaStream_t>(stream));
+}
+
 int bfp_block_exponent(const void* in, float* exp_out, int64_t rows, int64_t K, int dtype, int block_size, float eps, void* stream) {
     if (rows < 0 || K < 0 || block_size <= 0 || dtype < 0 || dtype > 2) return set_error(BFP_E_ARG, "bad argument");
     if (rows * K > 0 && (!in || !exp_out)) return set_error(BFP_E_ARG, "null pointer");

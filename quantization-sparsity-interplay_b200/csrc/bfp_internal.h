@@ -58,6 +58,9 @@ int pack_bf16_device(const QuantArgs& a, void* out_bf16, int64_t Kp, cudaStream_
 int gemm_bf16_device(const void* a_bf16, const void* b_bf16, const float* bias, float* out, int64_t T, int64_t N, int64_t Kp,
                      cudaStream_t st);
 
+size_t unstructured_workspace_bytes();
+int unstructured_device(const void* in, void* out, int64_t n, int dtype, unsigned long long k, void* workspace, cudaStream_t s);
+
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline int64_t packed_kp(int64_t K) { return round_up(K, 16); }
 inline int64_t packed_rows_pad(int64_t rows) { return round_up(rows, 256); }

@@ -305,7 +305,7 @@ def test_api_conventions_on_device(ops):
     assert torch.equal(y_in, ops._no_sparsity_float_to_bfp(x, 64, 7, 1e-8, "determ", "cuda"))
     assert ops.float_to_bfp_blocked(torch.empty(0, 64, device="cuda"), **args, identifier="w").shape == (0, 64)
     with pytest.raises(NotImplementedError):
-        ops.float_to_bfp_blocked(x, **dict(args, sparsity_mode="unstructured", sparsity_frac=0.5), identifier="w")
+        ops.float_to_bfp_blocked(x, **dict(args, sparsity_num_format="int"), identifier="w")
 
 
 def test_bfp_linear_module_matches_oracle(ops, oracle):
