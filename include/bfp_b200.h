@@ -103,6 +103,18 @@ size_t bfp_unstructured_workspace_bytes(void);
 int bfp_unstructured_sparsify(const void* in, void* out, int64_t numel, int dtype, uint64_t k, void* workspace,
                               void* stream);
 
+/* The 'int' number format (_quantize with sparsity_num_format == 'int', bfp_ops.py:111-120): SparseGPT's per-channel
+ * symmetric min/max INT-`bits` fake quantiser (int_ops.py Quantizer.configure/find_params/quantize, perchannel, sym).
+ * The tensor is viewed as [A, C, inner]; element i belongs to channel (i / inner) % C:
+ *   weight [C, ...]               : A = 1, inner = numel / C           (int_ops.py:40-43)
+ *   activation [.., C] (2-D, 3-D) : A = numel / C, inner = 1           (int_ops.py:47-50)
+ *   activation [N, C, H, W]       : A = N, inner = H * W               (int_ops.py:44-46)
+ * Output is fp32 for every input dtype (the reference promotes).  workspace: bfp_int_workspace_bytes(C) bytes of
+ * caller-owned device scratch. */
+size_t bfp_int_workspace_bytes(int64_t C);
+int bfp_int_quantize(const void* in, float* out, int64_t A, int64_t C, int64_t inner, int dtype, int bits,
+                     void* workspace, void* stream);
+
 /* get_exponent (bfp_ops.py:29-33): exp_out[rows, ceil(K/block_size)] fp32, in the arithmetic of `dtype`. */
 int bfp_block_exponent(const void* in, float* exp_out, int64_t rows, int64_t K, int dtype, int block_size, float eps,
                        void* stream);

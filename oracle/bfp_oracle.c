@@ -286,6 +286,38 @@ int oracle_unstructured_sparsify(const void *in, void *out, int64_t n, int dt, i
     return 0;
 }
 
+/* ---- 'int' number format ------------------------------------------------------------
+ * bfp_ops.py:111-120 -> int_ops.py Quantizer.configure(bits) :18-31 (maxq = 2^bits - 1, perchannel, sym),
+ * find_params(x, weight) :33-120, quantize :6-8, 111-114.  View [A, C, inner], channel of element i = (i/inner) % C.
+ * All arithmetic fp32 (find_params' fp32 zeros promote half inputs); output fp32.
+ */
+int oracle_int_quantize(const void *in, float *out, int64_t A, int64_t C, int64_t inner, int dt, int bits) {
+    const int64_t n = A * C * inner;
+    float *mn = (float *)malloc(sizeof(float) * (size_t)(C > 0 ? C : 1) * 3), *mx = mn + C, *sc = mx + C;
+    for (int64_t c = 0; c < C; ++c) { mn[c] = INFINITY; mx[c] = -INFINITY; }
+    for (int64_t i = 0; i < n; ++i) {
+        float v = load_elt(in, dt, i); int64_t c = (i / inner) % C;
+        if (v < mn[c]) mn[c] = v;
+        if (v > mx[c]) mx[c] = v;
+    }
+    const float maxq = (float)((1ll << bits) - 1), zero = (float)((double)(1ll << bits) / 2.0);   /* :23, :69 */
+    for (int64_t c = 0; c < C; ++c) {
+        float xmin = mn[c] < 0.0f ? mn[c] : 0.0f, xmax = mx[c] > 0.0f ? mx[c] : 0.0f;             /* :55-56 */
+        if (fabsf(xmin) > xmax) xmax = fabsf(xmin);                                                /* :59 */
+        if (xmin < 0.0f) xmin = -xmax;                                                             /* :60-62 */
+        if (xmin == 0.0f && xmax == 0.0f) { xmin = -1.0f; xmax = 1.0f; }                           /* :63-65 */
+        sc[c] = (xmax - xmin) / maxq;                                                              /* :67 */
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        float x = load_elt(in, dt, i), s = sc[(i / inner) % C];
+        float q = rintf(x / s) + zero;                                                             /* :7 */
+        q = q < 0.0f ? 0.0f : (q > maxq ? maxq : q);
+        out[i] = s * (q - zero);                                                                   /* :8 */
+    }
+    free(mn);
+    return 0;
+}
+
 /* ---- float_to_bfp_blocked for the 'bfp' + structured case ---------------
  * bfp_ops.py:124-149: first == 's' -> Q(S(t)), anything else -> S(Q(t)).
  * order: 0 = quantise only, 1 = sparsify then quantise, 2 = quantise then sparsify,

@@ -197,9 +197,40 @@ def _quantize(t, num_format, block_size, mant_bits, weight_mant_bits, sgd_update
             mant_bits = weight_mant_bits
         return _no_sparsity_float_to_bfp(t, block_size, mant_bits, epsilon, rounding_mode, device)
     elif num_format == 'int':
-        raise NotImplementedError("the 'int' (SparseGPT per-channel) format is not implemented in bfp_b200 yet "
-                                  "(SURVEY.md section 8, row f2)")
+        if sgd_update:
+            mant_bits = weight_mant_bits
+        return _int_quantize(t, mant_bits, weight=(identifier == 'w'))
     raise ValueError(f'Unknown quantization format: {num_format} given as argument')
+
+
+def _int_quantize(t, bits, weight):
+    """The 'int' format: int_ops.Quantizer (perchannel, sym) as used by bfp_ops.py:111-120 -- configure(bits),
+    find_params(t, weight), quantize(t) -- in four small kernels (csrc/bfp_int.cu).  fp32 output for every input dtype,
+    like the reference.  Channel = dim 0 for weights; last dim (2-D / 3-D) or dim 1 (4-D) for activations."""
+    if t.dtype not in _DT:
+        raise TypeError(f"bfp_b200 supports float32 / float16 / bfloat16 tensors, got {t.dtype}")
+    shape = tuple(t.shape)
+    if weight:
+        if len(shape) < 2:
+            raise IndexError("Dimension out of range (the reference flattens weights from dim 1)")
+        A, C, inner = 1, shape[0], (t.numel() // shape[0] if shape[0] else 0)
+    elif len(shape) == 4:
+        A, C, inner = shape[0], shape[1], shape[2] * shape[3]
+    elif len(shape) in (2, 3):
+        C = shape[-1]
+        A, inner = (t.numel() // C if C else 0), 1
+    else:
+        raise IndexError("int format: activations must be 2-D, 3-D or 4-D (int_ops.py:44-50)")
+    src = t.detach().contiguous()
+    dev_src = src if src.is_cuda else src.cuda()
+    out = torch.empty(shape, dtype=torch.float32, device=dev_src.device)
+    if src.numel():
+        L = _lib.lib()
+        with torch.cuda.device(dev_src.device):
+            ws = torch.empty(L.bfp_int_workspace_bytes(C) // 4 + 1, dtype=torch.int32, device=dev_src.device)
+            _lib.check(L.bfp_int_quantize(dev_src.data_ptr(), out.data_ptr(), A, C, inner, _DT[src.dtype], int(bits), ws.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream))
+    return out if src.is_cuda else out.cpu()
 
 
 def float_to_bfp_blocked(t, mant_bits, epsilon, rounding_mode, device, block_size,

@@ -158,6 +158,17 @@ int bfp_nm_sparsify(const void* in, void* out, int64_t rows, int64_t K, int dtyp
                         tie_rule, stream);
 }
 
+size_t bfp_int_workspace_bytes(int64_t C) { return int_workspace_bytes(C < 0 ? 0 : C); }
+
+int bfp_int_quantize(const void* in, float* out, int64_t A, int64_t C, int64_t inner, int dtype, int bits, void* workspace, void* stream) {
+    if (A < 0 || C < 0 || inner < 0 || dtype < 0 || dtype > 2) return set_error(BFP_E_ARG, "bad argument");
+    if (bits < 1 || bits > 23) return set_error(BFP_E_ARG, "bits must be in [1, 23]");
+    if (A * C * inner > 0 && (!in || !out || !workspace)) return set_error(BFP_E_ARG, "null pointer");
+    if (reinterpret_cast<uintptr_t>(workspace) % 4) return set_error(BFP_E_ALIGN, "workspace must be 4-byte aligned");
+    if (int rc = require_device()) return rc;
+    return int_quantize_device(in, out, A, C, inner, dtype, bits, workspace, static_cast<cudaStream_t>(stream));
+}
+
 size_t bfp_unstructured_workspace_bytes(void) { return unstructured_workspace_bytes(); }
 
 int bfp_unstructured_sparsify(const void* in, void* out, int64_t numel, int dtype, uint64_t k, void* workspace, void* stream) {

@@ -1,0 +1,133 @@
+// bfp_int.cu -- the SparseGPT-style per-channel symmetric INT-k fake quantiser.
+//
+// Replaces int_ops.Quantizer.configure/find_params/quantize as reached from _quantize with
+// sparsity_num_format == 'int' (bfp_ops.py:111-120; int_ops.py:6-8, 18-31, 33-120 with perchannel=True, sym=True):
+//   channel of a WEIGHT  [C, ...]        : dim 0 (int_ops.py:40-43)
+//   channel of an ACTIVATION [.., C]     : last dim for 2-D / 3-D, dim 1 for 4-D (int_ops.py:44-50)
+//   xmin = min(min_c, 0), xmax = max(max_c, 0); xmax = max(|xmin|, xmax); xmin = -xmax where xmin < 0;
+//   all-zero channel -> (-1, +1); scale = (xmax - xmin) / maxq; zero = (maxq + 1) / 2; maxq = 2^bits - 1
+//   y = scale * (clamp(round(x / scale) + zero, 0, maxq) - zero)
+// Every step is fp32 for every input dtype (the fp32 torch.zeros in find_params promotes half inputs, and the output
+// of the reference is fp32), so half inputs are converted exactly and the arithmetic below is literal.
+// The tensor is viewed as [A, C, inner]: element i has channel (i / inner) % C.
+#include <algorithm>
+
+#include "bfp_internal.h"
+#include "bfp_stream.cuh"
+
+namespace bfp {
+namespace {
+
+__device__ __forceinline__ int enc(float f) { const int b = __float_as_int(f); return b ^ ((b >> 31) & 0x7fffffff); }   // monotone
+__device__ __forceinline__ float dec(int e) { return __int_as_float(e ^ ((e >> 31) & 0x7fffffff)); }
+
+struct IntWs { int* mn; int* mx; float* scale; };
+
+__global__ void int_init_kernel(int* mn, int* mx, int64_t C) {
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < C; c += (int64_t)gridDim.x * blockDim.x) {
+        mn[c] = enc(__int_as_float(0x7f800000));
+        mx[c] = enc(__int_as_float(0xff800000));
+    }
+}
+
+// contiguous runs (inner >= 32): one warp per run (a, c)
+template <int DT>
+__global__ void __launch_bounds__(256) int_minmax_runs_kernel(const void* in, int64_t runs, int64_t C, int64_t inner, int* mn, int* mx) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t run = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; run < runs; run += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+        const int64_t base = run * inner;
+        float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
+        for (int64_t j = lane; j < inner; j += 32) { const float v = DType<DT>::load(in, base + j); lo = fminf(lo, v); hi = fmaxf(hi, v); }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off)); }
+        if (lane == 0) { const int64_t c = run % C; atomicMin(&mn[c], enc(lo)); atomicMax(&mx[c], enc(hi)); }
+    }
+}
+
+// inner == 1: thread per column, a chunk of rows per CTA row (coalesced across the warp)
+template <int DT>
+__global__ void __launch_bounds__(256) int_minmax_cols_kernel(const void* in, int64_t A, int64_t C, int64_t rows_per_cta, int* mn, int* mx) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const int64_t a0 = (int64_t)blockIdx.y * rows_per_cta, a1 = min(A, a0 + rows_per_cta);
+    float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
+    for (int64_t a = a0; a < a1; ++a) { const float v = DType<DT>::load(in, a * C + c); lo = fminf(lo, v); hi = fmaxf(hi, v); }
+    if (a0 < a1) { atomicMin(&mn[c], enc(lo)); atomicMax(&mx[c], enc(hi)); }
+}
+
+// anything else (1 < inner < 32): per-element atomics; rare shapes only
+template <int DT>
+__global__ void __launch_bounds__(256) int_minmax_generic_kernel(const void* in, int64_t n, int64_t C, int64_t inner, int* mn, int* mx) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = DType<DT>::load(in, i);
+        const int64_t c = (i / inner) % C;
+        atomicMin(&mn[c], enc(v)); atomicMax(&mx[c], enc(v));
+    }
+}
+
+__global__ void int_scale_kernel(const int* mn, const int* mx, float* scale, int64_t C, float maxq) {
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < C; c += (int64_t)gridDim.x * blockDim.x) {
+        float xmin = fminf(dec(mn[c]), 0.0f), xmax = fmaxf(dec(mx[c]), 0.0f);      // int_ops.py:55-56
+        xmax = fmaxf(fabsf(xmin), xmax);                                           // :59
+        if (xmin < 0.0f) xmin = -xmax;                                             // :60-62
+        if (xmin == 0.0f && xmax == 0.0f) { xmin = -1.0f; xmax = 1.0f; }           // :63-65
+        scale[c] = __fdiv_rn(xmax - xmin, maxq);                                   // :67
+    }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256) int_apply_kernel(const void* in, float* out, int64_t n, int64_t C, int64_t inner, const float* scale,
+                                                        float maxq, float zero) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float x = DType<DT>::load(in, i);
+        const float s = scale[(i / inner) % C];
+        const float q = fminf(fmaxf(rintf(__fdiv_rn(x, s)) + zero, 0.0f), maxq);   // int_ops.py:7
+        out[i] = s * (q - zero);                                                   // :8
+    }
+}
+
+template <int DT>
+int run(const void* in, float* out, int64_t A, int64_t C, int64_t inner, int bits, IntWs ws, cudaStream_t s) {
+    const int64_t n = A * C * inner;
+    const int sms = device_info().sm_count;
+    const float maxq = (float)((1ll << bits) - 1), zero = (float)(((1ll << bits)) / 2.0);
+    int_init_kernel<<<(int)std::min<int64_t>((C + 255) / 256, 1024), 256, 0, s>>>(ws.mn, ws.mx, C);
+    count_launch();
+    if (inner >= 32) {
+        const int64_t runs = A * C;
+        const int grid = (int)std::min<int64_t>((runs * 32 + 255) / 256, (int64_t)sms * 16);
+        int_minmax_runs_kernel<DT><<<grid, 256, 0, s>>>(in, runs, C, inner, ws.mn, ws.mx);
+    } else if (inner == 1) {
+        const int64_t col_ctas = (C + 255) / 256;
+        int64_t row_ctas = std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * 8 / col_ctas, (A + 63) / 64));
+        row_ctas = std::min<int64_t>(row_ctas, 65535);
+        const int64_t rows_per_cta = (A + row_ctas - 1) / row_ctas;
+        dim3 grid((unsigned)col_ctas, (unsigned)((A + rows_per_cta - 1) / rows_per_cta));
+        int_minmax_cols_kernel<DT><<<grid, 256, 0, s>>>(in, A, C, rows_per_cta, ws.mn, ws.mx);
+    } else {
+        int_minmax_generic_kernel<DT><<<(int)std::min<int64_t>((n + 255) / 256, (int64_t)sms * 16), 256, 0, s>>>(in, n, C, inner, ws.mn, ws.mx);
+    }
+    count_launch();
+    int_scale_kernel<<<(int)std::min<int64_t>((C + 255) / 256, 1024), 256, 0, s>>>(ws.mn, ws.mx, ws.scale, C, maxq);
+    count_launch();
+    int_apply_kernel<DT><<<(int)std::min<int64_t>((n + 255) / 256, (int64_t)sms * 16), 256, 0, s>>>(in, out, n, C, inner, ws.scale, maxq, zero);
+    count_launch();
+    return check_launch("int quantiser kernels");
+}
+}  // namespace
+
+size_t int_workspace_bytes(int64_t C) { return (size_t)C * 12 + 64; }
+
+int int_quantize_device(const void* in, float* out, int64_t A, int64_t C, int64_t inner, int dtype, int bits, void* workspace, cudaStream_t s) {
+    if (A * C * inner == 0) return BFP_OK;
+    IntWs ws;
+    ws.mn = static_cast<int*>(workspace); ws.mx = ws.mn + C; ws.scale = reinterpret_cast<float*>(ws.mx + C);
+    switch (dtype) {
+    case BFP_DT_F32: return run<BFP_DT_F32>(in, out, A, C, inner, bits, ws, s);
+    case BFP_DT_F16: return run<BFP_DT_F16>(in, out, A, C, inner, bits, ws, s);
+    case BFP_DT_BF16: return run<BFP_DT_BF16>(in, out, A, C, inner, bits, ws, s);
+    }
+    return set_error(BFP_E_ARG, "bad dtype");
+}
+
+}  // namespace bfp

@@ -58,6 +58,8 @@ int pack_bf16_device(const QuantArgs& a, void* out_bf16, int64_t Kp, cudaStream_
 int gemm_bf16_device(const void* a_bf16, const void* b_bf16, const float* bias, float* out, int64_t T, int64_t N, int64_t Kp,
                      cudaStream_t st);
 
+size_t int_workspace_bytes(int64_t C);
+int int_quantize_device(const void* in, float* out, int64_t A, int64_t C, int64_t inner, int dtype, int bits, void* workspace, cudaStream_t s);
 size_t unstructured_workspace_bytes();
 int unstructured_device(const void* in, void* out, int64_t n, int dtype, unsigned long long k, void* workspace, cudaStream_t s);
 

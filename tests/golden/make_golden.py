@@ -170,6 +170,34 @@ def main():
         put(store, f"lin_{first}_b", lin.bias.detach())
         put(store, f"lin_{first}_y", y)
 
+    # 6. the 'int' number format (bfp_ops.py:111-120 -> int_ops.Quantizer): weights and 2-D / 3-D / 4-D activations
+    g = torch.Generator().manual_seed(321)
+    int_in = {"w2d": torch.randn(12, 96, generator=g) * 0.3, "a3d": torch.randn(2, 9, 40, generator=g), "a4d": torch.randn(2, 5, 6, 8, generator=g)}
+    int_in["w2d"][1] = int_in["w2d"][1].abs()
+    int_in["w2d"][2] = 0.0
+    for name, t32 in int_in.items():
+        for dtn, dtype in DTYPES.items():
+            t = t32.to(dtype)
+            put(store, f"int_in_{name}_{dtn}", t)
+            for ident, bits in itertools.product(("w", "in"), (8, 4)):
+                args = ref_args(ref, sparsity_num_format="int", mant_bits=bits, w_sparsity=False, device=dev)
+                put(store, f"int_out_{name}_{dtn}_{ident}_b{bits}", ref.float_to_bfp_blocked(t.to(dev), **args, identifier=ident))
+
+    # 7. unstructured sparsity (bfp_ops.py:61-71).  Tie-free inputs for both devices; tie-heavy input only where the
+    #    tie order is a usable contract (torch-CUDA: index order).
+    g = torch.Generator().manual_seed(55)
+    un = {"randn": torch.randn(50, 333, generator=g)}
+    if dev != "cpu":
+        un["ties"] = torch.randint(-3, 4, (64, 257), generator=g).float()
+    for name, t32 in un.items():
+        for dtn in ("f32", "bf16"):
+            t = t32.to(DTYPES[dtn]) if name == "ties" else (t32 + torch.arange(t32.numel()).reshape(t32.shape) * 1e-3).to(torch.float32)
+            if dtn == "bf16" and name != "ties":
+                continue
+            put(store, f"un_in_{name}_{dtn}", t)
+            for frac in (0.5, 0.13, 0.9):
+                put(store, f"un_out_{name}_{dtn}_{frac}", ref._unstructured_sparsity(t.to(dev), dev, frac))
+
     store["__meta__"] = np.array([f"device={dev}", f"torch={torch.__version__}"])
     out = a.out or os.path.join(HERE, f"ref_{dev}.npz")
     os.makedirs(os.path.dirname(os.path.abspath(out)), exist_ok=True)

@@ -1,0 +1,87 @@
+"""GPU parity for the 'int' number format (sparsity_num_format='int', bfp_ops.py:111-120 -> int_ops.Quantizer;
+SURVEY.md section 8 row f2): bit-exact against the oracle, the golden fixtures and the live reference."""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+import _golden
+from _refload import load_reference, ref_args
+
+pytestmark = pytest.mark.gpu
+TORCH_DT = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available()
+    from qsi_b200 import bfp_ops, _lib
+    _lib.lib()
+    return bfp_ops
+
+
+def _args(ops, bits, **kw):
+    return ops.unpack_bfp_args(dict(num_format="bfp", sparsity_num_format="int", rounding_mode="determ", epsilon=1e-8, mant_bits=bits,
+                                    weight_mant_bits=15, block_size=64, device="cuda", **kw))
+
+
+@pytest.mark.parametrize("dt", ["f32", "bf16", "f16"])
+def test_int_format_matches_oracle(ops, oracle, dt):
+    g = torch.Generator().manual_seed(2)
+    for shape, ident, bits in itertools.product([(64, 1000), (3, 50, 96), (2, 7, 12, 20), (2, 7, 4, 4), (5, 8), (4096, 64)], ("w", "in"), (8, 4, 2)):
+        x = (torch.randn(*shape, generator=g) * 0.3).to(TORCH_DT[dt])
+        x.view(-1)[::11] = 0
+        if len(shape) == 2:
+            x[1] = x[1].abs()
+            x[2] = 0
+        y = ops.float_to_bfp_blocked(x.cuda(), **_args(ops, bits), identifier=ident)
+        assert y.dtype == torch.float32 and y.shape == x.shape
+        from oracle import bfp_oracle as O
+        o = oracle.int_quantize(O.from_torch(x)[0], bits, ident == "w", dt=dt)
+        assert _golden.mismatches(y.cpu().numpy(), o, "f32") == 0, (shape, ident, bits)
+        levels = torch.unique(y[0]).numel() if ident == "w" else 0
+        assert levels <= 2 ** bits
+
+
+@pytest.mark.parametrize("device", ["cuda", "cpu"])
+def test_int_format_and_unstructured_match_golden(ops, device):
+    from oracle import bfp_oracle as O
+    z = _golden.load(device)
+    if z is None or not any(k.startswith("int_in_") for k in z.files):
+        pytest.skip("not recorded")
+    n = 0
+    for k in z.files:
+        if k.startswith("int_out_"):
+            name, dtn, ident, bits = k[len("int_out_"):].rsplit("__", 1)[0].rsplit("_", 3)
+            x, dt = _golden.get(z, f"int_in_{name}_{dtn}")
+            y = ops.float_to_bfp_blocked(O.to_torch(x, dt).cuda(), **_args(ops, int(bits[1:])), identifier=ident)
+            assert _golden.mismatches(y.cpu().numpy(), z[k], "f32") == 0, k
+            n += 1
+        elif k.startswith("un_out_"):
+            name, dtn, frac = k[len("un_out_"):].rsplit("__", 1)[0].rsplit("_", 2)
+            x, dt = _golden.get(z, f"un_in_{name}_{dtn}")
+            y = ops._unstructured_sparsity(O.to_torch(x, dt).cuda(), "cuda", float(frac))
+            assert _golden.mismatches(O.from_torch(y)[0], z[k], dt) == 0, k
+            n += 1
+    assert n >= 36
+
+
+def test_int_format_with_sparsity_and_live_reference(ops, oracle):
+    """int format composed with 2:4 / unstructured sparsity in both orders, against the live reference when present."""
+    ref = load_reference()
+    g = torch.Generator().manual_seed(4)
+    w = torch.randn(96, 256, generator=g) * 0.05
+    for first, mode in itertools.product(("s", "q"), ("structured", "unstructured")):
+        a = _args(ops, 4, w_sparsity=True, N=2, M=4, first=first, sparsity_mode=mode, sparsity_frac=0.5)
+        y = ops.float_to_bfp_blocked(w.cuda(), **a, identifier="w").cpu().numpy()
+        sp = (lambda t: oracle.nm_sparsify(t, 2, 4)) if mode == "structured" else (lambda t: oracle.unstructured_sparsify(t, 0.5))
+        o = oracle.int_quantize(sp(w.numpy()), 4, True) if first == "s" else sp(oracle.int_quantize(w.numpy(), 4, True))
+        assert _golden.mismatches(y, o, "f32") == 0, (first, mode)
+        if ref is not None:
+            ra = ref_args(ref, sparsity_num_format="int", mant_bits=4, first=first, sparsity_mode=mode, device="cuda")
+            r = ref.float_to_bfp_blocked(w.cuda(), **ra, identifier="w").cpu().numpy()
+            assert _golden.mismatches(y, r, "f32") == 0, (first, mode, "reference")
+    # sgd_update switches to weight_mant_bits (bfp_ops.py:113-114)
+    y = ops.float_to_bfp_blocked(w.cuda(), **_args(ops, 4), identifier="w", sgd_update=True).cpu().numpy()
+    assert _golden.mismatches(y, oracle.int_quantize(w.numpy(), 15, True), "f32") == 0

@@ -189,3 +189,25 @@ def test_live_exponent_sweep_vs_reference(oracle):
     for _ in range(40):
         assert (oracle.bfp_exponent(x.numpy(), 1) == ref.get_exponent(x, 1e-8).numpy()).all()
         x = torch.nextafter(x, torch.tensor(float("inf")))
+
+
+@pytest.mark.parametrize("device", ["cpu", "cuda"])
+def test_oracle_matches_golden_int_format_and_unstructured(oracle, device):
+    z = _golden.load(device)
+    if z is None or not any(k.startswith("int_in_") for k in z.files):
+        pytest.skip("not recorded")
+    n = 0
+    for k in z.files:
+        if k.startswith("int_out_"):
+            name, dtn, ident, bits = k[len("int_out_"):].rsplit("__", 1)[0].rsplit("_", 3)
+            x, dt = _golden.get(z, f"int_in_{name}_{dtn}")
+            out = oracle.int_quantize(x, int(bits[1:]), ident == "w", dt=dt)
+            assert k.endswith("__f32") and _golden.mismatches(out, z[k], "f32") == 0, k       # fp32 output for every dtype
+            n += 1
+        elif k.startswith("un_out_"):
+            name, dtn, frac = k[len("un_out_"):].rsplit("__", 1)[0].rsplit("_", 2)
+            x, dt = _golden.get(z, f"un_in_{name}_{dtn}")
+            out = oracle.unstructured_sparsify(x, float(frac), dt=dt)
+            assert _golden.mismatches(out, z[k], dt) == 0, k
+            n += 1
+    assert n >= 36

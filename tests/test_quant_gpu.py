@@ -304,8 +304,9 @@ def test_api_conventions_on_device(ops):
     y_in = ops.float_to_bfp_blocked(x, **args, identifier="in")      # activations are not sparsified
     assert torch.equal(y_in, ops._no_sparsity_float_to_bfp(x, 64, 7, 1e-8, "determ", "cuda"))
     assert ops.float_to_bfp_blocked(torch.empty(0, 64, device="cuda"), **args, identifier="w").shape == (0, 64)
-    with pytest.raises(NotImplementedError):
-        ops.float_to_bfp_blocked(x, **dict(args, sparsity_num_format="int"), identifier="w")
+    with pytest.raises(AssertionError):                       # bfp_ops.py:130: only 'bfp' / 'fp32' / 'int' are accepted
+        ops.float_to_bfp_blocked(x, **dict(args, sparsity_num_format="fp8"), identifier="w")
+    assert ops.float_to_bfp_blocked(x, **dict(args, sparsity_num_format="int"), identifier="w").dtype == torch.float32
 
 
 def test_bfp_linear_module_matches_oracle(ops, oracle):
