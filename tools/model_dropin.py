@@ -1,0 +1,92 @@
+"""Model-level drop-in check (BASELINE.json configs[0] and [3]): stock `transformers` OPT-125M / ViT-B/16 with every
+block nn.Linear replaced by BFPLinear (and the ViT patch-embedding conv by BFPConv2d), exactly the substitution the
+reference's patched modeling_opt.py:162-176,325-335 / modeling_vit.py:168-215 make.  Runs the model once with this
+repo's bfp_ops and, when the reference sources are present, once with the reference's, and compares logits.
+
+    python tools/model_dropin.py [opt|vit] [--layers L] [--batch B] [--seq S] [--out file.json]
+"""
+import argparse, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+from qsi_b200 import bfp_ops as ours
+from _refload import load_reference
+
+OPT_TARGETS = ("q_proj", "k_proj", "v_proj", "out_proj", "fc1", "fc2")
+
+
+def swap(model, impl, kw, targets=None, conv_name="projection"):
+    n = 0
+    for parent in list(model.modules()):
+        for name, ch in list(parent.named_children()):
+            if isinstance(ch, torch.nn.Linear) and (targets is None or name in targets):
+                new = impl.BFPLinear(ch.in_features, ch.out_features, bias=ch.bias is not None, **dict(kw))
+                new.weight, new.bias = ch.weight, ch.bias
+                setattr(parent, name, new); n += 1
+            elif isinstance(ch, torch.nn.Conv2d) and name == conv_name:
+                new = impl.BFPConv2d(ch.in_channels, ch.out_channels, ch.kernel_size, ch.stride, ch.padding, ch.dilation, ch.groups,
+                                     bias=ch.bias is not None, **dict(kw))
+                new.weight, new.bias = ch.weight, ch.bias
+                setattr(parent, name, new); n += 1
+    return n
+
+
+def build(kind, layers):
+    import transformers
+    torch.manual_seed(0)
+    if kind == "opt":
+        cfg = transformers.OPTConfig()
+        if layers: cfg.num_hidden_layers = layers
+        return transformers.OPTForCausalLM(cfg).eval(), cfg
+    cfg = transformers.ViTConfig()
+    if layers: cfg.num_hidden_layers = layers
+    return transformers.ViTForImageClassification(cfg).eval(), cfg
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("kind", nargs="?", default="opt", choices=["opt", "vit"])
+    ap.add_argument("--layers", type=int, default=0); ap.add_argument("--batch", type=int, default=0); ap.add_argument("--seq", type=int, default=512)
+    ap.add_argument("--mant", type=int, default=0); ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    dev = "cuda"
+    m = a.mant or (7 if a.kind == "opt" else 5)            # config 0: HBFP8, config 3: BFP6
+    kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=m, weight_mant_bits=15,
+              block_size=64, w_sparsity=True, N=2, M=4, first="s", sparsity_mode="structured", sparsity_frac=0.5, device=dev)
+    res = {"model": a.kind, "mant_bits": m, "block": 64, "nm": "2:4 s->q"}
+    outs = {}
+    ref = load_reference()
+    for tag, impl in (("ours", ours), ("reference", ref)):
+        if impl is None:
+            continue
+        model, cfg = build(a.kind, a.layers)
+        n = swap(model, impl, kw, OPT_TARGETS if a.kind == "opt" else None)
+        model = model.to(dev)
+        g = torch.Generator().manual_seed(1)
+        if a.kind == "opt":
+            B = a.batch or 8
+            inp = dict(input_ids=torch.randint(0, cfg.vocab_size, (B, a.seq), generator=g).to(dev))
+        else:
+            B = a.batch or 256
+            inp = dict(pixel_values=torch.randn(B, 3, 224, 224, generator=g).to(dev))
+        with torch.no_grad():
+            y = model(**inp).logits
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            y = model(**inp).logits
+            torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        outs[tag] = y.float()
+        res[tag] = {"swapped_modules": n, "forward_s": dt, "logits_shape": list(y.shape), "finite": bool(torch.isfinite(y).all())}
+        print(tag, res[tag], flush=True)
+        del model
+    if "reference" in outs:
+        d = (outs["ours"] - outs["reference"])
+        res["rel_err_vs_reference"] = float(d.norm() / outs["reference"].norm())
+        res["max_abs_err"] = float(d.abs().max())
+        res["speedup_vs_reference_on_same_gpu"] = res["reference"]["forward_s"] / res["ours"]["forward_s"]
+        print("rel err vs reference:", res["rel_err_vs_reference"], "speed-up:", res["speedup_vs_reference_on_same_gpu"], flush=True)
+    if a.out:
+        json.dump(res, open(a.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
