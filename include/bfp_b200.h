@@ -177,6 +177,24 @@ int bfp_quantize_pack_bf16(const void* in, void* out_bf16, int64_t rows, int64_t
 int bfp_gemm_bf16(const void* a_bf16, const void* b_bf16, const float* bias, float* out, int64_t T, int64_t N, int64_t K,
                   void* stream);
 
+/* 2:4 structured-sparse variant of the BFP linear for weights pruned by _structured_N_M_sparsity with N=2, M=4
+ * (bfp_ops.py:73-91; the reference then multiplies the zero-filled dense tensor, bfp_ops.py:187-190).  The pruned
+ * exact-bf16 weight is stored compressed and the tensor core skips the zeros (tcgen05.mma.sp.kind::f16: 32 logical k per
+ * MMA instead of 16):
+ *   bfp_sp_layout:          sizes of the compressed form of a [rows, K] operand: Kc = kept bf16 per row (K padded to 128,
+ *                           halved), meta_bytes = ceil(rows/128) * ceil(K/128) * 2048.
+ *   bfp_compress_2to4_bf16: w_bf16 [rows, Kp] (bfp_quantize_pack_bf16 output, Kp = K rounded up to 8) -> w_comp bf16
+ *                           [rows, Kc] + w_meta (4-bit index nibbles in the order tcgen05.cp moves them to TMEM, see
+ *                           csrc/bfp_gemm_sp.cu).  *violations (device uint32, caller-zeroed) counts groups of four with
+ *                           more than two non-zeros, i.e. input that is not 2:4; the result is then not equivalent.
+ *   bfp_gemm_bf16_sp:       out[T,N] (fp32) = x[T,K] . W[N,K]^T + bias from the compressed W.  Same result contract as
+ *                           bfp_gemm_bf16 on the uncompressed operand (exact products, fp32 accumulation order differs). */
+int bfp_sp_layout(int64_t rows, int64_t K, int64_t* Kc, int64_t* meta_bytes);
+int bfp_compress_2to4_bf16(const void* w_bf16, int64_t rows, int64_t K, void* w_comp, void* w_meta, uint32_t* violations,
+                           void* stream);
+int bfp_gemm_bf16_sp(const void* x_bf16, const void* w_comp, const void* w_meta, const float* bias, float* out, int64_t T,
+                     int64_t N, int64_t K, void* stream);
+
 /* The 256-entry table behind BFP_TIE_TORCH_CPU for 2:4 (index = c0 + 4*c1 + 16*c2 + 64*c3 with
  * c_i = #{j : |v_j| < |v_i|}; value = 4-bit drop mask, 0xff = unreachable).  Exposed for the tests. */
 int bfp_debug_cpu_tie_lut(uint8_t out[256]);

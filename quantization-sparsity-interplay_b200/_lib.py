@@ -56,6 +56,9 @@ SIGNATURES = {
     "bfp_unpack": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _vp]),
     "bfp_quantize_pack_bf16": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _i32, _u64, _u64, _i32, _i32, _i32, _vp]),
     "bfp_gemm_bf16": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "bfp_sp_layout": (_i32, [_i64, _i64] + [ctypes.POINTER(_i64)] * 2),
+    "bfp_compress_2to4_bf16": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "bfp_gemm_bf16_sp": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "bfp_gemm_i8": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp]),
 }
 
@@ -94,3 +97,10 @@ def packed_layout(rows, K, block_size):
     kp, rp, nk = _i64(), _i64(), _i64()
     check(lib().bfp_packed_layout(int(rows), int(K), int(block_size), ctypes.byref(kp), ctypes.byref(rp), ctypes.byref(nk)))
     return kp.value, rp.value, nk.value
+
+
+def sp_layout(rows, K):
+    """(Kc, meta_bytes) of the 2:4-compressed form of a [rows, K] bf16 operand (include/bfp_b200.h)."""
+    kc, mb = _i64(), _i64()
+    check(lib().bfp_sp_layout(int(rows), int(K), ctypes.byref(kc), ctypes.byref(mb)))
+    return kc.value, mb.value

@@ -397,6 +397,48 @@ def bfp_linear_bf16(xb, wb, bias=None, out_shape=None):
     return out.view(out_shape) if out_shape is not None else out
 
 
+class SparseBF16:
+    """A 2:4-pruned exact-bf16 operand in the compressed form of include/bfp_b200.h (bfp_compress_2to4_bf16): the two kept
+    values of every group of four along K (`comp` bf16 [rows, Kc]) and the index nibbles (`meta` uint8)."""
+
+    def __init__(self, comp, meta, rows, K):
+        self.comp, self.meta, self.rows, self.K = comp, meta, rows, K
+
+
+def compress_2to4_bf16(wb, check=True):
+    """bf16 [rows, Kp] operand whose groups of four along K hold at most two non-zeros -> SparseBF16.  With check=True the
+    violation counter is read back (one sync; weights are compressed once and cached) and a non-2:4 input raises."""
+    assert wb.dtype == torch.bfloat16 and wb.dim() == 2 and wb.is_cuda and wb.is_contiguous()
+    rows, Kp = wb.shape
+    Kc, meta_bytes = _lib.sp_layout(rows, Kp)
+    comp = torch.empty((rows, Kc), dtype=torch.bfloat16, device=wb.device)
+    meta = torch.empty((meta_bytes,), dtype=torch.uint8, device=wb.device)
+    viol = torch.zeros((1,), dtype=torch.int32, device=wb.device)
+    if rows and Kp:
+        with torch.cuda.device(wb.device):
+            _lib.check(_lib.lib().bfp_compress_2to4_bf16(wb.data_ptr(), rows, Kp, comp.data_ptr(), meta.data_ptr(), viol.data_ptr(),
+                                                         torch.cuda.current_stream().cuda_stream))
+    if check and int(viol.item()) != 0:
+        raise ValueError(f"operand is not 2:4 sparse along K ({int(viol.item())} groups of 16 with a dense group of four)")
+    return SparseBF16(comp, meta, rows, Kp)
+
+
+def bfp_linear_bf16_sp(xb, ws, bias=None, out_shape=None):
+    """y = x w^T + bias with the 2:4-compressed weight `ws` (include/bfp_b200.h bfp_gemm_bf16_sp): tcgen05.mma.sp.kind::f16,
+    fp32 TMEM accumulation.  xb bf16 [T, Kp]."""
+    T, Kp = xb.shape
+    N = ws.rows
+    assert ws.K == Kp and xb.dtype == torch.bfloat16
+    out = torch.empty((T, N), dtype=torch.float32, device=xb.device)
+    b = bias.detach().to(dtype=torch.float32).contiguous() if bias is not None else None
+    if out.numel():
+        with torch.cuda.device(out.device):
+            _lib.check(_lib.lib().bfp_gemm_bf16_sp(xb.data_ptr(), ws.comp.data_ptr(), ws.meta.data_ptr(),
+                                                   b.data_ptr() if b is not None else None, out.data_ptr(), T, N, Kp,
+                                                   torch.cuda.current_stream().cuda_stream))
+    return out.view(out_shape) if out_shape is not None else out
+
+
 def _tensor_core_kind(x, w, bfp_args):
     """Which tensor-core contraction serves this configuration: 'bf16' (exact-bf16 operands, MMA-bound, any block size,
     mant_bits <= 8), 'i8' (int8 mantissas + per-block rescale, block 32/64/128, mant_bits <= 7) or None (fake-quant +

@@ -237,6 +237,24 @@ int bfp_gemm_bf16(const void* a_bf16, const void* b_bf16, const float* bias, flo
     return gemm_bf16_device(a_bf16, b_bf16, bias, out, T, N, round_up(K, 8), static_cast<cudaStream_t>(stream));
 }
 
+int bfp_sp_layout(int64_t rows, int64_t K, int64_t* Kc, int64_t* meta_bytes) { return sp_layout(rows, round_up(K, 8), Kc, meta_bytes); }
+
+int bfp_compress_2to4_bf16(const void* w_bf16, int64_t rows, int64_t K, void* w_comp, void* w_meta, uint32_t* violations, void* stream) {
+    if (rows < 0 || K < 0) return set_error(BFP_E_ARG, "bad argument");
+    if (rows * K > 0 && (!w_bf16 || !w_comp || !w_meta || !violations)) return set_error(BFP_E_ARG, "null pointer");
+    if (int rc = require_device()) return rc;
+    const int64_t Kp = round_up(K, 8);
+    return compress_2to4_bf16_device(w_bf16, rows, Kp, Kp, w_comp, w_meta, violations, static_cast<cudaStream_t>(stream));
+}
+
+int bfp_gemm_bf16_sp(const void* x_bf16, const void* w_comp, const void* w_meta, const float* bias, float* out, int64_t T, int64_t N,
+                     int64_t K, void* stream) {
+    if (T < 0 || N < 0 || K <= 0) return set_error(BFP_E_ARG, "bad argument");
+    if (T * N > 0 && (!x_bf16 || !w_comp || !w_meta || !out)) return set_error(BFP_E_ARG, "null pointer");
+    if (int rc = require_device()) return rc;
+    return gemm_bf16_sp_device(x_bf16, w_comp, w_meta, bias, out, T, N, round_up(K, 8), static_cast<cudaStream_t>(stream));
+}
+
 int bfp_unpack(const int8_t* mant, const float* scale_t, float* out, int64_t rows, int64_t K, int block_size, void* stream) {
     if (rows < 0 || K < 0 || block_size <= 0) return set_error(BFP_E_ARG, "bad argument");
     if (rows * K > 0 && (!mant || !scale_t || !out)) return set_error(BFP_E_ARG, "null pointer");

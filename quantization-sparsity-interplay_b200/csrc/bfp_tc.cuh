@@ -1,0 +1,203 @@
+// bfp_tc.cuh -- tcgen05 / TMA / mbarrier PTX wrappers and tensor-map helpers shared by the tensor-core kernels
+// (bfp_gemm.cu: dense int8 + bf16 kinds, bfp_gemm_sp.cu: 2:4 structured-sparse bf16 kind).  sm_100a only.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bfp_internal.h"
+
+namespace bfp {
+namespace gemm {
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: a protocol bug must surface as a trap within ~2 s, not as a hung GPU box
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint64_t t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity), "r"(20000u) : "memory");      // suspend-time hint (ns)
+        if (done) return;
+        if ((spin & 1023u) == 1023u) {
+            const uint64_t now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) __trap();
+        }
+    }
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 r;\n\telect.sync r|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(addr));
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+// packed fp32x2 arithmetic (sm_100): one issue slot for two lanes of the epilogue's rescale
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(uint64_t v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ void fma2_acc(uint64_t& acc, uint64_t a, uint64_t b) {      // acc += a * b, in place (no register moves)
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// int32 -> fp32 for |v| < 2^22 without the (slow) conversion pipe: bit pattern of (v + 1.5 * 2^23) as a float is
+// 0x4B400000 + v, so one integer add per value and one packed fp32 subtract per pair; exact.
+__device__ __forceinline__ uint64_t cvt2_s32(uint32_t a, uint32_t b) {
+    uint64_t m;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(m) : "r"(a + 0x4B400000u), "r"(b + 0x4B400000u));
+    return add2(m, 0xCB400000CB400000ull);              // (-12582912.0f, -12582912.0f)
+}
+// acc (f32x2) += float(a, b) * w for two int32 accumulator values (I2FP: 64 lanes/clk/SM, tools/microbench/pipe_rates.cu)
+__device__ __forceinline__ void rescale_pair_xu(uint64_t& acc, uint32_t a, uint32_t b, uint64_t w) {
+    asm("{\n\t.reg .f32 fa, fb;\n\t.reg .b64 f;\n\t"
+        "cvt.rn.f32.s32 fa, %1;\n\tcvt.rn.f32.s32 fb, %2;\n\t"
+        "mov.b64 f, {fa, fb};\n\t"
+        "fma.rn.f32x2 %0, f, %3, %0;\n\t}"
+        : "+l"(acc) : "r"(a), "r"(b), "l"(w));
+}
+// the same with the conversion on the integer + FMA pipes: for |v| < 2^22 the bits of float(v + 1.5 * 2^23) are
+// 0x4B400000 + v, so float(v) = as_float(v + 0x4B400000) - 12582912.0f exactly (|block sums| <= 128 * 127^2 < 2^22).
+// Measured slower than I2FP here (the integer adds land on the same half-rate pipe); kept for reference.
+__device__ __forceinline__ void rescale_pair_magic(uint64_t& acc, uint32_t a, uint32_t b, uint64_t w) {
+    asm("{\n\t.reg .b64 m, f;\n\t"
+        "mov.b64 m, {%1, %2};\n\t"
+        "add.rn.f32x2 f, m, %4;\n\t"
+        "fma.rn.f32x2 %0, f, %3, %0;\n\t}"
+        : "+l"(acc) : "r"(a + 0x4B400000u), "r"(b + 0x4B400000u), "l"(w), "l"(0xCB400000CB400000ull));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// start address >> 4 | LBO (ignored for swizzled K-major) = 1 | SBO = 1024 B (8 rows x 128 B) | version 1 | layout 2
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// Generic K-major shared-memory matrix descriptor: layout_type 0 = no swizzle (8-row x 16-byte core matrices), 2 = SWIZZLE_128B,
+// 4 = SWIZZLE_64B, 6 = SWIZZLE_32B; sbo = bytes between consecutive 8-row groups; lbo = bytes between core matrices along K
+// (ignored by the swizzled K-major modes).
+__device__ __forceinline__ uint64_t make_smem_desc_k(uint32_t smem_addr, uint32_t layout_type, uint32_t sbo, uint32_t lbo) {
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) | ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) |
+           (1ull << 46) | ((uint64_t)layout_type << 61);
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+inline int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t kbytes, int box_rows, bool bf16 = false) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return set_error(BFP_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)(bf16 ? kbytes / 2 : kbytes), (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kbytes};
+    cuuint32_t box[2] = {(cuuint32_t)(bf16 ? 64 : 128), (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_errorf(BFP_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return BFP_OK;
+}
+
+// 2-D bf16 tensor map with an explicit box and swizzle (make_map above is the 128-byte-box special case).
+inline int make_map_bf16(CUtensorMap* map, const void* ptr, int64_t rows, int64_t k_elems, int64_t row_stride_bytes, int box_k,
+                         int box_rows, CUtensorMapSwizzle swz) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return set_error(BFP_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)k_elems, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)row_stride_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_errorf(BFP_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return BFP_OK;
+}
+
+}  // namespace gemm
+}  // namespace bfp
