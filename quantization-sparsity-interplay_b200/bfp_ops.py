@@ -18,6 +18,7 @@ Semantics kept from the reference (line numbers refer to the reference file):
   * N:M ties follow the torch.topk backend the reference would have used for that tensor: torch-CUDA's rule (smallest
     by (|v|, index)) for CUDA tensors, torch-CPU's rule for CPU tensors (2:4 only); override with BFP_TIE_RULE=cuda|cpu.
 """
+import math
 import os
 
 import torch
@@ -439,19 +440,42 @@ def bfp_linear_bf16_sp(xb, ws, bias=None, out_shape=None):
     return out.view(out_shape) if out_shape is not None else out
 
 
+def _nm_fits_2to4(N, M):
+    """True when keeping any N of every M consecutive values along K (groups start at the row start) leaves at most two
+    non-zeros in every aligned group of four -- what tcgen05.mma.sp needs.  Worst case per window: each overlapping
+    M-group contributes min(N, overlap)."""
+    if N <= 0 or M <= 0 or N >= M:
+        return False
+    period = M * 4 // math.gcd(M, 4)
+    for w0 in range(0, period, 4):
+        overlap = {}
+        for i in range(w0, w0 + 4):
+            overlap[i // M] = overlap.get(i // M, 0) + 1
+        if sum(min(N, c) for c in overlap.values()) > 2:
+            return False
+    return True
+
+
 def _tensor_core_kind(x, w, bfp_args):
-    """Which tensor-core contraction serves this configuration: 'bf16' (exact-bf16 operands, MMA-bound, any block size,
-    mant_bits <= 8), 'i8' (int8 mantissas + per-block rescale, block 32/64/128, mant_bits <= 7) or None (fake-quant +
-    library GEMM, the reference's own structure).  BFP_GEMM_KIND=bf16|i8 picks between the first two (default bf16: it is
-    the faster of the two for every block size <= 64)."""
+    """Which tensor-core contraction serves this configuration:
+      'sp'   exact-bf16 operands, weight 2:4-compressed, tcgen05.mma.sp (w_sparsity with an N:M that fits 2:4);
+      'bf16' exact-bf16 operands, dense MMA (any block size, mant_bits <= 8);
+      'i8'   int8 mantissas + per-block rescale (block 32/64/128, mant_bits <= 7);
+      None   fake-quant + library GEMM, the reference's own structure.
+    BFP_GEMM_KIND=sp|bf16|i8 picks among the eligible ones (default: sp when the weight is 2:4, else bf16 -- the faster
+    of the dense two for every block size <= 64)."""
     if not _tensor_core_eligible(x, w, dict(bfp_args, block_size=64 if bfp_args['block_size'] > 0 else 0, mant_bits=min(bfp_args['mant_bits'], 7))):
         return None
     B, m = bfp_args['block_size'], bfp_args['mant_bits']
-    want = os.environ.get("BFP_GEMM_KIND", "bf16")
+    want = os.environ.get("BFP_GEMM_KIND", "")
     i8_ok = B in (32, 64, 128) and 1 <= m <= 7
     bf16_ok = 1 <= m <= 8 and B >= 4 and (B & (B - 1)) == 0
+    sp_ok = (bf16_ok and bfp_args['w_sparsity'] == True and bfp_args['sparsity_mode'] == 'structured'     # noqa: E712
+             and _nm_fits_2to4(bfp_args['N'], bfp_args['M']))
     if want == "i8" and i8_ok:
         return 'i8'
+    if want in ("", "sp") and sp_ok:
+        return 'sp'
     if bf16_ok:
         return 'bf16'
     return 'i8' if i8_ok else None
@@ -602,7 +626,10 @@ class BFPLinear(torch.nn.Linear):
         key = (kind, w.data_ptr(), w._version, tuple(w.shape), w.device)
         if self._packed_w is None or self._packed_w[0] != key:
             pack = pack_bfp if kind == 'i8' else pack_bfp_bf16
-            self._packed_w = (key, pack(w, identifier='w', **self.bfp_args))
+            packed = pack(w, identifier='w', **self.bfp_args)
+            if kind == 'sp':
+                packed = compress_2to4_bf16(packed)       # raises if the pruned weight is not 2:4 (cannot happen for sp_ok configs)
+            self._packed_w = (key, packed)
         return self._packed_w[1]
 
     def forward(self, input):
@@ -613,6 +640,10 @@ class BFPLinear(torch.nn.Linear):
             if kind == 'i8':
                 # inference fast path: pack activations on the fly, cached packed weight, tcgen05 int8 BFP GEMM
                 return bfp_linear_packed(pack_bfp(input, identifier='in', **self.bfp_args), self._packed_weight(kind), self.bias)
+            if kind == 'sp':
+                # 2:4-pruned weight: compressed once, tcgen05.mma.sp skips the zeros
+                return bfp_linear_bf16_sp(pack_bfp_bf16(input, identifier='in', **self.bfp_args), self._packed_weight(kind), self.bias,
+                                          out_shape=tuple(input.shape[:-1]) + (self.out_features,))
             if kind == 'bf16':
                 return bfp_linear_bf16(pack_bfp_bf16(input, identifier='in', **self.bfp_args), self._packed_weight(kind), self.bias,
                                        out_shape=tuple(input.shape[:-1]) + (self.out_features,))

@@ -34,116 +34,187 @@ namespace gemm_sp {
 
 using namespace gemm;
 
-constexpr int BW = 128;                      // out-features (rows of W) per tile = TMEM lanes
-constexpr int BT = 256;                      // tokens per tile = accumulator columns
-constexpr int KS = 64;                       // logical k per smem slab
-constexpr int kStages = 5;
-constexpr int kSmemW = BW * (KS / 2) * 2;    // 8 KB: 32 kept bf16 per row
-constexpr int kSmemX = BT * KS * 2;          // 32 KB
-constexpr int kSmemE = 2048;                 // one E atom (128 logical k), filled on even slabs
-constexpr int kStageBytes = kSmemW + kSmemX + kSmemE;          // 43008 = 42 * 1024
-constexpr int kSmemTotal = kStages * kStageBytes + 1024 + 1024;
+// CG = 1: one CTA per tile (128 out-features x 256 tokens).  CG = 2: a cluster pair shares a 256 x 256 tile through
+// tcgen05.mma.cta_group::2 -- each CTA stages its own 128 W rows and only HALF of the X tile, so the shared-memory feed per
+// MMA drops from 20 KB to 12 KB per SM (the 1-CTA kernel is feed-bound: 160 B/clk wanted, 128 B/clk available).
+template <int CG> struct Cfg {
+    static constexpr int BW = 128;                       // out-features (rows of W) per CTA = TMEM lanes
+    static constexpr int BT = 256;                       // tokens per tile = accumulator columns
+    static constexpr int XR = BT / CG;                   // X rows staged by one CTA
+    static constexpr int KS = 64;                        // logical k per smem slab
+    static constexpr int kSmemW = BW * (KS / 2) * 2;     // 8 KB: 32 kept bf16 per row
+    static constexpr int kSmemX = XR * KS * 2;           // 32 KB / 16 KB
+    static constexpr int kSmemE = 2048;                  // one E atom (128 logical k), filled on even slabs
+    static constexpr int kStageBytes = kSmemW + kSmemX + kSmemE;      // 43008 / 26624, multiples of 1024
+    static constexpr int kStages = CG == 1 ? 5 : 8;
+    static constexpr int kSmemTotal = kStages * kStageBytes + 1024 + 1024;
+    // D = F32, A = B = BF16, K-major, N = BT, M = BW * CG, sparse flag (bit 2); bits 0-1 = sparsity selector
+    static constexpr uint32_t kIdesc = (1u << 2) | (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BT >> 3) << 17) | ((uint32_t)((BW * CG) >> 4) << 24);
+};
+constexpr int kMaxStages = 8;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + kEpiWarps * 32;
 constexpr int kTmemCols = 512;
 constexpr int kTmemE = 256;                  // first E column
-constexpr int kERing = 4;                    // E atoms resident in TMEM (see the reuse argument in the MMA warp)
-// D = F32, A = B = BF16, K-major, N = BT, M = BW, sparse flag (bit 2), sparsity selector (bits 0-1) = 0
-constexpr uint32_t kIdescSp = (1u << 2) | (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BT >> 3) << 17) | ((uint32_t)(BW >> 4) << 24);
+constexpr int kERing = 8;                    // E atoms resident in TMEM: 2 * kERing - 1 >= kMaxStages (reuse argument in the MMA warp)
 
 struct Params {
-    const uint8_t* meta;        // [tiles_w][e_atoms][2048]
     const float* bias;          // [N] or nullptr
     float* out;                 // [T][N]
     int T, N;
     int num_k_slabs;            // ceil(K / 64)
     int e_atoms;                // ceil(K / 128)
-    int tiles_w, tiles_t;
+    int tiles_w, tiles_t;       // tiles_w counts CG * 128 rows
+    int debug;                  // timing experiments only (wrong results): bit 0 = every tile loads X tile 0, bit 1 = W tile 0
 };
 
 struct Barriers {
-    uint64_t full[kStages];
-    uint64_t empty[kStages];
+    uint64_t full[kMaxStages];
+    uint64_t empty[kMaxStages];
     uint64_t tmem_full;
     uint64_t tmem_empty;
     uint32_t tmem_base;
 };
 
+template <int CG>
 __device__ __forceinline__ void mma_sp_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t tmem_e, uint32_t idesc,
                                             uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %5, 0;\n\t"
-        "tcgen05.mma.sp.cta_group::1.kind::f16 [%0], %1, %2, [%3], %4, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(tmem_e), "r"(idesc), "r"(accumulate) : "memory");
+    if constexpr (CG == 1)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "tcgen05.mma.sp.cta_group::1.kind::f16 [%0], %1, %2, [%3], %4, p;\n\t}"
+            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(tmem_e), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "tcgen05.mma.sp.cta_group::2.kind::f16 [%0], %1, %2, [%3], %4, p;\n\t}"
+            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(tmem_e), "r"(idesc), "r"(accumulate) : "memory");
 }
+template <int CG>
 __device__ __forceinline__ void tmem_cp_128x128b(uint32_t tmem_dst, uint64_t smem_desc) {
-    asm volatile("tcgen05.cp.cta_group::1.128x128b [%0], %1;" ::"r"(tmem_dst), "l"(smem_desc) : "memory");
+    if constexpr (CG == 1) asm volatile("tcgen05.cp.cta_group::1.128x128b [%0], %1;" ::"r"(tmem_dst), "l"(smem_desc) : "memory");
+    else asm volatile("tcgen05.cp.cta_group::2.128x128b [%0], %1;" ::"r"(tmem_dst), "l"(smem_desc) : "memory");
+}
+// tcgen05.commit: CG = 2 arrives on the barrier at the same offset in both CTAs of the pair
+template <int CG>
+__device__ __forceinline__ void commit(uint64_t* bar) {
+    if constexpr (CG == 1) tc_commit(bar);
+    else asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                      ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// TMA tile load whose completion bytes land on `bar_addr` (a shared::cluster address; for CG = 2 the pair leader's barrier)
+template <int CG>
+__device__ __forceinline__ void tma_load_2d_to(void* dst, const CUtensorMap* map, uint32_t bar_addr, int c0, int c1) {
+    if constexpr (CG == 1)
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                     ::"r"(smem_u32(dst)), "l"(map), "r"(bar_addr), "r"(c0), "r"(c1) : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                     ::"r"(smem_u32(dst)), "l"(map), "r"(bar_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {      // shared::cta address -> shared::cluster address in CTA `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+template <int CG>
 __global__ void __launch_bounds__(kThreads, 1)
-bfp_gemm_bf16_sp_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const Params p) {
+bfp_gemm_bf16_sp_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
+                        const __grid_constant__ CUtensorMap map_e, const Params p) {
+    using C = Cfg<CG>;
+    constexpr int kStages = C::kStages, kStageBytes = C::kStageBytes, BW = C::BW, BT = C::BT, KS = C::KS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     Barriers* bars = reinterpret_cast<Barriers*>(smem + kStages * kStageBytes);
     auto stage_x = [&](int s) { return smem + s * kStageBytes; };
-    auto stage_w = [&](int s) { return smem + s * kStageBytes + kSmemX; };
-    auto stage_e = [&](int s) { return smem + s * kStageBytes + kSmemX + kSmemW; };
+    auto stage_w = [&](int s) { return smem + s * kStageBytes + C::kSmemX; };
+    auto stage_e = [&](int s) { return smem + s * kStageBytes + C::kSmemX + C::kSmemW; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();          // position in the CTA pair; 0 issues the MMAs
+    const int unit = (int)blockIdx.x / CG, num_units = (int)gridDim.x / CG;   // a unit = one CTA (CG 1) or one pair (CG 2)
     const int num_tiles = p.tiles_w * p.tiles_t;
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
         mbar_init(&bars->tmem_full, 1);
-        mbar_init(&bars->tmem_empty, kEpiWarps);
+        mbar_init(&bars->tmem_empty, kEpiWarps * CG);                 // the leader collects both CTAs' epilogue warps
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(kTmemCols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if constexpr (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 1) __syncthreads(); else cluster_sync_all();  // the peer's barriers must exist before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
     if (warp == 0) {
-        // ===================================== TMA producer =====================================
+        // ===================================== TMA producer (every CTA) =========================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int tw = tile % p.tiles_w, tt = tile / p.tiles_w;      // consecutive CTAs share the (larger) X tile
-                const uint8_t* meta_row = p.meta + (size_t)tw * p.e_atoms * kSmemE;
+            int uses = 0;
+            for (int tile = unit; tile < num_tiles; tile += num_units) {
+                const int tw = tile % p.tiles_w, tt = tile / p.tiles_w;      // consecutive units share the X tile
+                const int w_row = (tw * CG + (int)rank) * BW;                // this CTA's 128 W rows
+                const int x_row = tt * BT + (int)rank * C::XR;               // this CTA's share of the X tile
+                int e_row = (tw * CG + (int)rank) * p.e_atoms * 128;         // lane rows of this CTA's E atoms
+                int w_row_ld = w_row, x_row_ld = x_row;
+                if (p.debug & 1) x_row_ld = (int)rank * C::XR;
+                if (p.debug & 2) { w_row_ld = (int)rank * BW; e_row = (int)rank * p.e_atoms * 128; }
                 for (int ks = 0; ks < p.num_k_slabs; ++ks) {
+                    if ((p.debug & 4) && uses++ >= kStages) continue;       // experiment: MMAs re-read the first slabs, no loads
                     mbar_wait(&bars->empty[stage], phase ^ 1);
                     const bool with_e = (ks & 1) == 0;
-                    mbar_expect_tx(&bars->full[stage], kSmemW + kSmemX + (with_e ? kSmemE : 0));
-                    tma_load_2d(stage_x(stage), &map_x, &bars->full[stage], ks * KS, tt * BT);
-                    tma_load_2d(stage_w(stage), &map_w, &bars->full[stage], ks * (KS / 2), tw * BW);
-                    if (with_e) bulk_load(stage_e(stage), meta_row + (size_t)(ks >> 1) * kSmemE, kSmemE, &bars->full[stage]);
+                    // completion bytes of BOTH CTAs land on the leader's barrier; only the leader posts the expectation
+                    if (rank == 0) mbar_expect_tx(&bars->full[stage], (uint32_t)CG * (C::kSmemW + C::kSmemX + (with_e ? C::kSmemE : 0)));
+                    const uint32_t bar = CG == 1 ? smem_u32(&bars->full[stage]) : mapa_u32(smem_u32(&bars->full[stage]), 0);
+                    tma_load_2d_to<CG>(stage_x(stage), &map_x, bar, ks * KS, x_row_ld);
+                    tma_load_2d_to<CG>(stage_w(stage), &map_w, bar, ks * (KS / 2), w_row_ld);
+                    if (with_e) tma_load_2d_to<CG>(stage_e(stage), &map_e, bar, 0, e_row + (ks >> 1) * 128);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================================== MMA issuer =======================================
-        if (lane == 0) {
+        // ===================================== MMA issuer (leader CTA only) =====================
+        if (lane == 0 && rank == 0) {
             int stage = 0; uint32_t phase = 0;
             uint32_t tile_phase = 0;
             uint32_t eslot = kERing - 1;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(&bars->tmem_empty, tile_phase ^ 1);              // epilogue has drained the accumulator
+            int uses = 0;
+            for (int tile = unit; tile < num_tiles; tile += num_units) {
+                mbar_wait(&bars->tmem_empty, tile_phase ^ 1);              // every epilogue warp has drained the accumulator
                 tc_fence_after();
                 for (int ks = 0; ks < p.num_k_slabs; ++ks) {
-                    mbar_wait(&bars->full[stage], phase);
+                    if (!((p.debug & 4) && uses++ >= kStages)) mbar_wait(&bars->full[stage], phase);
                     tc_fence_after();
                     if ((ks & 1) == 0) {
-                        // E ring reuse: having seen full[] for this slab means the producer saw empty[] of the slab
-                        // kStages uses earlier, i.e. every MMA up to 5 slabs back has completed; the atom this slot held
-                        // was last read 7-8 slabs back (kERing atoms x 2 slabs), so the copy cannot overtake a reader.
+                        // E ring reuse: having seen full[] for this slab means the producers saw empty[] of the slab
+                        // kStages uses earlier, i.e. every MMA at least kStages slabs back has completed; the atom this slot
+                        // held was last read 2 * kERing - 1 = 15 slabs back, so the copy cannot overtake a reader.
                         eslot = (eslot + 1) & (kERing - 1);
-                        tmem_cp_128x128b(tmem_base + kTmemE + eslot * 4, make_smem_desc_k(smem_u32(stage_e(stage)), 0, 128, 128));
+                        tmem_cp_128x128b<CG>(tmem_base + kTmemE + eslot * 4, make_smem_desc_k(smem_u32(stage_e(stage)), 0, 128, 128));
                     }
                     const uint64_t dw = make_smem_desc_k(smem_u32(stage_w(stage)), 4, 512, 16);    // SWIZZLE_64B: 8 rows x 64 B
                     const uint64_t dx = make_smem_desc(smem_u32(stage_x(stage)));                  // SWIZZLE_128B
@@ -151,20 +222,21 @@ bfp_gemm_bf16_sp_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_
 #pragma unroll
                     for (int i = 0; i < 2; ++i)      // 32 logical k per MMA: 16 kept bf16 = 32 B of W (+2), 64 B of X (+4)
                         // the metadata address names an even column; the sparsity selector (idesc bits 0-1) picks the odd one
-                        mma_sp_bf16(tmem_base, dw + (uint64_t)(i * 2), dx + (uint64_t)(i * 4), ecol, kIdescSp | (uint32_t)i, (ks | i) != 0);
-                    tc_commit(&bars->empty[stage]);
+                        mma_sp_bf16<CG>(tmem_base, dw + (uint64_t)(i * 2), dx + (uint64_t)(i * 4), ecol, C::kIdesc | (uint32_t)i, (ks | i) != 0);
+                    commit<CG>(&bars->empty[stage]);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&bars->tmem_full);
+                commit<CG>(&bars->tmem_full);
                 tile_phase ^= 1;
             }
         }
     } else if (warp >= 4) {
-        // ===================================== epilogue =========================================
+        // ===================================== epilogue (every CTA) =============================
         const int ew = warp - 4, q = warp & 3, half = ew >> 2;
         const int n_in_tile = q * 32 + lane;
+        const uint32_t leader_tmem_empty = CG == 1 ? 0u : mapa_u32(smem_u32(&bars->tmem_empty), 0);
         uint32_t tile_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = unit; tile < num_tiles; tile += num_units) {
             const int tw = tile % p.tiles_w, tt = tile / p.tiles_w;
             mbar_wait(&bars->tmem_full, tile_phase);
             tc_fence_after();
@@ -175,10 +247,12 @@ bfp_gemm_bf16_sp_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->tmem_empty);                  // accumulator is free again
+            if (lane == 0) {                                                // accumulator is free again
+                if constexpr (CG == 1) mbar_arrive(&bars->tmem_empty); else mbar_arrive_cluster(leader_tmem_empty);
+            }
             tile_phase ^= 1;
 
-            const int n = tw * BW + n_in_tile;
+            const int n = (tw * CG + (int)rank) * BW + n_in_tile;
             const int t0 = tt * BT + half * (BT / 2);
             if (n < p.N) {
                 const float bv = p.bias ? p.bias[n] : 0.0f;
@@ -192,10 +266,11 @@ bfp_gemm_bf16_sp_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 1) __syncthreads(); else cluster_sync_all();       // the peer may still be signalling / reading this CTA
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+        if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
     }
 }
 
@@ -298,19 +373,38 @@ int gemm_bf16_sp_device(const void* x_bf16, const void* w_comp, const void* w_me
         return set_error(BFP_E_ALIGN, "operands must be 16-byte aligned");
     int64_t Kc, mb;
     sp_layout(N, Kp, &Kc, &mb);
+    const int sms = std::max(2, device_info().sm_count);
+    // CTA pairs (cta_group::2) unless the problem has a single 128-row W tile or the knob forces one CTA per tile
+    int cg = (N > 128) ? 2 : 1;
+    if (tuning().gemm_sp_cta_group == 1 || tuning().gemm_sp_cta_group == 2) cg = tuning().gemm_sp_cta_group;
     Params p;
-    p.meta = static_cast<const uint8_t*>(w_meta); p.bias = bias; p.out = out; p.T = (int)T; p.N = (int)N;
-    p.num_k_slabs = (int)((Kp + KS - 1) / KS);
+    p.bias = bias; p.out = out; p.T = (int)T; p.N = (int)N; p.debug = tuning().gemm_sp_debug;
+    p.num_k_slabs = (int)((Kp + 63) / 64);
     p.e_atoms = (int)(Kc / 64);
-    p.tiles_w = (int)((N + BW - 1) / BW);
-    p.tiles_t = (int)((T + BT - 1) / BT);
-    CUtensorMap map_w, map_x;
-    if (int rc = make_map_bf16(&map_w, w_comp, N, Kc, Kc * 2, KS / 2, BW, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
-    if (int rc = make_map_bf16(&map_x, x_bf16, T, Kp, Kp * 2, KS, BT, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    const cudaError_t e = cudaFuncSetAttribute(bfp_gemm_bf16_sp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
-    if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    const int grid = std::min(p.tiles_w * p.tiles_t, std::max(1, device_info().sm_count));
-    bfp_gemm_bf16_sp_kernel<<<grid, kThreads, kSmemTotal, st>>>(map_w, map_x, p);
+    p.tiles_w = (int)((N + 128 * cg - 1) / (128 * cg));
+    p.tiles_t = (int)((T + 255) / 256);
+    CUtensorMap map_w, map_x, map_e;
+    if (int rc = make_map_bf16(&map_w, w_comp, N, Kc, Kc * 2, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+    if (int rc = make_map_bf16(&map_x, x_bf16, T, Kp, Kp * 2, 64, 256 / cg, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_map_bytes(&map_e, w_meta, mb / 16, 16, 128)) return rc;
+    const int units = std::min(p.tiles_w * p.tiles_t, sms / cg);
+    cudaError_t e;
+    if (cg == 1) {
+        e = cudaFuncSetAttribute(bfp_gemm_bf16_sp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::kSmemTotal);
+        if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        bfp_gemm_bf16_sp_kernel<1><<<units, kThreads, Cfg<1>::kSmemTotal, st>>>(map_w, map_x, map_e, p);
+    } else {
+        e = cudaFuncSetAttribute(bfp_gemm_bf16_sp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::kSmemTotal);
+        if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)units * 2); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = Cfg<2>::kSmemTotal; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, bfp_gemm_bf16_sp_kernel<2>, map_w, map_x, map_e, p);
+        if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaLaunchKernelEx(bfp_gemm_bf16_sp_kernel<2>): %s", cudaGetErrorString(e));
+    }
     count_launch();
     return check_launch("bfp_gemm_bf16_sp_kernel");
 }

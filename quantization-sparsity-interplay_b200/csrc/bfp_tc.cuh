@@ -199,5 +199,19 @@ inline int make_map_bf16(CUtensorMap* map, const void* ptr, int64_t rows, int64_
     return BFP_OK;
 }
 
+// 2-D byte tensor map without swizzle: `rows` rows of `row_bytes` (>= 16) contiguous bytes, box = box_rows whole rows.
+inline int make_map_bytes(CUtensorMap* map, const void* ptr, int64_t rows, int row_bytes, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return set_error(BFP_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)row_bytes, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_errorf(BFP_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return BFP_OK;
+}
+
 }  // namespace gemm
 }  // namespace bfp

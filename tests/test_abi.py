@@ -130,3 +130,19 @@ def test_entry_point_exceptions_without_touching_the_gpu():
     lin.num_format = "weird"
     with pytest.raises(NotImplementedError):
         lin(t)
+
+
+def test_nm_patterns_that_fit_the_2to4_tensor_core_format():
+    """_nm_fits_2to4 against brute force: every choice of N survivors per M-group, worst aligned group of four."""
+    import itertools, math
+    from qsi_b200 import bfp_ops
+    for M in (1, 2, 3, 4, 6, 8, 12, 16):
+        for N in range(1, M):
+            period = M * 4 // math.gcd(M, 4)
+            worst = 0
+            for keeps in itertools.product(itertools.combinations(range(M), N), repeat=period // M):
+                mask = [(i % M) in keeps[i // M] for i in range(period)]
+                worst = max(worst, max(sum(mask[i:i + 4]) for i in range(0, period, 4)))
+            assert bfp_ops._nm_fits_2to4(N, M) == (worst <= 2), (N, M, worst)
+    assert bfp_ops._nm_fits_2to4(2, 4) and bfp_ops._nm_fits_2to4(1, 4) and bfp_ops._nm_fits_2to4(1, 2) and bfp_ops._nm_fits_2to4(2, 8)
+    assert not bfp_ops._nm_fits_2to4(4, 4) and not bfp_ops._nm_fits_2to4(0, 4) and not bfp_ops._nm_fits_2to4(3, 4)

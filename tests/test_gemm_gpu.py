@@ -157,7 +157,7 @@ def test_pack_bf16_equals_fake_quant(ops, dt):
             assert (pb[:, shape[-1]:] == 0).all()
 
 
-@pytest.mark.parametrize("kind", ["bf16", "i8"])
+@pytest.mark.parametrize("kind", ["sp", "bf16", "i8"])
 @pytest.mark.parametrize("first", ["s", "q"])
 @pytest.mark.parametrize("mB", [(7, 64), (5, 32), (3, 128), (3, 16)])
 def test_bfplinear_tensor_core_path_matches_oracle(ops, oracle, first, mB, kind, monkeypatch):
@@ -218,3 +218,105 @@ def test_gemm_llama7b_shapes_full_size(ops, NK):
     yb = ops.bfp_linear_bf16(ops.pack_bfp_bf16(x, identifier="in", **a), ops.pack_bfp_bf16(w, identifier="w", **a))
     assert ((yb[rows].double() - ref).norm() / ref.norm()).item() <= 1e-5
     assert ((yb - y).norm() / y.norm()).item() <= 2e-6
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 2:4 structured-sparse kind (bfp_compress_2to4_bf16 + bfp_gemm_bf16_sp, tcgen05.mma.sp)
+# ---------------------------------------------------------------------------------------------------------------------
+def _random_2to4(rows, K, g, scale=1.0):
+    """bf16 [rows, K] with at most two non-zeros per aligned group of four, including empty / single-entry groups and -0.0."""
+    w = torch.randn(rows, K, generator=g) * scale
+    grp = w.view(rows, -1, 4)
+    keep = torch.zeros_like(grp, dtype=torch.bool)
+    order = torch.rand(grp.shape, generator=g).argsort(dim=-1)
+    nkeep = torch.randint(0, 3, grp.shape[:2], generator=g)              # 0, 1 or 2 survivors
+    for j in range(2):
+        keep.scatter_(2, order[..., j:j + 1], (nkeep > j).unsqueeze(-1))
+    out = torch.where(keep, grp, torch.zeros_like(grp))
+    out[0, 0, 0] = -0.0
+    return out.view(rows, K).to(torch.bfloat16)
+
+
+def _decompress(ws, rows, K):
+    """numpy restatement of the documented layout (csrc/bfp_gemm_sp.cu header) -> dense fp32 [rows, K]."""
+    comp = ws.comp.float().cpu().numpy()
+    meta = ws.meta.cpu().numpy()
+    atoms = comp.shape[1] // 64
+    dense = np.zeros((rows, atoms * 128), dtype=np.float32)
+    for r in range(rows):
+        m = r & 127
+        m0, m1, m2 = m & 7, (m >> 3) & 1, m >> 4
+        for h in range(atoms * 8):
+            atom, k1, k2 = h >> 3, h & 1, (h >> 1) & 3
+            lane = m0 + 8 * k1 + 16 * m2
+            off = ((r >> 7) * atoms + atom) * 2048 + lane * 16 + k2 * 4 + m1 * 2
+            word = int(meta[off]) | (int(meta[off + 1]) << 8)
+            for gi in range(4):
+                nib = (word >> (4 * gi)) & 15
+                i0, i1 = nib & 3, nib >> 2
+                assert i0 < i1, (r, h, gi, nib)
+                dense[r, h * 16 + gi * 4 + i0] += comp[r, h * 8 + gi * 2]
+                dense[r, h * 16 + gi * 4 + i1] += comp[r, h * 8 + gi * 2 + 1]
+    return dense[:, :K]
+
+
+@pytest.mark.parametrize("shape", [(128, 128), (200, 264), (5, 8), (300, 1000)])
+def test_compress_2to4_layout_round_trip(ops, shape):
+    rows, K = shape
+    g = torch.Generator().manual_seed(rows * 7 + K)
+    wb = _random_2to4(rows, K, g).cuda()
+    ws = ops.compress_2to4_bf16(wb)
+    from qsi_b200 import _lib
+    Kc, mb = _lib.sp_layout(rows, K)
+    assert tuple(ws.comp.shape) == (rows, Kc) and ws.meta.numel() == mb and Kc == -(-K // 128) * 64
+    assert np.array_equal(_decompress(ws, rows, K), wb.float().cpu().numpy())
+
+
+def test_compress_rejects_dense_groups(ops):
+    wb = torch.zeros(16, 64, dtype=torch.bfloat16, device="cuda")
+    wb[3, 8:11] = 1.0                                  # three non-zeros in one group of four
+    with pytest.raises(ValueError):
+        ops.compress_2to4_bf16(wb)
+    assert ops.compress_2to4_bf16(wb, check=False).comp.shape == (16, 64)
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("shape", [(256, 128, 128), (512, 256, 448), (300, 200, 264), (77, 300, 136), (1, 8, 72), (1000, 1536, 2048)])
+def test_gemm_sp_exact_products(ops, shape, cta_group):
+    """Small-integer operands: the sparse kernel must return the exact integer matmul, for both CTA-group modes."""
+    from qsi_b200 import _lib
+    T, N, K = shape
+    g = torch.Generator().manual_seed(T + 3 * N + K)
+    wb = (_random_2to4(N, -(-K // 8) * 8, g) * 4).round().clamp(-15, 15).to(torch.bfloat16)
+    wb[:, K:] = 0
+    xb = torch.zeros(T, wb.shape[1], dtype=torch.bfloat16)
+    xb[:, :K] = torch.randint(-15, 16, (T, K), generator=g).to(torch.bfloat16)
+    bias = torch.randint(-5, 6, (N,), generator=g).float()
+    ref = xb.double() @ wb.double().t() + bias.double()
+    _lib.set_option("gemm_sp_cta_group", cta_group)
+    try:
+        y = ops.bfp_linear_bf16_sp(xb.cuda(), ops.compress_2to4_bf16(wb.cuda()), bias.cuda())
+    finally:
+        _lib.set_option("gemm_sp_cta_group", 0)
+    assert torch.equal(y.double().cpu(), ref)
+
+
+@pytest.mark.parametrize("NK", [(4096, 4096), (11008, 4096), (4096, 11008)])
+def test_gemm_sp_llama7b_shapes_full_size(ops, NK):
+    """BASELINE LLaMA-7B shapes, T = 4096, HBFP8 block 64, 2:4 s->q weights: sparse kernel == dense exact-bf16 kernel on the
+    uncompressed operand (same products, fp32 accumulation), and within 1e-5 of the fp64 matmul."""
+    N, K = NK
+    T = 4096
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(T, K, device="cuda", generator=g)
+    x[::97, ::53] *= 20.0
+    w = torch.randn(N, K, device="cuda", generator=g) * 0.02
+    a = ops.unpack_bfp_args(dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", mant_bits=7, block_size=64,
+                                 w_sparsity=True, N=2, M=4, first="s", sparsity_mode="structured", device="cuda"))
+    xb, wb = ops.pack_bfp_bf16(x, identifier="in", **a), ops.pack_bfp_bf16(w, identifier="w", **a)
+    y = ops.bfp_linear_bf16_sp(xb, ops.compress_2to4_bf16(wb))
+    yd = ops.bfp_linear_bf16(xb, wb)
+    assert ((y - yd).norm() / yd.norm()).item() <= 1e-6
+    rows = torch.arange(0, T, 61, device="cuda")
+    ref = xb[rows].double() @ wb.double().t()
+    assert ((y[rows].double() - ref).norm() / ref.norm()).item() <= 1e-5

@@ -1,0 +1,41 @@
+"""Dense vs 2:4-sparse exact-bf16 BFP GEMM at the LLaMA shapes (device-resident operands, CUDA events, rotating outputs)."""
+import argparse, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from qsi_b200 import _lib, bfp_ops as ops
+ap = argparse.ArgumentParser(); ap.add_argument("--iters", type=int, default=20); ap.add_argument("--out", default="")
+ap.add_argument("--shapes", default="7b,13b,65b"); a = ap.parse_args()
+SH = {"7b": [(4096, 4096, 4096), (4096, 11008, 4096), (4096, 4096, 11008)], "13b": [(4096, 5120, 5120), (4096, 13824, 5120), (4096, 5120, 13824)],
+      "65b": [(4096, 8192, 8192), (4096, 22016, 8192), (4096, 8192, 22016)]}
+kw = ops.unpack_bfp_args(dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", mant_bits=7, block_size=64,
+                              w_sparsity=True, N=2, M=4, first="s", sparsity_mode="structured", device="cuda"))
+L = _lib.lib(); res = []
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def timeit(fn, iters):
+    for _ in range(3): fn()
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(iters): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+for (T, N, K) in sum((SH[s] for s in a.shapes.split(",")), []):
+    x = torch.randn(T, K, device="cuda"); w = torch.randn(N, K, device="cuda") * 0.02
+    xb, wb = ops.pack_bfp_bf16(x, identifier="in", **kw), ops.pack_bfp_bf16(w, identifier="w", **kw)
+    ws = ops.compress_2to4_bf16(wb)
+    out = torch.empty(T, N, device="cuda"); st = torch.cuda.current_stream().cuda_stream
+    md = timeit(lambda: _lib.check(L.bfp_gemm_bf16(xb.data_ptr(), wb.data_ptr(), None, out.data_ptr(), T, N, K, st)), a.iters)
+    yd = out.clone()
+    _lib.set_option("gemm_sp_cta_group", 1)
+    msp1 = timeit(lambda: _lib.check(L.bfp_gemm_bf16_sp(xb.data_ptr(), ws.comp.data_ptr(), ws.meta.data_ptr(), None, out.data_ptr(), T, N, K, st)), a.iters)
+    _lib.set_option("gemm_sp_cta_group", 0)
+    msp = timeit(lambda: _lib.check(L.bfp_gemm_bf16_sp(xb.data_ptr(), ws.comp.data_ptr(), ws.meta.data_ptr(), None, out.data_ptr(), T, N, K, st)), a.iters)
+    rel = float((out - yd).norm() / yd.norm())
+    mc = timeit(lambda: ops.compress_2to4_bf16(wb, check=False), 5)
+    ops_ = 2.0 * T * N * K
+    print(f"T={T} N={N} K={K}: dense {md:.3f} ms = {ops_/md/1e9:.0f} TOPS | 2:4 sparse {msp:.3f} ms = {ops_/msp/1e9:.0f} dense-equivalent TOPS "
+          f"({ops_/msp/1e9/4500*100:.1f}% of 4500) x{md/msp:.2f} [1-CTA kernel: {ops_/msp1/1e9:.0f}] | rel diff {rel:.1e} | compress W {mc*1e3:.0f} us", flush=True)
+    res.append(dict(T=T, N=N, K=K, dense_ms=md, dense_tops=ops_ / md / 1e9, sparse_ms=msp, sparse_1cta_ms=msp1, sparse_tops_dense_equiv=ops_ / msp / 1e9, rel_diff=rel, compress_ms=mc))
+if a.out: json.dump(res, open(a.out, "w"), indent=1)

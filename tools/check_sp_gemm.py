@@ -42,9 +42,13 @@ def diag():
 
 def main():
     ap = argparse.ArgumentParser(); ap.add_argument("--diag", action="store_true"); a = ap.parse_args()
-    ok = diag()
-    worst = 0.0
-    for (T, N, K) in [(256, 128, 128), (512, 256, 448), (300, 200, 264), (4096, 4096, 4096), (1000, 11008, 4096)]:
+    from qsi_b200 import _lib
+    ok, worst = True, 0.0
+    for cg in (1, 2):
+      _lib.set_option("gemm_sp_cta_group", cg)
+      print("cta_group", cg)
+      ok = diag() and ok
+      for (T, N, K) in [(256, 128, 128), (512, 256, 448), (300, 200, 264), (77, 300, 136), (4096, 4096, 4096), (1000, 11008, 4096)]:
         torch.manual_seed(T + N + K)
         x = torch.randn(T, K, device="cuda"); w = torch.randn(N, K, device="cuda") * 0.02
         bias = torch.randn(N, device="cuda")
@@ -57,7 +61,7 @@ def main():
         rel_sp = float((y_sp.double() - ref).norm() / ref.norm()); rel_d = float((y_d.double() - ref).norm() / ref.norm())
         mx = float((y_sp.double() - ref).abs().max() / ref.abs().max())
         worst = max(worst, rel_sp)
-        print(f"T={T} N={N} K={K}: sparse rel {rel_sp:.3e} (max {mx:.3e}), dense rel {rel_d:.3e}, finite {bool(torch.isfinite(y_sp).all())}")
+        print(f"  T={T} N={N} K={K}: sparse rel {rel_sp:.3e} (max {mx:.3e}), dense rel {rel_d:.3e}, finite {bool(torch.isfinite(y_sp).all())}")
     print("RESULT", "PASS" if ok and worst <= 1e-5 else "FAIL", worst)
 
 

@@ -1,4 +1,4 @@
-"""A few launches of one GEMM kind for ncu.  python tools/prof_gemm.py [i8|bf16] [B] [T N K]"""
+"""A few launches of one GEMM kind for ncu.  python tools/prof_gemm.py [i8|bf16|sp|sp1] [B] [T N K]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -12,6 +12,11 @@ kw = ops.unpack_bfp_args(dict(num_format="bfp", sparsity_num_format="bfp", round
 if kind == "i8":
     xp, wp = ops.pack_bfp(x, identifier="in", **kw), ops.pack_bfp(w, identifier="w", **kw)
     for _ in range(4): y = ops.bfp_linear_packed(xp, wp)
+elif kind in ("sp", "sp1"):
+    _lib.set_option("gemm_sp_cta_group", 1 if kind == "sp1" else 0)
+    xb, wb = ops.pack_bfp_bf16(x, identifier="in", **kw), ops.pack_bfp_bf16(w, identifier="w", **kw)
+    ws = ops.compress_2to4_bf16(wb)
+    for _ in range(4): y = ops.bfp_linear_bf16_sp(xb, ws)
 else:
     xb, wb = ops.pack_bfp_bf16(x, identifier="in", **kw), ops.pack_bfp_bf16(w, identifier="w", **kw)
     for _ in range(4): y = ops.bfp_linear_bf16(xb, wb)
