@@ -21,6 +21,7 @@ struct Tuning {
     int stream_ctas_per_sm = 8;           // resident CTAs of the stream kernel per SM (grid = sm_count * this)
     int force_generic = 0;                // tests: route everything through the generic kernel
     int64_t host_chunk_bytes = 8 << 20;
+    int pdl = 1;                          // programmatic dependent launch for the streaming kernels (bfp_stream.cuh)
     int gemm_sp_debug = 0;                // timing experiments (wrong results): see bfp_gemm_sp.cu Params::debug
     int gemm_sp_cta_group = 0;            // 0 = CTA pairs (cta_group::2) when N > 128; 1 or 2 forces the mode
     int gemm_bf16_tile_n = 0;             // 0 = default tile (128x256); 128 or 256 forces the width  // bfp_quantize_host: input bytes per pipelined chunk

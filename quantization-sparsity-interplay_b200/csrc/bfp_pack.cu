@@ -52,6 +52,9 @@ __global__ void __launch_bounds__(kStreamThreads) pack_stream_kernel(const PackP
     constexpr int kTileVecs = kStreamThreads * kStreamUnroll;
     const int64_t n_tiles = (p.n_vec + kTileVecs - 1) / kTileVecs;
 
+    pdl_launch_dependents();          // see bfp_stream.cuh: launch overlap only, stream order preserved by pdl_wait
+    pdl_wait();
+
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t tile_base = tile * kTileVecs;
         const int rem = (int)min((int64_t)kTileVecs, p.n_vec - tile_base);
@@ -201,8 +204,9 @@ static int launch_pack_stream(const PackParams& p, bool sparse, cudaStream_t st)
     static const int occ_s = kernel_occupancy(pack_stream_kernel<DT, ORDER, 4, 2, STOC, FMT>, kStreamThreads);
     static const int occ_d = kernel_occupancy(pack_stream_kernel<DT, BFP_ORDER_QUANT_ONLY, 0, 0, STOC, FMT>, kStreamThreads);
     const int grid = stream_grid(sparse ? occ_s : occ_d, n_tiles);
-    if (sparse) pack_stream_kernel<DT, ORDER, 4, 2, STOC, FMT><<<grid, kStreamThreads, 0, st>>>(p);
-    else pack_stream_kernel<DT, BFP_ORDER_QUANT_ONLY, 0, 0, STOC, FMT><<<grid, kStreamThreads, 0, st>>>(p);
+    if (int rc = sparse ? launch_pdl(pack_stream_kernel<DT, ORDER, 4, 2, STOC, FMT>, grid, kStreamThreads, st, p)
+                        : launch_pdl(pack_stream_kernel<DT, BFP_ORDER_QUANT_ONLY, 0, 0, STOC, FMT>, grid, kStreamThreads, st, p))
+        return rc;
     count_launch();
     return check_launch("pack_stream_kernel");
 }

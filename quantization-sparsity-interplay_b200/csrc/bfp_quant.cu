@@ -46,6 +46,11 @@ __global__ void __launch_bounds__(kStreamThreads) quant_stream_kernel(const Stre
 
     const int64_t n_tiles = (p.n_vec + kTileVecs - 1) / kTileVecs;
 
+    // Programmatic dependent launch: let the next kernel on the stream get its CTAs resident while this one drains, and
+    // do not touch global memory before everything earlier on the stream has completed (stream order is preserved).
+    pdl_launch_dependents();
+    pdl_wait();
+
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t tile_base = tile * kTileVecs;
         const int rem = (int)min((int64_t)kTileVecs, p.n_vec - tile_base);   // vectors of this tile that exist
@@ -207,7 +212,7 @@ static int launch_stream_t(const StreamParams& p, cudaStream_t st) {
     static const int occ = kernel_occupancy(quant_stream_kernel<DT, ORDER, M, KD, TIE, STOC>, kStreamThreads);
     const int grid = stream_grid(occ, n_tiles);
     (void)di;
-    quant_stream_kernel<DT, ORDER, M, KD, TIE, STOC><<<grid, kStreamThreads, 0, st>>>(p);
+    if (int rc = launch_pdl(quant_stream_kernel<DT, ORDER, M, KD, TIE, STOC>, grid, kStreamThreads, st, p)) return rc;
     count_launch();
     return check_launch("quant_stream_kernel");
 }

@@ -1,11 +1,33 @@
 // bfp_stream.cuh -- helpers shared by the streaming kernels (fake-quant in bfp_quant.cu, packed in bfp_pack.cu).
 #pragma once
 #include "bfp_common.cuh"
+#include "bfp_internal.h"
 
 namespace bfp {
 
 constexpr int kStreamThreads = 256;
 constexpr int kStreamUnroll = 4;
+
+// ---------------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A kernel launched with launch_pdl may have its CTAs scheduled while the previous
+// kernel on the stream is still draining; pdl_wait() blocks until that kernel has completed and its writes are visible, so
+// stream-order semantics are unchanged -- only launch latency and the CTA prologue overlap the predecessor's tail.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class Kernel, class Params>
+inline int launch_pdl(Kernel kernel, int grid, int threads, cudaStream_t st, const Params& p) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = tuning().pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
+    if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaLaunchKernelEx: %s", cudaGetErrorString(e));
+    return BFP_OK;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // 128-bit streaming loads / stores

@@ -336,3 +336,35 @@ def test_bfp_linear_module_matches_oracle(ops, oracle):
     bq, _ = oracle.float_to_bfp_blocked(b.transpose(-1, -2).contiguous().cpu().numpy(), 7, 64, "sq")
     ref = np.matmul(aq.astype(np.float64), np.swapaxes(bq, -1, -2).astype(np.float64))
     assert np.linalg.norm(out.cpu().numpy() - ref) / np.linalg.norm(ref) <= 1e-5
+
+
+def test_pdl_launches_keep_stream_order():
+    """The streaming kernels are launched with programmatic stream serialization (their CTAs may be scheduled while the
+    previous kernel drains).  A chain of dependent calls -- each reads what the previous one wrote, in place included, with
+    torch kernels in between -- must give exactly the result of the same chain with PDL off and a sync after every step."""
+    from qsi_b200 import _lib, bfp_ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x0 = torch.randn(2048, 4096, device="cuda", generator=g)
+    args = bfp_ops.unpack_bfp_args(dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, block_size=64,
+                                        w_sparsity=True, N=2, M=4, sparsity_mode="structured", device="cuda"))
+
+    def chain(sync):
+        y = x0.clone()
+        for step in range(12):
+            m = 7 - (step % 5)
+            y = bfp_ops.float_to_bfp_blocked(y * 1.25 + 0.01, **dict(args, mant_bits=m, first="s" if step % 2 else "q"), identifier="w")
+            if sync:
+                torch.cuda.synchronize()
+            p = bfp_ops.pack_bfp_bf16(y, identifier="in", **dict(args, mant_bits=m))
+            y = p.float() + y
+            if sync:
+                torch.cuda.synchronize()
+        return y
+
+    _lib.set_option("pdl", 0)
+    try:
+        ref = chain(True)
+    finally:
+        _lib.set_option("pdl", 1)
+    for _ in range(3):
+        assert torch.equal(chain(False), ref)
