@@ -66,7 +66,11 @@ uint64_t bfp_launch_count(void);
 /* Runtime knobs (also read once from the environment: BFP_STREAM_CTAS_PER_SM, BFP_FORCE_GENERIC, BFP_HOST_CHUNK_MB):
  *   "stream_ctas_per_sm"  resident CTAs per SM the streaming quantiser sizes its grid for (default 8)
  *   "force_generic"       1 = route every call through the generic (ragged-shape) kernel; for tests
- *   "host_chunk_bytes"    input bytes per pipelined chunk of bfp_quantize_host (default 8 MiB)
+ *   "host_chunk_bytes"    largest pipelined chunk of bfp_quantize_host, input bytes (default 16 MiB)
+ *   "host_chunk_min_bytes" smallest chunk of its tapered schedule: chunks double from here at the start and halve towards
+ *                         the end, so pipeline fill and drain cost one small chunk each (default 1 MiB)
+ *   "pdl"                 1 (default) = the streaming kernels are launched with programmatic stream serialization
+ *   "gemm_sp_cta_group"   0 = bfp_gemm_bf16_sp uses CTA pairs (cta_group::2) when N > 128; 1 / 2 forces the mode
  *   "gemm_bf16_tile_n"    0 = bfp_gemm_bf16 uses its 128x256 tile (128x128 when N <= 128); 128 / 256 forces one */
 int bfp_set_option(const char* name, int64_t value);
 

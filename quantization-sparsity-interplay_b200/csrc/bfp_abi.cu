@@ -125,6 +125,7 @@ int bfp_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "stream_ctas_per_sm") && value > 0 && value <= 32) t.stream_ctas_per_sm = (int)value;
     else if (!strcmp(name, "force_generic")) t.force_generic = value != 0;
     else if (!strcmp(name, "host_chunk_bytes") && value >= 4096) t.host_chunk_bytes = value;
+    else if (!strcmp(name, "host_chunk_min_bytes") && value >= 4096) t.host_chunk_min_bytes = value;
     else if (!strcmp(name, "pdl") && (value == 0 || value == 1)) t.pdl = (int)value;
     else if (!strcmp(name, "gemm_sp_debug") && value >= 0 && value <= 7) t.gemm_sp_debug = (int)value;
     else if (!strcmp(name, "gemm_sp_cta_group") && value >= 0 && value <= 2) t.gemm_sp_cta_group = (int)value;

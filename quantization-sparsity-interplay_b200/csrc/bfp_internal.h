@@ -20,7 +20,8 @@ const DeviceInfo& device_info();          // of the current device (cached per d
 struct Tuning {
     int stream_ctas_per_sm = 8;           // resident CTAs of the stream kernel per SM (grid = sm_count * this)
     int force_generic = 0;                // tests: route everything through the generic kernel
-    int64_t host_chunk_bytes = 8 << 20;
+    int64_t host_chunk_bytes = 16 << 20;      // bfp_quantize_host: largest pipelined chunk (input bytes)
+    int64_t host_chunk_min_bytes = 1 << 20;   // ... and the smallest (first / last chunks of the tapered schedule)
     int pdl = 1;                          // programmatic dependent launch for the streaming kernels (bfp_stream.cuh)
     int gemm_sp_debug = 0;                // timing experiments (wrong results): see bfp_gemm_sp.cu Params::debug
     int gemm_sp_cta_group = 0;            // 0 = CTA pairs (cta_group::2) when N > 128; 1 or 2 forces the mode
