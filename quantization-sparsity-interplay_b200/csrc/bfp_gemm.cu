@@ -263,12 +263,15 @@ bfp_gemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 // ================================================================================================================
 // Two tile widths: 128x256 (4 stages of 48 KB, the default) and 128x128 (6 stages of 32 KB; for N <= 128 or forced with
 // bfp_set_option("gemm_bf16_tile_n", 128)).
-template <int TBN> struct Bf16Cfg {
-    static constexpr int kStages = TBN == 256 ? 4 : 6;
-    static constexpr int kStageBytes = kSmemA + TBN * BKB;
+// CG = 2: a cluster pair shares a 256 x 256 tile through tcgen05.mma.cta_group::2 (each CTA stages 128 rows of X and 128
+// rows of W per slab: 32 KB instead of 48 KB for the same MMA time, so the operand stream per SM drops by a third).
+template <int TBN, int CG> struct Bf16Cfg {
+    static constexpr int kRowsB = TBN / CG;                 // W rows staged by one CTA
+    static constexpr int kStageBytes = kSmemA + kRowsB * BKB;
+    static constexpr int kStages = CG == 2 ? 6 : (TBN == 256 ? 4 : 6);
     static constexpr int kSmemTotal = kStages * kStageBytes + kSmemBarriers + 1024;
-    // D = F32 (1 << 4), A = B = BF16 (1 << 7, 1 << 10), K-major, N >> 3, M >> 4
-    static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    // D = F32 (1 << 4), A = B = BF16 (1 << 7, 1 << 10), K-major, N >> 3, M >> 4 (M = 128 per CTA)
+    static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
     static constexpr int kColsPerThread = TBN / 2;          // 8 epilogue warps: 4 lane quarters x 2 column halves
 };
 
@@ -277,15 +280,23 @@ struct ParamsBf16 {
     float* out;
     int T, N;
     int num_k_stages;           // ceil(K / 64)
-    int tiles_m, tiles_n;
+    int tiles_m, tiles_n;       // tiles_m counts CG * 128 rows
 };
 
+template <int CG>
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    if constexpr (CG == 1)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 struct BarriersBf16 {
@@ -296,53 +307,63 @@ struct BarriersBf16 {
     uint32_t tmem_base;
 };
 
-template <int TBN>
+template <int TBN, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ParamsBf16 p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    using C = Bf16Cfg<TBN>;
+    using C = Bf16Cfg<TBN, CG>;
     constexpr int kStagesBf16 = C::kStages, kStageBytesBf16 = C::kStageBytes, kCols = C::kColsPerThread;
     BarriersBf16* bars = reinterpret_cast<BarriersBf16*>(smem + kStagesBf16 * kStageBytesBf16);
     auto stage_a = [&](int s) { return smem + s * kStageBytesBf16; };
     auto stage_b = [&](int s) { return smem + s * kStageBytesBf16 + kSmemA; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();
+    const int unit = (int)blockIdx.x / CG, num_units = (int)gridDim.x / CG;
     const int num_tiles = p.tiles_m * p.tiles_n;
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStagesBf16; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], kEpiWarps); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], kEpiWarps * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(kTmemCols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if constexpr (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 1) __syncthreads(); else cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = unit; tile < num_tiles; tile += num_units) {
                 const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
+                const int a_row = (tm * CG + (int)rank) * BM;                 // this CTA's 128 X rows
+                const int b_row = tn * TBN + (int)rank * C::kRowsB;           // this CTA's share of the W tile
                 for (int ks = 0; ks < p.num_k_stages; ++ks) {
                     mbar_wait(&bars->empty[stage], phase ^ 1);
-                    mbar_expect_tx(&bars->full[stage], kStageBytesBf16);
-                    tma_load_2d(stage_a(stage), &map_a, &bars->full[stage], ks * 64, tm * BM);
-                    tma_load_2d(stage_b(stage), &map_b, &bars->full[stage], ks * 64, tn * TBN);
+                    if (rank == 0) mbar_expect_tx(&bars->full[stage], (uint32_t)CG * kStageBytesBf16);   // both CTAs' bytes land on the leader
+                    const uint32_t bar = CG == 1 ? smem_u32(&bars->full[stage]) : mapa_u32(smem_u32(&bars->full[stage]), 0);
+                    tma_load_2d_to<CG>(stage_a(stage), &map_a, bar, ks * 64, a_row);
+                    tma_load_2d_to<CG>(stage_b(stage), &map_b, bar, ks * 64, b_row);
                     if (++stage == kStagesBf16) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {
             int stage = 0; uint32_t phase = 0;
             int buf = 0; uint32_t buf_phase[2] = {0, 0};
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = unit; tile < num_tiles; tile += num_units) {
                 mbar_wait(&bars->tmem_empty[buf], buf_phase[buf] ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)buf * TBN;
@@ -353,11 +374,11 @@ bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     const uint64_t db = make_smem_desc(smem_u32(stage_b(stage)));
 #pragma unroll
                     for (int i = 0; i < 4; ++i)         // 16 bf16 = 32 bytes of K per MMA: +2 in 16-byte units
-                        mma_bf16(d, da + (uint64_t)(i * 2), db + (uint64_t)(i * 2), C::kIdesc, (ks | i) != 0);
-                    tc_commit(&bars->empty[stage]);
+                        mma_bf16<CG>(d, da + (uint64_t)(i * 2), db + (uint64_t)(i * 2), C::kIdesc, (ks | i) != 0);
+                    commit<CG>(&bars->empty[stage]);
                     if (++stage == kStagesBf16) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&bars->tmem_full[buf]);
+                commit<CG>(&bars->tmem_full[buf]);
                 buf_phase[buf] ^= 1;
                 buf ^= 1;
             }
@@ -366,12 +387,12 @@ bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const int ew = warp - 4, q = warp & 3, half = ew >> 2;
         const int row_in_tile = q * 32 + lane;
         int buf = 0; uint32_t buf_phase[2] = {0, 0};
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = unit; tile < num_tiles; tile += num_units) {
             const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
             mbar_wait(&bars->tmem_full[buf], buf_phase[buf]);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TBN + half * kCols);
-            const int t = tm * BM + row_in_tile;
+            const int t = (tm * CG + (int)rank) * BM + row_in_tile;
             const int n0 = tn * TBN + half * kCols;
             float* dst = p.out + (int64_t)t * p.N + n0;
             const bool vec_ok = (p.N % 4 == 0) && (n0 + kCols <= p.N);
@@ -400,20 +421,23 @@ bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
+            if (lane == 0) {
+                if constexpr (CG == 1) mbar_arrive(&bars->tmem_empty[buf]);
+                else mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[buf]), 0));
+            }
             buf_phase[buf] ^= 1;
             buf ^= 1;
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 1) __syncthreads(); else cluster_sync_all();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+        if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
     }
 }
-
 
 }  // namespace gemm
 
@@ -447,6 +471,23 @@ int gemm_i8_device(const int8_t* a_mant, const float* a_scale_t, int64_t lda_s, 
     return check_launch("bfp_gemm_i8_kernel");
 }
 
+template <int TBN, int CG>
+static int launch_bf16(const CUtensorMap& map_a, const CUtensorMap& map_b, const gemm::ParamsBf16& p, int units, cudaStream_t st) {
+    using namespace gemm;
+    using C = Bf16Cfg<TBN, CG>;
+    cudaError_t e = cudaFuncSetAttribute(bfp_gemm_bf16_kernel<TBN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemTotal);
+    if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(units * CG)); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = C::kSmemTotal; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, bfp_gemm_bf16_kernel<TBN, CG>, map_a, map_b, p);
+    if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaLaunchKernelEx(bfp_gemm_bf16_kernel): %s", cudaGetErrorString(e));
+    return BFP_OK;
+}
+
 int gemm_bf16_device(const void* a_bf16, const void* b_bf16, const float* bias, float* out, int64_t T, int64_t N, int64_t Kp,
                      cudaStream_t st) {
     using namespace gemm;
@@ -458,28 +499,27 @@ int gemm_bf16_device(const void* a_bf16, const void* b_bf16, const float* bias, 
     ParamsBf16 p;
     p.bias = bias; p.out = out; p.T = (int)T; p.N = (int)N;
     p.num_k_stages = (int)((Kp + 63) / 64);
-    p.tiles_m = (int)((T + BM - 1) / BM);
-    // tile width: 128x256 unless N fits a narrow tile.  (Measured on B200, profiles/r01_gemm_bench_v3_tiles.log: the
-    // 128x128 tile is operand-feed-bound at ~1.05 PFLOP/s and loses to 128x256 (1.24-1.45) even where its wave
-    // efficiency is better, e.g. 4096x4096: 6.92 vs 3.46 waves.)
-    const int sms = std::max(1, device_info().sm_count);
+    // tile: CTA pairs on 256x256 (cta_group::2) unless the problem is a single 128-row or 128-column strip; the knobs
+    // gemm_bf16_cta_group (1 / 2) and gemm_bf16_tile_n (128 / 256, single-CTA mode only) force a variant.
+    // (Measured on B200, profiles/r01_gemm_bench_v3_tiles.log: the 128x128 tile is operand-feed-bound at ~1.05 PFLOP/s
+    // and loses to 128x256 (1.24-1.45) even where its wave efficiency is better.)
+    const int sms = std::max(2, device_info().sm_count);
+    int cg = (T > 128 && N > 128) ? 2 : 1;
+    if (tuning().gemm_bf16_cta_group == 1 || tuning().gemm_bf16_cta_group == 2) cg = tuning().gemm_bf16_cta_group;
     int tbn = N <= 128 ? 128 : 256;
-    if (tuning().gemm_bf16_tile_n == 128 || tuning().gemm_bf16_tile_n == 256) tbn = tuning().gemm_bf16_tile_n;
+    if (tuning().gemm_bf16_tile_n == 128 || tuning().gemm_bf16_tile_n == 256) { tbn = tuning().gemm_bf16_tile_n; if (tbn == 128) cg = 1; }
+    if (cg == 2) tbn = 256;
+    p.tiles_m = (int)((T + BM * cg - 1) / (BM * cg));
     p.tiles_n = (int)((N + tbn - 1) / tbn);
     CUtensorMap map_a, map_b;
     if (int rc = make_map(&map_a, a_bf16, T, Kp * 2, BM, true)) return rc;
-    if (int rc = make_map(&map_b, b_bf16, N, Kp * 2, tbn, true)) return rc;
-    const int grid = std::min(p.tiles_m * p.tiles_n, sms);
-    cudaError_t e;
-    if (tbn == 256) {
-        e = cudaFuncSetAttribute(bfp_gemm_bf16_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bf16Cfg<256>::kSmemTotal);
-        if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        bfp_gemm_bf16_kernel<256><<<grid, kThreads, Bf16Cfg<256>::kSmemTotal, st>>>(map_a, map_b, p);
-    } else {
-        e = cudaFuncSetAttribute(bfp_gemm_bf16_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Bf16Cfg<128>::kSmemTotal);
-        if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        bfp_gemm_bf16_kernel<128><<<grid, kThreads, Bf16Cfg<128>::kSmemTotal, st>>>(map_a, map_b, p);
-    }
+    if (int rc = make_map(&map_b, b_bf16, N, Kp * 2, tbn / cg, true)) return rc;
+    const int units = std::min(p.tiles_m * p.tiles_n, sms / cg);
+    int rc;
+    if (cg == 2) rc = launch_bf16<256, 2>(map_a, map_b, p, units, st);
+    else if (tbn == 256) rc = launch_bf16<256, 1>(map_a, map_b, p, units, st);
+    else rc = launch_bf16<128, 1>(map_a, map_b, p, units, st);
+    if (rc) return rc;
     count_launch();
     return check_launch("bfp_gemm_bf16_kernel");
 }

@@ -17,11 +17,15 @@
 // i.e. one 16-bit word per (row, 16 logical k) holding four nibbles idx0 | idx1 << 2 (positions of the two kept values).
 // (Layout restated from the public CUTLASS headers: Sm1xxGemmSparseConfig::TensorEAtom_MMA_F16 / UMMA::tmem_e_frg.)
 //
-// Kernel: persistent, one CTA per SM, 384 threads.  warp 0 = TMA producer (W slab 128 x 64 B SWIZZLE_64B, X slab
-// 256 x 128 B SWIZZLE_128B per 64 logical k; the E atom every second slab), warp 1 = MMA issuer (tcgen05.cp of E, two
-// MMAs per slab), warp 2 = TMEM allocator, warps 4-11 = epilogue.  TMEM: 256 accumulator columns + a 4-atom ring of E
-// columns; the single accumulator is drained into registers in one burst and handed back before the stores, so the
-// next tile's MMAs wait only for the tcgen05.ld burst, not for the global stores.
+// Kernel: persistent, 384 threads per CTA.  warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps
+// 4-11 = epilogue.  One smem slab = 128 logical k = one E atom = four MMAs: W 128 rows x 128 B (64 kept bf16), X two
+// 64-k swizzle atoms of XR rows x 128 B, E 2 KB as 16 TMA rows of 128 B -- every TMA row is a full 128 bytes because the
+// copy engine is request-rate-bound (measured ~2 clk per row: a 64-k slab with 64-byte W rows ran at 260 clk per MMA,
+// tools/exp_sp_mma_rate.py).  The E atom goes to TMEM by tcgen05.cp.128x128b into an 8-atom ring of columns (odd columns
+// are addressed through the sparsity selector); the single 256-column accumulator is drained into registers in one
+// tcgen05.ld burst and handed back before the global stores, so the next tile's MMAs wait only for the burst.
+// CG = 2 (default): a cluster pair issues cta_group::2 MMAs on a 256 x 256 tile, each CTA staging its own 128 W rows and
+// half of X; both CTAs' TMA bytes complete on the leader's mbarrier, tcgen05.commit multicasts the releases.
 #include <cuda.h>
 
 #include <algorithm>
@@ -41,28 +45,29 @@ template <int CG> struct Cfg {
     static constexpr int BW = 128;                       // out-features (rows of W) per CTA = TMEM lanes
     static constexpr int BT = 256;                       // tokens per tile = accumulator columns
     static constexpr int XR = BT / CG;                   // X rows staged by one CTA
-    static constexpr int KS = 64;                        // logical k per smem slab
-    static constexpr int kSmemW = BW * (KS / 2) * 2;     // 8 KB: 32 kept bf16 per row
-    static constexpr int kSmemX = XR * KS * 2;           // 32 KB / 16 KB
-    static constexpr int kSmemE = 2048;                  // one E atom (128 logical k), filled on even slabs
-    static constexpr int kStageBytes = kSmemW + kSmemX + kSmemE;      // 43008 / 26624, multiples of 1024
-    static constexpr int kStages = CG == 1 ? 5 : 8;
+    static constexpr int KS = 128;                       // logical k per smem slab = one E atom = four MMAs
+    static constexpr int kSmemW = BW * (KS / 2) * 2;     // 16 KB: 64 kept bf16 = one 128-byte swizzle row per W row
+    static constexpr int kSmemXAtom = XR * 128;          // one 64-k swizzle atom of X: 32 KB / 16 KB
+    static constexpr int kSmemX = 2 * kSmemXAtom;        // two atoms per slab
+    static constexpr int kSmemE = 2048;                  // one E atom
+    static constexpr int kStageBytes = kSmemW + kSmemX + kSmemE;      // 83968 / 51200, multiples of 1024
+    static constexpr int kStages = CG == 1 ? 2 : 4;
     static constexpr int kSmemTotal = kStages * kStageBytes + 1024 + 1024;
     // D = F32, A = B = BF16, K-major, N = BT, M = BW * CG, sparse flag (bit 2); bits 0-1 = sparsity selector
     static constexpr uint32_t kIdesc = (1u << 2) | (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BT >> 3) << 17) | ((uint32_t)((BW * CG) >> 4) << 24);
 };
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 4;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + kEpiWarps * 32;
 constexpr int kTmemCols = 512;
 constexpr int kTmemE = 256;                  // first E column
-constexpr int kERing = 8;                    // E atoms resident in TMEM: 2 * kERing - 1 >= kMaxStages (reuse argument in the MMA warp)
+constexpr int kERing = 8;                    // E atoms resident in TMEM: kERing > kMaxStages (reuse argument in the MMA warp)
 
 struct Params {
     const float* bias;          // [N] or nullptr
     float* out;                 // [T][N]
     int T, N;
-    int num_k_slabs;            // ceil(K / 64)
+    int num_k_slabs;            // ceil(K / 128)
     int e_atoms;                // ceil(K / 128)
     int tiles_w, tiles_t;       // tiles_w counts CG * 128 rows
     int debug;                  // timing experiments only (wrong results): bit 0 = every tile loads X tile 0, bit 1 = W tile 0
@@ -97,40 +102,6 @@ __device__ __forceinline__ void tmem_cp_128x128b(uint32_t tmem_dst, uint64_t sme
     if constexpr (CG == 1) asm volatile("tcgen05.cp.cta_group::1.128x128b [%0], %1;" ::"r"(tmem_dst), "l"(smem_desc) : "memory");
     else asm volatile("tcgen05.cp.cta_group::2.128x128b [%0], %1;" ::"r"(tmem_dst), "l"(smem_desc) : "memory");
 }
-// tcgen05.commit: CG = 2 arrives on the barrier at the same offset in both CTAs of the pair
-template <int CG>
-__device__ __forceinline__ void commit(uint64_t* bar) {
-    if constexpr (CG == 1) tc_commit(bar);
-    else asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                      ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-// TMA tile load whose completion bytes land on `bar_addr` (a shared::cluster address; for CG = 2 the pair leader's barrier)
-template <int CG>
-__device__ __forceinline__ void tma_load_2d_to(void* dst, const CUtensorMap* map, uint32_t bar_addr, int c0, int c1) {
-    if constexpr (CG == 1)
-        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                     ::"r"(smem_u32(dst)), "l"(map), "r"(bar_addr), "r"(c0), "r"(c1) : "memory");
-    else
-        asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                     ::"r"(smem_u32(dst)), "l"(map), "r"(bar_addr), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {      // shared::cta address -> shared::cluster address in CTA `rank`
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
 template <int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 bfp_gemm_bf16_sp_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
@@ -178,20 +149,22 @@ bfp_gemm_bf16_sp_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_
                 const int tw = tile % p.tiles_w, tt = tile / p.tiles_w;      // consecutive units share the X tile
                 const int w_row = (tw * CG + (int)rank) * BW;                // this CTA's 128 W rows
                 const int x_row = tt * BT + (int)rank * C::XR;               // this CTA's share of the X tile
-                int e_row = (tw * CG + (int)rank) * p.e_atoms * 128;         // lane rows of this CTA's E atoms
+                int e_row = (tw * CG + (int)rank) * p.e_atoms * 16;          // E atoms as 16 rows of 128 B (few, wide TMA rows)
                 int w_row_ld = w_row, x_row_ld = x_row;
                 if (p.debug & 1) x_row_ld = (int)rank * C::XR;
-                if (p.debug & 2) { w_row_ld = (int)rank * BW; e_row = (int)rank * p.e_atoms * 128; }
+                if (p.debug & 2) { w_row_ld = (int)rank * BW; e_row = (int)rank * p.e_atoms * 16; }
                 for (int ks = 0; ks < p.num_k_slabs; ++ks) {
                     if ((p.debug & 4) && uses++ >= kStages) continue;       // experiment: MMAs re-read the first slabs, no loads
                     mbar_wait(&bars->empty[stage], phase ^ 1);
-                    const bool with_e = (ks & 1) == 0;
                     // completion bytes of BOTH CTAs land on the leader's barrier; only the leader posts the expectation
-                    if (rank == 0) mbar_expect_tx(&bars->full[stage], (uint32_t)CG * (C::kSmemW + C::kSmemX + (with_e ? C::kSmemE : 0)));
+                    if (rank == 0) mbar_expect_tx(&bars->full[stage], (uint32_t)CG * kStageBytes);
                     const uint32_t bar = CG == 1 ? smem_u32(&bars->full[stage]) : mapa_u32(smem_u32(&bars->full[stage]), 0);
+                    // every TMA row is a full 128 bytes: the copy engine is request-rate-bound (~2 clk per row), so 64-byte
+                    // rows (a 64-k W slab) would halve its throughput
                     tma_load_2d_to<CG>(stage_x(stage), &map_x, bar, ks * KS, x_row_ld);
+                    tma_load_2d_to<CG>(stage_x(stage) + C::kSmemXAtom, &map_x, bar, ks * KS + 64, x_row_ld);
                     tma_load_2d_to<CG>(stage_w(stage), &map_w, bar, ks * (KS / 2), w_row_ld);
-                    if (with_e) tma_load_2d_to<CG>(stage_e(stage), &map_e, bar, 0, e_row + (ks >> 1) * 128);
+                    tma_load_2d_to<CG>(stage_e(stage), &map_e, bar, 0, e_row + ks * 16);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -209,20 +182,20 @@ bfp_gemm_bf16_sp_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_
                 for (int ks = 0; ks < p.num_k_slabs; ++ks) {
                     if (!((p.debug & 4) && uses++ >= kStages)) mbar_wait(&bars->full[stage], phase);
                     tc_fence_after();
-                    if ((ks & 1) == 0) {
-                        // E ring reuse: having seen full[] for this slab means the producers saw empty[] of the slab
-                        // kStages uses earlier, i.e. every MMA at least kStages slabs back has completed; the atom this slot
-                        // held was last read 2 * kERing - 1 = 15 slabs back, so the copy cannot overtake a reader.
-                        eslot = (eslot + 1) & (kERing - 1);
-                        tmem_cp_128x128b<CG>(tmem_base + kTmemE + eslot * 4, make_smem_desc_k(smem_u32(stage_e(stage)), 0, 128, 128));
-                    }
-                    const uint64_t dw = make_smem_desc_k(smem_u32(stage_w(stage)), 4, 512, 16);    // SWIZZLE_64B: 8 rows x 64 B
-                    const uint64_t dx = make_smem_desc(smem_u32(stage_x(stage)));                  // SWIZZLE_128B
-                    const uint32_t ecol = tmem_base + kTmemE + eslot * 4 + (uint32_t)(ks & 1) * 2;
+                    // E ring reuse: having seen full[] for this slab means the producers saw empty[] of the slab kStages
+                    // uses earlier, i.e. every MMA at least kStages slabs back has completed; the atom this slot held was
+                    // last read kERing (> kStages) slabs back, so the copy cannot overtake a reader.
+                    eslot = (eslot + 1) & (kERing - 1);
+                    tmem_cp_128x128b<CG>(tmem_base + kTmemE + eslot * 4, make_smem_desc_k(smem_u32(stage_e(stage)), 0, 128, 128));
+                    const uint64_t dw = make_smem_desc(smem_u32(stage_w(stage)));                        // SWIZZLE_128B
+                    const uint64_t dx0 = make_smem_desc(smem_u32(stage_x(stage)));
+                    const uint64_t dx1 = make_smem_desc(smem_u32(stage_x(stage) + C::kSmemXAtom));
+                    const uint32_t ecol = tmem_base + kTmemE + eslot * 4;
 #pragma unroll
-                    for (int i = 0; i < 2; ++i)      // 32 logical k per MMA: 16 kept bf16 = 32 B of W (+2), 64 B of X (+4)
+                    for (int i = 0; i < 4; ++i)      // 32 logical k per MMA: 16 kept bf16 = 32 B of W (+2), 64 B of X (+4, two per atom)
                         // the metadata address names an even column; the sparsity selector (idesc bits 0-1) picks the odd one
-                        mma_sp_bf16<CG>(tmem_base, dw + (uint64_t)(i * 2), dx + (uint64_t)(i * 4), ecol, C::kIdesc | (uint32_t)i, (ks | i) != 0);
+                        mma_sp_bf16<CG>(tmem_base, dw + (uint64_t)(i * 2), (i < 2 ? dx0 : dx1) + (uint64_t)((i & 1) * 4), ecol + (uint32_t)(i & 2),
+                                        C::kIdesc | (uint32_t)(i & 1), (ks | i) != 0);
                     commit<CG>(&bars->empty[stage]);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -379,14 +352,14 @@ int gemm_bf16_sp_device(const void* x_bf16, const void* w_comp, const void* w_me
     if (tuning().gemm_sp_cta_group == 1 || tuning().gemm_sp_cta_group == 2) cg = tuning().gemm_sp_cta_group;
     Params p;
     p.bias = bias; p.out = out; p.T = (int)T; p.N = (int)N; p.debug = tuning().gemm_sp_debug;
-    p.num_k_slabs = (int)((Kp + 63) / 64);
+    p.num_k_slabs = (int)((Kp + 127) / 128);
     p.e_atoms = (int)(Kc / 64);
     p.tiles_w = (int)((N + 128 * cg - 1) / (128 * cg));
     p.tiles_t = (int)((T + 255) / 256);
     CUtensorMap map_w, map_x, map_e;
-    if (int rc = make_map_bf16(&map_w, w_comp, N, Kc, Kc * 2, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+    if (int rc = make_map_bf16(&map_w, w_comp, N, Kc, Kc * 2, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     if (int rc = make_map_bf16(&map_x, x_bf16, T, Kp, Kp * 2, 64, 256 / cg, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    if (int rc = make_map_bytes(&map_e, w_meta, mb / 16, 16, 128)) return rc;
+    if (int rc = make_map_bytes(&map_e, w_meta, mb / 128, 128, 16)) return rc;
     const int units = std::min(p.tiles_w * p.tiles_t, sms / cg);
     cudaError_t e;
     if (cg == 1) {

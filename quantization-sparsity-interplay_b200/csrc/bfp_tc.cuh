@@ -146,6 +146,41 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// ---- CTA-pair (cta_group::2) helpers: CG = 1 degenerates to the single-CTA forms -----------------------------------
+// tcgen05.commit: CG = 2 arrives on the barrier at the same offset in both CTAs of the pair
+template <int CG>
+__device__ __forceinline__ void commit(uint64_t* bar) {
+    if constexpr (CG == 1) tc_commit(bar);
+    else asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                      ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// TMA tile load whose completion bytes land on `bar_addr` (a shared::cluster address; for CG = 2 the pair leader's barrier)
+template <int CG>
+__device__ __forceinline__ void tma_load_2d_to(void* dst, const CUtensorMap* map, uint32_t bar_addr, int c0, int c1) {
+    if constexpr (CG == 1)
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                     ::"r"(smem_u32(dst)), "l"(map), "r"(bar_addr), "r"(c0), "r"(c1) : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                     ::"r"(smem_u32(dst)), "l"(map), "r"(bar_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {      // shared::cta address -> shared::cluster address in CTA `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // Generic K-major shared-memory matrix descriptor: layout_type 0 = no swizzle (8-row x 16-byte core matrices), 2 = SWIZZLE_128B,
 // 4 = SWIZZLE_64B, 6 = SWIZZLE_32B; sbo = bytes between consecutive 8-row groups; lbo = bytes between core matrices along K
 // (ignored by the swizzled K-major modes).

@@ -127,13 +127,15 @@ def test_gemm_bf16_exact_products(ops, shape):
     bias = torch.randint(-5, 6, (N,), generator=g, device="cuda").float()
     from qsi_b200 import _lib
     ref = a.double() @ b.double().t() + bias.double()
-    for tile_n in (0, 128, 256):                      # auto, and both tile widths forced
+    for tile_n, cg in ((0, 0), (128, 1), (256, 1), (0, 2)):     # auto; both single-CTA tile widths; CTA pairs forced
         _lib.set_option("gemm_bf16_tile_n", tile_n)
+        _lib.set_option("gemm_bf16_cta_group", cg)
         try:
             y = ops.bfp_linear_bf16(ab, bb, bias)
         finally:
             _lib.set_option("gemm_bf16_tile_n", 0)
-        assert torch.equal(y.double(), ref), tile_n
+            _lib.set_option("gemm_bf16_cta_group", 0)
+        assert torch.equal(y.double(), ref), (tile_n, cg)
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])

@@ -13,11 +13,29 @@ L = _lib.lib(); res = []
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
 
-def timeit(fn, iters):
+import time
+try:
+    import pynvml
+    pynvml.nvmlInit(); _h = pynvml.nvmlDeviceGetHandleByIndex(0)
+    def sm_mhz(): return pynvml.nvmlDeviceGetClockInfo(_h, pynvml.NVML_CLOCK_SM)
+    def watts(): return pynvml.nvmlDeviceGetPowerUsage(_h) / 1000.0
+except Exception:
+    def sm_mhz(): return 0
+    def watts(): return 0.0
+CLK = {}
+
+
+def timeit(fn, iters, tag=None):
+    """cool-down, 3 warm-up launches, `iters` timed launches (CUDA events); the SM clock / power are sampled while the timed
+    launches are still queued, so a power-limited clock shows up next to the number it produced."""
+    torch.cuda.synchronize(); time.sleep(0.25)
     for _ in range(3): fn()
     torch.cuda.synchronize(); e0.record()
     for _ in range(iters): fn()
-    e1.record(); torch.cuda.synchronize()
+    e1.record()
+    c, w = sm_mhz(), watts()
+    torch.cuda.synchronize()
+    if tag: CLK[tag] = (c, w)
     return e0.elapsed_time(e1) / iters
 
 
@@ -26,16 +44,21 @@ for (T, N, K) in sum((SH[s] for s in a.shapes.split(",")), []):
     xb, wb = ops.pack_bfp_bf16(x, identifier="in", **kw), ops.pack_bfp_bf16(w, identifier="w", **kw)
     ws = ops.compress_2to4_bf16(wb)
     out = torch.empty(T, N, device="cuda"); st = torch.cuda.current_stream().cuda_stream
-    md = timeit(lambda: _lib.check(L.bfp_gemm_bf16(xb.data_ptr(), wb.data_ptr(), None, out.data_ptr(), T, N, K, st)), a.iters)
+    _lib.set_option("gemm_bf16_cta_group", 1)
+    md1 = timeit(lambda: _lib.check(L.bfp_gemm_bf16(xb.data_ptr(), wb.data_ptr(), None, out.data_ptr(), T, N, K, st)), a.iters)
+    _lib.set_option("gemm_bf16_cta_group", 0)
+    md = timeit(lambda: _lib.check(L.bfp_gemm_bf16(xb.data_ptr(), wb.data_ptr(), None, out.data_ptr(), T, N, K, st)), a.iters, "dense")
     yd = out.clone()
     _lib.set_option("gemm_sp_cta_group", 1)
     msp1 = timeit(lambda: _lib.check(L.bfp_gemm_bf16_sp(xb.data_ptr(), ws.comp.data_ptr(), ws.meta.data_ptr(), None, out.data_ptr(), T, N, K, st)), a.iters)
     _lib.set_option("gemm_sp_cta_group", 0)
-    msp = timeit(lambda: _lib.check(L.bfp_gemm_bf16_sp(xb.data_ptr(), ws.comp.data_ptr(), ws.meta.data_ptr(), None, out.data_ptr(), T, N, K, st)), a.iters)
+    msp = timeit(lambda: _lib.check(L.bfp_gemm_bf16_sp(xb.data_ptr(), ws.comp.data_ptr(), ws.meta.data_ptr(), None, out.data_ptr(), T, N, K, st)), a.iters, "sp")
+    xh, wh = xb.clone(), wb.clone()
+    mcb = timeit(lambda: torch.nn.functional.linear(xh, wh), a.iters, "cublas")
     rel = float((out - yd).norm() / yd.norm())
     mc = timeit(lambda: ops.compress_2to4_bf16(wb, check=False), 5)
     ops_ = 2.0 * T * N * K
-    print(f"T={T} N={N} K={K}: dense {md:.3f} ms = {ops_/md/1e9:.0f} TOPS | 2:4 sparse {msp:.3f} ms = {ops_/msp/1e9:.0f} dense-equivalent TOPS "
-          f"({ops_/msp/1e9/4500*100:.1f}% of 4500) x{md/msp:.2f} [1-CTA kernel: {ops_/msp1/1e9:.0f}] | rel diff {rel:.1e} | compress W {mc*1e3:.0f} us", flush=True)
-    res.append(dict(T=T, N=N, K=K, dense_ms=md, dense_tops=ops_ / md / 1e9, sparse_ms=msp, sparse_1cta_ms=msp1, sparse_tops_dense_equiv=ops_ / msp / 1e9, rel_diff=rel, compress_ms=mc))
+    print(f"T={T} N={N} K={K}: dense {md:.3f} ms = {ops_/md/1e9:.0f} TOPS [1-CTA: {ops_/md1/1e9:.0f}] | 2:4 sparse {msp:.3f} ms = {ops_/msp/1e9:.0f} dense-equivalent TOPS "
+          f"({ops_/msp/1e9/4500*100:.1f}% of 4500) x{md/msp:.2f} [1-CTA kernel: {ops_/msp1/1e9:.0f}] | rel diff {rel:.1e} | compress W {mc*1e3:.0f} us | cuBLAS bf16 {ops_/mcb/1e9:.0f} | clocks MHz/W dense {CLK['dense']} sp {CLK['sp']} cublas {CLK['cublas']}", flush=True)
+    res.append(dict(T=T, N=N, K=K, dense_ms=md, dense_1cta_ms=md1, dense_tops=ops_ / md / 1e9, sparse_ms=msp, cublas_bf16_ms=mcb, clocks=dict(CLK), sparse_1cta_ms=msp1, sparse_tops_dense_equiv=ops_ / msp / 1e9, rel_diff=rel, compress_ms=mc))
 if a.out: json.dump(res, open(a.out, "w"), indent=1)
