@@ -486,7 +486,7 @@ def _tensor_core_eligible(x, w, bfp_args):
     taken for inference on CUDA fp32 tensors when the configuration has a packed form."""
     if os.environ.get("BFP_LINEAR_PATH", "tc") != "tc":
         return False
-    if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad):
+    if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad) and os.environ.get("BFP_TRAIN_PATH", "tc") != "tc":
         return False
     return (x.is_cuda and w.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32
             and bfp_args['num_format'] == 'bfp' and bfp_args['sparsity_num_format'] == 'bfp'
@@ -591,6 +591,60 @@ def F_matmul_bfp(**kwargs):
     return torch.matmul
 
 
+def _pad_cols(t, cols):
+    """bf16 [r, c] -> contiguous [r, cols] (zero-padded); the GEMM operands need a contraction length that is a multiple of 8."""
+    if t.shape[1] == cols and t.is_contiguous():
+        return t
+    out = torch.zeros((t.shape[0], cols), dtype=t.dtype, device=t.device)
+    out[:, :t.shape[1]] = t
+    return out
+
+
+class _BFPLinearTC(torch.autograd.Function):
+    """BFPLinear forward AND backward on the tensor cores.  Same function as the reference's
+    new_op (bfp_ops.py:160-192): forward F.linear(Q_in(x), Q_w(w), bias); backward = F.linear's backward applied to the
+    output gradient quantised with identifier='grad' (:180-182), straight-through for x and w (:168-170):
+        grad_x = Q_g(gy) . Q_w(w)        grad_w = Q_g(gy)^T . Q_in(x)        grad_b = sum_t Q_g(gy)
+    All three contractions run on exact-bf16 BFP operands (bfp_gemm_bf16 / bfp_gemm_bf16_sp); the operands saved for
+    backward are the packed bf16 tensors (half the bytes of the reference's fp32 copies)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, bfp_args, dense_w, cached_w):
+        K, N = x.shape[-1], w.shape[0]
+        xb = pack_bfp_bf16(x, identifier='in', **bfp_args)                      # [T, Kp]
+        wb = cached_w if cached_w is not None else pack_bfp_bf16(w, identifier='w', **bfp_args)   # dense [N, Kp] or SparseBF16
+        out_shape = tuple(x.shape[:-1]) + (N,)
+        if isinstance(wb, SparseBF16):
+            y = bfp_linear_bf16_sp(xb, wb, bias, out_shape=out_shape)
+        else:
+            y = bfp_linear_bf16(xb, wb, bias, out_shape=out_shape)
+        ctx.bfp_args, ctx.K, ctx.N, ctx.x_shape, ctx.has_bias = bfp_args, K, N, tuple(x.shape), bias is not None
+        ctx.wb_dense = wb if not isinstance(wb, SparseBF16) else dense_w      # tensor, or a callable that packs it on demand
+        ctx.save_for_backward(xb)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (xb,) = ctx.saved_tensors
+        a, K, N = ctx.bfp_args, ctx.K, ctx.N
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gq = pack_bfp_bf16(gy.reshape(-1, N).float(), identifier='grad', **a)  # [T, Np], blocked along N (bfp_ops.py:181)
+        T, Np = gq.shape
+        grad_x = grad_w = grad_b = None
+        if need_x:
+            wb = ctx.wb_dense() if callable(ctx.wb_dense) else ctx.wb_dense     # dgrad contracts over N: the dense form
+            wbT = _pad_cols(wb[:, :K].t(), Np)                                  # [K, Np]
+            grad_x = bfp_linear_bf16(gq, wbT).view(ctx.x_shape)
+        if need_w:
+            Tp = -(-T // 8) * 8
+            gqT = _pad_cols(gq[:, :N].t(), Tp)                                  # [N, Tp]
+            xbT = _pad_cols(xb[:, :K].t(), Tp)                                  # [K, Tp]
+            grad_w = bfp_linear_bf16(gqT, xbT)                                  # [N, K]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            grad_b = gq[:, :N].float().sum(0)
+        return grad_x, grad_w, grad_b, None, None, None
+
+
 class BFPConv2d(torch.nn.Conv2d):
     """bfp_ops.py:247-268: input blocked along W, weight along kw; the convolution itself runs on the dequantised
     operands (conv as im2col + BFP GEMM is "next")."""
@@ -619,24 +673,40 @@ class BFPLinear(torch.nn.Linear):
         super().__init__(in_features, out_features, bias)
         self.num_format = self.bfp_args['num_format']
         self.linear_op = _get_bfp_op(F.linear, 'linear', self.bfp_args)
-        self._packed_w = None          # (key, packed weight): the weight is re-packed only when it changes
+        self._packed_w = None          # (key, packed weight) of the last kind used: re-packed only when the weight changes
+        self._packed_by_kind = {}
 
     def _packed_weight(self, kind):
         w = self.weight
         key = (kind, w.data_ptr(), w._version, tuple(w.shape), w.device)
-        if self._packed_w is None or self._packed_w[0] != key:
-            pack = pack_bfp if kind == 'i8' else pack_bfp_bf16
-            packed = pack(w, identifier='w', **self.bfp_args)
+        hit = self._packed_by_kind.get(kind)
+        if hit is None or hit[0] != key:
             if kind == 'sp':
-                packed = compress_2to4_bf16(packed)       # raises if the pruned weight is not 2:4 (cannot happen for sp_ok configs)
-            self._packed_w = (key, packed)
-        return self._packed_w[1]
+                # raises if the pruned weight is not 2:4 (cannot happen for sp_ok configs); the dense form is not kept
+                packed = compress_2to4_bf16(pack_bfp_bf16(w.detach(), identifier='w', **self.bfp_args))
+            else:
+                packed = (pack_bfp if kind == 'i8' else pack_bfp_bf16)(w.detach(), identifier='w', **self.bfp_args)
+            hit = (key, packed)
+            self._packed_by_kind = {k: v for k, v in self._packed_by_kind.items() if v[0][1:] == key[1:]}   # drop stale kinds
+            self._packed_by_kind[kind] = hit
+        self._packed_w = hit
+        return hit[1]
 
     def forward(self, input):
         if self.num_format == 'fp32':
             return F.linear(input, self.weight, self.bias)
         elif self.num_format == 'bfp':
-            kind = _tensor_core_kind(input, self.weight, self.bfp_args) if self.bfp_args['rounding_mode'] == rounding_modes.DETERM else None
+            determ = self.bfp_args['rounding_mode'] == rounding_modes.DETERM
+            training = torch.is_grad_enabled() and (input.requires_grad or self.weight.requires_grad)
+            kind = _tensor_core_kind(input, self.weight, self.bfp_args) if (determ or training) else None
+            if training and kind is not None and self.bfp_args['mant_bits'] <= 8 and self.bfp_args['grad_sparsity'] != True:   # noqa: E712
+                # training: forward + dgrad + wgrad on the tensor cores.  Stochastic rounding re-quantises the weight on
+                # every forward like the reference (no cache), and keeps it dense for the backward contraction over N.
+                tkind = kind if kind in ('sp', 'bf16') else 'bf16'
+                cached = self._packed_weight(tkind) if determ else None
+                return _BFPLinearTC.apply(input, self.weight, self.bias, self.bfp_args, (lambda: self._packed_weight('bf16')), cached)
+            if not determ:
+                kind = None
             if kind == 'i8':
                 # inference fast path: pack activations on the fly, cached packed weight, tcgen05 int8 BFP GEMM
                 return bfp_linear_packed(pack_bfp(input, identifier='in', **self.bfp_args), self._packed_weight(kind), self.bias)

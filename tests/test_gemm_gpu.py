@@ -322,3 +322,62 @@ def test_gemm_sp_llama7b_shapes_full_size(ops, NK):
     rows = torch.arange(0, T, 61, device="cuda")
     ref = xb[rows].double() @ wb.double().t()
     assert ((y[rows].double() - ref).norm() / ref.norm()).item() <= 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# training on the tensor cores (row f3): forward, dgrad and wgrad of BFPLinear vs the reference's structure
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("w_sparse", [True, False])
+@pytest.mark.parametrize("shape", [(3, 70, 512, 384), (5, 33, 200, 136), (1, 256, 1024, 768)])
+def test_bfplinear_training_on_tensor_cores(ops, shape, w_sparse, monkeypatch):
+    """grad_x = Q_g(gy) Q_w(w), grad_w = Q_g(gy)^T Q_in(x), grad_b = sum Q_g(gy) (bfp_ops.py:160-192) -- the tensor-core
+    autograd path against (1) the fake-quant path through torch autograd and (2) an fp64 restatement; tolerance 1e-5."""
+    b0, b1, K, N = shape
+    kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=7, block_size=64,
+              w_sparsity=w_sparse, N=2, M=4, first="s", sparsity_mode="structured", device="cuda")
+    torch.manual_seed(b0 + K)
+    lin = ops.BFPLinear(K, N, bias=True, **dict(kw)).cuda()
+    x0 = torch.randn(b0, b1, K, device="cuda")
+    gy = torch.randn(b0, b1, N, device="cuda") * 0.1
+    res = {}
+    for path in ("tc", "fakequant"):
+        monkeypatch.setenv("BFP_TRAIN_PATH", path)
+        monkeypatch.setenv("BFP_LINEAR_PATH", "tc" if path == "tc" else "fakequant")
+        lin.zero_grad()
+        x = x0.clone().requires_grad_(True)
+        y = lin(x)
+        y.backward(gy)
+        res[path] = (y.detach(), x.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone())
+        if path == "tc":
+            assert y.grad_fn.name().startswith("_BFPLinearTC"), y.grad_fn.name()
+    a = ops.unpack_bfp_args(dict(kw))
+    xq = ops.float_to_bfp_blocked(x0, **a, identifier="in").double().view(-1, K)
+    wq = ops.float_to_bfp_blocked(lin.weight.detach(), **a, identifier="w").double()
+    gq = ops.float_to_bfp_blocked(gy, **a, identifier="grad").double().view(-1, N)
+    ref = ((xq @ wq.t() + lin.bias.detach().double()).view(b0, b1, N), (gq @ wq).view(b0, b1, K), gq.t() @ xq, gq.sum(0))
+    for got in res.values():
+        for g, r in zip(got, ref):
+            assert ((g.double() - r).norm() / r.norm()).item() <= 1e-5
+    if w_sparse:
+        assert (res["tc"][2].view(N, -1, 4) != 0).sum(-1).float().mean() > 3.5      # STE: the weight gradient is dense
+
+
+def test_bfplinear_training_stochastic_rounding_runs_on_tensor_cores(ops):
+    """rounding_mode='stoc' (the reference's default): weights are re-quantised on every forward, the backward uses the
+    forward's draw; the result is an unbiased estimate of the fp32 linear, so a mean over draws converges."""
+    kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="stoc", epsilon=1e-8, mant_bits=5, block_size=32, device="cuda")
+    torch.manual_seed(3)
+    lin = ops.BFPLinear(256, 128, bias=False, **dict(kw)).cuda()
+    x = torch.randn(64, 256, device="cuda", requires_grad=True)
+    ys = []
+    for _ in range(64):
+        y = lin(x)
+        assert y.grad_fn.name().startswith("_BFPLinearTC")
+        ys.append(y.detach())
+    y.sum().backward()
+    assert x.grad is not None and torch.isfinite(x.grad).all() and lin.weight.grad.shape == lin.weight.shape
+    assert not torch.equal(ys[0], ys[1])                              # fresh uniforms per call
+    exact = x.detach() @ lin.weight.detach().t()
+    err1 = (ys[0] - exact).norm() / exact.norm()
+    errm = (torch.stack(ys).mean(0) - exact).norm() / exact.norm()
+    assert errm < 0.35 * err1, (float(err1), float(errm))            # averaging 64 draws shrinks the error ~8x
