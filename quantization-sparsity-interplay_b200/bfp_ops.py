@@ -500,6 +500,61 @@ def _tensor_core_eligible(x, w, bfp_args):
 # ---------------------------------------------------------------------------------------------------------------
 # bfp_ops.py:151-200: operand pre-processing and the autograd wrappers
 # ---------------------------------------------------------------------------------------------------------------
+# ---------------------------------------------------------------------------------------------------------------
+# Row f4: the wrapped matmul / conv2d on the tensor cores (inference).  Same functions as new_op(...) below with
+# op = torch.matmul / F.conv2d: both operands quantised along the contraction (bfp_ops.py:151-155), exact-bf16 operands,
+# fp32 accumulation in TMEM.
+# ---------------------------------------------------------------------------------------------------------------
+def _tc_inference_ok(x, w, bfp_args):
+    return (bfp_args['rounding_mode'] == rounding_modes.DETERM and not (torch.is_grad_enabled() and (x.requires_grad or w.requires_grad))
+            and _tensor_core_kind(x, w, bfp_args) is not None and 1 <= bfp_args['mant_bits'] <= 8)
+
+
+def _tc_matmul(x, w, bfp_args):
+    """torch.matmul(Q_in(x), Q_w(w^T)^T) for x [..., M, K], w [..., K, N] (F_matmul_bfp, bfp_ops.py:240-245 with transpose=True):
+    one GEMM when w is a matrix, one per broadcast batch entry otherwise."""
+    K, N = w.shape[-2], w.shape[-1]
+    if w.dim() == 2:
+        wb = pack_bfp_bf16(w.t(), identifier='w', **bfp_args)                          # [N, Kp], blocked along K
+        return bfp_linear_bf16(pack_bfp_bf16(x, identifier='in', **bfp_args), wb, None, out_shape=tuple(x.shape[:-1]) + (N,))
+    batch = torch.broadcast_shapes(x.shape[:-2], w.shape[:-2])
+    xe = x.expand(batch + x.shape[-2:]).reshape((-1,) + tuple(x.shape[-2:]))
+    we = w.expand(batch + w.shape[-2:]).reshape((-1, K, N))
+    M = x.shape[-2]
+    xb = pack_bfp_bf16(xe, identifier='in', **bfp_args).view(xe.shape[0], M, -1)       # [b, M, Kp]
+    wb = pack_bfp_bf16(we.transpose(-1, -2), identifier='w', **bfp_args).view(we.shape[0], N, -1)   # [b, N, Kp]
+    out = torch.empty((xe.shape[0], M, N), dtype=torch.float32, device=x.device)
+    L, stream = _lib.lib(), torch.cuda.current_stream().cuda_stream
+    with torch.cuda.device(x.device):
+        for b in range(xe.shape[0]):
+            _lib.check(L.bfp_gemm_bf16(xb[b].data_ptr(), wb[b].data_ptr(), None, out[b].data_ptr(), M, N, xb.shape[-1], stream))
+    return out.view(batch + (M, N))
+
+
+def _tc_conv2d(x, w, bias, stride, padding, dilation, groups, bfp_args):
+    """F.conv2d(Q_in(x), Q_w(w), ...) as im2col + BFP GEMM (BFPConv2d, bfp_ops.py:247-268): the input is blocked along W and the
+    weight along kw exactly like the reference (quantise FIRST, then unfold -- zero padding is applied to the quantised tensor
+    as F.conv2d does)."""
+    B, C, H, W = x.shape
+    O, _, kh, kw = w.shape
+    xq = pack_bfp_bf16(x, identifier='in', **bfp_args)[:, :W].reshape(B, C, H, W)       # exact bf16 values of Q_in(x)
+    cols = F.unfold(xq, (kh, kw), dilation=dilation, padding=padding, stride=stride)    # [B, C*kh*kw, L]
+    Lout = cols.shape[-1]
+    Kc = C * kh * kw
+    Kp = -(-Kc // 8) * 8
+    a = torch.zeros((B * Lout, Kp), dtype=torch.bfloat16, device=x.device) if Kp != Kc else torch.empty((B * Lout, Kp), dtype=torch.bfloat16, device=x.device)
+    a.view(B, Lout, Kp)[:, :, :Kc] = cols.transpose(1, 2)
+    wq = _pad_cols(pack_bfp_bf16(w, identifier='w', **bfp_args)[:, :kw].reshape(O, Kc), Kp)
+    y = bfp_linear_bf16(a, wq, bias)                                                    # [B*L, O]
+    Ho = (H + 2 * padding[0] - dilation[0] * (kh - 1) - 1) // stride[0] + 1
+    Wo = (W + 2 * padding[1] - dilation[1] * (kw - 1) - 1) // stride[1] + 1
+    return y.view(B, Lout, O).permute(0, 2, 1).reshape(B, O, Ho, Wo)
+
+
+def _pair(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+
+
 def MxM_pre_processing(x, w, transpose, **bfp_args):
     """bfp_ops.py:151-155: both operands are blocked along the contraction dim."""
     xq = float_to_bfp_blocked(x, **bfp_args, identifier='in')
@@ -544,6 +599,16 @@ def _gen_bfp_op(op, name, bfp_args, transpose=False):
     NewOpOut.__name__ = name + '_Out'
 
     def new_op(x, w, *args, **kwargs):
+        # inference fast paths on the tensor cores (row f4); anything else runs the reference's structure below
+        if torch.is_tensor(x) and torch.is_tensor(w) and x.dim() >= 2 and w.dim() >= 2 and _tc_inference_ok(x, w, bfp_args):
+            if op is torch.matmul and transpose and not args and not kwargs and x.shape[-1] == w.shape[-2]:
+                return _tc_matmul(x, w, bfp_args)
+            if op is F.linear and not transpose and w.dim() == 2 and len(args) <= 1 and not kwargs:
+                return bfp_linear_bf16(pack_bfp_bf16(x, identifier='in', **bfp_args), pack_bfp_bf16(w, identifier='w', **bfp_args),
+                                       args[0] if args else None, out_shape=tuple(x.shape[:-1]) + (w.shape[0],))
+            if op is F.conv2d and x.dim() == 4 and w.dim() == 4 and not kwargs and len(args) == 5 and args[4] == 1 \
+                    and not isinstance(args[2], str):
+                return _tc_conv2d(x, w, args[0], _pair(args[1]), _pair(args[2]), _pair(args[3]), 1, bfp_args)
         x, w = NewOpIn.apply(x, w)
         out = op(x, w, *args, **kwargs)
         return NewOpOut.apply(out)

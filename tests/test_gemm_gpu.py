@@ -381,3 +381,57 @@ def test_bfplinear_training_stochastic_rounding_runs_on_tensor_cores(ops):
     err1 = (ys[0] - exact).norm() / exact.norm()
     errm = (torch.stack(ys).mean(0) - exact).norm() / exact.norm()
     assert errm < 0.35 * err1, (float(err1), float(errm))            # averaging 64 draws shrinks the error ~8x
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# row f4: BFPConv2d as im2col + BFP GEMM, F_matmul_bfp / F_linear_bfp on the tensor cores
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [
+    dict(B=4, C=3, H=64, W=64, O=96, k=16, stride=16, padding=0, dilation=1),       # ViT patch embedding (kernel = stride)
+    dict(B=2, C=8, H=30, W=34, O=40, k=3, stride=1, padding=1, dilation=1),         # overlapping windows + zero padding
+    dict(B=3, C=5, H=33, W=40, O=24, k=(3, 5), stride=(2, 1), padding=(0, 2), dilation=(2, 1)),
+])
+@pytest.mark.parametrize("w_sparse", [False, True])
+def test_bfpconv2d_im2col_tensor_core_path(ops, cfg, w_sparse, monkeypatch):
+    kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=5, block_size=64,
+              w_sparsity=w_sparse, N=2, M=4, first="s", sparsity_mode="structured", device="cuda")
+    torch.manual_seed(cfg["O"])
+    conv = ops.BFPConv2d(cfg["C"], cfg["O"], cfg["k"], cfg["stride"], cfg["padding"], cfg["dilation"], 1, True, **dict(kw)).cuda()
+    x = torch.randn(cfg["B"], cfg["C"], cfg["H"], cfg["W"], device="cuda")
+    a = ops.unpack_bfp_args(dict(kw))
+    with torch.no_grad():
+        y = conv(x)
+        monkeypatch.setenv("BFP_LINEAR_PATH", "fakequant")
+        y_fq = conv(x)                                                              # the reference's structure (cuDNN on fake-quant)
+        monkeypatch.setenv("BFP_LINEAR_PATH", "tc")
+    xq = ops.float_to_bfp_blocked(x, **a, identifier="in").double()
+    wq = ops.float_to_bfp_blocked(conv.weight.detach(), **a, identifier="w").double()
+    ref = torch.nn.functional.conv2d(xq, wq, conv.bias.detach().double(), conv.stride, conv.padding, conv.dilation, 1)
+    assert y.shape == ref.shape == y_fq.shape
+    assert ((y.double() - ref).norm() / ref.norm()).item() <= 1e-5
+    assert ((y_fq.double() - ref).norm() / ref.norm()).item() <= 2e-3               # cuDNN may use TF32
+
+
+def test_f_matmul_and_f_linear_bfp_on_tensor_cores(ops):
+    kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=7, block_size=32, device="cuda")
+    a = ops.unpack_bfp_args(dict(kw))
+    mm, lin = ops.F_matmul_bfp(**dict(kw)), ops.F_linear_bfp(**dict(kw))
+    g = torch.Generator(device="cuda").manual_seed(9)
+
+    def q(t, ident):
+        return ops.float_to_bfp_blocked(t, **a, identifier=ident).double()
+
+    for xs, ws in (((2, 4, 48, 64), (2, 4, 64, 40)), ((5, 100, 96), (96, 72)), ((3, 1, 20, 128), (1, 6, 128, 24)), ((130, 200), (200, 264))):
+        x = torch.randn(*xs, device="cuda", generator=g)
+        w = torch.randn(*ws, device="cuda", generator=g)
+        with torch.no_grad():
+            y = mm(x, w)
+        ref = torch.matmul(q(x, "in"), q(w.transpose(-1, -2).contiguous(), "w").transpose(-1, -2))
+        assert y.shape == ref.shape and ((y.double() - ref).norm() / ref.norm()).item() <= 1e-5, (xs, ws)
+    x = torch.randn(7, 33, 160, device="cuda", generator=g)
+    w = torch.randn(88, 160, device="cuda", generator=g)
+    b = torch.randn(88, device="cuda", generator=g)
+    with torch.no_grad():
+        y = lin(x, w, b)
+    ref = q(x, "in") @ q(w, "w").t() + b.double()
+    assert ((y.double() - ref).norm() / ref.norm()).item() <= 1e-5
