@@ -70,10 +70,12 @@ def main():
             B = a.batch or 256
             inp = dict(pixel_values=torch.randn(B, 3, 224, 224, generator=g).to(dev))
         with torch.no_grad():
-            y = model(**inp).logits
+            for _ in range(3):                                  # weight packs, allocator, clocks
+                y = model(**inp).logits
             torch.cuda.synchronize(); t0 = time.perf_counter()
-            y = model(**inp).logits
-            torch.cuda.synchronize(); dt = time.perf_counter() - t0
+            for _ in range(5):
+                y = model(**inp).logits
+            torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 5
         outs[tag] = y.float()
         res[tag] = {"swapped_modules": n, "forward_s": dt, "logits_shape": list(y.shape), "finite": bool(torch.isfinite(y).all())}
         print(tag, res[tag], flush=True)
