@@ -247,6 +247,187 @@ bfp_gemm_bf16_sp_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_
     }
 }
 
+// ====================================================================================================================
+// Wide tile: 256 out-features x 480 tokens per CTA pair, two 240-column accumulators fed by the SAME W / E slab.
+// The 256-wide kernel above is bound by the SM's ingest port (50 KB of operands per 128-k slab per SM at 64 B/clk);
+// sharing each W slab and E atom between two X halves brings that to 78 KB per 480 tokens = 41.6 KB per 256 (-17 %), and
+// 480-token tiles also quantise better on 74 CTA pairs for the LLaMA shapes (4096^3: 1.95 waves instead of 3.46).
+//   smem: W/E ring of 3 slots (128 k: 16 KB + 2 KB) + X ring of 5 stages (64 k: 2 chunks x 120 rows x 128 B = 30 KB).
+//   TMEM: acc0 = columns [0,240), acc1 = [240,480), E ring = [480,512).
+//   MMA:  tcgen05.mma.sp.cta_group::2 with N = 240; per CTA the B operand is 120 rows (chunk c = this CTA's half of
+//         accumulator c's tokens: rows t0 + 240 c + 120 rank + [0,120)).
+//   Epilogue: warps 4-7 drain acc0, warps 8-11 acc1, 120 columns at a time (the 480 x 128 fp32 tile is the size of the
+//         whole register file); the accumulators are handed back after the second tcgen05.ld burst.
+// ====================================================================================================================
+namespace wide {
+constexpr int BW = 128, NT = 240, BT = 2 * NT;           // W rows per CTA, tokens per accumulator, tokens per tile
+constexpr int XC = NT / 2;                               // X rows per chunk per CTA (120)
+constexpr int kWeSlots = 3, kXStages = 5;
+constexpr int kSmemW = BW * 128, kSmemE = 2048, kWeBytes = kSmemW + kSmemE;          // 18 KB
+constexpr int kSmemXChunk = XC * 128, kXBytes = 2 * kSmemXChunk;                     // 15 KB, 30 KB
+constexpr int kSmemTotal = kWeSlots * kWeBytes + kXStages * kXBytes + 1024 + 1024;
+constexpr uint32_t kIdesc = (1u << 2) | (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)((BW * 2) >> 4) << 24);
+constexpr int kTmemEW = 480;
+struct Barriers {
+    uint64_t we_full[kWeSlots], we_empty[kWeSlots];
+    uint64_t x_full[kXStages], x_empty[kXStages];
+    uint64_t tmem_full, tmem_empty;
+    uint32_t tmem_base;
+};
+}  // namespace wide
+
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(addr));
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+bfp_gemm_bf16_sp_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
+                             const __grid_constant__ CUtensorMap map_e, const Params p) {
+    using namespace wide;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_x = smem + kWeSlots * kWeBytes;                       // 55296: multiple of 1024
+    wide::Barriers* bars = reinterpret_cast<wide::Barriers*>(smem_x + kXStages * kXBytes);
+    auto slot_w = [&](int s) { return smem + s * kWeBytes; };
+    auto slot_e = [&](int s) { return smem + s * kWeBytes + kSmemW; };
+    auto stage_x = [&](int s, int c) { return smem_x + s * kXBytes + c * kSmemXChunk; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int unit = (int)blockIdx.x / 2, num_units = (int)gridDim.x / 2;
+    const int num_tiles = p.tiles_w * p.tiles_t;
+    const int nk128 = p.num_k_slabs;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kWeSlots; ++s) { mbar_init(&bars->we_full[s], 1); mbar_init(&bars->we_empty[s], 1); }
+        for (int s = 0; s < kXStages; ++s) { mbar_init(&bars->x_full[s], 1); mbar_init(&bars->x_empty[s], 1); }
+        mbar_init(&bars->tmem_full, 1);
+        mbar_init(&bars->tmem_empty, kEpiWarps * 2);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        // ===================================== TMA producer (both CTAs) =========================
+        if (lane == 0) {
+            int ws = 0, xs = 0; uint32_t wphase = 0, xphase = 0;
+            for (int tile = unit; tile < num_tiles; tile += num_units) {
+                const int tw = tile % p.tiles_w, tt = tile / p.tiles_w;
+                const int w_row = (tw * 2 + (int)rank) * BW;
+                const int e_row = (tw * 2 + (int)rank) * p.e_atoms * 16;
+                const int x_row0 = tt * BT + (int)rank * XC;                 // chunk 0 (accumulator 0); chunk 1 is NT rows further
+                for (int k = 0; k < nk128; ++k) {
+                    mbar_wait(&bars->we_empty[ws], wphase ^ 1);
+                    if (rank == 0) mbar_expect_tx(&bars->we_full[ws], 2u * kWeBytes);
+                    const uint32_t wbar = mapa_u32(smem_u32(&bars->we_full[ws]), 0);
+                    tma_load_2d_to<2>(slot_w(ws), &map_w, wbar, k * 64, w_row);
+                    tma_load_2d_to<2>(slot_e(ws), &map_e, wbar, 0, e_row + k * 16);
+                    if (++ws == kWeSlots) { ws = 0; wphase ^= 1; }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        mbar_wait(&bars->x_empty[xs], xphase ^ 1);
+                        if (rank == 0) mbar_expect_tx(&bars->x_full[xs], 2u * kXBytes);
+                        const uint32_t xbar = mapa_u32(smem_u32(&bars->x_full[xs]), 0);
+                        tma_load_2d_to<2>(stage_x(xs, 0), &map_x, xbar, k * 128 + h * 64, x_row0);
+                        tma_load_2d_to<2>(stage_x(xs, 1), &map_x, xbar, k * 128 + h * 64, x_row0 + NT);
+                        if (++xs == kXStages) { xs = 0; xphase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer (leader CTA) ==========================
+        if (lane == 0 && rank == 0) {
+            int ws = 0, xs = 0; uint32_t wphase = 0, xphase = 0, tile_phase = 0, eslot = kERing - 1;
+            for (int tile = unit; tile < num_tiles; tile += num_units) {
+                mbar_wait(&bars->tmem_empty, tile_phase ^ 1);
+                tc_fence_after();
+                for (int k = 0; k < nk128; ++k) {
+                    mbar_wait(&bars->we_full[ws], wphase);
+                    tc_fence_after();
+                    // E ring: the slot's previous atom was read kERing (8) slabs ago; we_full of this slab implies the
+                    // producers saw we_empty of the slab kWeSlots (3) back, i.e. every MMA at least 3 slabs old is done.
+                    eslot = (eslot + 1) & (kERing - 1);
+                    const uint32_t ecol = tmem_base + kTmemEW + eslot * 4;
+                    tmem_cp_128x128b<2>(ecol, make_smem_desc_k(smem_u32(slot_e(ws)), 0, 128, 128));
+                    const uint64_t dw = make_smem_desc(smem_u32(slot_w(ws)));
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        mbar_wait(&bars->x_full[xs], xphase);
+                        tc_fence_after();
+                        const uint64_t dx0 = make_smem_desc(smem_u32(stage_x(xs, 0)));
+                        const uint64_t dx1 = make_smem_desc(smem_u32(stage_x(xs, 1)));
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const int j = h * 2 + i;                         // k32 step inside the 128-k slab
+                            const uint32_t acc = (uint32_t)((k | j) != 0);
+                            mma_sp_bf16<2>(tmem_base, dw + (uint64_t)(j * 2), dx0 + (uint64_t)(i * 4), ecol + (uint32_t)(j & 2), kIdesc | (uint32_t)(j & 1), acc);
+                            mma_sp_bf16<2>(tmem_base + NT, dw + (uint64_t)(j * 2), dx1 + (uint64_t)(i * 4), ecol + (uint32_t)(j & 2), kIdesc | (uint32_t)(j & 1), acc);
+                        }
+                        commit<2>(&bars->x_empty[xs]);
+                        if (++xs == kXStages) { xs = 0; xphase ^= 1; }
+                    }
+                    commit<2>(&bars->we_empty[ws]);
+                    if (++ws == kWeSlots) { ws = 0; wphase ^= 1; }
+                }
+                commit<2>(&bars->tmem_full);
+                tile_phase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================================== epilogue (both CTAs) =============================
+        const int q = warp & 3, a = (warp - 4) >> 2;                         // TMEM lane quarter, accumulator
+        const int n_in_tile = q * 32 + lane;
+        const uint32_t leader_tmem_empty = mapa_u32(smem_u32(&bars->tmem_empty), 0);
+        uint32_t tile_phase = 0;
+        for (int tile = unit; tile < num_tiles; tile += num_units) {
+            const int tw = tile % p.tiles_w, tt = tile / p.tiles_w;
+            const int n = (tw * 2 + (int)rank) * BW + n_in_tile;
+            const float bv = (p.bias && n < p.N) ? p.bias[n] : 0.0f;
+            mbar_wait(&bars->tmem_full, tile_phase);
+            tc_fence_after();
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * NT + pass * (NT / 2));
+                uint32_t r[NT / 2];                                          // 120 columns
+#pragma unroll
+                for (int c = 0; c < 7; ++c) tmem_ld16(taddr + c * 16, r + c * 16);
+                tmem_ld8(taddr + 112, r + 112);
+                tmem_ld_wait();
+                if (pass == 1) {                                             // everything this warp owns has left TMEM
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(leader_tmem_empty);
+                }
+                const int t0 = tt * BT + a * NT + pass * (NT / 2);
+                if (n < p.N) {
+                    float* dst = p.out + (int64_t)t0 * p.N + n;
+                    const int t_left = p.T - t0;
+#pragma unroll
+                    for (int j = 0; j < NT / 2; ++j)
+                        if (j < t_left) dst[(int64_t)j * p.N] = __uint_as_float(r[j]) + bv;
+                }
+            }
+            tile_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+}
+
 // ---- 2:4 compressor ------------------------------------------------------------------------------------------------
 // One thread per (row, 16 logical k): reads 16 bf16 (two 128-bit loads), writes the 8 kept values (one 128-bit store)
 // and the 16-bit metadata word.  Groups with fewer than two non-zeros are padded with a zero position (indices stay
@@ -356,10 +537,26 @@ int gemm_bf16_sp_device(const void* x_bf16, const void* w_comp, const void* w_me
     p.e_atoms = (int)(Kc / 64);
     p.tiles_w = (int)((N + 128 * cg - 1) / (128 * cg));
     p.tiles_t = (int)((T + 255) / 256);
+    // Tile width for CTA pairs: 256 tokens (one accumulator) or 480 (two accumulators sharing the W slab).  Both are bound
+    // by operand bytes per SM (50 KB vs 78 KB per 128-k slab), so pick the smaller waves x bytes product -- but only for long
+    // K: the wide tile's epilogue hands TMEM back later (two 120-column passes with the first pass's stores in between),
+    // a fixed cost per tile that outweighs the saving below ~48 slabs (measured, profiles/r01_gemm_sp_bench.log: K = 4096 /
+    // 5120 lose 3-14 %, K >= 8192 gain 6-13 %).
+    bool wide_tile = false;
+    if (cg == 2) {
+        const int64_t pairs = sms / 2;
+        const int64_t tiles256 = (int64_t)p.tiles_w * p.tiles_t, tiles480 = (int64_t)p.tiles_w * ((T + wide::BT - 1) / wide::BT);
+        const int64_t cost256 = (tiles256 + pairs - 1) / pairs * 50, cost480 = (tiles480 + pairs - 1) / pairs * 78;
+        wide_tile = cost480 < cost256 && p.num_k_slabs >= 48;
+        if (tuning().gemm_sp_tile == 256) wide_tile = false;
+        if (tuning().gemm_sp_tile == 480) wide_tile = true;
+        if (p.debug) wide_tile = false;
+    }
     CUtensorMap map_w, map_x, map_e;
     if (int rc = make_map_bf16(&map_w, w_comp, N, Kc, Kc * 2, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    if (int rc = make_map_bf16(&map_x, x_bf16, T, Kp, Kp * 2, 64, 256 / cg, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_map_bf16(&map_x, x_bf16, T, Kp, Kp * 2, 64, wide_tile ? wide::XC : 256 / cg, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     if (int rc = make_map_bytes(&map_e, w_meta, mb / 128, 128, 16)) return rc;
+    if (wide_tile) p.tiles_t = (int)((T + wide::BT - 1) / wide::BT);
     const int units = std::min(p.tiles_w * p.tiles_t, sms / cg);
     cudaError_t e;
     if (cg == 1) {
@@ -367,16 +564,19 @@ int gemm_bf16_sp_device(const void* x_bf16, const void* w_comp, const void* w_me
         if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         bfp_gemm_bf16_sp_kernel<1><<<units, kThreads, Cfg<1>::kSmemTotal, st>>>(map_w, map_x, map_e, p);
     } else {
-        e = cudaFuncSetAttribute(bfp_gemm_bf16_sp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::kSmemTotal);
+        const int smem_bytes = wide_tile ? wide::kSmemTotal : Cfg<2>::kSmemTotal;
+        e = wide_tile ? cudaFuncSetAttribute(bfp_gemm_bf16_sp_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)
+                      : cudaFuncSetAttribute(bfp_gemm_bf16_sp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)units * 2); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = Cfg<2>::kSmemTotal; cfg.stream = st;
+        cfg.gridDim = dim3((unsigned)units * 2); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, bfp_gemm_bf16_sp_kernel<2>, map_w, map_x, map_e, p);
-        if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaLaunchKernelEx(bfp_gemm_bf16_sp_kernel<2>): %s", cudaGetErrorString(e));
+        e = wide_tile ? cudaLaunchKernelEx(&cfg, bfp_gemm_bf16_sp_wide_kernel, map_w, map_x, map_e, p)
+                      : cudaLaunchKernelEx(&cfg, bfp_gemm_bf16_sp_kernel<2>, map_w, map_x, map_e, p);
+        if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaLaunchKernelEx(bfp_gemm_bf16_sp): %s", cudaGetErrorString(e));
     }
     count_launch();
     return check_launch("bfp_gemm_bf16_sp_kernel");

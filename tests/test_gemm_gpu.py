@@ -282,10 +282,11 @@ def test_compress_rejects_dense_groups(ops):
     assert ops.compress_2to4_bf16(wb, check=False).comp.shape == (16, 64)
 
 
-@pytest.mark.parametrize("cta_group", [1, 2])
-@pytest.mark.parametrize("shape", [(256, 128, 128), (512, 256, 448), (300, 200, 264), (77, 300, 136), (1, 8, 72), (1000, 1536, 2048)])
-def test_gemm_sp_exact_products(ops, shape, cta_group):
-    """Small-integer operands: the sparse kernel must return the exact integer matmul, for both CTA-group modes."""
+@pytest.mark.parametrize("cta_group,tile", [(1, 0), (2, 256), (2, 480)])
+@pytest.mark.parametrize("shape", [(256, 128, 128), (512, 256, 448), (300, 200, 264), (77, 300, 136), (1, 8, 72), (1000, 1536, 2048), (963, 520, 392)])
+def test_gemm_sp_exact_products(ops, shape, cta_group, tile):
+    """Small-integer operands: the sparse kernel must return the exact integer matmul, for both CTA-group modes and both
+    pair tile widths (256 tokens / one accumulator, 480 tokens / two accumulators)."""
     from qsi_b200 import _lib
     T, N, K = shape
     g = torch.Generator().manual_seed(T + 3 * N + K)
@@ -296,10 +297,12 @@ def test_gemm_sp_exact_products(ops, shape, cta_group):
     bias = torch.randint(-5, 6, (N,), generator=g).float()
     ref = xb.double() @ wb.double().t() + bias.double()
     _lib.set_option("gemm_sp_cta_group", cta_group)
+    _lib.set_option("gemm_sp_tile", tile)
     try:
         y = ops.bfp_linear_bf16_sp(xb.cuda(), ops.compress_2to4_bf16(wb.cuda()), bias.cuda())
     finally:
         _lib.set_option("gemm_sp_cta_group", 0)
+        _lib.set_option("gemm_sp_tile", 0)
     assert torch.equal(y.double().cpu(), ref)
 
 
