@@ -41,6 +41,7 @@ using namespace gemm;
 // CG = 1: one CTA per tile (128 out-features x 256 tokens).  CG = 2: a cluster pair shares a 256 x 256 tile through
 // tcgen05.mma.cta_group::2 -- each CTA stages its own 128 W rows and only HALF of the X tile, so the shared-memory feed per
 // MMA drops from 20 KB to 12 KB per SM (the 1-CTA kernel is feed-bound: 160 B/clk wanted, 128 B/clk available).
+constexpr int kSmemStaging = 8 * 2 * 1024;      // epilogue: per warp two [8 tokens][32 out-features] fp32 tiles for the TMA stores
 template <int CG> struct Cfg {
     static constexpr int BW = 128;                       // out-features (rows of W) per CTA = TMEM lanes
     static constexpr int BT = 256;                       // tokens per tile = accumulator columns
@@ -52,7 +53,7 @@ template <int CG> struct Cfg {
     static constexpr int kSmemE = 2048;                  // one E atom
     static constexpr int kStageBytes = kSmemW + kSmemX + kSmemE;      // 83968 / 51200, multiples of 1024
     static constexpr int kStages = CG == 1 ? 2 : 4;
-    static constexpr int kSmemTotal = kStages * kStageBytes + 1024 + 1024;
+    static constexpr int kSmemTotal = kStages * kStageBytes + kSmemStaging + 1024 + 1024;
     // D = F32, A = B = BF16, K-major, N = BT, M = BW * CG, sparse flag (bit 2); bits 0-1 = sparsity selector
     static constexpr uint32_t kIdesc = (1u << 2) | (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BT >> 3) << 17) | ((uint32_t)((BW * CG) >> 4) << 24);
 };
@@ -70,6 +71,7 @@ struct Params {
     int num_k_slabs;            // ceil(K / 128)
     int e_atoms;                // ceil(K / 128)
     int tiles_w, tiles_t;       // tiles_w counts CG * 128 rows
+    int out_tma;                // 1 = the epilogue stages the tile in smem and writes it with TMA stores (needs N % 4 == 0)
     int debug;                  // timing experiments only (wrong results): bit 0 = every tile loads X tile 0, bit 1 = W tile 0
 };
 
@@ -102,15 +104,50 @@ __device__ __forceinline__ void tmem_cp_128x128b(uint32_t tmem_dst, uint64_t sme
     if constexpr (CG == 1) asm volatile("tcgen05.cp.cta_group::1.128x128b [%0], %1;" ::"r"(tmem_dst), "l"(smem_desc) : "memory");
     else asm volatile("tcgen05.cp.cta_group::2.128x128b [%0], %1;" ::"r"(tmem_dst), "l"(smem_desc) : "memory");
 }
+// Epilogue store of NC accumulator columns (tokens t0 .. t0+NC-1) of this warp's 32 out-features n0 .. n0+31.
+// TMA path: the warp transposes 8 tokens at a time through a private double-buffered smem tile [8 t][32 n] and one lane
+// issues a TMA store per tile (8 full 128-byte rows; rows / columns beyond T / N are clipped by the copy engine).  Plain
+// path (N % 4 != 0): one 128-byte warp store per token.  Measured on B200: the st.global epilogue cost ~28 % of the whole
+// kernel at K = 4096 (it slows the operand stream while it runs, tools/exp_sp_tile_overhead.py).
+template <int NC>
+__device__ __forceinline__ void store_columns(const Params& p, const CUtensorMap* map_out, float* stg, const uint32_t* r, float bv,
+                                              int n0, int lane, int t0) {
+    if (p.debug & 8) return;
+    if (p.out_tma) {
+        const uint64_t pol = l2_policy_evict_first();
+#pragma unroll
+        for (int rd = 0; rd < NC / 8; ++rd) {
+            float* buf = stg + (rd & 1) * 256;
+            if (lane == 0) tma_store_wait_read<1>();          // the store that last read this buffer (two rounds ago) is done with it
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) buf[j * 32 + lane] = __uint_as_float(r[rd * 8 + j]) + bv;
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { tma_store_2d_hint(map_out, buf, n0, t0 + rd * 8, pol); tma_store_commit(); }
+        }
+    } else {
+        const int n = n0 + lane;
+        if (n < p.N) {
+            float* dst = p.out + (int64_t)t0 * p.N + n;
+            const int t_left = p.T - t0;
+#pragma unroll
+            for (int j = 0; j < NC; ++j)
+                if (j < t_left) dst[(int64_t)j * p.N] = __uint_as_float(r[j]) + bv;
+        }
+    }
+}
+
 template <int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 bfp_gemm_bf16_sp_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
-                        const __grid_constant__ CUtensorMap map_e, const Params p) {
+                        const __grid_constant__ CUtensorMap map_e, const __grid_constant__ CUtensorMap map_out, const Params p) {
     using C = Cfg<CG>;
     constexpr int kStages = C::kStages, kStageBytes = C::kStageBytes, BW = C::BW, BT = C::BT, KS = C::KS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    Barriers* bars = reinterpret_cast<Barriers*>(smem + kStages * kStageBytes);
+    float* staging = reinterpret_cast<float*>(smem + kStages * kStageBytes);
+    Barriers* bars = reinterpret_cast<Barriers*>(smem + kStages * kStageBytes + kSmemStaging);
     auto stage_x = [&](int s) { return smem + s * kStageBytes; };
     auto stage_w = [&](int s) { return smem + s * kStageBytes + C::kSmemX; };
     auto stage_e = [&](int s) { return smem + s * kStageBytes + C::kSmemX + C::kSmemW; };
@@ -145,6 +182,7 @@ bfp_gemm_bf16_sp_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             int uses = 0;
+            const uint64_t pol_keep = l2_policy_evict_last();
             for (int tile = unit; tile < num_tiles; tile += num_units) {
                 const int tw = tile % p.tiles_w, tt = tile / p.tiles_w;      // consecutive units share the X tile
                 const int w_row = (tw * CG + (int)rank) * BW;                // this CTA's 128 W rows
@@ -161,10 +199,10 @@ bfp_gemm_bf16_sp_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_
                     const uint32_t bar = CG == 1 ? smem_u32(&bars->full[stage]) : mapa_u32(smem_u32(&bars->full[stage]), 0);
                     // every TMA row is a full 128 bytes: the copy engine is request-rate-bound (~2 clk per row), so 64-byte
                     // rows (a 64-k W slab) would halve its throughput
-                    tma_load_2d_to<CG>(stage_x(stage), &map_x, bar, ks * KS, x_row_ld);
-                    tma_load_2d_to<CG>(stage_x(stage) + C::kSmemXAtom, &map_x, bar, ks * KS + 64, x_row_ld);
-                    tma_load_2d_to<CG>(stage_w(stage), &map_w, bar, ks * (KS / 2), w_row_ld);
-                    tma_load_2d_to<CG>(stage_e(stage), &map_e, bar, 0, e_row + ks * 16);
+                    tma_load_2d_to_hint<CG>(stage_x(stage), &map_x, bar, ks * KS, x_row_ld, pol_keep);
+                    tma_load_2d_to_hint<CG>(stage_x(stage) + C::kSmemXAtom, &map_x, bar, ks * KS + 64, x_row_ld, pol_keep);
+                    tma_load_2d_to_hint<CG>(stage_w(stage), &map_w, bar, ks * (KS / 2), w_row_ld, pol_keep);
+                    tma_load_2d_to_hint<CG>(stage_e(stage), &map_e, bar, 0, e_row + ks * 16, pol_keep);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -225,17 +263,11 @@ bfp_gemm_bf16_sp_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_
             }
             tile_phase ^= 1;
 
-            const int n = (tw * CG + (int)rank) * BW + n_in_tile;
-            const int t0 = tt * BT + half * (BT / 2);
-            if (n < p.N) {
-                const float bv = p.bias ? p.bias[n] : 0.0f;
-                float* dst = p.out + (int64_t)t0 * p.N + n;
-                const int t_left = p.T - t0;
-#pragma unroll
-                for (int j = 0; j < BT / 2; ++j)
-                    if (j < t_left) dst[(int64_t)j * p.N] = __uint_as_float(r[j]) + bv;
-            }
+            const int n0 = (tw * CG + (int)rank) * BW + q * 32;
+            const float bv = (p.bias && n0 + lane < p.N) ? p.bias[n0 + lane] : 0.0f;
+            store_columns<BT / 2>(p, &map_out, staging + ew * 512, r, bv, n0, lane, tt * BT + half * (BT / 2));
         }
+        if (p.out_tma && lane == 0) tma_store_wait_all<0>();                 // smem (and the stores) must outlive the CTA's exit
     }
 
     tc_fence_before();
@@ -265,7 +297,7 @@ constexpr int XC = NT / 2;                               // X rows per chunk per
 constexpr int kWeSlots = 3, kXStages = 5;
 constexpr int kSmemW = BW * 128, kSmemE = 2048, kWeBytes = kSmemW + kSmemE;          // 18 KB
 constexpr int kSmemXChunk = XC * 128, kXBytes = 2 * kSmemXChunk;                     // 15 KB, 30 KB
-constexpr int kSmemTotal = kWeSlots * kWeBytes + kXStages * kXBytes + 1024 + 1024;
+constexpr int kSmemTotal = kWeSlots * kWeBytes + kXStages * kXBytes + kSmemStaging + 1024 + 1024;
 constexpr uint32_t kIdesc = (1u << 2) | (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)((BW * 2) >> 4) << 24);
 constexpr int kTmemEW = 480;
 struct Barriers {
@@ -283,12 +315,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t* r) {
 
 __global__ void __launch_bounds__(kThreads, 1)
 bfp_gemm_bf16_sp_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
-                             const __grid_constant__ CUtensorMap map_e, const Params p) {
+                             const __grid_constant__ CUtensorMap map_e, const __grid_constant__ CUtensorMap map_out, const Params p) {
     using namespace wide;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_x = smem + kWeSlots * kWeBytes;                       // 55296: multiple of 1024
-    wide::Barriers* bars = reinterpret_cast<wide::Barriers*>(smem_x + kXStages * kXBytes);
+    float* staging = reinterpret_cast<float*>(smem_x + kXStages * kXBytes);
+    wide::Barriers* bars = reinterpret_cast<wide::Barriers*>(smem_x + kXStages * kXBytes + kSmemStaging);
     auto slot_w = [&](int s) { return smem + s * kWeBytes; };
     auto slot_e = [&](int s) { return smem + s * kWeBytes + kSmemW; };
     auto stage_x = [&](int s, int c) { return smem_x + s * kXBytes + c * kSmemXChunk; };
@@ -319,6 +352,7 @@ bfp_gemm_bf16_sp_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __
         // ===================================== TMA producer (both CTAs) =========================
         if (lane == 0) {
             int ws = 0, xs = 0; uint32_t wphase = 0, xphase = 0;
+            const uint64_t pol_keep = l2_policy_evict_last();
             for (int tile = unit; tile < num_tiles; tile += num_units) {
                 const int tw = tile % p.tiles_w, tt = tile / p.tiles_w;
                 const int w_row = (tw * 2 + (int)rank) * BW;
@@ -328,16 +362,16 @@ bfp_gemm_bf16_sp_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __
                     mbar_wait(&bars->we_empty[ws], wphase ^ 1);
                     if (rank == 0) mbar_expect_tx(&bars->we_full[ws], 2u * kWeBytes);
                     const uint32_t wbar = mapa_u32(smem_u32(&bars->we_full[ws]), 0);
-                    tma_load_2d_to<2>(slot_w(ws), &map_w, wbar, k * 64, w_row);
-                    tma_load_2d_to<2>(slot_e(ws), &map_e, wbar, 0, e_row + k * 16);
+                    tma_load_2d_to_hint<2>(slot_w(ws), &map_w, wbar, k * 64, w_row, pol_keep);
+                    tma_load_2d_to_hint<2>(slot_e(ws), &map_e, wbar, 0, e_row + k * 16, pol_keep);
                     if (++ws == kWeSlots) { ws = 0; wphase ^= 1; }
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         mbar_wait(&bars->x_empty[xs], xphase ^ 1);
                         if (rank == 0) mbar_expect_tx(&bars->x_full[xs], 2u * kXBytes);
                         const uint32_t xbar = mapa_u32(smem_u32(&bars->x_full[xs]), 0);
-                        tma_load_2d_to<2>(stage_x(xs, 0), &map_x, xbar, k * 128 + h * 64, x_row0);
-                        tma_load_2d_to<2>(stage_x(xs, 1), &map_x, xbar, k * 128 + h * 64, x_row0 + NT);
+                        tma_load_2d_to_hint<2>(stage_x(xs, 0), &map_x, xbar, k * 128 + h * 64, x_row0, pol_keep);
+                        tma_load_2d_to_hint<2>(stage_x(xs, 1), &map_x, xbar, k * 128 + h * 64, x_row0 + NT, pol_keep);
                         if (++xs == kXStages) { xs = 0; xphase ^= 1; }
                     }
                 }
@@ -407,17 +441,12 @@ bfp_gemm_bf16_sp_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(leader_tmem_empty);
                 }
-                const int t0 = tt * BT + a * NT + pass * (NT / 2);
-                if (n < p.N) {
-                    float* dst = p.out + (int64_t)t0 * p.N + n;
-                    const int t_left = p.T - t0;
-#pragma unroll
-                    for (int j = 0; j < NT / 2; ++j)
-                        if (j < t_left) dst[(int64_t)j * p.N] = __uint_as_float(r[j]) + bv;
-                }
+                store_columns<NT / 2>(p, &map_out, staging + (warp - 4) * 512, r, bv, (tw * 2 + (int)rank) * BW + q * 32, lane,
+                                      tt * BT + a * NT + pass * (NT / 2));
             }
             tile_phase ^= 1;
         }
+        if (p.out_tma && lane == 0) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
@@ -537,32 +566,33 @@ int gemm_bf16_sp_device(const void* x_bf16, const void* w_comp, const void* w_me
     p.e_atoms = (int)(Kc / 64);
     p.tiles_w = (int)((N + 128 * cg - 1) / (128 * cg));
     p.tiles_t = (int)((T + 255) / 256);
-    // Tile width for CTA pairs: 256 tokens (one accumulator) or 480 (two accumulators sharing the W slab).  Both are bound
-    // by operand bytes per SM (50 KB vs 78 KB per 128-k slab), so pick the smaller waves x bytes product -- but only for long
-    // K: the wide tile's epilogue hands TMEM back later (two 120-column passes with the first pass's stores in between),
-    // a fixed cost per tile that outweighs the saving below ~48 slabs (measured, profiles/r01_gemm_sp_bench.log: K = 4096 /
-    // 5120 lose 3-14 %, K >= 8192 gain 6-13 %).
+    // Tile width for CTA pairs: 256 tokens (one accumulator) or 480 (two accumulators sharing the W slab: 78 KB instead of
+    // 2 x 50 KB of operands per SM for 480 tokens).  A 480-token wave measured 1.5-1.95x a 256-token wave over the nine
+    // LLaMA shapes (profiles/r01_gemm_sp_bench.log), so the wide tile is taken when it needs fewer than 1/1.7 of the waves.
     bool wide_tile = false;
     if (cg == 2) {
         const int64_t pairs = sms / 2;
         const int64_t tiles256 = (int64_t)p.tiles_w * p.tiles_t, tiles480 = (int64_t)p.tiles_w * ((T + wide::BT - 1) / wide::BT);
-        const int64_t cost256 = (tiles256 + pairs - 1) / pairs * 50, cost480 = (tiles480 + pairs - 1) / pairs * 78;
-        wide_tile = cost480 < cost256 && p.num_k_slabs >= 48;
+        const int64_t waves256 = (tiles256 + pairs - 1) / pairs, waves480 = (tiles480 + pairs - 1) / pairs;
+        wide_tile = waves480 * 17 < waves256 * 10 && p.num_k_slabs >= 16;
         if (tuning().gemm_sp_tile == 256) wide_tile = false;
         if (tuning().gemm_sp_tile == 480) wide_tile = true;
-        if (p.debug) wide_tile = false;
+        if (p.debug & 7) wide_tile = false;
     }
     CUtensorMap map_w, map_x, map_e;
     if (int rc = make_map_bf16(&map_w, w_comp, N, Kc, Kc * 2, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     if (int rc = make_map_bf16(&map_x, x_bf16, T, Kp, Kp * 2, 64, wide_tile ? wide::XC : 256 / cg, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     if (int rc = make_map_bytes(&map_e, w_meta, mb / 128, 128, 16)) return rc;
+    CUtensorMap map_out = map_e;
+    p.out_tma = (N % 4 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 && tuning().gemm_out_tma) ? 1 : 0;
+    if (p.out_tma) if (int rc = make_map_f32(&map_out, out, T, N, N * 4, 32, 8)) return rc;
     if (wide_tile) p.tiles_t = (int)((T + wide::BT - 1) / wide::BT);
     const int units = std::min(p.tiles_w * p.tiles_t, sms / cg);
     cudaError_t e;
     if (cg == 1) {
         e = cudaFuncSetAttribute(bfp_gemm_bf16_sp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::kSmemTotal);
         if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        bfp_gemm_bf16_sp_kernel<1><<<units, kThreads, Cfg<1>::kSmemTotal, st>>>(map_w, map_x, map_e, p);
+        bfp_gemm_bf16_sp_kernel<1><<<units, kThreads, Cfg<1>::kSmemTotal, st>>>(map_w, map_x, map_e, map_out, p);
     } else {
         const int smem_bytes = wide_tile ? wide::kSmemTotal : Cfg<2>::kSmemTotal;
         e = wide_tile ? cudaFuncSetAttribute(bfp_gemm_bf16_sp_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)
@@ -574,8 +604,8 @@ int gemm_bf16_sp_device(const void* x_bf16, const void* w_comp, const void* w_me
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        e = wide_tile ? cudaLaunchKernelEx(&cfg, bfp_gemm_bf16_sp_wide_kernel, map_w, map_x, map_e, p)
-                      : cudaLaunchKernelEx(&cfg, bfp_gemm_bf16_sp_kernel<2>, map_w, map_x, map_e, p);
+        e = wide_tile ? cudaLaunchKernelEx(&cfg, bfp_gemm_bf16_sp_wide_kernel, map_w, map_x, map_e, map_out, p)
+                      : cudaLaunchKernelEx(&cfg, bfp_gemm_bf16_sp_kernel<2>, map_w, map_x, map_e, map_out, p);
         if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaLaunchKernelEx(bfp_gemm_bf16_sp): %s", cudaGetErrorString(e));
     }
     count_launch();

@@ -25,6 +25,7 @@ struct Tuning {
     int pdl = 1;                          // programmatic dependent launch for the streaming kernels (bfp_stream.cuh)
     int gemm_sp_debug = 0;                // timing experiments (wrong results): see bfp_gemm_sp.cu Params::debug
     int gemm_bf16_cta_group = 0;          // dense bf16 kind: 0 = CTA pairs when T > 128 and N > 128; 1 or 2 forces the mode
+    int gemm_out_tma = 1;                 // GEMM epilogues write the output tile with TMA stores (0 = plain st.global)
     int gemm_sp_tile = 0;                 // sparse kind on CTA pairs: 0 = pick 256- or 480-token tiles by cost; 256 / 480 forces one
     int gemm_sp_cta_group = 0;            // 0 = CTA pairs (cta_group::2) when N > 128; 1 or 2 forces the mode
     int gemm_bf16_tile_n = 0;             // 0 = default tile (128x256); 128 or 256 forces the width  // bfp_quantize_host: input bytes per pipelined chunk

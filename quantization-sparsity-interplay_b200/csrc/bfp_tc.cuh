@@ -146,6 +146,32 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// ---- TMA stores (epilogues): smem tile -> global through the copy engine, full 128-byte rows, no LSU store instructions --
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+// L2 eviction policies: the output tile is written once and never re-read by the kernel (evict_first), the operands are
+// re-read by every tile of the other dimension (evict_last) -- without this the output stream pushes the operands out of L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, const void* smem_src, int c0, int c1, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ---- CTA-pair (cta_group::2) helpers: CG = 1 degenerates to the single-CTA forms -----------------------------------
 // tcgen05.commit: CG = 2 arrives on the barrier at the same offset in both CTAs of the pair
 template <int CG>
@@ -155,6 +181,15 @@ __device__ __forceinline__ void commit(uint64_t* bar) {
                       ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 // TMA tile load whose completion bytes land on `bar_addr` (a shared::cluster address; for CG = 2 the pair leader's barrier)
+template <int CG>
+__device__ __forceinline__ void tma_load_2d_to_hint(void* dst, const CUtensorMap* map, uint32_t bar_addr, int c0, int c1, uint64_t policy) {
+    if constexpr (CG == 1)
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+                     ::"r"(smem_u32(dst)), "l"(map), "r"(bar_addr), "r"(c0), "r"(c1), "l"(policy) : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+                     ::"r"(smem_u32(dst)), "l"(map), "r"(bar_addr), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
 template <int CG>
 __device__ __forceinline__ void tma_load_2d_to(void* dst, const CUtensorMap* map, uint32_t bar_addr, int c0, int c1) {
     if constexpr (CG == 1)
@@ -230,6 +265,20 @@ inline int make_map_bf16(CUtensorMap* map, const void* ptr, int64_t rows, int64_
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_errorf(BFP_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return BFP_OK;
+}
+
+// 2-D fp32 tensor map without swizzle (output tiles written by TMA stores): `rows` rows of `cols` floats, row stride in bytes.
+inline int make_map_f32(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t row_stride_bytes, int box_cols, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return set_error(BFP_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)row_stride_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_errorf(BFP_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return BFP_OK;
 }
