@@ -269,7 +269,8 @@ template <int TBN, int CG> struct Bf16Cfg {
     static constexpr int kRowsB = TBN / CG;                 // W rows staged by one CTA
     static constexpr int kStageBytes = kSmemA + kRowsB * BKB;
     static constexpr int kStages = CG == 2 ? 6 : (TBN == 256 ? 4 : 6);
-    static constexpr int kSmemTotal = kStages * kStageBytes + kSmemBarriers + 1024;
+    static constexpr int kSmemStaging = 8 * 4096;                            // per epilogue warp one [32 t][32 n] fp32 tile (SWIZZLE_128B)
+    static constexpr int kSmemTotal = kStages * kStageBytes + kSmemStaging + kSmemBarriers + 1024;
     // D = F32 (1 << 4), A = B = BF16 (1 << 7, 1 << 10), K-major, N >> 3, M >> 4 (M = 128 per CTA)
     static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
     static constexpr int kColsPerThread = TBN / 2;          // 8 epilogue warps: 4 lane quarters x 2 column halves
@@ -278,6 +279,7 @@ template <int TBN, int CG> struct Bf16Cfg {
 struct ParamsBf16 {
     const float* bias;
     float* out;
+    int out_tma;                // 1 = epilogue writes through smem + TMA stores (needs N % 4 == 0)
     int T, N;
     int num_k_stages;           // ceil(K / 64)
     int tiles_m, tiles_n;       // tiles_m counts CG * 128 rows
@@ -309,12 +311,14 @@ struct BarriersBf16 {
 
 template <int TBN, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
-bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ParamsBf16 p) {
+bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                     const __grid_constant__ CUtensorMap map_out, const ParamsBf16 p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     using C = Bf16Cfg<TBN, CG>;
     constexpr int kStagesBf16 = C::kStages, kStageBytesBf16 = C::kStageBytes, kCols = C::kColsPerThread;
-    BarriersBf16* bars = reinterpret_cast<BarriersBf16*>(smem + kStagesBf16 * kStageBytesBf16);
+    uint8_t* staging = smem + kStagesBf16 * kStageBytesBf16;                  // 1024-aligned (stage sizes are multiples of 1024)
+    BarriersBf16* bars = reinterpret_cast<BarriersBf16*>(staging + C::kSmemStaging);
     auto stage_a = [&](int s) { return smem + s * kStageBytesBf16; };
     auto stage_b = [&](int s) { return smem + s * kStageBytesBf16 + kSmemA; };
 
@@ -345,6 +349,7 @@ bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            const uint64_t pol_keep = l2_policy_evict_last();                 // operands are re-read by other tiles; the output is not
             for (int tile = unit; tile < num_tiles; tile += num_units) {
                 const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
                 const int a_row = (tm * CG + (int)rank) * BM;                 // this CTA's 128 X rows
@@ -353,8 +358,8 @@ bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     mbar_wait(&bars->empty[stage], phase ^ 1);
                     if (rank == 0) mbar_expect_tx(&bars->full[stage], (uint32_t)CG * kStageBytesBf16);   // both CTAs' bytes land on the leader
                     const uint32_t bar = CG == 1 ? smem_u32(&bars->full[stage]) : mapa_u32(smem_u32(&bars->full[stage]), 0);
-                    tma_load_2d_to<CG>(stage_a(stage), &map_a, bar, ks * 64, a_row);
-                    tma_load_2d_to<CG>(stage_b(stage), &map_b, bar, ks * 64, b_row);
+                    tma_load_2d_to_hint<CG>(stage_a(stage), &map_a, bar, ks * 64, a_row, pol_keep);
+                    tma_load_2d_to_hint<CG>(stage_b(stage), &map_b, bar, ks * 64, b_row, pol_keep);
                     if (++stage == kStagesBf16) { stage = 0; phase ^= 1; }
                 }
             }
@@ -396,6 +401,42 @@ bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             const int n0 = tn * TBN + half * kCols;
             float* dst = p.out + (int64_t)t * p.N + n0;
             const bool vec_ok = (p.N % 4 == 0) && (n0 + kCols <= p.N);
+            if (p.out_tma) {
+                // 32 columns at a time: the warp's [32 t][32 n] block goes to a swizzled smem tile (16-byte chunk c of row t at
+                // chunk c ^ (t & 7): conflict-free 128-bit shared stores) and leaves through one TMA store of full 128-byte rows;
+                // rows / columns beyond T / N are clipped by the copy engine.
+                const uint64_t pol = l2_policy_evict_first();
+                uint8_t* sbuf = staging + ew * 4096;
+#pragma unroll
+                for (int c = 0; c < kCols / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld16(taddr + c * 32, r);
+                    tmem_ld16(taddr + c * 32 + 16, r + 16);
+                    tmem_ld_wait();
+                    if (lane == 0) tma_store_wait_read<0>();                  // single staging tile: the previous store must have read it
+
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 o = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                        if (p.bias) {
+                            const int nb = n0 + c * 32 + 4 * j;
+                            if (nb + 3 < p.N) {
+                                const float4 bv = *reinterpret_cast<const float4*>(p.bias + nb);
+                                o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                            } else {
+                                if (nb < p.N) o.x += p.bias[nb];
+                                if (nb + 1 < p.N) o.y += p.bias[nb + 1];
+                                if (nb + 2 < p.N) o.z += p.bias[nb + 2];
+                            }
+                        }
+                        *reinterpret_cast<float4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) { tma_store_2d_hint(&map_out, sbuf, n0 + c * 32, (tm * CG + (int)rank) * BM + q * 32, pol); tma_store_commit(); }
+                }
+            } else {
 #pragma unroll
             for (int c = 0; c < kCols / 16; ++c) {
                 uint32_t r[16];
@@ -419,6 +460,7 @@ bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     }
                 }
             }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -428,6 +470,7 @@ bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             buf_phase[buf] ^= 1;
             buf ^= 1;
         }
+        if (p.out_tma && lane == 0) tma_store_wait_all<0>();                 // the staging tiles must outlive the last store
     }
 
     tc_fence_before();
@@ -472,7 +515,8 @@ int gemm_i8_device(const int8_t* a_mant, const float* a_scale_t, int64_t lda_s, 
 }
 
 template <int TBN, int CG>
-static int launch_bf16(const CUtensorMap& map_a, const CUtensorMap& map_b, const gemm::ParamsBf16& p, int units, cudaStream_t st) {
+static int launch_bf16(const CUtensorMap& map_a, const CUtensorMap& map_b, const CUtensorMap& map_out, const gemm::ParamsBf16& p, int units,
+                       cudaStream_t st) {
     using namespace gemm;
     using C = Bf16Cfg<TBN, CG>;
     cudaError_t e = cudaFuncSetAttribute(bfp_gemm_bf16_kernel<TBN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemTotal);
@@ -483,7 +527,7 @@ static int launch_bf16(const CUtensorMap& map_a, const CUtensorMap& map_b, const
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, bfp_gemm_bf16_kernel<TBN, CG>, map_a, map_b, p);
+    e = cudaLaunchKernelEx(&cfg, bfp_gemm_bf16_kernel<TBN, CG>, map_a, map_b, map_out, p);
     if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaLaunchKernelEx(bfp_gemm_bf16_kernel): %s", cudaGetErrorString(e));
     return BFP_OK;
 }
@@ -514,11 +558,14 @@ int gemm_bf16_device(const void* a_bf16, const void* b_bf16, const float* bias, 
     CUtensorMap map_a, map_b;
     if (int rc = make_map(&map_a, a_bf16, T, Kp * 2, BM, true)) return rc;
     if (int rc = make_map(&map_b, b_bf16, N, Kp * 2, tbn / cg, true)) return rc;
+    CUtensorMap map_out = map_a;
+    p.out_tma = (N % 4 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 && tuning().gemm_out_tma) ? 1 : 0;
+    if (p.out_tma) if (int rc = make_map_f32(&map_out, out, T, N, N * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     const int units = std::min(p.tiles_m * p.tiles_n, sms / cg);
     int rc;
-    if (cg == 2) rc = launch_bf16<256, 2>(map_a, map_b, p, units, st);
-    else if (tbn == 256) rc = launch_bf16<256, 1>(map_a, map_b, p, units, st);
-    else rc = launch_bf16<128, 1>(map_a, map_b, p, units, st);
+    if (cg == 2) rc = launch_bf16<256, 2>(map_a, map_b, map_out, p, units, st);
+    else if (tbn == 256) rc = launch_bf16<256, 1>(map_a, map_b, map_out, p, units, st);
+    else rc = launch_bf16<128, 1>(map_a, map_b, map_out, p, units, st);
     if (rc) return rc;
     count_launch();
     return check_launch("bfp_gemm_bf16_kernel");

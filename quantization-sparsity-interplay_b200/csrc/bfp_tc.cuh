@@ -270,7 +270,8 @@ inline int make_map_bf16(CUtensorMap* map, const void* ptr, int64_t rows, int64_
 }
 
 // 2-D fp32 tensor map without swizzle (output tiles written by TMA stores): `rows` rows of `cols` floats, row stride in bytes.
-inline int make_map_f32(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t row_stride_bytes, int box_cols, int box_rows) {
+inline int make_map_f32(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t row_stride_bytes, int box_cols, int box_rows,
+                        CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_NONE) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return set_error(BFP_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -278,7 +279,7 @@ inline int make_map_f32(CUtensorMap* map, const void* ptr, int64_t rows, int64_t
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    swz, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_errorf(BFP_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return BFP_OK;
 }

@@ -127,15 +127,17 @@ def test_gemm_bf16_exact_products(ops, shape):
     bias = torch.randint(-5, 6, (N,), generator=g, device="cuda").float()
     from qsi_b200 import _lib
     ref = a.double() @ b.double().t() + bias.double()
-    for tile_n, cg in ((0, 0), (128, 1), (256, 1), (0, 2)):     # auto; both single-CTA tile widths; CTA pairs forced
+    for tile_n, cg, tma in ((0, 0, 1), (128, 1, 1), (256, 1, 1), (0, 2, 1), (0, 2, 0), (256, 1, 0)):   # auto; tile widths; CTA pairs; plain-store epilogue
         _lib.set_option("gemm_bf16_tile_n", tile_n)
         _lib.set_option("gemm_bf16_cta_group", cg)
+        _lib.set_option("gemm_out_tma", tma)
         try:
             y = ops.bfp_linear_bf16(ab, bb, bias)
         finally:
             _lib.set_option("gemm_bf16_tile_n", 0)
             _lib.set_option("gemm_bf16_cta_group", 0)
-        assert torch.equal(y.double(), ref), (tile_n, cg)
+            _lib.set_option("gemm_out_tma", 1)
+        assert torch.equal(y.double(), ref), (tile_n, cg, tma)
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
@@ -282,7 +284,7 @@ def test_compress_rejects_dense_groups(ops):
     assert ops.compress_2to4_bf16(wb, check=False).comp.shape == (16, 64)
 
 
-@pytest.mark.parametrize("cta_group,tile", [(1, 0), (2, 256), (2, 480)])
+@pytest.mark.parametrize("cta_group,tile", [(1, 0), (2, 256), (2, 480), (2, -256), (2, -480)])   # negative: plain-store epilogue
 @pytest.mark.parametrize("shape", [(256, 128, 128), (512, 256, 448), (300, 200, 264), (77, 300, 136), (1, 8, 72), (1000, 1536, 2048), (963, 520, 392)])
 def test_gemm_sp_exact_products(ops, shape, cta_group, tile):
     """Small-integer operands: the sparse kernel must return the exact integer matmul, for both CTA-group modes and both
@@ -297,12 +299,14 @@ def test_gemm_sp_exact_products(ops, shape, cta_group, tile):
     bias = torch.randint(-5, 6, (N,), generator=g).float()
     ref = xb.double() @ wb.double().t() + bias.double()
     _lib.set_option("gemm_sp_cta_group", cta_group)
-    _lib.set_option("gemm_sp_tile", tile)
+    _lib.set_option("gemm_sp_tile", abs(tile))
+    _lib.set_option("gemm_out_tma", 0 if tile < 0 else 1)
     try:
         y = ops.bfp_linear_bf16_sp(xb.cuda(), ops.compress_2to4_bf16(wb.cuda()), bias.cuda())
     finally:
         _lib.set_option("gemm_sp_cta_group", 0)
         _lib.set_option("gemm_sp_tile", 0)
+        _lib.set_option("gemm_out_tma", 1)
     assert torch.equal(y.double().cpu(), ref)
 
 
