@@ -71,8 +71,19 @@ struct Params {
     int num_k_slabs;            // ceil(K / 128)
     int e_atoms;                // ceil(K / 128)
     int tiles_w, tiles_t;       // tiles_w counts CG * 128 rows
+    int64_t ld_out;             // row stride of `out` in floats (plain-store path)
     int out_tma;                // 1 = the epilogue stages the tile in smem and writes it with TMA stores (needs N % 4 == 0)
     int debug;                  // timing experiments only (wrong results): bit 0 = every tile loads X tile 0, bit 1 = W tile 0
+};
+
+// Output destinations of the epilogue's TMA stores.  n = 1: the caller's [T, N] tensor.  n = G > 1: the fused all-gather of
+// the column-parallel linear -- destination g is this rank's column slice inside rank g's full [T, N_total] output (own
+// HBM or a peer's over NVLink, symmetric memory), so the tile is stored G times straight from the staging smem tile and no
+// separate collective (nor the transposing copy after it) is needed.
+constexpr int kMaxDests = 8;
+struct OutMaps {
+    CUtensorMap m[kMaxDests];
+    int n;
 };
 
 struct Barriers {
@@ -110,7 +121,7 @@ __device__ __forceinline__ void tmem_cp_128x128b(uint32_t tmem_dst, uint64_t sme
 // path (N % 4 != 0): one 128-byte warp store per token.  Measured on B200: the st.global epilogue cost ~28 % of the whole
 // kernel at K = 4096 (it slows the operand stream while it runs, tools/exp_sp_tile_overhead.py).
 template <int NC>
-__device__ __forceinline__ void store_columns(const Params& p, const CUtensorMap* map_out, float* stg, const uint32_t* r, float bv,
+__device__ __forceinline__ void store_columns(const Params& p, const OutMaps& outs, float* stg, const uint32_t* r, float bv,
                                               int n0, int lane, int t0) {
     if (p.debug & 8) return;
     if (p.out_tma) {
@@ -118,22 +129,26 @@ __device__ __forceinline__ void store_columns(const Params& p, const CUtensorMap
 #pragma unroll
         for (int rd = 0; rd < NC / 8; ++rd) {
             float* buf = stg + (rd & 1) * 256;
-            if (lane == 0) tma_store_wait_read<1>();          // the store that last read this buffer (two rounds ago) is done with it
+            // the stores that last read this buffer (two rounds ago; one bulk group per round) are done with it
+            if (lane == 0) tma_store_wait_read<1>();
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; ++j) buf[j * 32 + lane] = __uint_as_float(r[rd * 8 + j]) + bv;
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) { tma_store_2d_hint(map_out, buf, n0, t0 + rd * 8, pol); tma_store_commit(); }
+            if (lane == 0) {
+                for (int g = 0; g < outs.n; ++g) tma_store_2d_hint(&outs.m[g], buf, n0, t0 + rd * 8, pol);
+                tma_store_commit();
+            }
         }
     } else {
         const int n = n0 + lane;
         if (n < p.N) {
-            float* dst = p.out + (int64_t)t0 * p.N + n;
+            float* dst = p.out + (int64_t)t0 * p.ld_out + n;
             const int t_left = p.T - t0;
 #pragma unroll
             for (int j = 0; j < NC; ++j)
-                if (j < t_left) dst[(int64_t)j * p.N] = __uint_as_float(r[j]) + bv;
+                if (j < t_left) dst[(int64_t)j * p.ld_out] = __uint_as_float(r[j]) + bv;
         }
     }
 }
@@ -141,7 +156,7 @@ __device__ __forceinline__ void store_columns(const Params& p, const CUtensorMap
 template <int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 bfp_gemm_bf16_sp_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
-                        const __grid_constant__ CUtensorMap map_e, const __grid_constant__ CUtensorMap map_out, const Params p) {
+                        const __grid_constant__ CUtensorMap map_e, const __grid_constant__ OutMaps outs, const Params p) {
     using C = Cfg<CG>;
     constexpr int kStages = C::kStages, kStageBytes = C::kStageBytes, BW = C::BW, BT = C::BT, KS = C::KS;
     extern __shared__ uint8_t smem_raw[];
@@ -265,7 +280,7 @@ bfp_gemm_bf16_sp_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_
 
             const int n0 = (tw * CG + (int)rank) * BW + q * 32;
             const float bv = (p.bias && n0 + lane < p.N) ? p.bias[n0 + lane] : 0.0f;
-            store_columns<BT / 2>(p, &map_out, staging + ew * 512, r, bv, n0, lane, tt * BT + half * (BT / 2));
+            store_columns<BT / 2>(p, outs, staging + ew * 512, r, bv, n0, lane, tt * BT + half * (BT / 2));
         }
         if (p.out_tma && lane == 0) tma_store_wait_all<0>();                 // smem (and the stores) must outlive the CTA's exit
     }
@@ -315,7 +330,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t* r) {
 
 __global__ void __launch_bounds__(kThreads, 1)
 bfp_gemm_bf16_sp_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
-                             const __grid_constant__ CUtensorMap map_e, const __grid_constant__ CUtensorMap map_out, const Params p) {
+                             const __grid_constant__ CUtensorMap map_e, const __grid_constant__ OutMaps outs, const Params p) {
     using namespace wide;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -441,7 +456,7 @@ bfp_gemm_bf16_sp_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(leader_tmem_empty);
                 }
-                store_columns<NT / 2>(p, &map_out, staging + (warp - 4) * 512, r, bv, (tw * 2 + (int)rank) * BW + q * 32, lane,
+                store_columns<NT / 2>(p, outs, staging + (warp - 4) * 512, r, bv, (tw * 2 + (int)rank) * BW + q * 32, lane,
                                       tt * BT + a * NT + pass * (NT / 2));
             }
             tile_phase ^= 1;
@@ -548,8 +563,17 @@ int compress_2to4_bf16_device(const void* w_bf16, int64_t rows, int64_t K, int64
 
 int gemm_bf16_sp_device(const void* x_bf16, const void* w_comp, const void* w_meta, const float* bias, float* out, int64_t T, int64_t N,
                         int64_t Kp, cudaStream_t st) {
+    float* outs[1] = {out};
+    return gemm_bf16_sp_multi_device(x_bf16, w_comp, w_meta, bias, outs, 1, N, T, N, Kp, st);
+}
+
+int gemm_bf16_sp_multi_device(const void* x_bf16, const void* w_comp, const void* w_meta, const float* bias, float* const* out_ptrs, int n_out,
+                              int64_t ld_out, int64_t T, int64_t N, int64_t Kp, cudaStream_t st) {
     using namespace gemm_sp;
     if (T == 0 || N == 0) return BFP_OK;
+    if (n_out < 1 || n_out > kMaxDests) return set_error(BFP_E_ARG, "1 to 8 output destinations");
+    if (ld_out < N) return set_error(BFP_E_ARG, "output row stride smaller than N");
+    float* out = out_ptrs[0];
     if (Kp % 8 != 0 || Kp <= 0) return set_error(BFP_E_ARG, "bf16 operand K must be a positive multiple of 8");
     if (T > INT32_MAX || N > INT32_MAX || Kp > INT32_MAX) return set_error(BFP_E_ARG, "dimension too large");
     if (reinterpret_cast<uintptr_t>(x_bf16) % 16 || reinterpret_cast<uintptr_t>(w_comp) % 16 || reinterpret_cast<uintptr_t>(w_meta) % 16)
@@ -561,7 +585,7 @@ int gemm_bf16_sp_device(const void* x_bf16, const void* w_comp, const void* w_me
     int cg = (N > 128) ? 2 : 1;
     if (tuning().gemm_sp_cta_group == 1 || tuning().gemm_sp_cta_group == 2) cg = tuning().gemm_sp_cta_group;
     Params p;
-    p.bias = bias; p.out = out; p.T = (int)T; p.N = (int)N; p.debug = tuning().gemm_sp_debug;
+    p.bias = bias; p.out = out; p.T = (int)T; p.N = (int)N; p.ld_out = ld_out; p.debug = tuning().gemm_sp_debug;
     p.num_k_slabs = (int)((Kp + 127) / 128);
     p.e_atoms = (int)(Kc / 64);
     p.tiles_w = (int)((N + 128 * cg - 1) / (128 * cg));
@@ -583,9 +607,16 @@ int gemm_bf16_sp_device(const void* x_bf16, const void* w_comp, const void* w_me
     if (int rc = make_map_bf16(&map_w, w_comp, N, Kc, Kc * 2, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     if (int rc = make_map_bf16(&map_x, x_bf16, T, Kp, Kp * 2, 64, wide_tile ? wide::XC : 256 / cg, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     if (int rc = make_map_bytes(&map_e, w_meta, mb / 128, 128, 16)) return rc;
-    CUtensorMap map_out = map_e;
-    p.out_tma = (N % 4 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 && tuning().gemm_out_tma) ? 1 : 0;
-    if (p.out_tma) if (int rc = make_map_f32(&map_out, out, T, N, N * 4, 32, 8)) return rc;
+    OutMaps map_out;
+    map_out.n = n_out;
+    for (int g = 0; g < kMaxDests; ++g) map_out.m[g] = map_e;
+    bool aligned = ld_out % 4 == 0;
+    for (int g = 0; g < n_out; ++g) aligned = aligned && out_ptrs[g] && reinterpret_cast<uintptr_t>(out_ptrs[g]) % 16 == 0;
+    p.out_tma = (aligned && (tuning().gemm_out_tma || n_out > 1)) ? 1 : 0;
+    if (n_out > 1 && !p.out_tma) return set_error(BFP_E_ALIGN, "multi-destination output needs 16-byte aligned slices and a row stride that is a multiple of 4");
+    // each map covers exactly the [T, N] slice (row stride ld_out), so the copy engine clips at the slice's edge
+    for (int g = 0; g < (p.out_tma ? n_out : 0); ++g)
+        if (int rc = make_map_f32(&map_out.m[g], out_ptrs[g], T, N, ld_out * 4, 32, 8)) return rc;
     if (wide_tile) p.tiles_t = (int)((T + wide::BT - 1) / wide::BT);
     const int units = std::min(p.tiles_w * p.tiles_t, sms / cg);
     cudaError_t e;

@@ -96,6 +96,8 @@ class ColumnParallelBFPLinear(torch.nn.Module):
         self.in_features, self.out_features = in_features, out_features
         self.lo, self.hi = column_shard(out_features, self.rank, self.world)
         self.local = BFPLinear(in_features, self.hi - self.lo, bias=bias, **bfp_kwargs)
+        self._symm = None            # (key, [(buffer, handle)] * 2, turn): symmetric full-output buffers of the fused path
+        self._fused_failed = None
 
     @torch.no_grad()
     def load_full(self, weight, bias=None):
@@ -105,7 +107,60 @@ class ColumnParallelBFPLinear(torch.nn.Module):
             self.local.bias.copy_(bias[self.lo:self.hi])
         return self
 
-    def forward(self, x):
+    # ---- fused path: the all-gather happens in the GEMM epilogue (peer-memory TMA stores), no NCCL call ----------------
+    def _fused_ok(self, x):
+        """2:4 sparse tensor-core kind, inference, CUDA, more than one rank, slices 16-byte aligned."""
+        import os
+        from . import bfp_ops
+        if self.world == 1 or not x.is_cuda or os.environ.get("BFP_COLUMN_PARALLEL", "fused") != "fused" or self._fused_failed:
+            return False
+        if torch.is_grad_enabled() and (x.requires_grad or self.local.weight.requires_grad):
+            return False
+        if self.local.bfp_args['rounding_mode'] != bfp_ops.rounding_modes.DETERM or self.local.num_format != 'bfp':
+            return False
+        return (bfp_ops._tensor_core_kind(x, self.local.weight, self.local.bfp_args) == 'sp' and self.out_features % 4 == 0
+                and all(column_shard(self.out_features, r, self.world)[0] % 4 == 0 for r in range(self.world)))
+
+    def _fused_forward(self, x, alias_output=False):
+        """y = [x W_0^T | ... | x W_{G-1}^T]: every rank runs bfp_gemm_bf16_sp_gather on its shard and the epilogue stores the
+        tile into ALL ranks' full outputs (torch symmetric memory: own HBM + peers over NVLink).  Two symmetric buffers
+        alternate so a barrier before the kernel is enough to know the target is free; a barrier after it makes every
+        slice visible everywhere.  alias_output=True returns the symmetric buffer itself (valid until the second-next call)."""
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib, bfp_ops
+        K = x.shape[-1]
+        T = x.numel() // K
+        key = (T, x.device)
+        if self._symm is None or self._symm[0] != key:
+            group = self.group if self.group is not None else dist.group.WORLD
+            bufs = []
+            for _ in range(2):
+                b = symm_mem.empty((T, self.out_features), dtype=torch.float32, device=x.device)
+                bufs.append((b, symm_mem.rendezvous(b, group)))
+            self._symm = (key, bufs, 0)
+        _, bufs, turn = self._symm
+        buf, hdl = bufs[turn]
+        self._symm = (key, bufs, turn ^ 1)
+        xb = bfp_ops.pack_bfp_bf16(x, identifier='in', **self.local.bfp_args)
+        ws = self.local._packed_weight('sp')
+        bias = self.local.bias.detach().float().contiguous() if self.local.bias is not None else None
+        ptrs = (ctypes.c_void_p * self.world)(*[int(hdl.buffer_ptrs[r]) + self.lo * 4 for r in range(self.world)])
+        hdl.barrier(channel=0)                                       # nobody is still reading this buffer's previous contents
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().bfp_gemm_bf16_sp_gather(xb.data_ptr(), ws.comp.data_ptr(), ws.meta.data_ptr(),
+                                                          bias.data_ptr() if bias is not None else None, ptrs, self.world, self.out_features,
+                                                          T, self.hi - self.lo, xb.shape[1], torch.cuda.current_stream().cuda_stream))
+        hdl.barrier(channel=1)                                       # every rank's slices have landed in every buffer
+        out = buf if alias_output else buf.clone()
+        return out.view(tuple(x.shape[:-1]) + (self.out_features,))
+
+    def forward(self, x, alias_output=False):
+        if self._fused_ok(x):
+            try:
+                return self._fused_forward(x, alias_output)
+            except (RuntimeError, AttributeError, ImportError) as e:   # symmetric memory unavailable on this system: NCCL path
+                self._fused_failed = repr(e)
         y = self.local(x)                                           # [..., N_local]
         if self.world == 1:
             return y

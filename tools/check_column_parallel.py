@@ -11,7 +11,11 @@ kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", e
           w_sparsity=True, N=2, M=4, first="s", sparsity_mode="structured", device="cuda")
 T = 4096
 res = []
-for name, (N, K) in (("65b q_proj", (8192, 8192)), ("65b up_proj", (22016, 8192)), ("65b down_proj", (8192, 22016))):
+SHAPES = (("65b q_proj", (8192, 8192)), ("65b up_proj", (22016, 8192)), ("65b down_proj", (8192, 22016)))
+if "--small" in sys.argv:                      # quick functional check (tests/test_dist_gpu.py)
+    sys.argv.remove("--small"); T = 520
+    SHAPES = (("small even", (1024, 512)), ("small uneven shards", (1096, 640)))
+for name, (N, K) in SHAPES:
     g = torch.Generator(device=dev).manual_seed(5)
     w = torch.randn(N, K, device=dev, generator=g) * 0.02
     x = torch.randn(T, K, device=dev, generator=g)
@@ -30,9 +34,15 @@ for name, (N, K) in (("65b q_proj", (8192, 8192)), ("65b up_proj", (22016, 8192)
             for _ in range(n): fn()
             e1.record(); torch.cuda.synchronize()
             return qd.max_over_ranks(e0.elapsed_time(e1) / n, dev)
-        ms_fwd = timed(lambda: cp(x)); ms_local = timed(lambda: cp.local(x)); ms_full = timed(lambda: full(x))
-    row = dict(layer=name, N=N, K=K, T=T, world=world, bit_equal_to_single_gpu=ok, fwd_ms=ms_fwd, local_ms=ms_local, single_gpu_ms=ms_full,
-               tops=2.0 * T * N * K / ms_fwd / 1e9, speedup_vs_1gpu=ms_full / ms_fwd)
+        fused = cp._fused_ok(x) and cp._fused_failed is None
+        ms_fwd = timed(lambda: cp(x)); ms_alias = timed(lambda: cp(x, alias_output=True)); ms_local = timed(lambda: cp.local(x)); ms_full = timed(lambda: full(x))
+        os.environ["BFP_COLUMN_PARALLEL"] = "nccl"
+        y_nccl = cp(x); ok_nccl = torch.equal(y_nccl, y_ref)
+        ms_nccl = timed(lambda: cp(x))
+        os.environ["BFP_COLUMN_PARALLEL"] = "fused"
+    row = dict(layer=name, N=N, K=K, T=T, world=world, fused_path=bool(fused), fused_failed=cp._fused_failed, bit_equal_to_single_gpu=ok,
+               nccl_path_bit_equal=ok_nccl, fwd_ms=ms_fwd, fwd_alias_ms=ms_alias, nccl_fwd_ms=ms_nccl, local_ms=ms_local, single_gpu_ms=ms_full,
+               tops=2.0 * T * N * K / ms_alias / 1e9, speedup_vs_1gpu=ms_full / ms_alias, fused_vs_nccl=ms_nccl / ms_alias)
     res.append(row)
     if rank == 0: print(json.dumps(row), flush=True)
     del w, x, cp, full, y, y_ref
