@@ -14,7 +14,7 @@ res = []
 SHAPES = (("65b q_proj", (8192, 8192)), ("65b up_proj", (22016, 8192)), ("65b down_proj", (8192, 22016)))
 if "--small" in sys.argv:                      # quick functional check (tests/test_dist_gpu.py)
     sys.argv.remove("--small"); T = 520
-    SHAPES = (("small even", (1024, 512)), ("small uneven shards", (1096, 640)))
+    SHAPES = (("small even", (1024, 512)), ("small uneven shards", (1097, 640)))
 for name, (N, K) in SHAPES:
     g = torch.Generator(device=dev).manual_seed(5)
     w = torch.randn(N, K, device=dev, generator=g) * 0.02
