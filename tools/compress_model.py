@@ -1,0 +1,48 @@
+"""BASELINE config 5 (first half): whole-model compression pass, sharded by tensor over the ranks (layer l -> rank l % G, no
+collective).  Every rank quantises + 2:4-sparsifies its layers' weights (fp32 -> fp32 fake-quant, HBFP8 block 64, s->q); tensors
+are generated on the device per layer (a 65B model is 259 GB in fp32).  Device time = max over ranks (CUDA events).
+    torchrun --nproc-per-node G tools/compress_model.py [--model llama-65b] [--out file.json]"""
+import argparse, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from qsi_b200 import bfp_ops, dist as qd, _lib
+ap = argparse.ArgumentParser(); ap.add_argument("--model", default="llama-65b"); ap.add_argument("--layers", type=int, default=0); ap.add_argument("--out", default=""); ap.add_argument("--raw", action="store_true", help="C-ABI calls into preallocated outputs (no torch allocation in the timed region)")
+a = ap.parse_args()
+rank, local_rank, world = qd.init()
+torch.cuda.set_device(local_rank); dev = torch.device("cuda", local_rank)
+args = bfp_ops.unpack_bfp_args(dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=7, block_size=64,
+                                    w_sparsity=True, N=2, M=4, first="s", sparsity_mode="structured", device="cuda"))
+tensors = qd.shard_by_layer(qd.model_tensors(a.model, a.layers or None), rank, world)
+shapes = qd.LAYER_SHAPES[a.model]
+g = torch.Generator(device=dev).manual_seed(rank)
+bufs = [torch.randn(n, k, device=dev, generator=g) * 0.02 for n, k in shapes]          # one layer's worth of weights, regenerated in place
+my_layers = sorted({t[0] for t in tensors})
+elems = 0; ms = 0.0
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for w in bufs: bfp_ops.float_to_bfp_blocked(w, **args, identifier="w")                 # warm-up
+torch.cuda.synchronize(); qd.barrier(dev)
+n0 = _lib.launch_count()
+for l in my_layers:
+    for w in bufs: w.mul_(1.0 + 1e-3 * ((l % 7) - 3))                                   # new values per layer (outside the timed region)
+    torch.cuda.synchronize()
+    e0.record()
+    if a.raw:
+        if l == my_layers[0]: outs_raw = [torch.empty_like(w) for w in bufs]
+        st = torch.cuda.current_stream().cuda_stream
+        for w, o in zip(bufs, outs_raw):
+            _lib.check(_lib.lib().bfp_quantize(w.data_ptr(), o.data_ptr(), w.shape[0], w.shape[1], 0, 0, 64, 7, 1e-8, 0, 0, 0, 2, 4, 1, 0, st))
+        outs = None
+    else:
+        outs = [bfp_ops.float_to_bfp_blocked(w, **args, identifier="w") for w in bufs]
+    e1.record(); torch.cuda.synchronize()
+    ms += e0.elapsed_time(e1); elems += sum(w.numel() for w in bufs)
+    del outs
+launches = _lib.launch_count() - n0
+ms_max = qd.max_over_ranks(ms, dev); total = qd.sum_over_ranks(elems, dev)
+if rank == 0:
+    res = dict(model=a.model, n_gpus=world, layers=len({t[0] for t in qd.model_tensors(a.model, a.layers or None)}), elements=total,
+               device_ms_max_over_ranks=ms_max, aggregate_GBps=total * 8 / ms_max / 1e6, per_gpu_GBps=total * 8 / ms_max / 1e6 / world,
+               launches_rank0=launches, sharding="layer l -> rank l % G, no collective")
+    print(json.dumps(res))
+    if a.out: json.dump(res, open(a.out, "w"), indent=1)
+if world > 1: torch.distributed.destroy_process_group()
