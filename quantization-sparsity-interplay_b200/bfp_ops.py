@@ -756,6 +756,26 @@ class BFPConv2d(torch.nn.Conv2d):
         raise NotImplementedError('NumFormat not implemented')
 
 
+# One-entry cache of the last packed activation: sibling projections (q/k/v, gate/up) are called back to back with the SAME
+# tensor object, and its packed form depends only on (values, block_size, mant_bits, epsilon).  The entry holds a reference to
+# the tensor itself (so its storage cannot be recycled under the key) and its version counter (in-place writes invalidate).
+# Not used while a CUDA graph is being captured (the capture must contain the pack it replays).
+_ACT_CACHE = {}
+
+
+def _packed_activation(x, bfp_args):
+    if os.environ.get("BFP_ACT_CACHE", "1") != "1" or torch.cuda.is_current_stream_capturing():
+        return pack_bfp_bf16(x, identifier='in', **bfp_args)
+    key = (bfp_args['block_size'], bfp_args['mant_bits'], float(bfp_args['epsilon']), bfp_args['in_sparsity'] == True,   # noqa: E712
+           bfp_args['N'], bfp_args['M'], bfp_args['first'])
+    hit = _ACT_CACHE.get(x.device)
+    if hit is not None and hit[0] is x and hit[1] == x._version and hit[2] == key:
+        return hit[3]
+    xb = pack_bfp_bf16(x, identifier='in', **bfp_args)
+    _ACT_CACHE[x.device] = (x, x._version, key, xb)
+    return xb
+
+
 class BFPLinear(torch.nn.Linear):
     """bfp_ops.py:270-287: nn.Linear whose operands are BFP-quantised (activations id 'in', weights id 'w') on every
     forward; parameters and state-dict are nn.Linear's.  The bias is never quantised."""
@@ -804,10 +824,10 @@ class BFPLinear(torch.nn.Linear):
                 return bfp_linear_packed(pack_bfp(input, identifier='in', **self.bfp_args), self._packed_weight(kind), self.bias)
             if kind == 'sp':
                 # 2:4-pruned weight: compressed once, tcgen05.mma.sp skips the zeros
-                return bfp_linear_bf16_sp(pack_bfp_bf16(input, identifier='in', **self.bfp_args), self._packed_weight(kind), self.bias,
+                return bfp_linear_bf16_sp(_packed_activation(input, self.bfp_args), self._packed_weight(kind), self.bias,
                                           out_shape=tuple(input.shape[:-1]) + (self.out_features,))
             if kind == 'bf16':
-                return bfp_linear_bf16(pack_bfp_bf16(input, identifier='in', **self.bfp_args), self._packed_weight(kind), self.bias,
+                return bfp_linear_bf16(_packed_activation(input, self.bfp_args), self._packed_weight(kind), self.bias,
                                        out_shape=tuple(input.shape[:-1]) + (self.out_features,))
             return self.linear_op(input, self.weight, self.bias)
         raise NotImplementedError('NumFormat not implemented')

@@ -442,3 +442,50 @@ def test_f_matmul_and_f_linear_bfp_on_tensor_cores(ops):
         y = lin(x, w, b)
     ref = q(x, "in") @ q(w, "w").t() + b.double()
     assert ((y.double() - ref).norm() / ref.norm()).item() <= 1e-5
+
+
+def test_bfplinear_forward_is_cuda_graph_capturable(ops):
+    """Everything BFPLinear.forward launches (activation pack + tensor-core GEMM; cached weight) goes to the current stream
+    with no host synchronisation, so it can be captured once and replayed (the launch-bound regime of small layers)."""
+    kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=7, block_size=64,
+              w_sparsity=True, N=2, M=4, first="s", sparsity_mode="structured", device="cuda")
+    torch.manual_seed(11)
+    lins = [ops.BFPLinear(512, 768, bias=True, **dict(kw)).cuda(), ops.BFPLinear(768, 256, bias=False, **dict(dict(kw), w_sparsity=False)).cuda()]
+    x = torch.randn(300, 512, device="cuda")
+    with torch.no_grad():
+        ref = lins[1](lins[0](x))                       # also packs + caches the weights outside the capture
+        side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            lins[1](lins[0](x))
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            y = lins[1](lins[0](x))
+        for trial in range(3):
+            x.copy_(torch.randn(300, 512, device="cuda"))
+            g.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(y, lins[1](lins[0](x))), trial
+    assert ref.shape == y.shape
+
+
+def test_packed_activation_cache_is_safe(ops):
+    """Sibling projections reuse the packed form of the same input tensor object; an in-place write or a different tensor
+    (even at the same address) must miss."""
+    kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=7, block_size=64, device="cuda")
+    from qsi_b200 import _lib
+    torch.manual_seed(2)
+    q, k = ops.BFPLinear(256, 128, bias=False, **dict(kw)).cuda(), ops.BFPLinear(256, 64, bias=False, **dict(kw)).cuda()
+    x = torch.randn(96, 256, device="cuda")
+    with torch.no_grad():
+        q(x); k(x)                                           # weights packed, x's packed form cached
+        n0 = _lib.launch_count(); yq = q(x); yk = k(x); same = _lib.launch_count() - n0
+        assert same == 2                                     # two GEMMs; the pack of x was made by the calls above
+        x.mul_(2.0)                                          # in-place: version bump -> repack
+        n0 = _lib.launch_count(); yq2 = q(x); assert _lib.launch_count() - n0 == 2
+        assert torch.equal(yq2, 2 * yq)
+        ptr = x.data_ptr(); del x
+        z = torch.randn(96, 256, device="cuda")              # very likely the same address, a different tensor
+        yz = q(z)
+        assert torch.equal(yz, ops.bfp_linear_bf16(ops.pack_bfp_bf16(z, identifier="in", **q.bfp_args), q._packed_weight("bf16")))
+        assert ptr == ptr and yk.shape == (96, 64)
