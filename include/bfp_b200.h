@@ -69,6 +69,11 @@ uint64_t bfp_launch_count(void);
  *   "host_chunk_bytes"    largest pipelined chunk of bfp_quantize_host, input bytes (default 16 MiB)
  *   "host_chunk_min_bytes" smallest chunk of its tapered schedule: chunks double from here at the start and halve towards
  *                         the end, so pipeline fill and drain cost one small chunk each (default 1 MiB)
+ *   "quant_tma"           1 = TMA-staged variant of the streaming quantiser (cp.async.bulk -> smem ring); slower than the
+ *                         default direct 128-bit loads on B200, kept for comparison
+ *   "gemm_out_tma"        1 (default) = GEMM epilogues write through smem + TMA stores; 0 = plain st.global
+ *   "gemm_sp_tile"        0 = sparse GEMM picks its 256- or 480-token pair tile by cost; 256 / 480 forces one
+ *   "gemm_bf16_cta_group" 0 = dense bf16 GEMM uses CTA pairs when T > 128 and N > 128; 1 / 2 forces the mode
  *   "pdl"                 1 (default) = the streaming kernels are launched with programmatic stream serialization
  *   "gemm_sp_cta_group"   0 = bfp_gemm_bf16_sp uses CTA pairs (cta_group::2) when N > 128; 1 / 2 forces the mode
  *   "gemm_bf16_tile_n"    0 = bfp_gemm_bf16 uses its 128x256 tile (128x128 when N <= 128); 128 / 256 forces one */

@@ -38,6 +38,7 @@ Tuning& tuning() {
         Tuning x;
         if (const char* s = getenv("BFP_STREAM_CTAS_PER_SM")) x.stream_ctas_per_sm = atoi(s) > 0 ? atoi(s) : x.stream_ctas_per_sm;
         if (const char* s = getenv("BFP_FORCE_GENERIC")) x.force_generic = atoi(s);
+        if (const char* s = getenv("BFP_QUANT_TMA")) x.quant_tma = atoi(s) ? 1 : 0;
         if (const char* s = getenv("BFP_HOST_CHUNK_MB")) x.host_chunk_bytes = (int64_t)(atoi(s) > 0 ? atoi(s) : 16) << 20;
         return x;
     }();
@@ -126,6 +127,7 @@ int bfp_set_option(const char* name, int64_t value) {
     else if (!strcmp(name, "force_generic")) t.force_generic = value != 0;
     else if (!strcmp(name, "host_chunk_bytes") && value >= 4096) t.host_chunk_bytes = value;
     else if (!strcmp(name, "host_chunk_min_bytes") && value >= 4096) t.host_chunk_min_bytes = value;
+    else if (!strcmp(name, "quant_tma") && (value == 0 || value == 1)) t.quant_tma = (int)value;
     else if (!strcmp(name, "pdl") && (value == 0 || value == 1)) t.pdl = (int)value;
     else if (!strcmp(name, "gemm_sp_debug") && value >= 0 && value <= 31) t.gemm_sp_debug = (int)value;
     else if (!strcmp(name, "gemm_bf16_cta_group") && value >= 0 && value <= 2) t.gemm_bf16_cta_group = (int)value;

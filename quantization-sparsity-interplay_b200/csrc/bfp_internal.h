@@ -22,6 +22,7 @@ struct Tuning {
     int force_generic = 0;                // tests: route everything through the generic kernel
     int64_t host_chunk_bytes = 16 << 20;      // bfp_quantize_host: largest pipelined chunk (input bytes)
     int64_t host_chunk_min_bytes = 1 << 20;   // ... and the smallest (first / last chunks of the tapered schedule)
+    int quant_tma = 0;                    // 1 = TMA-staged (cp.async.bulk -> smem ring) variant of the streaming quantiser
     int pdl = 1;                          // programmatic dependent launch for the streaming kernels (bfp_stream.cuh)
     int gemm_sp_debug = 0;                // timing experiments (wrong results): see bfp_gemm_sp.cu Params::debug
     int gemm_bf16_cta_group = 0;          // dense bf16 kind: 0 = CTA pairs when T > 128 and N > 128; 1 or 2 forces the mode

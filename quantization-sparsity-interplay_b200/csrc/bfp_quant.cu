@@ -33,6 +33,62 @@ struct StreamParams {
 };
 
 
+// One 128-bit vector (4 fp32 / 8 half elements of one block's lane) through mask -> block max (butterfly over the lanes that
+// share the block) -> scale -> round -> mask, in the order ORDER.  vec_index = flat index of the vector (Philox counter).
+// Every lane of the warp must call this (the butterfly shuffles are warp-wide).
+template <int DT, int ORDER, int M, int KD, int TIE, bool STOC>
+__device__ __forceinline__ void process_vec(const uint4& raw, const StreamParams& p, int64_t vec_index, uint4* out) {
+    using D = DType<DT>;
+    constexpr int V = D::kVec;
+    constexpr bool kQuant = ORDER != BFP_ORDER_SPARSIFY_ONLY;
+    constexpr bool kSparseFirst = ORDER == BFP_ORDER_SPARSIFY_QUANT || ORDER == BFP_ORDER_SPARSIFY_ONLY;
+    constexpr bool kSparseLast = ORDER == BFP_ORDER_QUANT_SPARSIFY;
+    constexpr int kOutVecs = (STOC && V == 8) ? 2 : 1;     // fp32 output of 8 half inputs = two 16-B stores
+    float v[V];
+    unpack_vec<DT>(raw, v);
+    uint32_t amax = 0u;
+    if (kQuant && kSparseFirst) {
+        // the block max always survives an N:M mask with N >= 1, so max over the unmasked keys is the
+        // masked block's max (SURVEY.md appendix A.4 i)
+#pragma unroll
+        for (int i = 0; i < V; ++i) amax = max(amax, abs_bits(v[i]));
+    }
+    if (kSparseFirst) mask_vec<M, KD, TIE, V>(v, p.kdrop);
+    if (kQuant) {
+        if (!kSparseFirst) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) amax = max(amax, abs_bits(v[i]));
+        }
+        // butterfly over the lanes that share this block; every lane of the warp executes every shuffle
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1)
+            if (off < p.lanes_per_block) amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+        const BlockScale sc = make_scale<DT>(amax, p.m, p.eps);
+        float un[STOC ? V : 1];
+        if (STOC) {
+#pragma unroll
+            for (int q = 0; q < V / 4; ++q) {
+                const uint4 r = philox4x32_10((uint64_t)(p.ctr_base + vec_index * (V / 4) + q), p.offset, p.seed);
+                un[4 * q] = u01(r.x); un[4 * q + 1] = u01(r.y); un[4 * q + 2] = u01(r.z); un[4 * q + 3] = u01(r.w);
+            }
+        }
+        if (sc.fast) {                                 // one branch per vector, uniform across the block's lanes
+#pragma unroll
+            for (int i = 0; i < V; ++i) v[i] = quant_elt_fast<STOC>(v[i], sc, STOC ? un[i] : 0.0f);
+        } else {
+#pragma unroll
+            for (int i = 0; i < V; ++i) v[i] = quant_elt_slow<DT, STOC>(v[i], sc.delta, sc.vmax, STOC ? un[i] : 0.0f);
+        }
+    }
+    if (kSparseLast) mask_vec<M, KD, TIE, V>(v, p.kdrop);
+    if (kOutVecs == 1) {
+        out[0] = STOC ? pack_vec<BFP_DT_F32>(v) : pack_vec<DT>(v);
+    } else {
+        out[0] = pack_vec<BFP_DT_F32>(v);
+        out[kOutVecs - 1] = pack_vec<BFP_DT_F32>(v + 4);
+    }
+}
+
 // ORDER: BFP_ORDER_*.  M / KD / TIE: see mask_vec.  STOC: stochastic rounding (fp32 output).
 template <int DT, int ORDER, int M, int KD, int TIE, bool STOC>
 __global__ void __launch_bounds__(kStreamThreads) quant_stream_kernel(const StreamParams p) {
@@ -64,51 +120,100 @@ __global__ void __launch_bounds__(kStreamThreads) quant_stream_kernel(const Stre
 #pragma unroll
         for (int u = 0; u < kStreamUnroll; ++u) {
             const int li = (int)threadIdx.x + u * kStreamThreads;
-            float v[V];
-            unpack_vec<DT>(raw[u], v);
-            uint32_t amax = 0u;
-            if (kQuant && kSparseFirst) {
-                // the block max always survives an N:M mask with N >= 1, so max over the unmasked keys is the
-                // masked block's max (SURVEY.md appendix A.4 i)
-#pragma unroll
-                for (int i = 0; i < V; ++i) amax = max(amax, abs_bits(v[i]));
-            }
-            if (kSparseFirst) mask_vec<M, KD, TIE, V>(v, p.kdrop);
-            if (kQuant) {
-                if (!kSparseFirst) {
-#pragma unroll
-                    for (int i = 0; i < V; ++i) amax = max(amax, abs_bits(v[i]));
-                }
-                // butterfly over the lanes that share this block; every lane of the warp executes every shuffle
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1)
-                    if (off < p.lanes_per_block) amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, off));
-                const BlockScale sc = make_scale<DT>(amax, p.m, p.eps);
-                float un[STOC ? V : 1];
-                if (STOC) {
-#pragma unroll
-                    for (int q = 0; q < V / 4; ++q) {
-                        const uint4 r = philox4x32_10((uint64_t)(p.ctr_base + (tile_base + li) * (V / 4) + q), p.offset, p.seed);
-                        un[4 * q] = u01(r.x); un[4 * q + 1] = u01(r.y); un[4 * q + 2] = u01(r.z); un[4 * q + 3] = u01(r.w);
-                    }
-                }
-                if (sc.fast) {                                 // one branch per vector, uniform across the block's lanes
-#pragma unroll
-                    for (int i = 0; i < V; ++i) v[i] = quant_elt_fast<STOC>(v[i], sc, STOC ? un[i] : 0.0f);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < V; ++i) v[i] = quant_elt_slow<DT, STOC>(v[i], sc.delta, sc.vmax, STOC ? un[i] : 0.0f);
-                }
-            }
-            if (kSparseLast) mask_vec<M, KD, TIE, V>(v, p.kdrop);
+            uint4 o[kOutVecs];
+            process_vec<DT, ORDER, M, KD, TIE, STOC>(raw[u], p, tile_base + li, o);
             if (li < rem) {
                 uint4* dst = p.out + (tile_base + li) * kOutVecs;
-                if (kOutVecs == 1) {
-                    st_stream(dst, STOC ? pack_vec<BFP_DT_F32>(v) : pack_vec<DT>(v));
-                } else {
-                    st_stream(dst, pack_vec<BFP_DT_F32>(v));
-                    st_stream(dst + 1, pack_vec<BFP_DT_F32>(v + 4));
-                }
+                st_stream(dst, o[0]);
+                if (kOutVecs == 2) st_stream(dst + 1, o[kOutVecs - 1]);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMA-staged variant of the stream kernel: a producer warp moves 16 KB tiles global -> shared with cp.async.bulk (the copy
+// engine, completion on an mbarrier) into a ring of kTmaStages tiles; eight consumer warps read their vectors from shared
+// memory (conflict-free 128-bit loads), hand the slot back at once, and run the same per-vector code.  Loads are issued
+// kTmaStages tiles ahead of the arithmetic by one thread instead of by every thread just before use.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kTmaStages = 6;
+constexpr int kTmaUnroll = 1;                      // vectors per consumer thread per tile: 4 KB tiles keep 7 CTAs (1792 consumers) per SM
+constexpr int kTmaThreads = kStreamThreads + 32;
+
+__device__ __forceinline__ uint32_t q_smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void q_mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = q_smem_u32(bar);
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity), "r"(100000u) : "memory");
+}
+
+template <int DT, int ORDER, int M, int KD, int TIE, bool STOC>
+__global__ void __launch_bounds__(kTmaThreads) quant_tma_kernel(const StreamParams p) {
+    using D = DType<DT>;
+    constexpr int V = D::kVec;
+    constexpr int kOutVecs = (STOC && V == 8) ? 2 : 1;
+    constexpr int kTileVecs = kStreamThreads * kTmaUnroll;
+    extern __shared__ __align__(128) uint8_t q_dyn_smem[];
+    uint4 (*ring)[kTileVecs] = reinterpret_cast<uint4 (*)[kTileVecs]>(q_dyn_smem);
+    uint64_t* full = reinterpret_cast<uint64_t*>(q_dyn_smem + kTmaStages * kTileVecs * 16);
+    uint64_t* empty = full + kTmaStages;
+
+    const int64_t n_tiles = (p.n_vec + kTileVecs - 1) / kTileVecs;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kTmaStages; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(q_smem_u32(&full[s])), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(q_smem_u32(&empty[s])), "r"(kStreamThreads / 32));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    pdl_launch_dependents();
+    pdl_wait();
+
+    if (warp == kStreamThreads / 32) {
+        // ---- producer: one lane issues the bulk copies ----
+        if (lane == 0) {
+            int s = 0; uint32_t phase = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int64_t tile_base = tile * kTileVecs;
+                const uint32_t bytes = (uint32_t)min((int64_t)kTileVecs, p.n_vec - tile_base) * 16u;
+                q_mbar_wait(&empty[s], phase ^ 1);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(q_smem_u32(&full[s])), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(q_smem_u32(&ring[s][0])), "l"(p.in + tile_base), "r"(bytes), "r"(q_smem_u32(&full[s])) : "memory");
+                if (++s == kTmaStages) { s = 0; phase ^= 1; }
+            }
+        }
+        return;
+    }
+    // ---- consumers ----
+    int s = 0; uint32_t phase = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t tile_base = tile * kTileVecs;
+        const int rem = (int)min((int64_t)kTileVecs, p.n_vec - tile_base);
+        q_mbar_wait(&full[s], phase);
+        uint4 raw[kTmaUnroll];
+#pragma unroll
+        for (int u = 0; u < kTmaUnroll; ++u) {
+            const int li = (int)threadIdx.x + u * kStreamThreads;
+            raw[u] = (li < rem) ? ring[s][li] : make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(q_smem_u32(&empty[s])) : "memory");   // slot read: refill it
+        if (++s == kTmaStages) { s = 0; phase ^= 1; }
+#pragma unroll
+        for (int u = 0; u < kTmaUnroll; ++u) {
+            const int li = (int)threadIdx.x + u * kStreamThreads;
+            uint4 o[kOutVecs];
+            process_vec<DT, ORDER, M, KD, TIE, STOC>(raw[u], p, tile_base + li, o);
+            if (li < rem) {
+                uint4* dst = p.out + (tile_base + li) * kOutVecs;
+                st_stream(dst, o[0]);
+                if (kOutVecs == 2) st_stream(dst + 1, o[kOutVecs - 1]);
             }
         }
     }
@@ -212,6 +317,20 @@ static int launch_stream_t(const StreamParams& p, cudaStream_t st) {
     static const int occ = kernel_occupancy(quant_stream_kernel<DT, ORDER, M, KD, TIE, STOC>, kStreamThreads);
     const int grid = stream_grid(occ, n_tiles);
     (void)di;
+    if (tuning().quant_tma) {
+        constexpr int kTmaSmem = kTmaStages * kStreamThreads * kTmaUnroll * 16 + 2 * kTmaStages * 8;
+        static const int occ_t = [] {
+            cudaFuncSetAttribute(quant_tma_kernel<DT, ORDER, M, KD, TIE, STOC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmem);
+            int occ = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quant_tma_kernel<DT, ORDER, M, KD, TIE, STOC>, kTmaThreads, kTmaSmem) != cudaSuccess || occ < 1) occ = 2;
+            return occ;
+        }();
+        const int64_t n_tiles_t = (p.n_vec + kStreamThreads * kTmaUnroll - 1) / (kStreamThreads * kTmaUnroll);
+        const int grid_t = (int)std::min<int64_t>(n_tiles_t, (int64_t)di.sm_count * occ_t);
+        if (int rc = launch_pdl(quant_tma_kernel<DT, ORDER, M, KD, TIE, STOC>, grid_t, kTmaThreads, st, p, kTmaSmem)) return rc;
+        count_launch();
+        return check_launch("quant_tma_kernel");
+    }
     if (int rc = launch_pdl(quant_stream_kernel<DT, ORDER, M, KD, TIE, STOC>, grid, kStreamThreads, st, p)) return rc;
     count_launch();
     return check_launch("quant_stream_kernel");

@@ -12,6 +12,7 @@ ap.add_argument("--quick", action="store_true")
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--out", default="")
 ap.add_argument("--pdl", default="1")
+ap.add_argument("--tma", default="0")
 a = ap.parse_args()
 L = _lib.lib()
 dev = torch.device("cuda", 0)
@@ -29,9 +30,10 @@ for dtn in a.dtypes.split(","):
         nbuf = max(2, int(600e6 // (shape[0] * shape[1] * tdt.itemsize)) + 1)
         xs = [(torch.randn(*shape, device=dev) * 0.02).to(tdt) for _ in range(nbuf)]
         ys = [torch.empty_like(xs[0]) for _ in range(2)]
-        for ctas, pdl in itertools.product([int(c) for c in a.ctas.split(",")], [int(c) for c in a.pdl.split(",")]):
+        for ctas, pdl, tma in itertools.product([int(c) for c in a.ctas.split(",")], [int(c) for c in a.pdl.split(",")], [int(c) for c in a.tma.split(",")]):
             _lib.set_option("stream_ctas_per_sm", ctas)
             _lib.set_option("pdl", pdl)
+            _lib.set_option("quant_tma", tma)
             for (m, b, o), rnd in itertools.product(cfgs, (0, 1)):
                 if rnd and (o == "s" or a.quick and o != "sq"):
                     continue
@@ -50,8 +52,8 @@ for dtn in a.dtypes.split(","):
                 us = e0.elapsed_time(e1) * 1e3 / a.iters
                 nbytes = shape[0] * shape[1] * (tdt.itemsize + (4 if rnd else tdt.itemsize))
                 gbs = nbytes / us / 1e3
-                res.append(dict(dtype=dtn, shape=shape, ctas=ctas, pdl=pdl, m=m, B=b, order=o, stoc=rnd, us=round(us, 2), GBps=round(gbs, 1)))
-                print(f"{dtn:5s} {str(shape):14s} ctas={ctas:2d} pdl={pdl} m={m} B={b:3d} {o:2s} {'stoc' if rnd else 'near'}  {us:8.2f} us  {gbs:8.1f} GB/s", flush=True)
+                res.append(dict(dtype=dtn, shape=shape, ctas=ctas, pdl=pdl, tma=tma, m=m, B=b, order=o, stoc=rnd, us=round(us, 2), GBps=round(gbs, 1)))
+                print(f"{dtn:5s} {str(shape):14s} ctas={ctas:2d} pdl={pdl} tma={tma} m={m} B={b:3d} {o:2s} {'stoc' if rnd else 'near'}  {us:8.2f} us  {gbs:8.1f} GB/s", flush=True)
         del xs, ys
 # reference points: torch copy of the same sizes
 for shape in shapes:
