@@ -767,7 +767,7 @@ def _packed_activation(x, bfp_args):
     if os.environ.get("BFP_ACT_CACHE", "1") != "1" or torch.cuda.is_current_stream_capturing():
         return pack_bfp_bf16(x, identifier='in', **bfp_args)
     key = (bfp_args['block_size'], bfp_args['mant_bits'], float(bfp_args['epsilon']), bfp_args['in_sparsity'] == True,   # noqa: E712
-           bfp_args['N'], bfp_args['M'], bfp_args['first'])
+           bfp_args['N'], bfp_args['M'], bfp_args['first'], _stream(x.device))        # same stream: the entry is ordered before its reuse
     hit = _ACT_CACHE.get(x.device)
     if hit is not None and hit[0] is x and hit[1] == x._version and hit[2] == key:
         return hit[3]
