@@ -218,6 +218,11 @@ int bfp_gemm_bf16_sp_gather(const void* x_bf16, const void* w_comp, const void* 
  * c_i = #{j : |v_j| < |v_i|}; value = 4-bit drop mask, 0xff = unreachable).  Exposed for the tests. */
 int bfp_debug_cpu_tie_lut(uint8_t out[256]);
 
+/* The table behind the half-precision block exponent (csrc/bfp_common.cuh): for s = 2^k (1 + f 2^-mb) in fp16 (mb = 10) or
+ * bf16 (mb = 7), ceil(log2(s) rounded to the dtype) = k + (f + 1 >= out[k + 128]); 0 = not tabulated (the kernels then evaluate
+ * the formula).  Exposed for the tests, which compare it with torch's own log2 on every (k, f). */
+int bfp_debug_exp_table(int dtype, uint16_t out[256]);
+
 #ifdef __cplusplus
 }
 #endif

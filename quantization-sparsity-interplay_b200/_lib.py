@@ -51,6 +51,7 @@ SIGNATURES = {
     "bfp_quantize_host": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _i32, _u64, _u64, _i32, _i32, _i32, _i32]),
     "bfp_host_staging_release": (_i32, []),
     "bfp_debug_cpu_tie_lut": (_i32, [_vp]),
+    "bfp_debug_exp_table": (_i32, [_i32, _vp]),
     "bfp_packed_layout": (_i32, [_i64, _i64, _i32] + [ctypes.POINTER(_i64)] * 3),
     "bfp_quantize_pack": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _i32, _u64, _u64, _i32, _i32, _i32, _vp]),
     "bfp_unpack": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _vp]),

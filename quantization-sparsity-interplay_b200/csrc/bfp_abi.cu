@@ -288,6 +288,11 @@ int bfp_gemm_i8(const int8_t* a_mant, const float* a_scale_t, const int8_t* b_ma
                           block_size, static_cast<cudaStream_t>(stream));
 }
 
+int bfp_debug_exp_table(int dtype, uint16_t out[256]) {
+    if (int rc = require_device()) return rc;
+    return debug_exp_table(dtype, out);
+}
+
 int bfp_debug_cpu_tie_lut(uint8_t out[256]) {
     if (int rc = require_device()) return rc;
     return debug_cpu_tie_lut(out);

@@ -103,6 +103,57 @@ __device__ __noinline__ float3 make_scale_slow(float s, int m) {
 // ~20 instructions and this branch is taken for ~1.5e-5 of the blocks).
 static __device__ __noinline__ int exponent_near_pow2(float s) { return (int)ceilf(log2f(s)); }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Half-precision block exponent without log2f.  For fp16 / bf16 tensors torch evaluates ceil(log2(s)) with log2(s) ROUNDED TO
+// THE DTYPE first, so e is k or k+1 depending on where the mantissa f of s = 2^k (1 + f 2^-mb)
+// sits relative to a threshold that depends on k (the spacing of the dtype at magnitude |k|).  The thresholds are not
+// derived: a one-time kernel evaluates the literal formula (the same libdevice log2f as before) for every (k, f), checks
+// that it is a step function of f, and stores the step position; the hot path does one table load and one compare.
+// Entry 0 = "not tabulated" (before initialisation, or a k whose step check failed): evaluate the formula as before.
+// ---------------------------------------------------------------------------------------------------------------
+static __device__ uint16_t g_exp_step[2][256];           // [0] fp16, [1] bf16; index k + 128; value = step position + 1
+
+template <int DT> struct HalfBits;
+template <> struct HalfBits<BFP_DT_F16> { static constexpr int kMant = 10, kTable = 0; };
+template <> struct HalfBits<BFP_DT_BF16> { static constexpr int kMant = 7, kTable = 1; };
+
+template <int DT>
+static __global__ void exp_table_init_kernel() {
+    using D = DType<DT>;
+    constexpr int MB = HalfBits<DT>::kMant;
+    const int k = (int)threadIdx.x - 128;
+    uint32_t value = 0;
+    if (k >= -126 && k <= 127) {
+        int step = 1 << MB;                               // first f with e = k + 1 (1 << MB: none)
+        bool valid = true;
+        for (int f = 0; f < (1 << MB); ++f) {
+            const float s = __uint_as_float(((uint32_t)(k + 127) << 23) | ((uint32_t)f << (23 - MB)));
+            const int e = (int)ceilf(D::rnd(log2f(s)));
+            if (e == k + 1) { if (step == (1 << MB)) step = f; }
+            else if (e == k) { if (step != (1 << MB)) valid = false; }      // back down after the step: not monotone
+            else valid = false;
+        }
+        if (valid) value = (uint32_t)step + 1u;
+    }
+    g_exp_step[HalfBits<DT>::kTable][threadIdx.x] = (uint16_t)value;
+}
+
+// Per translation unit and device, once: fills this TU's copy of the table.  Skipped (formula path stays in use) while the
+// caller's stream is being captured into a CUDA graph.
+static inline void ensure_exp_tables(cudaStream_t user_stream) {
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(user_stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return; }
+    cudaStream_t st;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return; }
+    exp_table_init_kernel<BFP_DT_F16><<<1, 256, 0, st>>>();
+    exp_table_init_kernel<BFP_DT_BF16><<<1, 256, 0, st>>>();
+    if (cudaStreamSynchronize(st) == cudaSuccess) done[dev] = true; else cudaGetLastError();
+    cudaStreamDestroy(st);
+}
+
 template <int DT>
 __device__ __forceinline__ BlockScale make_scale(uint32_t amax_bits, int m, float eps) {
     using D = DType<DT>;
@@ -119,7 +170,11 @@ __device__ __forceinline__ BlockScale make_scale(uint32_t amax_bits, int m, floa
             // (fp32 spacing near |k| <= 127 is at most 2^-17), so ceil(log2f(s)) = k + 1 without evaluating it.
             e = ((sb & 0x7fffffu) > 128u) ? k + 1 : exponent_near_pow2(s);
         } else {
-            e = (int)ceilf(D::rnd(log2f(s)));             // bfp_ops.py:33  .log2().ceil(), log2 rounded to the dtype
+            constexpr int MB = HalfBits<DT == BFP_DT_F32 ? BFP_DT_F16 : DT>::kMant;
+            const uint32_t step1 = g_exp_step[HalfBits<DT == BFP_DT_F32 ? BFP_DT_F16 : DT>::kTable][k + 128];
+            const uint32_t f = (sb >> (23 - MB)) & ((1u << MB) - 1u);
+            if (step1 != 0u) e = k + (int)(f + 1u >= step1);          // tabulated step of ceil(rnd(log2 s)) in f
+            else e = (int)ceilf(D::rnd(log2f(s)));        // bfp_ops.py:33  .log2().ceil(), log2 rounded to the dtype
         }
         ok = (e - m >= D::kMinScaleExp) && (e <= D::kMaxExp) && (e >= D::kMinExp);
     }

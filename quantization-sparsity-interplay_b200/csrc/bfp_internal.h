@@ -56,6 +56,7 @@ int block_exponent_device(const void* in, float* e_out, int64_t rows, int64_t K,
 int quantize_host(const QuantArgs& a);
 int host_staging_release();
 int debug_cpu_tie_lut(uint8_t out[256]);
+int debug_exp_table(int dtype, uint16_t out[256]);
 int pack_device(const QuantArgs& a, int8_t* mant, float* scale_t, int64_t Kp, int64_t rows_pad, cudaStream_t st);
 int unpack_device(const int8_t* mant, const float* scale_t, float* out, int64_t rows, int64_t K, int64_t Kp, int64_t rows_pad, int B,
                   cudaStream_t st);

@@ -262,10 +262,12 @@ static int pack_fmt(const QuantArgs& a, int8_t* mant, float* scale_t, int64_t Kp
 }
 
 int pack_device(const QuantArgs& a, int8_t* mant, float* scale_t, int64_t Kp, int64_t rows_pad, cudaStream_t st) {
+    if (a.in_dtype != BFP_DT_F32) ensure_exp_tables(st);
     return pack_fmt<0>(a, mant, scale_t, Kp, rows_pad, st);
 }
 // dequantised bf16 [rows, Kp] (Kp = K rounded up to 8 elements)
 int pack_bf16_device(const QuantArgs& a, void* out_bf16, int64_t Kp, cudaStream_t st) {
+    if (a.in_dtype != BFP_DT_F32) ensure_exp_tables(st);
     return pack_fmt<1>(a, static_cast<int8_t*>(out_bf16), nullptr, Kp, 0, st);
 }
 

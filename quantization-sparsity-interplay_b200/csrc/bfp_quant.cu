@@ -429,6 +429,7 @@ static int quantize_dt(const QuantArgs& a, cudaStream_t st) {
 }
 
 int quantize_device(const QuantArgs& a, cudaStream_t st) {
+    if (a.in_dtype != BFP_DT_F32) ensure_exp_tables(st);
     switch (a.in_dtype) {
     case BFP_DT_F32: return quantize_dt<BFP_DT_F32>(a, st);
     case BFP_DT_F16: return quantize_dt<BFP_DT_F16>(a, st);
@@ -437,7 +438,18 @@ int quantize_device(const QuantArgs& a, cudaStream_t st) {
     return set_error(BFP_E_ARG, "bad dtype");
 }
 
+int debug_exp_table(int dtype, uint16_t out[256]) {
+    if (dtype != BFP_DT_F16 && dtype != BFP_DT_BF16) return set_error(BFP_E_ARG, "fp16 / bf16 only");
+    ensure_exp_tables(nullptr);
+    uint16_t all[2][256];
+    const cudaError_t e = cudaMemcpyFromSymbol(all, g_exp_step, sizeof(all));
+    if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaMemcpyFromSymbol: %s", cudaGetErrorString(e));
+    for (int i = 0; i < 256; ++i) out[i] = all[dtype == BFP_DT_BF16 ? 1 : 0][i];
+    return BFP_OK;
+}
+
 int block_exponent_device(const void* in, float* e_out, int64_t rows, int64_t K, int dtype, int B, float eps, cudaStream_t st) {
+    if (dtype != BFP_DT_F32) ensure_exp_tables(st);
     const int64_t units = rows * ((K + B - 1) / B);
     if (units == 0) return BFP_OK;
     const int grid = (int)std::min<int64_t>((units + 127) / 128, (int64_t)device_info().sm_count * 16);

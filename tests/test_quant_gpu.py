@@ -368,3 +368,27 @@ def test_pdl_launches_keep_stream_order():
         _lib.set_option("pdl", 1)
     for _ in range(3):
         assert torch.equal(chain(False), ref)
+
+
+@pytest.mark.parametrize("dtn", ["bf16", "f16"])
+def test_half_precision_exponent_table_matches_torch_log2(dtn):
+    """The kernels take ceil(log2(s)) for fp16 / bf16 blocks from a table of step positions (csrc/bfp_common.cuh).  Every
+    (exponent, mantissa) pair of the dtype is checked against torch's own evaluation on the GPU: s.log2().ceil() (bfp_ops.py:33)."""
+    import ctypes
+    from qsi_b200 import _lib
+    dt, code, mb = (torch.bfloat16, _lib.DT_BF16, 7) if dtn == "bf16" else (torch.float16, _lib.DT_F16, 10)
+    tab = (ctypes.c_uint16 * 256)()
+    _lib.check(_lib.lib().bfp_debug_exp_table(code, tab))
+    tab = np.array(tab, dtype=np.int64)
+    krange = range(-100, 127) if dtn == "bf16" else range(-24, 16)
+    assert all(tab[k + 128] != 0 for k in krange), "fast-path exponents must be tabulated"
+    ks = torch.tensor(list(krange), dtype=torch.float64)
+    f = torch.arange(1 << mb, dtype=torch.float64)
+    s = (torch.exp2(ks)[:, None] * (1.0 + f[None, :] / (1 << mb))).to(dt).cuda()        # exact: every value is representable
+    e_torch = s.log2().ceil().float().cpu().numpy()
+    step = tab[[k + 128 for k in krange]] - 1
+    e_table = np.array(list(krange))[:, None] + (np.arange(1 << mb)[None, :] >= step[:, None])
+    # fp16 subnormals (k < -14) carry fewer mantissa bits: only the f that survive the conversion exactly are real inputs
+    exact = (s.double().cpu() == torch.exp2(ks)[:, None] * (1.0 + f[None, :] / (1 << mb))).numpy()
+    assert exact[[i for i, k in enumerate(krange) if k >= (-14 if dtn == "f16" else -126)]].all()
+    assert np.array_equal(e_table[exact], e_torch[exact])
