@@ -86,11 +86,81 @@ __global__ void __launch_bounds__(256) int_apply_kernel(const void* in, float* o
     }
 }
 
+// Weights (A == 1: one channel per row of K = inner elements): ONE pass.  A CTA keeps its row in registers (NV 128-bit
+// vectors per thread), reduces min / max across the block, derives the scale and applies it to the registers: 8 B/element of
+// traffic (4 in + 4 out for fp32) instead of the three passes (12 B/element + atomics) of the general path.
+template <int DT, int NV>
+__global__ void __launch_bounds__(256) int_rows_fused_kernel(const void* in, float* out, int64_t rows, int64_t K, float maxq, float zero) {
+    constexpr int V = DType<DT>::kVec;
+    __shared__ float s_lo[8], s_hi[8];
+    const int64_t nv = K / V;                               // <= 256 * NV, checked by the host
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        const uint4* src = static_cast<const uint4*>(in) + row * nv;
+        uint4 raw[NV];
+        float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
+#pragma unroll
+        for (int u = 0; u < NV; ++u) {
+            const int64_t j = threadIdx.x + u * 256;
+            if (j < nv) raw[u] = ld_stream(src + j);
+        }
+#pragma unroll
+        for (int u = 0; u < NV; ++u) {
+            const int64_t j = threadIdx.x + u * 256;
+            if (j < nv) {
+                float v[V];
+                unpack_vec<DT>(raw[u], v);
+#pragma unroll
+                for (int e = 0; e < V; ++e) { lo = fminf(lo, v[e]); hi = fmaxf(hi, v[e]); }
+            }
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off)); }
+        if (lane == 0) { s_lo[warp] = lo; s_hi[warp] = hi; }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { lo = fminf(lo, s_lo[w]); hi = fmaxf(hi, s_hi[w]); }
+        float xmin = fminf(lo, 0.0f), xmax = fmaxf(hi, 0.0f);                          // int_ops.py:55-56
+        xmax = fmaxf(fabsf(xmin), xmax);                                               // :59
+        if (xmin < 0.0f) xmin = -xmax;                                                 // :60-62
+        if (xmin == 0.0f && xmax == 0.0f) { xmin = -1.0f; xmax = 1.0f; }               // :63-65
+        const float sc = __fdiv_rn(xmax - xmin, maxq);                                 // :67
+        float4* dst = reinterpret_cast<float4*>(out + row * K);
+#pragma unroll
+        for (int u = 0; u < NV; ++u) {
+            const int64_t j = threadIdx.x + u * 256;
+            if (j < nv) {
+                float v[V];
+                unpack_vec<DT>(raw[u], v);
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    const float q = fminf(fmaxf(rintf(__fdiv_rn(v[e], sc)) + zero, 0.0f), maxq);   // int_ops.py:7
+                    v[e] = sc * (q - zero);                                                        // :8
+                }
+#pragma unroll
+                for (int f4 = 0; f4 < V / 4; ++f4)
+                    st_stream(reinterpret_cast<uint4*>(dst + j * (V / 4) + f4), pack_vec<BFP_DT_F32>(v + 4 * f4));
+            }
+        }
+        __syncthreads();                                    // s_lo / s_hi are rewritten by the next row
+    }
+}
+
 template <int DT>
 int run(const void* in, float* out, int64_t A, int64_t C, int64_t inner, int bits, IntWs ws, cudaStream_t s) {
     const int64_t n = A * C * inner;
     const int sms = device_info().sm_count;
     const float maxq = (float)((1ll << bits) - 1), zero = (float)(((1ll << bits)) / 2.0);
+    constexpr int V = DType<DT>::kVec;
+    if (A == 1 && inner % V == 0 && inner / V <= 256 * 16 && reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0) {
+        const int64_t nv = inner / V;
+        const int grid = (int)std::min<int64_t>(C, (int64_t)sms * 4);
+        if (nv <= 256 * 4) int_rows_fused_kernel<DT, 4><<<grid, 256, 0, s>>>(in, out, C, inner, maxq, zero);
+        else if (nv <= 256 * 8) int_rows_fused_kernel<DT, 8><<<grid, 256, 0, s>>>(in, out, C, inner, maxq, zero);
+        else int_rows_fused_kernel<DT, 16><<<grid, 256, 0, s>>>(in, out, C, inner, maxq, zero);
+        count_launch();
+        return check_launch("int_rows_fused_kernel");
+    }
     int_init_kernel<<<(int)std::min<int64_t>((C + 255) / 256, 1024), 256, 0, s>>>(ws.mn, ws.mx, C);
     count_launch();
     if (inner >= 32) {
