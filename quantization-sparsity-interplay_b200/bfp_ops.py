@@ -510,12 +510,15 @@ def _tensor_core_kind(x, w, bfp_args):
 
 def _tensor_core_eligible(x, w, bfp_args):
     """The packed tensor-core path computes the same function as quantise + F.linear (fp32 accumulate order aside); it is
-    taken for inference on CUDA fp32 tensors when the configuration has a packed form."""
+    taken on CUDA tensors when the configuration has a packed form: fp32 (inference and training), fp16 / bf16 (inference:
+    the contraction accumulates in fp32 like the library HGEMM the reference calls and is rounded to the dtype once)."""
     if os.environ.get("BFP_LINEAR_PATH", "tc") != "tc":
         return False
-    if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad) and os.environ.get("BFP_TRAIN_PATH", "tc") != "tc":
+    training = torch.is_grad_enabled() and (x.requires_grad or w.requires_grad)
+    if training and os.environ.get("BFP_TRAIN_PATH", "tc") != "tc":
         return False
-    return (x.is_cuda and w.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32
+    dtype_ok = x.dtype == w.dtype and (x.dtype == torch.float32 or (x.dtype in (torch.float16, torch.bfloat16) and not training))
+    return (x.is_cuda and w.is_cuda and dtype_ok
             and bfp_args['num_format'] == 'bfp' and bfp_args['sparsity_num_format'] == 'bfp'
             and 1 <= bfp_args['mant_bits'] <= 7 and bfp_args['block_size'] in (32, 64, 128)
             and not (bfp_args['in_sparsity'] == True)                                                # noqa: E712
@@ -629,13 +632,13 @@ def _gen_bfp_op(op, name, bfp_args, transpose=False):
         # inference fast paths on the tensor cores (row f4); anything else runs the reference's structure below
         if torch.is_tensor(x) and torch.is_tensor(w) and x.dim() >= 2 and w.dim() >= 2 and _tc_inference_ok(x, w, bfp_args):
             if op is torch.matmul and transpose and not args and not kwargs and x.shape[-1] == w.shape[-2]:
-                return _tc_matmul(x, w, bfp_args)
+                return _tc_matmul(x, w, bfp_args).to(x.dtype)
             if op is F.linear and not transpose and w.dim() == 2 and len(args) <= 1 and not kwargs:
                 return bfp_linear_bf16(pack_bfp_bf16(x, identifier='in', **bfp_args), pack_bfp_bf16(w, identifier='w', **bfp_args),
-                                       args[0] if args else None, out_shape=tuple(x.shape[:-1]) + (w.shape[0],))
+                                       args[0] if args else None, out_shape=tuple(x.shape[:-1]) + (w.shape[0],)).to(x.dtype)
             if op is F.conv2d and x.dim() == 4 and w.dim() == 4 and not kwargs and len(args) == 5 and args[4] == 1 \
                     and not isinstance(args[2], str):
-                return _tc_conv2d(x, w, args[0], _pair(args[1]), _pair(args[2]), _pair(args[3]), 1, bfp_args)
+                return _tc_conv2d(x, w, args[0], _pair(args[1]), _pair(args[2]), _pair(args[3]), 1, bfp_args).to(x.dtype)
         x, w = NewOpIn.apply(x, w)
         out = op(x, w, *args, **kwargs)
         return NewOpOut.apply(out)
@@ -819,15 +822,18 @@ class BFPLinear(torch.nn.Linear):
                 return _BFPLinearTC.apply(input, self.weight, self.bias, self.bfp_args, (lambda: self._packed_weight('bf16')), cached)
             if not determ:
                 kind = None
+            y = None
             if kind == 'i8':
                 # inference fast path: pack activations on the fly, cached packed weight, tcgen05 int8 BFP GEMM
-                return bfp_linear_packed(pack_bfp(input, identifier='in', **self.bfp_args), self._packed_weight(kind), self.bias)
-            if kind == 'sp':
+                y = bfp_linear_packed(pack_bfp(input, identifier='in', **self.bfp_args), self._packed_weight(kind), self.bias)
+            elif kind == 'sp':
                 # 2:4-pruned weight: compressed once, tcgen05.mma.sp skips the zeros
-                return bfp_linear_bf16_sp(_packed_activation(input, self.bfp_args), self._packed_weight(kind), self.bias,
-                                          out_shape=tuple(input.shape[:-1]) + (self.out_features,))
-            if kind == 'bf16':
-                return bfp_linear_bf16(_packed_activation(input, self.bfp_args), self._packed_weight(kind), self.bias,
+                y = bfp_linear_bf16_sp(_packed_activation(input, self.bfp_args), self._packed_weight(kind), self.bias,
                                        out_shape=tuple(input.shape[:-1]) + (self.out_features,))
+            elif kind == 'bf16':
+                y = bfp_linear_bf16(_packed_activation(input, self.bfp_args), self._packed_weight(kind), self.bias,
+                                    out_shape=tuple(input.shape[:-1]) + (self.out_features,))
+            if y is not None:
+                return y if input.dtype == torch.float32 else y.to(input.dtype)     # fp32 accumulation, one rounding to the dtype
             return self.linear_op(input, self.weight, self.bias)
         raise NotImplementedError('NumFormat not implemented')

@@ -489,3 +489,31 @@ def test_packed_activation_cache_is_safe(ops):
         yz = q(z)
         assert torch.equal(yz, ops.bfp_linear_bf16(ops.pack_bfp_bf16(z, identifier="in", **q.bfp_args), q._packed_weight("bf16")))
         assert ptr == ptr and yk.shape == (96, 64)
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("w_sparse", [True, False])
+def test_bfplinear_half_precision_inference_on_tensor_cores(ops, dt, w_sparse, monkeypatch):
+    """fp16 / bf16 modules (how the reference runs LLaMA): the tensor-core path accumulates in fp32 and rounds to the dtype once,
+    like the library HGEMM the reference calls on the fake-quantised operands.  Against the fp64 contraction of the SAME
+    quantised operands the result must be the correctly rounded value up to one unit in the last place."""
+    kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=7, block_size=64,
+              w_sparsity=w_sparse, N=2, M=4, first="s", sparsity_mode="structured", device="cuda")
+    torch.manual_seed(5)
+    lin = ops.BFPLinear(1024, 768, bias=True, **dict(kw)).cuda().to(dt)
+    x = torch.randn(4, 130, 1024, device="cuda").to(dt)
+    a = ops.unpack_bfp_args(dict(kw))
+    with torch.no_grad():
+        y = lin(x)
+        assert y.dtype == dt and lin._packed_w is not None and lin._packed_w[0][0] == ("sp" if w_sparse else "bf16")
+        monkeypatch.setenv("BFP_LINEAR_PATH", "fakequant")
+        y_ref = lin(x)                                       # the reference's structure: fused fake-quant + torch HGEMM
+        monkeypatch.setenv("BFP_LINEAR_PATH", "tc")
+    xq = ops.float_to_bfp_blocked(x, **a, identifier="in").double()
+    wq = ops.float_to_bfp_blocked(lin.weight.detach(), **a, identifier="w").double()
+    exact = xq @ wq.t() + lin.bias.detach().double()
+    for got in (y, y_ref):
+        err = (got.double() - exact).abs()
+        ulp = torch.maximum(exact.abs(), torch.tensor(1e-3, device="cuda", dtype=torch.float64)) * (2.0 ** (-10 if dt == torch.float16 else -7))
+        assert (err <= ulp).all()
+    assert ((y.double() - y_ref.double()).abs() <= 2.0 ** (-9 if dt == torch.float16 else -6) * exact.abs().clamp_min(1e-3)).all()
