@@ -208,11 +208,17 @@ int bfp_gemm_bf16_sp(const void* x_bf16, const void* w_comp, const void* w_meta,
  * split by output rows over G GPUs).  Same contraction as bfp_gemm_bf16_sp on this rank's weight shard W[N, K]; the
  * result tile is written n_out times: out_slices[g] points at this rank's column slice inside GPU g's full
  * [T, ld_out] fp32 output (its own memory or a peer's mapped over NVLink, e.g. torch symmetric memory), row stride ld_out
- * floats.  Every slice pointer must be 16-byte aligned and ld_out a multiple of 4.  The caller orders the kernel against the
+ * elements of out_dtype (BFP_DT_F32 / F16 / BF16).  Every slice pointer and the row stride in bytes must be multiples of 16.  The caller orders the kernel against the
  * peers with a barrier before (buffers free) and after (stores visible) -- no NCCL call, no transposing copy. */
 int bfp_gemm_bf16_sp_gather(const void* x_bf16, const void* w_comp, const void* w_meta, const float* bias,
-                            float* const* out_slices, int n_out, int64_t ld_out, int64_t T, int64_t N, int64_t K,
-                            void* stream);
+                            void* const* out_slices, int n_out, int out_dtype, int64_t ld_out, int64_t T, int64_t N,
+                            int64_t K, void* stream);
+
+/* bfp_gemm_bf16_sp with an explicit output dtype and row stride: out_dtype BFP_DT_F32, or BFP_DT_F16 / BFP_DT_BF16 for half
+ * precision modules -- the fp32 accumulator (+ bias) is rounded to the dtype once in the epilogue, which is what the library
+ * HGEMM the reference calls on fake-quantised fp16 tensors does, and halves the output traffic.  ld_out in elements. */
+int bfp_gemm_bf16_sp_ex(const void* x_bf16, const void* w_comp, const void* w_meta, const float* bias, void* out,
+                        int out_dtype, int64_t ld_out, int64_t T, int64_t N, int64_t K, void* stream);
 
 /* The 256-entry table behind BFP_TIE_TORCH_CPU for 2:4 (index = c0 + 4*c1 + 16*c2 + 64*c3 with
  * c_i = #{j : |v_j| < |v_i|}; value = 4-bit drop mask, 0xff = unreachable).  Exposed for the tests. */

@@ -60,7 +60,8 @@ SIGNATURES = {
     "bfp_sp_layout": (_i32, [_i64, _i64] + [ctypes.POINTER(_i64)] * 2),
     "bfp_compress_2to4_bf16": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "bfp_gemm_bf16_sp": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
-    "bfp_gemm_bf16_sp_gather": (_i32, [_vp, _vp, _vp, _vp, ctypes.POINTER(_vp), _i32, _i64, _i64, _i64, _i64, _vp]),
+    "bfp_gemm_bf16_sp_gather": (_i32, [_vp, _vp, _vp, _vp, ctypes.POINTER(_vp), _i32, _i32, _i64, _i64, _i64, _i64, _vp]),
+    "bfp_gemm_bf16_sp_ex": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _i64, _vp]),
     "bfp_gemm_i8": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp]),
 }
 

@@ -451,19 +451,19 @@ def compress_2to4_bf16(wb, check=True):
     return SparseBF16(comp, meta, rows, Kp)
 
 
-def bfp_linear_bf16_sp(xb, ws, bias=None, out_shape=None):
-    """y = x w^T + bias with the 2:4-compressed weight `ws` (include/bfp_b200.h bfp_gemm_bf16_sp): tcgen05.mma.sp.kind::f16,
-    fp32 TMEM accumulation.  xb bf16 [T, Kp]."""
+def bfp_linear_bf16_sp(xb, ws, bias=None, out_shape=None, out_dtype=torch.float32):
+    """y = x w^T + bias with the 2:4-compressed weight `ws` (include/bfp_b200.h bfp_gemm_bf16_sp_ex): tcgen05.mma.sp.kind::f16,
+    fp32 TMEM accumulation; the epilogue writes fp32, or rounds once to fp16 / bf16 (`out_dtype`).  xb bf16 [T, Kp]."""
     T, Kp = xb.shape
     N = ws.rows
     assert ws.K == Kp and xb.dtype == torch.bfloat16
-    out = torch.empty((T, N), dtype=torch.float32, device=xb.device)
+    out = torch.empty((T, N), dtype=out_dtype, device=xb.device)
     b = bias.detach().to(dtype=torch.float32).contiguous() if bias is not None else None
     if out.numel():
         with _on(out.device):
-            _lib.check(_lib.lib().bfp_gemm_bf16_sp(xb.data_ptr(), ws.comp.data_ptr(), ws.meta.data_ptr(),
-                                                   b.data_ptr() if b is not None else None, out.data_ptr(), T, N, Kp,
-                                                   _stream()))
+            _lib.check(_lib.lib().bfp_gemm_bf16_sp_ex(xb.data_ptr(), ws.comp.data_ptr(), ws.meta.data_ptr(),
+                                                      b.data_ptr() if b is not None else None, out.data_ptr(), _DT[out_dtype], N, T, N, Kp,
+                                                      _stream()))
     return out.view(out_shape) if out_shape is not None else out
 
 
@@ -829,7 +829,7 @@ class BFPLinear(torch.nn.Linear):
             elif kind == 'sp':
                 # 2:4-pruned weight: compressed once, tcgen05.mma.sp skips the zeros
                 y = bfp_linear_bf16_sp(_packed_activation(input, self.bfp_args), self._packed_weight(kind), self.bias,
-                                       out_shape=tuple(input.shape[:-1]) + (self.out_features,))
+                                       out_shape=tuple(input.shape[:-1]) + (self.out_features,), out_dtype=input.dtype)
             elif kind == 'bf16':
                 y = bfp_linear_bf16(_packed_activation(input, self.bfp_args), self._packed_weight(kind), self.bias,
                                     out_shape=tuple(input.shape[:-1]) + (self.out_features,))

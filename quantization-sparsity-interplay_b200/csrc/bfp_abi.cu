@@ -264,12 +264,22 @@ int bfp_gemm_bf16_sp(const void* x_bf16, const void* w_comp, const void* w_meta,
     return gemm_bf16_sp_device(x_bf16, w_comp, w_meta, bias, out, T, N, round_up(K, 8), static_cast<cudaStream_t>(stream));
 }
 
-int bfp_gemm_bf16_sp_gather(const void* x_bf16, const void* w_comp, const void* w_meta, const float* bias, float* const* out_slices, int n_out,
-                            int64_t ld_out, int64_t T, int64_t N, int64_t K, void* stream) {
+int bfp_gemm_bf16_sp_gather(const void* x_bf16, const void* w_comp, const void* w_meta, const float* bias, void* const* out_slices, int n_out,
+                            int out_dtype, int64_t ld_out, int64_t T, int64_t N, int64_t K, void* stream) {
     if (T < 0 || N < 0 || K <= 0 || n_out < 1 || !out_slices) return set_error(BFP_E_ARG, "bad argument");
     if (T * N > 0 && (!x_bf16 || !w_comp || !w_meta)) return set_error(BFP_E_ARG, "null pointer");
     if (int rc = require_device()) return rc;
-    return gemm_bf16_sp_multi_device(x_bf16, w_comp, w_meta, bias, out_slices, n_out, ld_out, T, N, round_up(K, 8), static_cast<cudaStream_t>(stream));
+    return gemm_bf16_sp_multi_device(x_bf16, w_comp, w_meta, bias, out_slices, n_out, out_dtype, ld_out, T, N, round_up(K, 8),
+                                     static_cast<cudaStream_t>(stream));
+}
+
+int bfp_gemm_bf16_sp_ex(const void* x_bf16, const void* w_comp, const void* w_meta, const float* bias, void* out, int out_dtype, int64_t ld_out,
+                        int64_t T, int64_t N, int64_t K, void* stream) {
+    if (T < 0 || N < 0 || K <= 0) return set_error(BFP_E_ARG, "bad argument");
+    if (T * N > 0 && (!x_bf16 || !w_comp || !w_meta || !out)) return set_error(BFP_E_ARG, "null pointer");
+    if (int rc = require_device()) return rc;
+    void* outs[1] = {out};
+    return gemm_bf16_sp_multi_device(x_bf16, w_comp, w_meta, bias, outs, 1, out_dtype, ld_out, T, N, round_up(K, 8), static_cast<cudaStream_t>(stream));
 }
 
 int bfp_unpack(const int8_t* mant, const float* scale_t, float* out, int64_t rows, int64_t K, int block_size, void* stream) {

@@ -72,6 +72,7 @@ struct Params {
     int e_atoms;                // ceil(K / 128)
     int tiles_w, tiles_t;       // tiles_w counts CG * 128 rows
     int64_t ld_out;             // row stride of `out` in floats (plain-store path)
+    int out_dtype;              // BFP_DT_F32, or BFP_DT_F16 / BFP_DT_BF16: the fp32 accumulator (+ bias) is rounded to it once
     int out_tma;                // 1 = the epilogue stages the tile in smem and writes it with TMA stores (needs N % 4 == 0)
     int debug;                  // timing experiments only (wrong results): bit 0 = every tile loads X tile 0, bit 1 = W tile 0
 };
@@ -132,8 +133,17 @@ __device__ __forceinline__ void store_columns(const Params& p, const OutMaps& ou
             // the stores that last read this buffer (two rounds ago; one bulk group per round) are done with it
             if (lane == 0) tma_store_wait_read<1>();
             __syncwarp();
+            if (p.out_dtype == BFP_DT_F32) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) buf[j * 32 + lane] = __uint_as_float(r[rd * 8 + j]) + bv;
+                for (int j = 0; j < 8; ++j) buf[j * 32 + lane] = __uint_as_float(r[rd * 8 + j]) + bv;
+            } else {                                             // [8 t][32 n] of 2-byte values: 64-byte rows
+                uint16_t* hb = reinterpret_cast<uint16_t*>(buf);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float o = __uint_as_float(r[rd * 8 + j]) + bv;
+                    hb[j * 32 + lane] = p.out_dtype == BFP_DT_F16 ? __half_as_ushort(__float2half_rn(o)) : __bfloat16_as_ushort(__float2bfloat16_rn(o));
+                }
+            }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
@@ -144,11 +154,20 @@ __device__ __forceinline__ void store_columns(const Params& p, const OutMaps& ou
     } else {
         const int n = n0 + lane;
         if (n < p.N) {
-            float* dst = p.out + (int64_t)t0 * p.ld_out + n;
             const int t_left = p.T - t0;
+            if (p.out_dtype == BFP_DT_F32) {
+                float* dst = p.out + (int64_t)t0 * p.ld_out + n;
 #pragma unroll
-            for (int j = 0; j < NC; ++j)
-                if (j < t_left) dst[(int64_t)j * p.ld_out] = __uint_as_float(r[j]) + bv;
+                for (int j = 0; j < NC; ++j)
+                    if (j < t_left) dst[(int64_t)j * p.ld_out] = __uint_as_float(r[j]) + bv;
+            } else {
+                uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) + (int64_t)t0 * p.ld_out + n;
+#pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                    const float o = __uint_as_float(r[j]) + bv;
+                    if (j < t_left) dst[(int64_t)j * p.ld_out] = p.out_dtype == BFP_DT_F16 ? __half_as_ushort(__float2half_rn(o)) : __bfloat16_as_ushort(__float2bfloat16_rn(o));
+                }
+            }
         }
     }
 }
@@ -563,17 +582,19 @@ int compress_2to4_bf16_device(const void* w_bf16, int64_t rows, int64_t K, int64
 
 int gemm_bf16_sp_device(const void* x_bf16, const void* w_comp, const void* w_meta, const float* bias, float* out, int64_t T, int64_t N,
                         int64_t Kp, cudaStream_t st) {
-    float* outs[1] = {out};
-    return gemm_bf16_sp_multi_device(x_bf16, w_comp, w_meta, bias, outs, 1, N, T, N, Kp, st);
+    void* outs[1] = {out};
+    return gemm_bf16_sp_multi_device(x_bf16, w_comp, w_meta, bias, outs, 1, BFP_DT_F32, N, T, N, Kp, st);
 }
 
-int gemm_bf16_sp_multi_device(const void* x_bf16, const void* w_comp, const void* w_meta, const float* bias, float* const* out_ptrs, int n_out,
-                              int64_t ld_out, int64_t T, int64_t N, int64_t Kp, cudaStream_t st) {
+int gemm_bf16_sp_multi_device(const void* x_bf16, const void* w_comp, const void* w_meta, const float* bias, void* const* out_ptrs, int n_out,
+                              int out_dtype, int64_t ld_out, int64_t T, int64_t N, int64_t Kp, cudaStream_t st) {
     using namespace gemm_sp;
     if (T == 0 || N == 0) return BFP_OK;
     if (n_out < 1 || n_out > kMaxDests) return set_error(BFP_E_ARG, "1 to 8 output destinations");
     if (ld_out < N) return set_error(BFP_E_ARG, "output row stride smaller than N");
-    float* out = out_ptrs[0];
+    if (out_dtype != BFP_DT_F32 && out_dtype != BFP_DT_F16 && out_dtype != BFP_DT_BF16) return set_error(BFP_E_ARG, "bad output dtype");
+    float* out = static_cast<float*>(out_ptrs[0]);
+    const int out_es = out_dtype == BFP_DT_F32 ? 4 : 2;
     if (Kp % 8 != 0 || Kp <= 0) return set_error(BFP_E_ARG, "bf16 operand K must be a positive multiple of 8");
     if (T > INT32_MAX || N > INT32_MAX || Kp > INT32_MAX) return set_error(BFP_E_ARG, "dimension too large");
     if (reinterpret_cast<uintptr_t>(x_bf16) % 16 || reinterpret_cast<uintptr_t>(w_comp) % 16 || reinterpret_cast<uintptr_t>(w_meta) % 16)
@@ -585,7 +606,7 @@ int gemm_bf16_sp_multi_device(const void* x_bf16, const void* w_comp, const void
     int cg = (N > 128) ? 2 : 1;
     if (tuning().gemm_sp_cta_group == 1 || tuning().gemm_sp_cta_group == 2) cg = tuning().gemm_sp_cta_group;
     Params p;
-    p.bias = bias; p.out = out; p.T = (int)T; p.N = (int)N; p.ld_out = ld_out; p.debug = tuning().gemm_sp_debug;
+    p.bias = bias; p.out = out; p.T = (int)T; p.N = (int)N; p.ld_out = ld_out; p.out_dtype = out_dtype; p.debug = tuning().gemm_sp_debug;
     p.num_k_slabs = (int)((Kp + 127) / 128);
     p.e_atoms = (int)(Kc / 64);
     p.tiles_w = (int)((N + 128 * cg - 1) / (128 * cg));
@@ -610,13 +631,13 @@ int gemm_bf16_sp_multi_device(const void* x_bf16, const void* w_comp, const void
     OutMaps map_out;
     map_out.n = n_out;
     for (int g = 0; g < kMaxDests; ++g) map_out.m[g] = map_e;
-    bool aligned = ld_out % 4 == 0;
+    bool aligned = (ld_out * out_es) % 16 == 0;
     for (int g = 0; g < n_out; ++g) aligned = aligned && out_ptrs[g] && reinterpret_cast<uintptr_t>(out_ptrs[g]) % 16 == 0;
     p.out_tma = (aligned && (tuning().gemm_out_tma || n_out > 1)) ? 1 : 0;
-    if (n_out > 1 && !p.out_tma) return set_error(BFP_E_ALIGN, "multi-destination output needs 16-byte aligned slices and a row stride that is a multiple of 4");
+    if (n_out > 1 && !p.out_tma) return set_error(BFP_E_ALIGN, "multi-destination output needs 16-byte aligned slices and a row stride that is a multiple of 16 bytes");
     // each map covers exactly the [T, N] slice (row stride ld_out), so the copy engine clips at the slice's edge
     for (int g = 0; g < (p.out_tma ? n_out : 0); ++g)
-        if (int rc = make_map_f32(&map_out.m[g], out_ptrs[g], T, N, ld_out * 4, 32, 8)) return rc;
+        if (int rc = make_map_out(&map_out.m[g], out_ptrs[g], out_dtype, T, N, ld_out * out_es, 32, 8)) return rc;
     if (wide_tile) p.tiles_t = (int)((T + wide::BT - 1) / wide::BT);
     const int units = std::min(p.tiles_w * p.tiles_t, sms / cg);
     cudaError_t e;

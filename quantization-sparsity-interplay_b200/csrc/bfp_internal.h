@@ -72,8 +72,8 @@ int compress_2to4_bf16_device(const void* w_bf16, int64_t rows, int64_t Kp, int6
                               cudaStream_t st);
 int gemm_bf16_sp_device(const void* x_bf16, const void* w_comp, const void* w_meta, const float* bias, float* out, int64_t T, int64_t N,
                         int64_t Kp, cudaStream_t st);
-int gemm_bf16_sp_multi_device(const void* x_bf16, const void* w_comp, const void* w_meta, const float* bias, float* const* out_ptrs, int n_out,
-                              int64_t ld_out, int64_t T, int64_t N, int64_t Kp, cudaStream_t st);
+int gemm_bf16_sp_multi_device(const void* x_bf16, const void* w_comp, const void* w_meta, const float* bias, void* const* out_ptrs, int n_out,
+                              int out_dtype, int64_t ld_out, int64_t T, int64_t N, int64_t Kp, cudaStream_t st);
 
 size_t int_workspace_bytes(int64_t C);
 int int_quantize_device(const void* in, float* out, int64_t A, int64_t C, int64_t inner, int dtype, int bits, void* workspace, cudaStream_t s);

@@ -118,8 +118,8 @@ class ColumnParallelBFPLinear(torch.nn.Module):
             return False
         if self.local.bfp_args['rounding_mode'] != bfp_ops.rounding_modes.DETERM or self.local.num_format != 'bfp':
             return False
-        return (bfp_ops._tensor_core_kind(x, self.local.weight, self.local.bfp_args) == 'sp' and self.out_features % 4 == 0
-                and all(column_shard(self.out_features, r, self.world)[0] % 4 == 0 for r in range(self.world)))
+        return (bfp_ops._tensor_core_kind(x, self.local.weight, self.local.bfp_args) == 'sp' and self.out_features % 8 == 0
+                and all(column_shard(self.out_features, r, self.world)[0] % 8 == 0 for r in range(self.world)))
 
     def _fused_forward(self, x, alias_output=False):
         """y = [x W_0^T | ... | x W_{G-1}^T]: every rank runs bfp_gemm_bf16_sp_gather on its shard and the epilogue stores the
@@ -131,12 +131,12 @@ class ColumnParallelBFPLinear(torch.nn.Module):
         from . import _lib, bfp_ops
         K = x.shape[-1]
         T = x.numel() // K
-        key = (T, x.device)
+        key = (T, x.device, x.dtype)
         if self._symm is None or self._symm[0] != key:
             group = self.group if self.group is not None else dist.group.WORLD
             bufs = []
             for _ in range(2):
-                b = symm_mem.empty((T, self.out_features), dtype=torch.float32, device=x.device)
+                b = symm_mem.empty((T, self.out_features), dtype=x.dtype, device=x.device)
                 bufs.append((b, symm_mem.rendezvous(b, group)))
             self._symm = (key, bufs, 0)
         _, bufs, turn = self._symm
@@ -145,12 +145,13 @@ class ColumnParallelBFPLinear(torch.nn.Module):
         xb = bfp_ops.pack_bfp_bf16(x, identifier='in', **self.local.bfp_args)
         ws = self.local._packed_weight('sp')
         bias = self.local.bias.detach().float().contiguous() if self.local.bias is not None else None
-        ptrs = (ctypes.c_void_p * self.world)(*[int(hdl.buffer_ptrs[r]) + self.lo * 4 for r in range(self.world)])
+        es = buf.element_size()
+        ptrs = (ctypes.c_void_p * self.world)(*[int(hdl.buffer_ptrs[r]) + self.lo * es for r in range(self.world)])
         hdl.barrier(channel=0)                                       # nobody is still reading this buffer's previous contents
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().bfp_gemm_bf16_sp_gather(xb.data_ptr(), ws.comp.data_ptr(), ws.meta.data_ptr(),
-                                                          bias.data_ptr() if bias is not None else None, ptrs, self.world, self.out_features,
-                                                          T, self.hi - self.lo, xb.shape[1], torch.cuda.current_stream().cuda_stream))
+                                                          bias.data_ptr() if bias is not None else None, ptrs, self.world, bfp_ops._DT[x.dtype],
+                                                          self.out_features, T, self.hi - self.lo, xb.shape[1], torch.cuda.current_stream().cuda_stream))
         hdl.barrier(channel=1)                                       # every rank's slices have landed in every buffer
         out = buf if alias_output else buf.clone()
         return out.view(tuple(x.shape[:-1]) + (self.out_features,))

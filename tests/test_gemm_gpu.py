@@ -308,6 +308,20 @@ def test_gemm_sp_exact_products(ops, shape, cta_group, tile):
         _lib.set_option("gemm_sp_tile", 0)
         _lib.set_option("gemm_out_tma", 1)
     assert torch.equal(y.double().cpu(), ref)
+    # half-precision outputs are the same fp32 accumulators rounded once in the epilogue
+    if wb.shape[0] % 8 == 0:
+        _lib.set_option("gemm_sp_cta_group", cta_group)
+        _lib.set_option("gemm_sp_tile", abs(tile))
+        _lib.set_option("gemm_out_tma", 0 if tile < 0 else 1)
+        try:
+            ws = ops.compress_2to4_bf16(wb.cuda())
+            for dt in (torch.float16, torch.bfloat16):
+                yh = ops.bfp_linear_bf16_sp(xb.cuda(), ws, bias.cuda(), out_dtype=dt)
+                assert yh.dtype == dt and torch.equal(yh, y.to(dt)), dt
+        finally:
+            _lib.set_option("gemm_sp_cta_group", 0)
+            _lib.set_option("gemm_sp_tile", 0)
+            _lib.set_option("gemm_out_tma", 1)
 
 
 @pytest.mark.parametrize("NK", [(4096, 4096), (11008, 4096), (4096, 11008)])
