@@ -3,7 +3,9 @@ block nn.Linear replaced by BFPLinear (and the ViT patch-embedding conv by BFPCo
 reference's patched modeling_opt.py:162-176,325-335 / modeling_vit.py:168-215 make.  Runs the model once with this
 repo's bfp_ops and, when the reference sources are present, once with the reference's, and compares logits.
 
-    python tools/model_dropin.py [opt|vit] [--layers L] [--batch B] [--seq S] [--out file.json]
+    python tools/model_dropin.py [opt|vit|llama] [--layers L] [--batch B] [--seq S] [--dtype fp32|fp16|bf16] [--out file.json]
+(llama: a LLaMA-architecture decoder at reduced width -- hidden 2048, 4 layers by default -- with all seven projections of
+every layer swapped, run in fp16 like the reference's LLaMA scripts)
 """
 import argparse, json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -13,6 +15,7 @@ from qsi_b200 import bfp_ops as ours
 from _refload import load_reference
 
 OPT_TARGETS = ("q_proj", "k_proj", "v_proj", "out_proj", "fc1", "fc2")
+LLAMA_TARGETS = ("q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj")
 
 
 def swap(model, impl, kw, targets=None, conv_name="projection"):
@@ -38,6 +41,10 @@ def build(kind, layers):
         cfg = transformers.OPTConfig()
         if layers: cfg.num_hidden_layers = layers
         return transformers.OPTForCausalLM(cfg).eval(), cfg
+    if kind == "llama":
+        cfg = transformers.LlamaConfig(hidden_size=2048, intermediate_size=5504, num_hidden_layers=layers or 4, num_attention_heads=16,
+                                       num_key_value_heads=16, vocab_size=32000, max_position_embeddings=2048)
+        return transformers.LlamaForCausalLM(cfg).eval(), cfg
     cfg = transformers.ViTConfig()
     if layers: cfg.num_hidden_layers = layers
     return transformers.ViTForImageClassification(cfg).eval(), cfg
@@ -45,30 +52,33 @@ def build(kind, layers):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("kind", nargs="?", default="opt", choices=["opt", "vit"])
+    ap.add_argument("kind", nargs="?", default="opt", choices=["opt", "vit", "llama"])
+    ap.add_argument("--dtype", default="", choices=["", "fp32", "fp16", "bf16"])
     ap.add_argument("--layers", type=int, default=0); ap.add_argument("--batch", type=int, default=0); ap.add_argument("--seq", type=int, default=512)
     ap.add_argument("--mant", type=int, default=0); ap.add_argument("--out", default="")
     a = ap.parse_args()
     dev = "cuda"
-    m = a.mant or (7 if a.kind == "opt" else 5)            # config 0: HBFP8, config 3: BFP6
+    m = a.mant or (5 if a.kind == "vit" else 7)            # config 0: HBFP8, config 3: BFP6
+    dtn = a.dtype or ("fp16" if a.kind == "llama" else "fp32")
+    tdt = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}[dtn]
     kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=m, weight_mant_bits=15,
               block_size=64, w_sparsity=True, N=2, M=4, first="s", sparsity_mode="structured", sparsity_frac=0.5, device=dev)
-    res = {"model": a.kind, "mant_bits": m, "block": 64, "nm": "2:4 s->q"}
+    res = {"model": a.kind, "mant_bits": m, "block": 64, "nm": "2:4 s->q", "dtype": dtn}
     outs = {}
     ref = load_reference()
     for tag, impl in (("ours", ours), ("reference", ref)):
         if impl is None:
             continue
         model, cfg = build(a.kind, a.layers)
-        n = swap(model, impl, kw, OPT_TARGETS if a.kind == "opt" else None)
-        model = model.to(dev)
+        n = swap(model, impl, kw, OPT_TARGETS if a.kind == "opt" else (LLAMA_TARGETS if a.kind == "llama" else None))
+        model = model.to(dev).to(tdt)
         g = torch.Generator().manual_seed(1)
-        if a.kind == "opt":
-            B = a.batch or 8
+        if a.kind in ("opt", "llama"):
+            B = a.batch or (8 if a.kind == "opt" else 4)
             inp = dict(input_ids=torch.randint(0, cfg.vocab_size, (B, a.seq), generator=g).to(dev))
         else:
             B = a.batch or 256
-            inp = dict(pixel_values=torch.randn(B, 3, 224, 224, generator=g).to(dev))
+            inp = dict(pixel_values=torch.randn(B, 3, 224, 224, generator=g).to(dev).to(tdt))
         with torch.no_grad():
             for _ in range(3):                                  # weight packs, allocator, clocks
                 y = model(**inp).logits
