@@ -185,6 +185,9 @@ int bfp_quantize_pack_bf16(const void* in, void* out_bf16, int64_t rows, int64_t
                            int order, void* stream);
 int bfp_gemm_bf16(const void* a_bf16, const void* b_bf16, const float* bias, float* out, int64_t T, int64_t N, int64_t K,
                   void* stream);
+/* ... with the output dtype chosen: BFP_DT_F32, or BFP_DT_F16 / BFP_DT_BF16 (accumulator + bias rounded once in the epilogue). */
+int bfp_gemm_bf16_ex(const void* a_bf16, const void* b_bf16, const float* bias, void* out, int out_dtype, int64_t T, int64_t N,
+                     int64_t K, void* stream);
 
 /* 2:4 structured-sparse variant of the BFP linear for weights pruned by _structured_N_M_sparsity with N=2, M=4
  * (bfp_ops.py:73-91; the reference then multiplies the zero-filled dense tensor, bfp_ops.py:187-190).  The pruned

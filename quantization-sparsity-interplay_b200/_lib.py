@@ -57,6 +57,7 @@ SIGNATURES = {
     "bfp_unpack": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _vp]),
     "bfp_quantize_pack_bf16": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _i32, _u64, _u64, _i32, _i32, _i32, _vp]),
     "bfp_gemm_bf16": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "bfp_gemm_bf16_ex": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp]),
     "bfp_sp_layout": (_i32, [_i64, _i64] + [ctypes.POINTER(_i64)] * 2),
     "bfp_compress_2to4_bf16": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "bfp_gemm_bf16_sp": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),

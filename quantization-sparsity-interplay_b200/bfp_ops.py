@@ -410,18 +410,18 @@ def pack_bfp_bf16(t, identifier='', philox=None, **bfp_args):
     return out
 
 
-def bfp_linear_bf16(xb, wb, bias=None, out_shape=None):
-    """y = x w^T + bias on exact-bf16 BFP operands (include/bfp_b200.h bfp_gemm_bf16): tcgen05.mma.kind::f16, fp32 TMEM
-    accumulation, no per-block rescale.  xb [T, Kp], wb [N, Kp] bf16."""
+def bfp_linear_bf16(xb, wb, bias=None, out_shape=None, out_dtype=torch.float32):
+    """y = x w^T + bias on exact-bf16 BFP operands (include/bfp_b200.h bfp_gemm_bf16_ex): tcgen05.mma.kind::f16, fp32 TMEM
+    accumulation, no per-block rescale; the epilogue writes fp32 or rounds once to fp16 / bf16.  xb [T, Kp], wb [N, Kp] bf16."""
     T, Kp = xb.shape
     N = wb.shape[0]
     assert wb.shape[1] == Kp and xb.dtype == torch.bfloat16 and wb.dtype == torch.bfloat16
-    out = torch.empty((T, N), dtype=torch.float32, device=xb.device)
+    out = torch.empty((T, N), dtype=out_dtype, device=xb.device)
     b = bias.detach().to(dtype=torch.float32).contiguous() if bias is not None else None
     if out.numel():
         with _on(out.device):
-            _lib.check(_lib.lib().bfp_gemm_bf16(xb.data_ptr(), wb.data_ptr(), b.data_ptr() if b is not None else None, out.data_ptr(),
-                                                T, N, Kp, _stream()))
+            _lib.check(_lib.lib().bfp_gemm_bf16_ex(xb.data_ptr(), wb.data_ptr(), b.data_ptr() if b is not None else None, out.data_ptr(),
+                                                   _DT[out_dtype], T, N, Kp, _stream()))
     return out.view(out_shape) if out_shape is not None else out
 
 
@@ -832,7 +832,7 @@ class BFPLinear(torch.nn.Linear):
                                        out_shape=tuple(input.shape[:-1]) + (self.out_features,), out_dtype=input.dtype)
             elif kind == 'bf16':
                 y = bfp_linear_bf16(_packed_activation(input, self.bfp_args), self._packed_weight(kind), self.bias,
-                                    out_shape=tuple(input.shape[:-1]) + (self.out_features,))
+                                    out_shape=tuple(input.shape[:-1]) + (self.out_features,), out_dtype=input.dtype)
             if y is not None:
                 return y if input.dtype == torch.float32 else y.to(input.dtype)     # fp32 accumulation, one rounding to the dtype
             return self.linear_op(input, self.weight, self.bias)

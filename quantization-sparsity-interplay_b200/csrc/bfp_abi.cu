@@ -246,6 +246,14 @@ int bfp_gemm_bf16(const void* a_bf16, const void* b_bf16, const float* bias, flo
     return gemm_bf16_device(a_bf16, b_bf16, bias, out, T, N, round_up(K, 8), static_cast<cudaStream_t>(stream));
 }
 
+int bfp_gemm_bf16_ex(const void* a_bf16, const void* b_bf16, const float* bias, void* out, int out_dtype, int64_t T, int64_t N, int64_t K,
+                     void* stream) {
+    if (T < 0 || N < 0 || K <= 0) return set_error(BFP_E_ARG, "bad argument");
+    if (T * N > 0 && (!a_bf16 || !b_bf16 || !out)) return set_error(BFP_E_ARG, "null pointer");
+    if (int rc = require_device()) return rc;
+    return gemm_bf16_ex_device(a_bf16, b_bf16, bias, out, out_dtype, T, N, round_up(K, 8), static_cast<cudaStream_t>(stream));
+}
+
 int bfp_sp_layout(int64_t rows, int64_t K, int64_t* Kc, int64_t* meta_bytes) { return sp_layout(rows, round_up(K, 8), Kc, meta_bytes); }
 
 int bfp_compress_2to4_bf16(const void* w_bf16, int64_t rows, int64_t K, void* w_comp, void* w_meta, uint32_t* violations, void* stream) {

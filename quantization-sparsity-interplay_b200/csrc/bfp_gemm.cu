@@ -279,7 +279,8 @@ template <int TBN, int CG> struct Bf16Cfg {
 struct ParamsBf16 {
     const float* bias;
     float* out;
-    int out_tma;                // 1 = epilogue writes through smem + TMA stores (needs N % 4 == 0)
+    int out_dtype;              // BFP_DT_F32, or F16 / BF16: accumulator (+ bias) rounded once in the epilogue
+    int out_tma;                // 1 = epilogue writes through smem + TMA stores (needs 16-byte aligned rows)
     int T, N;
     int num_k_stages;           // ceil(K / 64)
     int tiles_m, tiles_n;       // tiles_m counts CG * 128 rows
@@ -407,6 +408,34 @@ bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 // rows / columns beyond T / N are clipped by the copy engine.
                 const uint64_t pol = l2_policy_evict_first();
                 uint8_t* sbuf = staging + ew * 4096;
+                if (p.out_dtype != BFP_DT_F32) {
+                // half outputs: 64 columns per round = one 128-byte row of 2-byte values per token, same swizzled tile
+#pragma unroll
+                for (int c = 0; c < kCols / 64; ++c) {
+                    uint32_t r[64];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) tmem_ld16(taddr + c * 64 + i * 16, r + i * 16);
+                    tmem_ld_wait();
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {                  // chunk j = columns 8j .. 8j+7
+                        uint32_t w[4];
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const int nb = n0 + c * 64 + 8 * j + 2 * h;
+                            float o0 = __uint_as_float(r[8 * j + 2 * h]), o1 = __uint_as_float(r[8 * j + 2 * h + 1]);
+                            if (p.bias) { if (nb < p.N) o0 += p.bias[nb]; if (nb + 1 < p.N) o1 += p.bias[nb + 1]; }
+                            if (p.out_dtype == BFP_DT_F16) { const __half2 hh = __floats2half2_rn(o0, o1); w[h] = *reinterpret_cast<const uint32_t*>(&hh); }
+                            else { const __nv_bfloat162 hh = __floats2bfloat162_rn(o0, o1); w[h] = *reinterpret_cast<const uint32_t*>(&hh); }
+                        }
+                        *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) { tma_store_2d_hint(&map_out, sbuf, n0 + c * 64, (tm * CG + (int)rank) * BM + q * 32, pol); tma_store_commit(); }
+                }
+                } else {
 #pragma unroll
                 for (int c = 0; c < kCols / 32; ++c) {
                     uint32_t r[32];
@@ -436,13 +465,24 @@ bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     __syncwarp();
                     if (lane == 0) { tma_store_2d_hint(&map_out, sbuf, n0 + c * 32, (tm * CG + (int)rank) * BM + q * 32, pol); tma_store_commit(); }
                 }
+                }
             } else {
 #pragma unroll
             for (int c = 0; c < kCols / 16; ++c) {
                 uint32_t r[16];
                 tmem_ld16(taddr + c * 16, r);
                 tmem_ld_wait();
-                if (t < p.T) {
+                if (t < p.T && p.out_dtype != BFP_DT_F32) {
+                    uint16_t* hd = reinterpret_cast<uint16_t*>(p.out) + (int64_t)t * p.N + n0 + c * 16;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int nn = n0 + c * 16 + j;
+                        if (nn < p.N) {
+                            const float o = __uint_as_float(r[j]) + (p.bias ? p.bias[nn] : 0.0f);
+                            hd[j] = p.out_dtype == BFP_DT_F16 ? __half_as_ushort(__float2half_rn(o)) : __bfloat16_as_ushort(__float2bfloat16_rn(o));
+                        }
+                    }
+                } else if (t < p.T) {
                     if (vec_ok) {
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
@@ -534,14 +574,22 @@ static int launch_bf16(const CUtensorMap& map_a, const CUtensorMap& map_b, const
 
 int gemm_bf16_device(const void* a_bf16, const void* b_bf16, const float* bias, float* out, int64_t T, int64_t N, int64_t Kp,
                      cudaStream_t st) {
+    return gemm_bf16_ex_device(a_bf16, b_bf16, bias, out, BFP_DT_F32, T, N, Kp, st);
+}
+
+int gemm_bf16_ex_device(const void* a_bf16, const void* b_bf16, const float* bias, void* out_v, int out_dtype, int64_t T, int64_t N, int64_t Kp,
+                        cudaStream_t st) {
     using namespace gemm;
     if (T == 0 || N == 0) return BFP_OK;
+    if (out_dtype != BFP_DT_F32 && out_dtype != BFP_DT_F16 && out_dtype != BFP_DT_BF16) return set_error(BFP_E_ARG, "bad output dtype");
+    float* out = static_cast<float*>(out_v);
+    const int out_es = out_dtype == BFP_DT_F32 ? 4 : 2;
     if (Kp % 8 != 0 || Kp <= 0) return set_error(BFP_E_ARG, "bf16 operand K must be a positive multiple of 8");
     if (T > INT32_MAX || N > INT32_MAX || Kp > INT32_MAX) return set_error(BFP_E_ARG, "dimension too large");
     if (reinterpret_cast<uintptr_t>(a_bf16) % 16 || reinterpret_cast<uintptr_t>(b_bf16) % 16)
         return set_error(BFP_E_ALIGN, "bf16 operands must be 16-byte aligned");
     ParamsBf16 p;
-    p.bias = bias; p.out = out; p.T = (int)T; p.N = (int)N;
+    p.bias = bias; p.out = out; p.out_dtype = out_dtype; p.T = (int)T; p.N = (int)N;
     p.num_k_stages = (int)((Kp + 63) / 64);
     // tile: CTA pairs on 256x256 (cta_group::2) unless the problem is a single 128-row or 128-column strip; the knobs
     // gemm_bf16_cta_group (1 / 2) and gemm_bf16_tile_n (128 / 256, single-CTA mode only) force a variant.
@@ -559,8 +607,8 @@ int gemm_bf16_device(const void* a_bf16, const void* b_bf16, const float* bias, 
     if (int rc = make_map(&map_a, a_bf16, T, Kp * 2, BM, true)) return rc;
     if (int rc = make_map(&map_b, b_bf16, N, Kp * 2, tbn / cg, true)) return rc;
     CUtensorMap map_out = map_a;
-    p.out_tma = (N % 4 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 && tuning().gemm_out_tma) ? 1 : 0;
-    if (p.out_tma) if (int rc = make_map_f32(&map_out, out, T, N, N * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    p.out_tma = ((N * out_es) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 && tuning().gemm_out_tma) ? 1 : 0;
+    if (p.out_tma) if (int rc = make_map_out(&map_out, out, out_dtype, T, N, N * out_es, out_es == 4 ? 32 : 64, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     const int units = std::min(p.tiles_m * p.tiles_n, sms / cg);
     int rc;
     if (cg == 2) rc = launch_bf16<256, 2>(map_a, map_b, map_out, p, units, st);

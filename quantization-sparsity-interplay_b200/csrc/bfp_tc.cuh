@@ -287,8 +287,9 @@ inline int make_map_f32(CUtensorMap* map, const void* ptr, int64_t rows, int64_t
 }
 
 // Output tile map for any of the three output dtypes (no swizzle).
-inline int make_map_out(CUtensorMap* map, const void* ptr, int dtype, int64_t rows, int64_t cols, int64_t row_stride_bytes, int box_cols, int box_rows) {
-    if (dtype == BFP_DT_F32) return make_map_f32(map, ptr, rows, cols, row_stride_bytes, box_cols, box_rows);
+inline int make_map_out(CUtensorMap* map, const void* ptr, int dtype, int64_t rows, int64_t cols, int64_t row_stride_bytes, int box_cols, int box_rows,
+                        CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_NONE) {
+    if (dtype == BFP_DT_F32) return make_map_f32(map, ptr, rows, cols, row_stride_bytes, box_cols, box_rows, swz);
     EncodeTiledFn fn = encode_fn();
     if (!fn) return set_error(BFP_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -296,7 +297,7 @@ inline int make_map_out(CUtensorMap* map, const void* ptr, int dtype, int64_t ro
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, dtype == BFP_DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
-                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_errorf(BFP_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return BFP_OK;
 }
