@@ -31,7 +31,15 @@ struct PackParams {
     float eps;
     int kdrop;
     uint64_t seed, offset;
+    uint32_t vec_per_row, slots_per_row;   // padded-row mode (bf16 format only): see StreamParams in bfp_quant.cu; 0 = flat
 };
+
+__device__ __forceinline__ int64_t pack_real_vec(const PackParams& p, int64_t g) {
+    if (p.slots_per_row == 0u) return g < p.n_vec ? g : -1;
+    if (g >= p.n_vec) return -1;
+    const uint32_t row = (uint32_t)((uint64_t)g / p.slots_per_row), slot = (uint32_t)((uint64_t)g - (uint64_t)row * p.slots_per_row);
+    return slot < p.vec_per_row ? (int64_t)row * p.vec_per_row + slot : -1;
+}
 
 __device__ __forceinline__ uint32_t pack4_s8(const float* q) {
     // q are integers in [-127, 127] (or -0.0): cvt.rni.s8 via int conversion, then byte pack
@@ -57,18 +65,17 @@ __global__ void __launch_bounds__(kStreamThreads) pack_stream_kernel(const PackP
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t tile_base = tile * kTileVecs;
-        const int rem = (int)min((int64_t)kTileVecs, p.n_vec - tile_base);
-        const uint4* src = p.in + tile_base;
         uint4 raw[kStreamUnroll];
+        int64_t rv[kStreamUnroll];                                            // real vector index, -1 = padding / out of range
 #pragma unroll
         for (int u = 0; u < kStreamUnroll; ++u) {
-            const int li = (int)threadIdx.x + u * kStreamThreads;
-            raw[u] = (li < rem) ? ld_stream(src + li) : make_uint4(0u, 0u, 0u, 0u);
+            rv[u] = pack_real_vec(p, tile_base + (int)threadIdx.x + u * kStreamThreads);
+            raw[u] = rv[u] >= 0 ? ld_stream(p.in + rv[u]) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
         for (int u = 0; u < kStreamUnroll; ++u) {
-            const int li = (int)threadIdx.x + u * kStreamThreads;
-            const int64_t vi = tile_base + li;
+            const int64_t vi = rv[u];
+            const bool live = vi >= 0;
             float v[V];
             unpack_vec<DT>(raw[u], v);
             uint32_t amax = 0u;
@@ -101,7 +108,7 @@ __global__ void __launch_bounds__(kStreamThreads) pack_stream_kernel(const PackP
             }
             if (kSparseLast) mask_vec<M, KD, BFP_TIE_TORCH_CUDA, V>(q, p.kdrop);   // same order as masking q * delta
             if (FMT == 1) {
-                if (li < rem) {
+                if (live) {
                     const float d = sc.fast ? sc.delta : __int_as_float(0x7fc00000);
                     uint32_t w[V / 2];
 #pragma unroll
@@ -113,7 +120,7 @@ __global__ void __launch_bounds__(kStreamThreads) pack_stream_kernel(const PackP
                     if (V == 4) *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
                     else *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[V / 2 - 2], w[V / 2 - 1]);
                 }
-            } else if (li < rem) {
+            } else if (live) {
                 if (V == 4) {
                     *reinterpret_cast<uint32_t*>(p.mant + vi * 4) = pack4_s8(q);
                 } else {
@@ -221,9 +228,22 @@ static int pack_dt(const QuantArgs& a, int8_t* mant, float* scale_t, int64_t Kp,
                 reinterpret_cast<uintptr_t>(a.in) % 16 == 0 && reinterpret_cast<uintptr_t>(mant) % 16 == 0 &&
                 a.rows * nkb < (int64_t)1 << 32 && !tuning().force_generic;
     if (sparse) fast = fast && a.M == 4 && a.N == 2;
-    if (fast) {
+    // padded-row mode for the bf16 operand format: vector-aligned rows whose length is not a multiple of the block
+    bool padded = false;
+    if (!fast && FMT == 1 && !tuning().force_generic) {
+        padded = (a.K % V == 0) && (a.K % a.B != 0) && (a.B & (a.B - 1)) == 0 && a.B >= V && a.B <= 32 * V && Kp == a.K &&
+                 reinterpret_cast<uintptr_t>(a.in) % 16 == 0 && reinterpret_cast<uintptr_t>(mant) % 16 == 0 && a.K / V < (int64_t)1 << 31 &&
+                 a.rows < (int64_t)1 << 31 && (!sparse || (a.M == 4 && a.N == 2 && a.K % 4 == 0));
+    }
+    if (fast || padded) {
         PackParams p;
         p.in = static_cast<const uint4*>(a.in); p.mant = mant; p.scale_t = scale_t; p.n_vec = numel / V; p.Kp = Kp;
+        p.vec_per_row = p.slots_per_row = 0;
+        if (padded) {
+            p.vec_per_row = (uint32_t)(a.K / V);
+            p.slots_per_row = (uint32_t)(round_up(a.K, a.B) / V);
+            p.n_vec = a.rows * (int64_t)p.slots_per_row;
+        }
         p.rows_pad = rows_pad; p.nkb = (uint32_t)nkb; p.lanes_per_block = a.B / V; p.lpb_shift = __builtin_ctz(a.B / V);
         p.m = a.m; p.eps = a.eps; p.kdrop = sparse ? a.M - a.N : 0; p.seed = a.seed; p.offset = a.offset;
         switch (a.order) {

@@ -30,7 +30,19 @@ struct StreamParams {
     int kdrop;              // M - N
     uint64_t seed, offset;
     int64_t ctr_base;       // Philox counter of vector 0 (= flat element index / 4)
+    // Padded-row mode (K a multiple of the vector width but not of the block size): every row is seen as slots_per_row
+    // vector slots (a whole number of blocks), of which the first vec_per_row exist; the rest read as zeros -- exactly the
+    // F.pad of bfp_ops.py:52 -- and are never stored.  n_vec then counts SLOTS.  0 = flat mode (rows do not matter).
+    uint32_t vec_per_row, slots_per_row;
 };
+
+// slot index g -> index of the real vector (or -1 for a padding slot / beyond the tensor)
+__device__ __forceinline__ int64_t real_vec(const StreamParams& p, int64_t g) {
+    if (p.slots_per_row == 0u) return g < p.n_vec ? g : -1;
+    if (g >= p.n_vec) return -1;
+    const uint32_t row = (uint32_t)((uint64_t)g / p.slots_per_row), slot = (uint32_t)((uint64_t)g - (uint64_t)row * p.slots_per_row);
+    return slot < p.vec_per_row ? (int64_t)row * p.vec_per_row + slot : -1;
+}
 
 
 // One 128-bit vector (4 fp32 / 8 half elements of one block's lane) through mask -> block max (butterfly over the lanes that
@@ -109,21 +121,19 @@ __global__ void __launch_bounds__(kStreamThreads) quant_stream_kernel(const Stre
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t tile_base = tile * kTileVecs;
-        const int rem = (int)min((int64_t)kTileVecs, p.n_vec - tile_base);   // vectors of this tile that exist
-        const uint4* src = p.in + tile_base;
         uint4 raw[kStreamUnroll];
+        int64_t rv[kStreamUnroll];                                            // real vector index, -1 = padding / out of range
 #pragma unroll
         for (int u = 0; u < kStreamUnroll; ++u) {
-            const int li = (int)threadIdx.x + u * kStreamThreads;
-            raw[u] = (li < rem) ? ld_stream(src + li) : make_uint4(0u, 0u, 0u, 0u);
+            rv[u] = real_vec(p, tile_base + (int)threadIdx.x + u * kStreamThreads);
+            raw[u] = rv[u] >= 0 ? ld_stream(p.in + rv[u]) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
         for (int u = 0; u < kStreamUnroll; ++u) {
-            const int li = (int)threadIdx.x + u * kStreamThreads;
             uint4 o[kOutVecs];
-            process_vec<DT, ORDER, M, KD, TIE, STOC>(raw[u], p, tile_base + li, o);
-            if (li < rem) {
-                uint4* dst = p.out + (tile_base + li) * kOutVecs;
+            process_vec<DT, ORDER, M, KD, TIE, STOC>(raw[u], p, rv[u], o);
+            if (rv[u] >= 0) {
+                uint4* dst = p.out + rv[u] * kOutVecs;
                 st_stream(dst, o[0]);
                 if (kOutVecs == 2) st_stream(dst + 1, o[kOutVecs - 1]);
             }
@@ -317,7 +327,7 @@ static int launch_stream_t(const StreamParams& p, cudaStream_t st) {
     static const int occ = kernel_occupancy(quant_stream_kernel<DT, ORDER, M, KD, TIE, STOC>, kStreamThreads);
     const int grid = stream_grid(occ, n_tiles);
     (void)di;
-    if (tuning().quant_tma) {
+    if (tuning().quant_tma && p.slots_per_row == 0) {
         constexpr int kTmaSmem = kTmaStages * kStreamThreads * kTmaUnroll * 16 + 2 * kTmaStages * 8;
         static const int occ_t = [] {
             cudaFuncSetAttribute(quant_tma_kernel<DT, ORDER, M, KD, TIE, STOC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmem);
@@ -409,12 +419,26 @@ static int quantize_dt(const QuantArgs& a, cudaStream_t st) {
     if (quant) fast = fast && is_pow2(a.B) && a.B >= V && a.B <= 32 * V && (a.K % a.B == 0);
     if (sparse) fast = fast && is_pow2(a.M) && a.M <= V && (a.K % a.M == 0) && !(a.tie == BFP_TIE_TORCH_CPU && !(a.M == 4 && a.N == 2));
     if (!quant) fast = fast && (a.K % V == 0 || true);      // groups never straddle vectors: M | V and M | K
+    // padded-row mode: rows are vector-aligned (K % V == 0) but not block-aligned -- the ViT patch-embedding input (K = 224),
+    // conv weights (K = kw < B), odd widths like 4100
+    bool padded = false;
+    if (!fast && quant && !tuning().force_generic) {
+        padded = (a.K % V == 0) && (a.index_base % 4 == 0) && (reinterpret_cast<uintptr_t>(a.in) % 16 == 0) && (reinterpret_cast<uintptr_t>(a.out) % 16 == 0) &&
+                 is_pow2(a.B) && a.B >= V && a.B <= 32 * V && (a.K % a.B != 0) && a.K / V < (int64_t)1 << 31 && a.rows < (int64_t)1 << 31;
+        if (sparse) padded = padded && is_pow2(a.M) && a.M <= V && (a.K % a.M == 0) && !(a.tie == BFP_TIE_TORCH_CPU && !(a.M == 4 && a.N == 2));
+    }
     if (tuning().force_generic) fast = false;
-    if (fast) {
+    if (fast || padded) {
         StreamParams p;
         p.in = static_cast<const uint4*>(a.in);
         p.out = static_cast<uint4*>(a.out);
         p.n_vec = numel / V;
+        p.vec_per_row = p.slots_per_row = 0;
+        if (padded) {
+            p.vec_per_row = (uint32_t)(a.K / V);
+            p.slots_per_row = (uint32_t)(round_up(a.K, a.B) / V);
+            p.n_vec = a.rows * (int64_t)p.slots_per_row;
+        }
         p.lanes_per_block = quant ? a.B / V : 1;
         p.m = a.m; p.eps = a.eps; p.kdrop = sparse ? a.M - a.N : 0;
         p.seed = a.seed; p.offset = a.offset; p.ctr_base = a.index_base / 4;
