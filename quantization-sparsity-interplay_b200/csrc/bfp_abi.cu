@@ -132,7 +132,7 @@ int bfp_set_option(const char* name, int64_t value) {
     else if (!strcmp(name, "gemm_sp_debug") && value >= 0 && value <= 31) t.gemm_sp_debug = (int)value;
     else if (!strcmp(name, "gemm_bf16_cta_group") && value >= 0 && value <= 2) t.gemm_bf16_cta_group = (int)value;
     else if (!strcmp(name, "gemm_out_tma") && (value == 0 || value == 1)) t.gemm_out_tma = (int)value;
-    else if (!strcmp(name, "gemm_sp_tile") && (value == 0 || value == 256 || value == 480)) t.gemm_sp_tile = (int)value;
+    else if (!strcmp(name, "gemm_sp_tile") && (value == 0 || value == 240 || value == 256 || value == 480)) t.gemm_sp_tile = (int)value;
     else if (!strcmp(name, "gemm_sp_cta_group") && value >= 0 && value <= 2) t.gemm_sp_cta_group = (int)value;
     else if (!strcmp(name, "gemm_bf16_tile_n") && (value == 0 || value == 128 || value == 256)) t.gemm_bf16_tile_n = (int)value;
     else return set_errorf(BFP_E_ARG, "unknown option or bad value: %s", name);

@@ -121,7 +121,7 @@ __device__ __forceinline__ void tmem_cp_128x128b(uint32_t tmem_dst, uint64_t sme
 // issues a TMA store per tile (8 full 128-byte rows; rows / columns beyond T / N are clipped by the copy engine).  Plain
 // path (N % 4 != 0): one 128-byte warp store per token.  Measured on B200: the st.global epilogue cost ~28 % of the whole
 // kernel at K = 4096 (it slows the operand stream while it runs, tools/exp_sp_tile_overhead.py).
-template <int NC>
+template <int NC, bool HALF>
 __device__ __forceinline__ void store_columns(const Params& p, const OutMaps& outs, float* stg, const uint32_t* r, float bv,
                                               int n0, int lane, int t0) {
     if (p.debug & 8) return;
@@ -133,7 +133,7 @@ __device__ __forceinline__ void store_columns(const Params& p, const OutMaps& ou
             // the stores that last read this buffer (two rounds ago; one bulk group per round) are done with it
             if (lane == 0) tma_store_wait_read<1>();
             __syncwarp();
-            if (p.out_dtype == BFP_DT_F32) {
+            if (!HALF) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) buf[j * 32 + lane] = __uint_as_float(r[rd * 8 + j]) + bv;
             } else {                                             // [8 t][32 n] of 2-byte values: 64-byte rows
@@ -147,7 +147,10 @@ __device__ __forceinline__ void store_columns(const Params& p, const OutMaps& ou
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-                for (int g = 0; g < outs.n; ++g) tma_store_2d_hint(&outs.m[g], buf, n0, t0 + rd * 8, pol);
+                tma_store_2d_hint(&outs.m[0], buf, n0, t0 + rd * 8, pol);
+                if (outs.n > 1) {                                 // fused all-gather: the same tile to every peer's buffer
+                    for (int g = 1; g < outs.n; ++g) tma_store_2d_hint(&outs.m[g], buf, n0, t0 + rd * 8, pol);
+                }
                 tma_store_commit();
             }
         }
@@ -155,7 +158,7 @@ __device__ __forceinline__ void store_columns(const Params& p, const OutMaps& ou
         const int n = n0 + lane;
         if (n < p.N) {
             const int t_left = p.T - t0;
-            if (p.out_dtype == BFP_DT_F32) {
+            if (!HALF) {
                 float* dst = p.out + (int64_t)t0 * p.ld_out + n;
 #pragma unroll
                 for (int j = 0; j < NC; ++j)
@@ -172,7 +175,7 @@ __device__ __forceinline__ void store_columns(const Params& p, const OutMaps& ou
     }
 }
 
-template <int CG>
+template <int CG, bool HALF>
 __global__ void __launch_bounds__(kThreads, 1)
 bfp_gemm_bf16_sp_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
                         const __grid_constant__ CUtensorMap map_e, const __grid_constant__ OutMaps outs, const Params p) {
@@ -299,7 +302,7 @@ bfp_gemm_bf16_sp_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_
 
             const int n0 = (tw * CG + (int)rank) * BW + q * 32;
             const float bv = (p.bias && n0 + lane < p.N) ? p.bias[n0 + lane] : 0.0f;
-            store_columns<BT / 2>(p, outs, staging + ew * 512, r, bv, n0, lane, tt * BT + half * (BT / 2));
+            store_columns<BT / 2, HALF>(p, outs, staging + ew * 512, r, bv, n0, lane, tt * BT + half * (BT / 2));
         }
         if (p.out_tma && lane == 0) tma_store_wait_all<0>();                 // smem (and the stores) must outlive the CTA's exit
     }
@@ -347,6 +350,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t* r) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(addr));
 }
 
+template <bool HALF>
 __global__ void __launch_bounds__(kThreads, 1)
 bfp_gemm_bf16_sp_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
                              const __grid_constant__ CUtensorMap map_e, const __grid_constant__ OutMaps outs, const Params p) {
@@ -475,10 +479,146 @@ bfp_gemm_bf16_sp_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(leader_tmem_empty);
                 }
-                store_columns<NT / 2>(p, outs, staging + (warp - 4) * 512, r, bv, (tw * 2 + (int)rank) * BW + q * 32, lane,
+                store_columns<NT / 2, HALF>(p, outs, staging + (warp - 4) * 512, r, bv, (tw * 2 + (int)rank) * BW + q * 32, lane,
                                       tt * BT + a * NT + pass * (NT / 2));
             }
             tile_phase ^= 1;
+        }
+        if (p.out_tma && lane == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+}
+
+// ====================================================================================================================
+// Ping-pong tile: 256 out-features x 240 tokens per CTA pair, TWO 240-column accumulators used alternately by consecutive
+// tiles, so the epilogue of tile i (tcgen05.ld, bias, transposed TMA stores) runs entirely under the main loop of tile i+1 and
+// the MMA issuer never waits for a drain.  The single-accumulator 256-token kernel pays ~3 us per tile for that hand-over
+// (tools/exp_sp_tile_overhead.py), which is 15-20 % of a K = 4096 tile.  Same slab structure as the 256-token kernel with
+// 120 X rows per CTA: W 16 KB + X 2 x 15 KB + E 2 KB = 48 KB per 128 k, four stages.
+//   TMEM: acc0 = columns [0,240), acc1 = [240,480), E ring = [480,512).
+// ====================================================================================================================
+namespace pp {
+constexpr int BW = 128, NT = 240, XC = NT / 2;
+constexpr int kStages = 4;
+constexpr int kSmemW = BW * 128, kSmemE = 2048, kSmemXAtom = XC * 128;              // 16 KB, 2 KB, 15 KB
+constexpr int kStageBytes = kSmemW + 2 * kSmemXAtom + kSmemE;                       // 49152
+constexpr int kSmemTotal = kStages * kStageBytes + kSmemStaging + 1024 + 1024;
+constexpr uint32_t kIdesc = (1u << 2) | (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)((BW * 2) >> 4) << 24);
+constexpr int kTmemEP = 480;
+struct Barriers {
+    uint64_t full[kStages], empty[kStages];
+    uint64_t tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+}  // namespace pp
+
+template <bool HALF>
+__global__ void __launch_bounds__(kThreads, 1)
+bfp_gemm_bf16_sp_pp_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
+                           const __grid_constant__ CUtensorMap map_e, const __grid_constant__ OutMaps outs, const Params p) {
+    using namespace pp;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* staging = reinterpret_cast<float*>(smem + kStages * kStageBytes);
+    pp::Barriers* bars = reinterpret_cast<pp::Barriers*>(smem + kStages * kStageBytes + kSmemStaging);
+    auto stage_w = [&](int s) { return smem + s * kStageBytes; };
+    auto stage_x = [&](int s, int a) { return smem + s * kStageBytes + kSmemW + a * kSmemXAtom; };
+    auto stage_e = [&](int s) { return smem + s * kStageBytes + kSmemW + 2 * kSmemXAtom; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int unit = (int)blockIdx.x / 2, num_units = (int)gridDim.x / 2;
+    const int num_tiles = p.tiles_w * p.tiles_t;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], kEpiWarps * 2); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            const uint64_t pol_keep = l2_policy_evict_last();
+            for (int tile = unit; tile < num_tiles; tile += num_units) {
+                const int tw = tile % p.tiles_w, tt = tile / p.tiles_w;
+                const int w_row = (tw * 2 + (int)rank) * BW, x_row = tt * NT + (int)rank * XC;
+                const int e_row = (tw * 2 + (int)rank) * p.e_atoms * 16;
+                for (int ks = 0; ks < p.num_k_slabs; ++ks) {
+                    mbar_wait(&bars->empty[stage], phase ^ 1);
+                    if (rank == 0) mbar_expect_tx(&bars->full[stage], 2u * kStageBytes);
+                    const uint32_t bar = mapa_u32(smem_u32(&bars->full[stage]), 0);
+                    tma_load_2d_to_hint<2>(stage_x(stage, 0), &map_x, bar, ks * 128, x_row, pol_keep);
+                    tma_load_2d_to_hint<2>(stage_x(stage, 1), &map_x, bar, ks * 128 + 64, x_row, pol_keep);
+                    tma_load_2d_to_hint<2>(stage_w(stage), &map_w, bar, ks * 64, w_row, pol_keep);
+                    tma_load_2d_to_hint<2>(stage_e(stage), &map_e, bar, 0, e_row + ks * 16, pol_keep);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            int stage = 0; uint32_t phase = 0, eslot = kERing - 1;
+            int buf = 0; uint32_t buf_phase[2] = {0, 0};
+            for (int tile = unit; tile < num_tiles; tile += num_units) {
+                mbar_wait(&bars->tmem_empty[buf], buf_phase[buf] ^ 1);      // drained two tiles ago: normally already free
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)buf * NT;
+                for (int ks = 0; ks < p.num_k_slabs; ++ks) {
+                    mbar_wait(&bars->full[stage], phase);
+                    tc_fence_after();
+                    eslot = (eslot + 1) & (kERing - 1);               // reuse distance kERing (8) slabs > kStages (4): see the 256-token kernel
+                    const uint32_t ecol = tmem_base + kTmemEP + eslot * 4;
+                    tmem_cp_128x128b<2>(ecol, make_smem_desc_k(smem_u32(stage_e(stage)), 0, 128, 128));
+                    const uint64_t dw = make_smem_desc(smem_u32(stage_w(stage)));
+                    const uint64_t dx0 = make_smem_desc(smem_u32(stage_x(stage, 0))), dx1 = make_smem_desc(smem_u32(stage_x(stage, 1)));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        mma_sp_bf16<2>(d, dw + (uint64_t)(i * 2), (i < 2 ? dx0 : dx1) + (uint64_t)((i & 1) * 4), ecol + (uint32_t)(i & 2),
+                                       kIdesc | (uint32_t)(i & 1), (ks | i) != 0);
+                    commit<2>(&bars->empty[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                commit<2>(&bars->tmem_full[buf]);
+                buf_phase[buf] ^= 1;
+                buf ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        const int ew = warp - 4, q = warp & 3, half = ew >> 2;
+        int buf = 0; uint32_t buf_phase[2] = {0, 0};
+        for (int tile = unit; tile < num_tiles; tile += num_units) {
+            const int tw = tile % p.tiles_w, tt = tile / p.tiles_w;
+            mbar_wait(&bars->tmem_full[buf], buf_phase[buf]);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NT + half * (NT / 2));
+            uint32_t r[NT / 2];                                              // 120 columns
+#pragma unroll
+            for (int c = 0; c < 7; ++c) tmem_ld16(taddr + c * 16, r + c * 16);
+            tmem_ld8(taddr + 112, r + 112);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[buf]), 0));
+            buf_phase[buf] ^= 1;
+            buf ^= 1;
+            const int n0 = (tw * 2 + (int)rank) * BW + q * 32;
+            const float bv = (p.bias && n0 + lane < p.N) ? p.bias[n0 + lane] : 0.0f;
+            store_columns<NT / 2, HALF>(p, outs, staging + ew * 512, r, bv, n0, lane, tt * NT + half * (NT / 2));
         }
         if (p.out_tma && lane == 0) tma_store_wait_all<0>();
     }
@@ -611,22 +751,29 @@ int gemm_bf16_sp_multi_device(const void* x_bf16, const void* w_comp, const void
     p.e_atoms = (int)(Kc / 64);
     p.tiles_w = (int)((N + 128 * cg - 1) / (128 * cg));
     p.tiles_t = (int)((T + 255) / 256);
-    // Tile width for CTA pairs: 256 tokens (one accumulator) or 480 (two accumulators sharing the W slab: 78 KB instead of
-    // 2 x 50 KB of operands per SM for 480 tokens).  A 480-token wave measured 1.5-1.95x a 256-token wave over the nine
-    // LLaMA shapes (profiles/r01_gemm_sp_bench.log), so the wide tile is taken when it needs fewer than 1/1.7 of the waves.
-    bool wide_tile = false;
+    // Three pair tiles, chosen from measurements over the nine LLaMA shapes (profiles/r01_gemm_sp_bench.log):
+    //   480 tokens, two accumulators sharing each W slab (78 KB instead of 2 x 50 KB of operands per SM per 480 tokens): a wave
+    //       costs 1.5-1.95x a 256-token wave plus a larger hand-over, so it is taken for K >= 6144 when it needs fewer than
+    //       1/1.7 of the waves;
+    //   240 tokens, two accumulators ping-ponged between consecutive tiles (no hand-over stall, fitted cost 1.03 S per wave
+    //       against S + 2.9 for the single-accumulator tile, S = 128-k slabs);
+    //   256 tokens, one accumulator, otherwise.
+    bool wide_tile = false, pp_tile = false;
     if (cg == 2) {
-        const int64_t pairs = sms / 2;
+        const int64_t pairs = sms / 2, S = p.num_k_slabs;
         const int64_t tiles256 = (int64_t)p.tiles_w * p.tiles_t, tiles480 = (int64_t)p.tiles_w * ((T + wide::BT - 1) / wide::BT);
-        const int64_t waves256 = (tiles256 + pairs - 1) / pairs, waves480 = (tiles480 + pairs - 1) / pairs;
-        wide_tile = waves480 * 17 < waves256 * 10 && p.num_k_slabs >= 16;
-        if (tuning().gemm_sp_tile == 256) wide_tile = false;
-        if (tuning().gemm_sp_tile == 480) wide_tile = true;
-        if (p.debug & 7) wide_tile = false;
+        const int64_t tiles240 = (int64_t)p.tiles_w * ((T + pp::NT - 1) / pp::NT);
+        const int64_t waves256 = (tiles256 + pairs - 1) / pairs, waves480 = (tiles480 + pairs - 1) / pairs, waves240 = (tiles240 + pairs - 1) / pairs;
+        wide_tile = waves480 * 17 < waves256 * 10 && S >= 48;
+        pp_tile = !wide_tile && waves240 * 1026 * S < waves256 * (1000 * S + 2900);
+        if (tuning().gemm_sp_tile == 256) { wide_tile = false; pp_tile = false; }
+        if (tuning().gemm_sp_tile == 480) { wide_tile = true; pp_tile = false; }
+        if (tuning().gemm_sp_tile == 240) { wide_tile = false; pp_tile = true; }
+        if (p.debug & 7) { wide_tile = false; pp_tile = false; }
     }
     CUtensorMap map_w, map_x, map_e;
     if (int rc = make_map_bf16(&map_w, w_comp, N, Kc, Kc * 2, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    if (int rc = make_map_bf16(&map_x, x_bf16, T, Kp, Kp * 2, 64, wide_tile ? wide::XC : 256 / cg, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_map_bf16(&map_x, x_bf16, T, Kp, Kp * 2, 64, (wide_tile || pp_tile) ? wide::XC : 256 / cg, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     if (int rc = make_map_bytes(&map_e, w_meta, mb / 128, 128, 16)) return rc;
     OutMaps map_out;
     map_out.n = n_out;
@@ -639,26 +786,27 @@ int gemm_bf16_sp_multi_device(const void* x_bf16, const void* w_comp, const void
     for (int g = 0; g < (p.out_tma ? n_out : 0); ++g)
         if (int rc = make_map_out(&map_out.m[g], out_ptrs[g], out_dtype, T, N, ld_out * out_es, 32, 8)) return rc;
     if (wide_tile) p.tiles_t = (int)((T + wide::BT - 1) / wide::BT);
+    if (pp_tile) p.tiles_t = (int)((T + pp::NT - 1) / pp::NT);
     const int units = std::min(p.tiles_w * p.tiles_t, sms / cg);
-    cudaError_t e;
-    if (cg == 1) {
-        e = cudaFuncSetAttribute(bfp_gemm_bf16_sp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::kSmemTotal);
-        if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        bfp_gemm_bf16_sp_kernel<1><<<units, kThreads, Cfg<1>::kSmemTotal, st>>>(map_w, map_x, map_e, map_out, p);
-    } else {
-        const int smem_bytes = wide_tile ? wide::kSmemTotal : Cfg<2>::kSmemTotal;
-        e = wide_tile ? cudaFuncSetAttribute(bfp_gemm_bf16_sp_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)
-                      : cudaFuncSetAttribute(bfp_gemm_bf16_sp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-        if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    const bool half = out_dtype != BFP_DT_F32;
+    const void* kern;
+    int smem_bytes;
+    if (cg == 1) { kern = half ? (const void*)bfp_gemm_bf16_sp_kernel<1, true> : (const void*)bfp_gemm_bf16_sp_kernel<1, false>; smem_bytes = Cfg<1>::kSmemTotal; }
+    else if (wide_tile) { kern = half ? (const void*)bfp_gemm_bf16_sp_wide_kernel<true> : (const void*)bfp_gemm_bf16_sp_wide_kernel<false>; smem_bytes = wide::kSmemTotal; }
+    else if (pp_tile) { kern = half ? (const void*)bfp_gemm_bf16_sp_pp_kernel<true> : (const void*)bfp_gemm_bf16_sp_pp_kernel<false>; smem_bytes = pp::kSmemTotal; }
+    else { kern = half ? (const void*)bfp_gemm_bf16_sp_kernel<2, true> : (const void*)bfp_gemm_bf16_sp_kernel<2, false>; smem_bytes = Cfg<2>::kSmemTotal; }
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)units * 2); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
+        cfg.gridDim = dim3((unsigned)units * cg); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[0].val.clusterDim.x = cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        e = wide_tile ? cudaLaunchKernelEx(&cfg, bfp_gemm_bf16_sp_wide_kernel, map_w, map_x, map_e, map_out, p)
-                      : cudaLaunchKernelEx(&cfg, bfp_gemm_bf16_sp_kernel<2>, map_w, map_x, map_e, map_out, p);
-        if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaLaunchKernelEx(bfp_gemm_bf16_sp): %s", cudaGetErrorString(e));
+        void* args[5] = {(void*)&map_w, (void*)&map_x, (void*)&map_e, (void*)&map_out, (void*)&p};
+        e = cudaLaunchKernelExC(&cfg, kern, args);
+        if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaLaunchKernelExC(bfp_gemm_bf16_sp): %s", cudaGetErrorString(e));
     }
     count_launch();
     return check_launch("bfp_gemm_bf16_sp_kernel");

@@ -292,11 +292,11 @@ def test_compress_rejects_dense_groups(ops):
     assert ops.compress_2to4_bf16(wb, check=False).comp.shape == (16, 64)
 
 
-@pytest.mark.parametrize("cta_group,tile", [(1, 0), (2, 256), (2, 480), (2, -256), (2, -480)])   # negative: plain-store epilogue
+@pytest.mark.parametrize("cta_group,tile", [(1, 0), (2, 256), (2, 480), (2, 240), (2, -256), (2, -480), (2, -240)])   # negative: plain-store epilogue
 @pytest.mark.parametrize("shape", [(256, 128, 128), (512, 256, 448), (300, 200, 264), (77, 300, 136), (1, 8, 72), (1000, 1536, 2048), (963, 520, 392)])
 def test_gemm_sp_exact_products(ops, shape, cta_group, tile):
     """Small-integer operands: the sparse kernel must return the exact integer matmul, for both CTA-group modes and both
-    pair tile widths (256 tokens / one accumulator, 480 tokens / two accumulators)."""
+    pair tiles (256 tokens / one accumulator, 480 tokens / two accumulators of one tile, 240 tokens / two accumulators ping-ponged)."""
     from qsi_b200 import _lib
     T, N, K = shape
     g = torch.Generator().manual_seed(T + 3 * N + K)

@@ -49,21 +49,24 @@ for (T, N, K) in sum((SH[s] for s in a.shapes.split(",")), []):
     _lib.set_option("gemm_bf16_cta_group", 0)
     md = timeit(lambda: _lib.check(L.bfp_gemm_bf16(xb.data_ptr(), wb.data_ptr(), None, out.data_ptr(), T, N, K, st)), a.iters, "dense")
     yd = out.clone()
+    def sp_call(): _lib.check(L.bfp_gemm_bf16_sp(xb.data_ptr(), ws.comp.data_ptr(), ws.meta.data_ptr(), None, out.data_ptr(), T, N, K, st))
     _lib.set_option("gemm_sp_cta_group", 1)
-    msp1 = timeit(lambda: _lib.check(L.bfp_gemm_bf16_sp(xb.data_ptr(), ws.comp.data_ptr(), ws.meta.data_ptr(), None, out.data_ptr(), T, N, K, st)), a.iters)
+    msp1 = timeit(sp_call, a.iters)
     _lib.set_option("gemm_sp_cta_group", 0)
-    _lib.set_option("gemm_sp_tile", 256)
-    msp256 = timeit(lambda: _lib.check(L.bfp_gemm_bf16_sp(xb.data_ptr(), ws.comp.data_ptr(), ws.meta.data_ptr(), None, out.data_ptr(), T, N, K, st)), a.iters)
-    _lib.set_option("gemm_sp_tile", 480)
-    msp480 = timeit(lambda: _lib.check(L.bfp_gemm_bf16_sp(xb.data_ptr(), ws.comp.data_ptr(), ws.meta.data_ptr(), None, out.data_ptr(), T, N, K, st)), a.iters)
+    best = {256: 1e9, 240: 1e9, 480: 1e9, 0: 1e9}
+    for rnd in range(3):                                   # interleaved rounds, best of three: the variants see the same thermal state
+        for tile in (256, 240, 480, 0):
+            _lib.set_option("gemm_sp_tile", tile)
+            best[tile] = min(best[tile], timeit(sp_call, a.iters, "sp" if tile == 0 else None))
     _lib.set_option("gemm_sp_tile", 0)
-    msp = timeit(lambda: _lib.check(L.bfp_gemm_bf16_sp(xb.data_ptr(), ws.comp.data_ptr(), ws.meta.data_ptr(), None, out.data_ptr(), T, N, K, st)), a.iters, "sp")
+    msp256, msp240, msp480, msp = best[256], best[240], best[480], best[0]
+    sp_call()
     xh, wh = xb.clone(), wb.clone()
     mcb = timeit(lambda: torch.nn.functional.linear(xh, wh), a.iters, "cublas")
     rel = float((out - yd).norm() / yd.norm())
     mc = timeit(lambda: ops.compress_2to4_bf16(wb, check=False), 5)
     ops_ = 2.0 * T * N * K
     print(f"T={T} N={N} K={K}: dense {md:.3f} ms = {ops_/md/1e9:.0f} TOPS [1-CTA: {ops_/md1/1e9:.0f}] | 2:4 sparse {msp:.3f} ms = {ops_/msp/1e9:.0f} dense-equivalent TOPS "
-          f"({ops_/msp/1e9/4500*100:.1f}% of 4500) x{md/msp:.2f} [tile 256: {ops_/msp256/1e9:.0f}, tile 480: {ops_/msp480/1e9:.0f}, 1-CTA: {ops_/msp1/1e9:.0f}] | rel diff {rel:.1e} | compress W {mc*1e3:.0f} us | cuBLAS bf16 {ops_/mcb/1e9:.0f} | clocks MHz/W dense {CLK['dense']} sp {CLK['sp']} cublas {CLK['cublas']}", flush=True)
-    res.append(dict(T=T, N=N, K=K, dense_ms=md, dense_1cta_ms=md1, dense_tops=ops_ / md / 1e9, sparse_ms=msp, sparse_tile256_ms=msp256, sparse_tile480_ms=msp480, cublas_bf16_ms=mcb, clocks=dict(CLK), sparse_1cta_ms=msp1, sparse_tops_dense_equiv=ops_ / msp / 1e9, rel_diff=rel, compress_ms=mc))
+          f"({ops_/msp/1e9/4500*100:.1f}% of 4500) x{md/msp:.2f} [tile 256: {ops_/msp256/1e9:.0f}, tile 240pp: {ops_/msp240/1e9:.0f}, tile 480: {ops_/msp480/1e9:.0f}, 1-CTA: {ops_/msp1/1e9:.0f}] | rel diff {rel:.1e} | compress W {mc*1e3:.0f} us | cuBLAS bf16 {ops_/mcb/1e9:.0f} | clocks MHz/W dense {CLK['dense']} sp {CLK['sp']} cublas {CLK['cublas']}", flush=True)
+    res.append(dict(T=T, N=N, K=K, dense_ms=md, dense_1cta_ms=md1, dense_tops=ops_ / md / 1e9, sparse_ms=msp, sparse_tile256_ms=msp256, sparse_tile240pp_ms=msp240, sparse_tile480_ms=msp480, cublas_bf16_ms=mcb, clocks=dict(CLK), sparse_1cta_ms=msp1, sparse_tops_dense_equiv=ops_ / msp / 1e9, rel_diff=rel, compress_ms=mc))
 if a.out: json.dump(res, open(a.out, "w"), indent=1)
