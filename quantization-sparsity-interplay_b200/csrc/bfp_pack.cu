@@ -51,7 +51,7 @@ __device__ __forceinline__ uint32_t pack4_s8(const float* q) {
 // the mantissas (Kp == K) and a block's (row, kb) follows from its flat index.
 // FMT: 0 = int8 mantissas + block-major fp32 scale table; 1 = dequantised bf16 (exact for m <= 8: q has <= 8 significant
 // bits and 2^(e-m) only moves the exponent), the operand format of the exact bf16 tensor-core GEMM.
-template <int DT, int ORDER, int M, int KD, bool STOC, int FMT>
+template <int DT, int ORDER, int M, int KD, bool STOC, int FMT, bool PADDED>
 __global__ void __launch_bounds__(kStreamThreads) pack_stream_kernel(const PackParams p) {
     using D = DType<DT>;
     constexpr int V = D::kVec;
@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(kStreamThreads) pack_stream_kernel(const PackP
         int64_t rv[kStreamUnroll];                                            // real vector index, -1 = padding / out of range
 #pragma unroll
         for (int u = 0; u < kStreamUnroll; ++u) {
-            rv[u] = pack_real_vec(p, tile_base + (int)threadIdx.x + u * kStreamThreads);
+            const int64_t g = tile_base + (int)threadIdx.x + u * kStreamThreads;
+            rv[u] = PADDED ? pack_real_vec(p, g) : (g < p.n_vec ? g : -1);
             raw[u] = rv[u] >= 0 ? ld_stream(p.in + rv[u]) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
@@ -208,11 +209,25 @@ __global__ void __launch_bounds__(256) unpack_kernel(const int8_t* mant, const f
 template <int DT, int ORDER, bool STOC, int FMT>
 static int launch_pack_stream(const PackParams& p, bool sparse, cudaStream_t st) {
     const int64_t n_tiles = (p.n_vec + kStreamThreads * kStreamUnroll - 1) / (kStreamThreads * kStreamUnroll);
-    static const int occ_s = kernel_occupancy(pack_stream_kernel<DT, ORDER, 4, 2, STOC, FMT>, kStreamThreads);
-    static const int occ_d = kernel_occupancy(pack_stream_kernel<DT, BFP_ORDER_QUANT_ONLY, 0, 0, STOC, FMT>, kStreamThreads);
+    if (p.slots_per_row != 0) {                           // padded rows (bf16 format only)
+        if constexpr (FMT == 1) {
+            static const int occ_ps = kernel_occupancy(pack_stream_kernel<DT, ORDER, 4, 2, STOC, FMT, true>, kStreamThreads);
+            static const int occ_pd = kernel_occupancy(pack_stream_kernel<DT, BFP_ORDER_QUANT_ONLY, 0, 0, STOC, FMT, true>, kStreamThreads);
+            const int gridp = stream_grid(sparse ? occ_ps : occ_pd, n_tiles);
+            if (int rc = sparse ? launch_pdl(pack_stream_kernel<DT, ORDER, 4, 2, STOC, FMT, true>, gridp, kStreamThreads, st, p)
+                                : launch_pdl(pack_stream_kernel<DT, BFP_ORDER_QUANT_ONLY, 0, 0, STOC, FMT, true>, gridp, kStreamThreads, st, p))
+                return rc;
+            count_launch();
+            return check_launch("pack_stream_kernel (padded rows)");
+        } else {
+            return set_error(BFP_E_UNSUPPORTED, "internal: padded rows are implemented for the bf16 operand format only");
+        }
+    }
+    static const int occ_s = kernel_occupancy(pack_stream_kernel<DT, ORDER, 4, 2, STOC, FMT, false>, kStreamThreads);
+    static const int occ_d = kernel_occupancy(pack_stream_kernel<DT, BFP_ORDER_QUANT_ONLY, 0, 0, STOC, FMT, false>, kStreamThreads);
     const int grid = stream_grid(sparse ? occ_s : occ_d, n_tiles);
-    if (int rc = sparse ? launch_pdl(pack_stream_kernel<DT, ORDER, 4, 2, STOC, FMT>, grid, kStreamThreads, st, p)
-                        : launch_pdl(pack_stream_kernel<DT, BFP_ORDER_QUANT_ONLY, 0, 0, STOC, FMT>, grid, kStreamThreads, st, p))
+    if (int rc = sparse ? launch_pdl(pack_stream_kernel<DT, ORDER, 4, 2, STOC, FMT, false>, grid, kStreamThreads, st, p)
+                        : launch_pdl(pack_stream_kernel<DT, BFP_ORDER_QUANT_ONLY, 0, 0, STOC, FMT, false>, grid, kStreamThreads, st, p))
         return rc;
     count_launch();
     return check_launch("pack_stream_kernel");

@@ -102,7 +102,7 @@ __device__ __forceinline__ void process_vec(const uint4& raw, const StreamParams
 }
 
 // ORDER: BFP_ORDER_*.  M / KD / TIE: see mask_vec.  STOC: stochastic rounding (fp32 output).
-template <int DT, int ORDER, int M, int KD, int TIE, bool STOC>
+template <int DT, int ORDER, int M, int KD, int TIE, bool STOC, bool PADDED>
 __global__ void __launch_bounds__(kStreamThreads) quant_stream_kernel(const StreamParams p) {
     using D = DType<DT>;
     constexpr int V = D::kVec;
@@ -122,20 +122,42 @@ __global__ void __launch_bounds__(kStreamThreads) quant_stream_kernel(const Stre
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t tile_base = tile * kTileVecs;
         uint4 raw[kStreamUnroll];
-        int64_t rv[kStreamUnroll];                                            // real vector index, -1 = padding / out of range
+        if constexpr (!PADDED) {
+            // flat mode: 32-bit in-tile indexing, one bounds compare per vector
+            const int rem = (int)min((int64_t)kTileVecs, p.n_vec - tile_base);   // vectors of this tile that exist
+            const uint4* src = p.in + tile_base;
 #pragma unroll
-        for (int u = 0; u < kStreamUnroll; ++u) {
-            rv[u] = real_vec(p, tile_base + (int)threadIdx.x + u * kStreamThreads);
-            raw[u] = rv[u] >= 0 ? ld_stream(p.in + rv[u]) : make_uint4(0u, 0u, 0u, 0u);
-        }
+            for (int u = 0; u < kStreamUnroll; ++u) {
+                const int li = (int)threadIdx.x + u * kStreamThreads;
+                raw[u] = (li < rem) ? ld_stream(src + li) : make_uint4(0u, 0u, 0u, 0u);
+            }
 #pragma unroll
-        for (int u = 0; u < kStreamUnroll; ++u) {
-            uint4 o[kOutVecs];
-            process_vec<DT, ORDER, M, KD, TIE, STOC>(raw[u], p, rv[u], o);
-            if (rv[u] >= 0) {
-                uint4* dst = p.out + rv[u] * kOutVecs;
-                st_stream(dst, o[0]);
-                if (kOutVecs == 2) st_stream(dst + 1, o[kOutVecs - 1]);
+            for (int u = 0; u < kStreamUnroll; ++u) {
+                const int li = (int)threadIdx.x + u * kStreamThreads;
+                uint4 o[kOutVecs];
+                process_vec<DT, ORDER, M, KD, TIE, STOC>(raw[u], p, tile_base + li, o);
+                if (li < rem) {
+                    uint4* dst = p.out + (tile_base + li) * kOutVecs;
+                    st_stream(dst, o[0]);
+                    if (kOutVecs == 2) st_stream(dst + 1, o[kOutVecs - 1]);
+                }
+            }
+        } else {
+            int64_t rv[kStreamUnroll];                                        // real vector index, -1 = padding / out of range
+#pragma unroll
+            for (int u = 0; u < kStreamUnroll; ++u) {
+                rv[u] = real_vec(p, tile_base + (int)threadIdx.x + u * kStreamThreads);
+                raw[u] = rv[u] >= 0 ? ld_stream(p.in + rv[u]) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < kStreamUnroll; ++u) {
+                uint4 o[kOutVecs];
+                process_vec<DT, ORDER, M, KD, TIE, STOC>(raw[u], p, rv[u], o);
+                if (rv[u] >= 0) {
+                    uint4* dst = p.out + rv[u] * kOutVecs;
+                    st_stream(dst, o[0]);
+                    if (kOutVecs == 2) st_stream(dst + 1, o[kOutVecs - 1]);
+                }
             }
         }
     }
@@ -324,7 +346,13 @@ static int launch_stream_t(const StreamParams& p, cudaStream_t st) {
     const int64_t n_tiles = (p.n_vec + tile_vecs - 1) / tile_vecs;
     if (n_tiles == 0) return BFP_OK;
     const DeviceInfo& di = device_info();
-    static const int occ = kernel_occupancy(quant_stream_kernel<DT, ORDER, M, KD, TIE, STOC>, kStreamThreads);
+    if (p.slots_per_row != 0) {
+        static const int occ_p = kernel_occupancy(quant_stream_kernel<DT, ORDER, M, KD, TIE, STOC, true>, kStreamThreads);
+        if (int rc = launch_pdl(quant_stream_kernel<DT, ORDER, M, KD, TIE, STOC, true>, stream_grid(occ_p, n_tiles), kStreamThreads, st, p)) return rc;
+        count_launch();
+        return check_launch("quant_stream_kernel (padded rows)");
+    }
+    static const int occ = kernel_occupancy(quant_stream_kernel<DT, ORDER, M, KD, TIE, STOC, false>, kStreamThreads);
     const int grid = stream_grid(occ, n_tiles);
     (void)di;
     if (tuning().quant_tma && p.slots_per_row == 0) {
@@ -341,7 +369,7 @@ static int launch_stream_t(const StreamParams& p, cudaStream_t st) {
         count_launch();
         return check_launch("quant_tma_kernel");
     }
-    if (int rc = launch_pdl(quant_stream_kernel<DT, ORDER, M, KD, TIE, STOC>, grid, kStreamThreads, st, p)) return rc;
+    if (int rc = launch_pdl(quant_stream_kernel<DT, ORDER, M, KD, TIE, STOC, false>, grid, kStreamThreads, st, p)) return rc;
     count_launch();
     return check_launch("quant_stream_kernel");
 }
