@@ -215,6 +215,9 @@ def main():
 
     sampler = ClockSampler(local_rank)
     sampler.start()
+    t_wait = time.time()
+    while sampler.proc is not None and not sampler.rows and time.time() - t_wait < 4.0:   # nvidia-smi takes ~1 s to print its first row
+        time.sleep(0.05)
     t_gpu0 = time.time()
     for i in range(a.warmup):
         device_step(i)
