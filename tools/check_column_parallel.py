@@ -12,17 +12,21 @@ kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", e
 T = 4096
 res = []
 SHAPES = (("65b q_proj", (8192, 8192)), ("65b up_proj", (22016, 8192)), ("65b down_proj", (8192, 22016)))
+DT = torch.float32
+for flag, dt in (("--fp16", torch.float16), ("--bf16", torch.bfloat16)):
+    if flag in sys.argv:
+        sys.argv.remove(flag); DT = dt
 if "--small" in sys.argv:                      # quick functional check (tests/test_dist_gpu.py)
     sys.argv.remove("--small"); T = 520
     SHAPES = (("small even", (1024, 512)), ("small uneven shards", (1097, 640)))
 for name, (N, K) in SHAPES:
     g = torch.Generator(device=dev).manual_seed(5)
-    w = torch.randn(N, K, device=dev, generator=g) * 0.02
-    x = torch.randn(T, K, device=dev, generator=g)
-    cp = qd.ColumnParallelBFPLinear(K, N, bias=False, **dict(kw)).to(dev).load_full(w)
+    w = (torch.randn(N, K, device=dev, generator=g) * 0.02).to(DT)
+    x = torch.randn(T, K, device=dev, generator=g).to(DT)
+    cp = qd.ColumnParallelBFPLinear(K, N, bias=False, **dict(kw)).to(dev).to(DT).load_full(w)
     with torch.no_grad():
         y = cp(x)
-        full = ops.BFPLinear(K, N, bias=False, **dict(kw)).to(dev)
+        full = ops.BFPLinear(K, N, bias=False, **dict(kw)).to(dev).to(DT)
         full.weight.copy_(w)
         y_ref = full(x)
         ok = torch.equal(y, y_ref)
@@ -40,7 +44,7 @@ for name, (N, K) in SHAPES:
         y_nccl = cp(x); ok_nccl = torch.equal(y_nccl, y_ref)
         ms_nccl = timed(lambda: cp(x))
         os.environ["BFP_COLUMN_PARALLEL"] = "fused"
-    row = dict(layer=name, N=N, K=K, T=T, world=world, fused_path=bool(fused), fused_failed=cp._fused_failed, bit_equal_to_single_gpu=ok,
+    row = dict(layer=name, dtype=str(DT)[6:], N=N, K=K, T=T, world=world, fused_path=bool(fused), fused_failed=cp._fused_failed, bit_equal_to_single_gpu=ok,
                nccl_path_bit_equal=ok_nccl, fwd_ms=ms_fwd, fwd_alias_ms=ms_alias, nccl_fwd_ms=ms_nccl, local_ms=ms_local, single_gpu_ms=ms_full,
                tops=2.0 * T * N * K / ms_alias / 1e9, speedup_vs_1gpu=ms_full / ms_alias, fused_vs_nccl=ms_nccl / ms_alias)
     res.append(row)
