@@ -125,7 +125,35 @@ template <int NC, bool HALF>
 __device__ __forceinline__ void store_columns(const Params& p, const OutMaps& outs, float* stg, const uint32_t* r, float bv,
                                               int n0, int lane, int t0) {
     if (p.debug & 8) return;
-    if (p.out_tma) {
+    if (p.out_tma && HALF) {
+        // Half-precision output: 32 out-features are only 64 bytes per token, so the two warps of adjacent lane quarters
+        // (same tokens, out-features n0 .. n0+63 together) share one [8 t][64 n] tile of full 128-byte rows -- the unit both
+        // the L2 and, for the fused all-gather, NVLink move efficiently -- synchronised by a 64-thread named barrier.
+        const uint64_t pol = l2_policy_evict_first();
+        const int ew = ((int)threadIdx.x >> 5) - 4, odd = ew & 1, bar_id = 1 + (ew >> 1);
+        uint16_t* pstg = reinterpret_cast<uint16_t*>(stg - odd * 512);            // the even warp's 2 KB: two 1 KB tiles
+        const bool leader = !odd && lane == 0;
+#pragma unroll
+        for (int rd = 0; rd < NC / 8; ++rd) {
+            uint16_t* hb = pstg + (rd & 1) * 512;
+            if (leader) tma_store_wait_read<1>();
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");           // tile free (the leader's stores of two rounds ago have read it)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float o = __uint_as_float(r[rd * 8 + j]) + bv;
+                hb[j * 64 + odd * 32 + lane] = p.out_dtype == BFP_DT_F16 ? __half_as_ushort(__float2half_rn(o)) : __bfloat16_as_ushort(__float2bfloat16_rn(o));
+            }
+            fence_proxy_async_smem();
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");           // both warps have written
+            if (leader) {
+                tma_store_2d_hint(&outs.m[0], hb, n0, t0 + rd * 8, pol);          // leader's n0 is the pair's first out-feature
+                if (outs.n > 1) {
+                    for (int g = 1; g < outs.n; ++g) tma_store_2d_hint(&outs.m[g], hb, n0, t0 + rd * 8, pol);
+                }
+                tma_store_commit();
+            }
+        }
+    } else if (p.out_tma) {
         const uint64_t pol = l2_policy_evict_first();
 #pragma unroll
         for (int rd = 0; rd < NC / 8; ++rd) {
@@ -133,17 +161,8 @@ __device__ __forceinline__ void store_columns(const Params& p, const OutMaps& ou
             // the stores that last read this buffer (two rounds ago; one bulk group per round) are done with it
             if (lane == 0) tma_store_wait_read<1>();
             __syncwarp();
-            if (!HALF) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) buf[j * 32 + lane] = __uint_as_float(r[rd * 8 + j]) + bv;
-            } else {                                             // [8 t][32 n] of 2-byte values: 64-byte rows
-                uint16_t* hb = reinterpret_cast<uint16_t*>(buf);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float o = __uint_as_float(r[rd * 8 + j]) + bv;
-                    hb[j * 32 + lane] = p.out_dtype == BFP_DT_F16 ? __half_as_ushort(__float2half_rn(o)) : __bfloat16_as_ushort(__float2bfloat16_rn(o));
-                }
-            }
+            for (int j = 0; j < 8; ++j) buf[j * 32 + lane] = __uint_as_float(r[rd * 8 + j]) + bv;
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
@@ -784,7 +803,7 @@ int gemm_bf16_sp_multi_device(const void* x_bf16, const void* w_comp, const void
     if (n_out > 1 && !p.out_tma) return set_error(BFP_E_ALIGN, "multi-destination output needs 16-byte aligned slices and a row stride that is a multiple of 16 bytes");
     // each map covers exactly the [T, N] slice (row stride ld_out), so the copy engine clips at the slice's edge
     for (int g = 0; g < (p.out_tma ? n_out : 0); ++g)
-        if (int rc = make_map_out(&map_out.m[g], out_ptrs[g], out_dtype, T, N, ld_out * out_es, 32, 8)) return rc;
+        if (int rc = make_map_out(&map_out.m[g], out_ptrs[g], out_dtype, T, N, ld_out * out_es, out_es == 4 ? 32 : 64, 8)) return rc;
     if (wide_tile) p.tiles_t = (int)((T + wide::BT - 1) / wide::BT);
     if (pp_tile) p.tiles_t = (int)((T + pp::NT - 1) / pp::NT);
     const int units = std::min(p.tiles_w * p.tiles_t, sms / cg);
