@@ -136,7 +136,8 @@ __device__ __forceinline__ void store_columns(const Params& p, const OutMaps& ou
 #pragma unroll
         for (int rd = 0; rd < NC / 8; ++rd) {
             uint16_t* hb = pstg + (rd & 1) * 512;
-            if (leader) tma_store_wait_read<1>();
+            // round 0 starts on tile 0 again whatever the previous call ended on (NC / 8 may be odd): wait for every earlier read
+            if (leader) { if (rd == 0) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }
             asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");           // tile free (the leader's stores of two rounds ago have read it)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -158,8 +159,9 @@ __device__ __forceinline__ void store_columns(const Params& p, const OutMaps& ou
 #pragma unroll
         for (int rd = 0; rd < NC / 8; ++rd) {
             float* buf = stg + (rd & 1) * 256;
-            // the stores that last read this buffer (two rounds ago; one bulk group per round) are done with it
-            if (lane == 0) tma_store_wait_read<1>();
+            // the stores that last read this buffer (two rounds ago; one bulk group per round) are done with it; round 0 starts
+            // on tile 0 again whatever the previous call ended on (NC / 8 may be odd), so it waits for every earlier read
+            if (lane == 0) { if (rd == 0) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; ++j) buf[j * 32 + lane] = __uint_as_float(r[rd * 8 + j]) + bv;
