@@ -392,3 +392,36 @@ def test_half_precision_exponent_table_matches_torch_log2(dtn):
     exact = (s.double().cpu() == torch.exp2(ks)[:, None] * (1.0 + f[None, :] / (1 << mb))).numpy()
     assert exact[[i for i, k in enumerate(krange) if k >= (-14 if dtn == "f16" else -126)]].all()
     assert np.array_equal(e_table[exact], e_torch[exact])
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape,B,sparse", [((16, 3, 224, 224), 64, False), ((768, 3, 16, 16), 64, True), ((515, 4100), 64, True), ((33, 40), 32, True),
+                                            ((7, 1048), 128, False)])
+def test_padded_row_mode_equals_generic_path(dt, shape, B, sparse):
+    """Rows that are vector-aligned but not block-aligned (the ViT patch-embedding input, conv weights, odd widths) run on the
+    streaming kernel with zero-padded slots; the result must equal the gather-style generic kernel bit for bit, for the
+    fake-quant output (nearest and stochastic) and for the bf16 operand pack."""
+    from qsi_b200 import _lib, bfp_ops
+    V = 4 if dt == torch.float32 else 8
+    if shape[-1] % V:
+        pytest.skip("row length not vector-aligned for this dtype: generic path either way")
+    g = torch.Generator().manual_seed(sum(shape) + B)
+    x = (torch.randn(*shape, generator=g) * 0.3).to(dt).cuda()
+    x.view(-1)[::97] *= 40.0
+    for first, rmode in (("s", "determ"), ("q", "determ"), ("s", "stoc")):
+        a = bfp_ops.unpack_bfp_args(dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode=rmode, epsilon=1e-8, mant_bits=5, block_size=B,
+                                         w_sparsity=sparse, N=2, M=4, first=first, sparsity_mode="structured", device="cuda"))
+        outs, packs = [], []
+        for generic in (0, 1):
+            _lib.set_option("force_generic", generic)
+            try:
+                outs.append(bfp_ops._fused(x, bfp_ops._order_for(a, "w"), block_size=B, mant_bits=5, epsilon=1e-8, rounding_mode=rmode, N=2, M=4,
+                                           philox=(1234, 5)))
+                if rmode == "determ":
+                    packs.append(bfp_ops.pack_bfp_bf16(x, identifier="w", **a))
+            finally:
+                _lib.set_option("force_generic", 0)
+        assert outs[0].dtype == outs[1].dtype and torch.equal(outs[0].view(torch.int16 if outs[0].element_size() == 2 else torch.int32),
+                                                             outs[1].view(torch.int16 if outs[1].element_size() == 2 else torch.int32)), (first, rmode)
+        if packs:
+            assert torch.equal(packs[0].view(torch.int16), packs[1].view(torch.int16)), (first, "pack")
