@@ -124,6 +124,14 @@ size_t bfp_int_workspace_bytes(int64_t C);
 int bfp_int_quantize(const void* in, float* out, int64_t A, int64_t C, int64_t inner, int dtype, int bits,
                      void* workspace, void* stream);
 
+/* 2-D weights [C, K] with N:4 structured sparsity and the 'int' format in ONE pass (float_to_bfp_blocked with
+ * sparsity_num_format == 'int', sparsity_mode == 'structured', bfp_ops.py:143-149): order BFP_ORDER_SPARSIFY_QUANT =
+ * _quantize(_sparsify(t)), BFP_ORDER_QUANT_SPARSIFY = _sparsify(_quantize(t)).  torch-CUDA tie rule.  Needs M == 4,
+ * 0 < N < 4, 16-byte aligned buffers, K a multiple of 4 (fp32) / 8 (half) and K <= 16384 (fp32) / 32768 (half);
+ * BFP_E_UNSUPPORTED otherwise (compose bfp_nm_sparsify and bfp_int_quantize). */
+int bfp_int_quantize_nm(const void* in, float* out, int64_t C, int64_t K, int dtype, int bits, int N, int M, int order,
+                        void* stream);
+
 /* get_exponent (bfp_ops.py:29-33): exp_out[rows, ceil(K/block_size)] fp32, in the arithmetic of `dtype`. */
 int bfp_block_exponent(const void* in, float* exp_out, int64_t rows, int64_t K, int dtype, int block_size, float eps,
                        void* stream);

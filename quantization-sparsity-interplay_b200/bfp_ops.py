@@ -261,6 +261,27 @@ def _int_quantize(t, bits, weight):
     return out if src.is_cuda else out.cpu()
 
 
+def _int_nm_fusable(t, N, M):
+    """2-D weights whose rows fit one CTA's registers: N:4 mask and INT per-channel quantiser in a single pass."""
+    if M != 4 or not (0 < N < 4) or t.dim() != 2 or t.dtype not in _DT:
+        return False
+    vec = 4 if t.dtype == torch.float32 else 8
+    K = t.shape[1]
+    return t.numel() > 0 and K % vec == 0 and K // vec <= 4096
+
+
+def _int_quantize_nm(t, bits, N, M, order):
+    """_quantize(_sparsify(t)) / _sparsify(_quantize(t)) for the 'int' format with N:4 sparsity (bfp_ops.py:143-149 over
+    :73-91 and int_ops.py), one kernel: each CTA holds a weight row in registers."""
+    src = t.detach().contiguous()
+    dev_src = src if src.is_cuda else src.cuda()
+    out = torch.empty(tuple(t.shape), dtype=torch.float32, device=dev_src.device)
+    with _on(dev_src.device):
+        _lib.check(_lib.lib().bfp_int_quantize_nm(dev_src.data_ptr(), out.data_ptr(), src.shape[0], src.shape[1], _DT[src.dtype],
+                                                  int(bits), int(N), int(M), order, _stream()))
+    return out if src.is_cuda else out.cpu()
+
+
 def float_to_bfp_blocked(t, mant_bits, epsilon, rounding_mode, device, block_size,
                          num_format, weight_mant_bits, in_sparsity, w_sparsity, grad_sparsity,
                          sparsity_frac, N, M, sparsity_num_format, first, sparsity_mode, identifier='', sgd_update=False,
@@ -287,6 +308,11 @@ def float_to_bfp_blocked(t, mant_bits, epsilon, rounding_mode, device, block_siz
             order = _lib.ORDER_SPARSIFY_QUANT if first == 's' else _lib.ORDER_QUANT_SPARSIFY
         return _fused(t, order, block_size=block_size, mant_bits=m, epsilon=epsilon, rounding_mode=rounding_mode,
                       N=N, M=M)
+
+    if (sparsity and sparsity_mode == 'structured' and sparsity_num_format == 'int' and identifier == 'w'
+            and _int_nm_fusable(t, N, M)):
+        bits = weight_mant_bits if sgd_update else mant_bits                            # bfp_ops.py:113-114
+        return _int_quantize_nm(t, bits, N, M, _lib.ORDER_SPARSIFY_QUANT if first == 's' else _lib.ORDER_QUANT_SPARSIFY)
 
     if first == 's':
         sparse_t = _sparsify(t, sparsity, sparsity_mode, device, N, M, sparsity_frac)
@@ -390,8 +416,6 @@ def pack_bfp_bf16(t, identifier='', philox=None, **bfp_args):
     mant_bits <= 8: q * 2^(e-m) has at most 8 significant bits.  Any block size."""
     assert (bfp_args['num_format'] == 'bfp') and (bfp_args['sparsity_num_format'] == 'bfp') and (bfp_args['block_size'] > 0)
     order = _order_for(bfp_args, identifier)
-    if order != _lib.ORDER_QUANT_ONLY and bfp_args['sparsity_mode'] != 'structured':
-        raise NotImplementedError("packed operands support structured N:M sparsity only")
     if not t.is_cuda:
         raise ValueError("pack_bfp_bf16 needs a CUDA tensor")
     src = t.detach().contiguous()
@@ -399,6 +423,13 @@ def pack_bfp_bf16(t, identifier='', philox=None, **bfp_args):
     rows = src.numel() // K if K else 0
     Kp = -(-K // 8) * 8
     out = (torch.empty if Kp == K else torch.zeros)((rows, Kp), dtype=torch.bfloat16, device=src.device)
+    if order != _lib.ORDER_QUANT_ONLY and bfp_args['sparsity_mode'] != 'structured':
+        # global magnitude pruning is a whole-tensor selection, not a per-vector one: compose the radix-select kernels with
+        # the quantiser exactly like bfp_ops.py:143-149, then narrow to bf16 -- exact, the values are BFP values or zeros
+        y = float_to_bfp_blocked(src, identifier=identifier, **bfp_args)
+        if rows and K:
+            out[:, :K].copy_(y.reshape(rows, K))
+        return out
     rounding = _rounding_code(bfp_args['rounding_mode'])
     seed, offset = (philox if philox is not None else _PhiloxState.next()) if rounding == _lib.ROUND_STOCHASTIC else (0, 0)
     if rows and K:
@@ -495,7 +526,8 @@ def _tensor_core_kind(x, w, bfp_args):
         return None
     B, m = bfp_args['block_size'], bfp_args['mant_bits']
     want = os.environ.get("BFP_GEMM_KIND", "")
-    i8_ok = B in (32, 64, 128) and 1 <= m <= 7
+    unstructured = bfp_args['w_sparsity'] == True and bfp_args['sparsity_mode'] == 'unstructured'            # noqa: E712
+    i8_ok = B in (32, 64, 128) and 1 <= m <= 7 and not unstructured
     bf16_ok = 1 <= m <= 8 and B >= 4 and (B & (B - 1)) == 0
     sp_ok = (bf16_ok and bfp_args['w_sparsity'] == True and bfp_args['sparsity_mode'] == 'structured'     # noqa: E712
              and _nm_fits_2to4(bfp_args['N'], bfp_args['M']))
@@ -522,9 +554,10 @@ def _tensor_core_eligible(x, w, bfp_args):
             and bfp_args['num_format'] == 'bfp' and bfp_args['sparsity_num_format'] == 'bfp'
             and 1 <= bfp_args['mant_bits'] <= 7 and bfp_args['block_size'] in (32, 64, 128)
             and not (bfp_args['in_sparsity'] == True)                                                # noqa: E712
-            and (bfp_args['w_sparsity'] != True or (bfp_args['sparsity_mode'] == 'structured'      # noqa: E712
-                                                    and 0 < bfp_args['N'] <= bfp_args['M'] <= 64
-                                                    and (bfp_args['first'] == 's' or bfp_args['block_size'] % bfp_args['M'] == 0))))
+            and (bfp_args['w_sparsity'] != True                                                    # noqa: E712
+                 or (bfp_args['sparsity_mode'] == 'unstructured' and 0 < bfp_args['sparsity_frac'] and 1 <= bfp_args['mant_bits'] <= 8)
+                 or (bfp_args['sparsity_mode'] == 'structured' and 0 < bfp_args['N'] <= bfp_args['M'] <= 64
+                     and (bfp_args['first'] == 's' or bfp_args['block_size'] % bfp_args['M'] == 0))))
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -549,10 +582,11 @@ def _tc_matmul(x, w, bfp_args):
         return bfp_linear_bf16(pack_bfp_bf16(x, identifier='in', **bfp_args), wb, None, out_shape=tuple(x.shape[:-1]) + (N,))
     batch = torch.broadcast_shapes(x.shape[:-2], w.shape[:-2])
     xe = x.expand(batch + x.shape[-2:]).reshape((-1,) + tuple(x.shape[-2:]))
-    we = w.expand(batch + w.shape[-2:]).reshape((-1, K, N))
     M = x.shape[-2]
     xb = pack_bfp_bf16(xe, identifier='in', **bfp_args).view(xe.shape[0], M, -1)       # [b, M, Kp]
-    wb = pack_bfp_bf16(we.transpose(-1, -2), identifier='w', **bfp_args).view(we.shape[0], N, -1)   # [b, N, Kp]
+    # the weight is quantised in its OWN shape (a global magnitude threshold must not see broadcast copies), then broadcast
+    wb = pack_bfp_bf16(w.transpose(-1, -2), identifier='w', **bfp_args)
+    wb = wb.view(tuple(w.shape[:-2]) + (N, wb.shape[-1])).expand(batch + (N, wb.shape[-1])).reshape(xe.shape[0], N, -1)   # [b, N, Kp]
     out = torch.empty((xe.shape[0], M, N), dtype=torch.float32, device=x.device)
     L, stream = _lib.lib(), _stream(x.device)
     with _on(x.device):

@@ -178,6 +178,16 @@ int bfp_int_quantize(const void* in, float* out, int64_t A, int64_t C, int64_t i
     return int_quantize_device(in, out, A, C, inner, dtype, bits, workspace, static_cast<cudaStream_t>(stream));
 }
 
+int bfp_int_quantize_nm(const void* in, float* out, int64_t C, int64_t K, int dtype, int bits, int N, int M, int order, void* stream) {
+    if (C < 0 || K < 0 || dtype < 0 || dtype > 2) return set_error(BFP_E_ARG, "bad argument");
+    if (bits < 1 || bits > 23) return set_error(BFP_E_ARG, "bits must be in [1, 23]");
+    if (order != BFP_ORDER_SPARSIFY_QUANT && order != BFP_ORDER_QUANT_SPARSIFY) return set_error(BFP_E_ARG, "order must be s->q or q->s");
+    if (M != 4 || N < 1 || N > 3) return set_error(BFP_E_UNSUPPORTED, "fused INT + N:M supports M == 4 with 0 < N < 4; compose bfp_nm_sparsify and bfp_int_quantize otherwise");
+    if (C * K > 0 && (!in || !out)) return set_error(BFP_E_ARG, "null pointer");
+    if (int rc = require_device()) return rc;
+    return int_quantize_nm_device(in, out, C, K, dtype, bits, N, order, static_cast<cudaStream_t>(stream));
+}
+
 size_t bfp_unstructured_workspace_bytes(void) { return unstructured_workspace_bytes(); }
 
 int bfp_unstructured_sparsify(const void* in, void* out, int64_t numel, int dtype, uint64_t k, void* workspace, void* stream) {

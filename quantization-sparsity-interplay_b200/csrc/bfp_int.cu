@@ -89,8 +89,22 @@ __global__ void __launch_bounds__(256) int_apply_kernel(const void* in, float* o
 // Weights (A == 1: one channel per row of K = inner elements): ONE pass.  A CTA keeps its row in registers (NV 128-bit
 // vectors per thread), reduces min / max across the block, derives the scale and applies it to the registers: 8 B/element of
 // traffic (4 in + 4 out for fp32) instead of the three passes (12 B/element + atomics) of the general path.
-template <int DT, int NV>
-__global__ void __launch_bounds__(256) int_rows_fused_kernel(const void* in, float* out, int64_t rows, int64_t K, float maxq, float zero) {
+//
+// ORDER adds the N:4 magnitude mask of bfp_ops.py:73-91 to the same pass (groups of 4 never straddle a 128-bit vector):
+// 1 = mask, then quantise the masked row (first == 's': the min / max see the zeros); 2 = quantise, then mask the quantised
+// values (their ties decide).  torch-CUDA tie rule, like the stand-alone N:M kernel.
+template <int V>
+__device__ __forceinline__ void mask_vec4(float* v, int kdrop) {
+#pragma unroll
+    for (int g = 0; g < V / 4; ++g) {
+        if (kdrop == 2) nm_mask4<2>(v + 4 * g);
+        else if (kdrop == 1) nm_mask4<1>(v + 4 * g);
+        else nm_mask4<3>(v + 4 * g);
+    }
+}
+
+template <int DT, int NV, int ORDER>
+__global__ void __launch_bounds__(256) int_rows_fused_kernel(const void* in, float* out, int64_t rows, int64_t K, float maxq, float zero, int kdrop) {
     constexpr int V = DType<DT>::kVec;
     __shared__ float s_lo[8], s_hi[8];
     const int64_t nv = K / V;                               // <= 256 * NV, checked by the host
@@ -110,6 +124,7 @@ __global__ void __launch_bounds__(256) int_rows_fused_kernel(const void* in, flo
             if (j < nv) {
                 float v[V];
                 unpack_vec<DT>(raw[u], v);
+                if (ORDER == 1) { mask_vec4<V>(v, kdrop); raw[u] = pack_vec<DT>(v); }     // kept values are unchanged, dropped become +0
 #pragma unroll
                 for (int e = 0; e < V; ++e) { lo = fminf(lo, v[e]); hi = fmaxf(hi, v[e]); }
             }
@@ -137,6 +152,7 @@ __global__ void __launch_bounds__(256) int_rows_fused_kernel(const void* in, flo
                     const float q = fminf(fmaxf(rintf(__fdiv_rn(v[e], sc)) + zero, 0.0f), maxq);   // int_ops.py:7
                     v[e] = sc * (q - zero);                                                        // :8
                 }
+                if (ORDER == 2) mask_vec4<V>(v, kdrop);
 #pragma unroll
                 for (int f4 = 0; f4 < V / 4; ++f4)
                     st_stream(reinterpret_cast<uint4*>(dst + j * (V / 4) + f4), pack_vec<BFP_DT_F32>(v + 4 * f4));
@@ -147,20 +163,36 @@ __global__ void __launch_bounds__(256) int_rows_fused_kernel(const void* in, flo
 }
 
 template <int DT>
+bool rows_fusable(const void* in, const float* out, int64_t inner) {
+    constexpr int V = DType<DT>::kVec;
+    return inner % V == 0 && inner / V <= 256 * 16 && reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0;
+}
+
+template <int DT, int ORDER>
+int run_rows(const void* in, float* out, int64_t C, int64_t inner, int bits, int kdrop, cudaStream_t s) {
+    const float maxq = (float)((1ll << bits) - 1), zero = (float)(((1ll << bits)) / 2.0);
+    const int64_t nv = inner / DType<DT>::kVec;
+    const int grid = (int)std::min<int64_t>(C, (int64_t)device_info().sm_count * 4);
+    if (nv <= 256 * 4) int_rows_fused_kernel<DT, 4, ORDER><<<grid, 256, 0, s>>>(in, out, C, inner, maxq, zero, kdrop);
+    else if (nv <= 256 * 8) int_rows_fused_kernel<DT, 8, ORDER><<<grid, 256, 0, s>>>(in, out, C, inner, maxq, zero, kdrop);
+    else int_rows_fused_kernel<DT, 16, ORDER><<<grid, 256, 0, s>>>(in, out, C, inner, maxq, zero, kdrop);
+    count_launch();
+    return check_launch("int_rows_fused_kernel");
+}
+
+template <int DT>
+int run_nm(const void* in, float* out, int64_t C, int64_t K, int bits, int N, int order, cudaStream_t s) {
+    if (!rows_fusable<DT>(in, out, K))
+        return set_error(BFP_E_UNSUPPORTED, "fused INT + N:4 needs 16-byte aligned buffers, K a multiple of the vector width and K <= 4096 vectors");
+    return order == BFP_ORDER_SPARSIFY_QUANT ? run_rows<DT, 1>(in, out, C, K, bits, 4 - N, s) : run_rows<DT, 2>(in, out, C, K, bits, 4 - N, s);
+}
+
+template <int DT>
 int run(const void* in, float* out, int64_t A, int64_t C, int64_t inner, int bits, IntWs ws, cudaStream_t s) {
     const int64_t n = A * C * inner;
     const int sms = device_info().sm_count;
     const float maxq = (float)((1ll << bits) - 1), zero = (float)(((1ll << bits)) / 2.0);
-    constexpr int V = DType<DT>::kVec;
-    if (A == 1 && inner % V == 0 && inner / V <= 256 * 16 && reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0) {
-        const int64_t nv = inner / V;
-        const int grid = (int)std::min<int64_t>(C, (int64_t)sms * 4);
-        if (nv <= 256 * 4) int_rows_fused_kernel<DT, 4><<<grid, 256, 0, s>>>(in, out, C, inner, maxq, zero);
-        else if (nv <= 256 * 8) int_rows_fused_kernel<DT, 8><<<grid, 256, 0, s>>>(in, out, C, inner, maxq, zero);
-        else int_rows_fused_kernel<DT, 16><<<grid, 256, 0, s>>>(in, out, C, inner, maxq, zero);
-        count_launch();
-        return check_launch("int_rows_fused_kernel");
-    }
+    if (A == 1 && rows_fusable<DT>(in, out, inner)) return run_rows<DT, 0>(in, out, C, inner, bits, 0, s);
     int_init_kernel<<<(int)std::min<int64_t>((C + 255) / 256, 1024), 256, 0, s>>>(ws.mn, ws.mx, C);
     count_launch();
     if (inner >= 32) {
@@ -196,6 +228,16 @@ int int_quantize_device(const void* in, float* out, int64_t A, int64_t C, int64_
     case BFP_DT_F32: return run<BFP_DT_F32>(in, out, A, C, inner, bits, ws, s);
     case BFP_DT_F16: return run<BFP_DT_F16>(in, out, A, C, inner, bits, ws, s);
     case BFP_DT_BF16: return run<BFP_DT_BF16>(in, out, A, C, inner, bits, ws, s);
+    }
+    return set_error(BFP_E_ARG, "bad dtype");
+}
+
+int int_quantize_nm_device(const void* in, float* out, int64_t C, int64_t K, int dtype, int bits, int N, int order, cudaStream_t s) {
+    if (C * K == 0) return BFP_OK;
+    switch (dtype) {
+    case BFP_DT_F32: return run_nm<BFP_DT_F32>(in, out, C, K, bits, N, order, s);
+    case BFP_DT_F16: return run_nm<BFP_DT_F16>(in, out, C, K, bits, N, order, s);
+    case BFP_DT_BF16: return run_nm<BFP_DT_BF16>(in, out, C, K, bits, N, order, s);
     }
     return set_error(BFP_E_ARG, "bad dtype");
 }

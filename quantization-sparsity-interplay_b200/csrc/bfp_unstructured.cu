@@ -48,6 +48,8 @@ __device__ __forceinline__ void keys_of(const uint4& raw, uint32_t* k) {
 
 template <int DT>
 __global__ void __launch_bounds__(kThreadsU) hist_scalar_kernel(const void* in, int64_t n, SelectState* st, int pass, int shift, int bits) {
+    pdl_launch_dependents();   // launch overlap only: pdl_wait() orders this kernel after everything earlier on the stream
+    pdl_wait();
     __shared__ unsigned int sh[kBins];
     for (int i = threadIdx.x; i < kBins; i += kThreadsU) sh[i] = 0;
     __syncthreads();
@@ -63,6 +65,8 @@ __global__ void __launch_bounds__(kThreadsU) hist_scalar_kernel(const void* in, 
 
 template <int DT>
 __global__ void __launch_bounds__(kThreadsU) hist_kernel(const void* in, int64_t n, SelectState* st, int pass, int shift, int bits) {
+    pdl_launch_dependents();   // launch overlap only: pdl_wait() orders this kernel after everything earlier on the stream
+    pdl_wait();
     constexpr int V = DType<DT>::kVec;
     __shared__ unsigned int sh[kBins];
     for (int i = threadIdx.x; i < kBins; i += kThreadsU) sh[i] = 0;
@@ -101,6 +105,8 @@ __global__ void __launch_bounds__(kThreadsU) hist_kernel(const void* in, int64_t
 // increments of a warp instruction never conflict; the copies are summed at the end.
 template <int DT>
 __global__ void __launch_bounds__(kThreadsU) hist0_kernel(const void* in, int64_t n, SelectState* st) {
+    pdl_launch_dependents();   // launch overlap only: pdl_wait() orders this kernel after everything earlier on the stream
+    pdl_wait();
     constexpr int V = DType<DT>::kVec;
     __shared__ unsigned int sh[256 * 32];
     for (int i = threadIdx.x; i < 256 * 32; i += kThreadsU) sh[i] = 0;
@@ -129,6 +135,8 @@ __global__ void __launch_bounds__(kThreadsU) hist0_kernel(const void* in, int64_
 // one block of 1024 threads, four bins each: inclusive scan of the histogram, then the (unique) bin whose cumulative count
 // first reaches `need` fixes its digit into the prefix.  After the last pass it also records how many keys equal tau.
 __global__ void __launch_bounds__(1024) select_kernel(SelectState* st, int pass, int shift, int bits, unsigned long long k_init, int last) {
+    pdl_launch_dependents();   // launch overlap only: pdl_wait() orders this kernel after everything earlier on the stream
+    pdl_wait();
     __shared__ unsigned long long warp_sum[32];
     const int nb = 1 << bits, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const unsigned long long need = pass == 0 ? k_init : st->need;
@@ -172,6 +180,8 @@ __global__ void __launch_bounds__(1024) select_kernel(SelectState* st, int pass,
 // Only needed when SOME but not all of the keys equal to tau are dropped (index order then decides); otherwise a no-op.
 template <int DT>
 __global__ void __launch_bounds__(kThreadsU) tie_count_kernel(const void* in, int64_t n, int64_t per, SelectState* st) {
+    pdl_launch_dependents();   // launch overlap only: pdl_wait() orders this kernel after everything earlier on the stream
+    pdl_wait();
     if (st->need == st->ties_total) return;
     using D = DType<DT>;
     constexpr int V = D::kVec;
@@ -202,6 +212,8 @@ __global__ void __launch_bounds__(kThreadsU) tie_count_kernel(const void* in, in
 
 template <int DT>
 __global__ void __launch_bounds__(kThreadsU) apply_kernel(const void* in, void* out, int64_t n, int64_t per, const SelectState* st) {
+    pdl_launch_dependents();   // launch overlap only: pdl_wait() orders this kernel after everything earlier on the stream
+    pdl_wait();
     using D = DType<DT>;
     constexpr int V = D::kVec;
     const uint32_t tau = st->prefix_value;
@@ -293,6 +305,21 @@ __global__ void __launch_bounds__(kThreadsU) apply_kernel(const void* in, void* 
     }
 }
 
+// every kernel of the pipeline is launched with programmatic stream serialization: its launch latency hides behind the
+// predecessor, and griddepcontrol.wait at its top keeps the data dependence.  Measured (tools/ab_unstructured_pdl.py): 97 -> 85 us
+// at 16 M elements, neutral at 45 M, 10 % SLOWER at 180 M (early-resident dependents take SM slots from the tail of a long
+// kernel), so only tensors up to 32 M elements use it.
+template <class... KArgs, class... Args>
+static cudaError_t launch_u(bool overlap, void (*kernel)(KArgs...), int grid, int threads, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = overlap ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 template <int DT>
 int run(const void* in, void* out, int64_t n, unsigned long long k, SelectState* st, cudaStream_t s) {
     const int sms = device_info().sm_count;
@@ -303,17 +330,18 @@ int run(const void* in, void* out, int64_t n, unsigned long long k, SelectState*
     const int64_t vecs = n_hist / DType<DT>::kVec;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((vecs + kThreadsU - 1) / kThreadsU, (int64_t)sms * 8));
     const int shifts[3] = {23, 11, 0}, bits[3] = {8, 12, 11};
+    const bool pdl = tuning().pdl && n <= (int64_t(32) << 20);
     static const bool dbg = getenv("BFP_UNSTRUCTURED_TIMING") != nullptr;      // per-phase device times on stderr (tools only)
     cudaEvent_t ev[9]; int nev = 0;
     auto mark = [&] { if (dbg) { cudaEventCreate(&ev[nev]); cudaEventRecord(ev[nev], s); ++nev; } };
     mark();
     for (int p = 0; p < 3; ++p) {
-        if (aligned && p == 0) hist0_kernel<DT><<<grid, kThreadsU, 0, s>>>(in, n, st);
-        else if (aligned) hist_kernel<DT><<<grid, kThreadsU, 0, s>>>(in, n, st, p, shifts[p], bits[p]);
-        else hist_scalar_kernel<DT><<<(int)std::min<int64_t>((n + kThreadsU - 1) / kThreadsU, (int64_t)sms * 8), kThreadsU, 0, s>>>(in, n, st, p, shifts[p], bits[p]);
+        if (aligned && p == 0) launch_u(pdl, hist0_kernel<DT>, grid, kThreadsU, s, in, n, st);
+        else if (aligned) launch_u(pdl, hist_kernel<DT>, grid, kThreadsU, s, in, n, st, p, shifts[p], bits[p]);
+        else launch_u(pdl, hist_scalar_kernel<DT>, (int)std::min<int64_t>((n + kThreadsU - 1) / kThreadsU, (int64_t)sms * 8), kThreadsU, s, in, n, st, p, shifts[p], bits[p]);
         count_launch();
         mark();
-        select_kernel<<<1, 1024, 0, s>>>(st, p, shifts[p], bits[p], k, p == 2);
+        launch_u(pdl, select_kernel, 1, 1024, s, st, p, shifts[p], bits[p], k, (int)(p == 2));
         count_launch();
         mark();
     }
@@ -321,10 +349,10 @@ int run(const void* in, void* out, int64_t n, unsigned long long k, SelectState*
     int64_t per = (n + ctas - 1) / ctas;
     per = (per + kThreadsU * 8 - 1) / (kThreadsU * 8) * (kThreadsU * 8);      // multiple of the tile and of the vector width
     const int ctas_used = (int)((n + per - 1) / per);
-    tie_count_kernel<DT><<<ctas_used, kThreadsU, 0, s>>>(in, n, per, st);
+    launch_u(pdl, tie_count_kernel<DT>, ctas_used, kThreadsU, s, in, n, per, st);
     count_launch();
     mark();
-    apply_kernel<DT><<<ctas_used, kThreadsU, 0, s>>>(in, out, n, per, st);
+    launch_u(pdl, apply_kernel<DT>, ctas_used, kThreadsU, s, in, out, n, per, (const SelectState*)st);
     count_launch();
     mark();
     if (dbg) {

@@ -539,3 +539,42 @@ def test_bfplinear_half_precision_inference_on_tensor_cores(ops, dt, w_sparse, m
         ulp = torch.maximum(exact.abs(), torch.tensor(1e-3, device="cuda", dtype=torch.float64)) * (2.0 ** (-10 if dt == torch.float16 else -7))
         assert (err <= ulp).all()
     assert ((y.double() - y_ref.double()).abs() <= 2.0 ** (-9 if dt == torch.float16 else -6) * exact.abs().clamp_min(1e-3)).all()
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16])
+@pytest.mark.parametrize("first", ["s", "q"])
+def test_bfplinear_unstructured_sparsity_runs_on_tensor_cores(ops, dt, first, monkeypatch):
+    """sparsity_mode='unstructured' (4 of the reference's 7 LM scripts): the weight goes through the radix-select kernels and
+    the quantiser once, is cached as an exact-bf16 operand, and the contraction runs on the dense tcgen05 kernel -- the
+    same function as fake-quant + F.linear."""
+    kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=5, block_size=64,
+              w_sparsity=True, N=2, M=4, first=first, sparsity_mode="unstructured", sparsity_frac=0.5, device="cuda")
+    torch.manual_seed(7)
+    lin = ops.BFPLinear(1000, 520, bias=True, **dict(kw)).cuda().to(dt)          # K = 1000: ragged last block, padded pack
+    x = torch.randn(2, 77, 1000, device="cuda").to(dt)
+    a = ops.unpack_bfp_args(dict(kw))
+    with torch.no_grad():
+        y = lin(x)
+        assert y.dtype == dt and lin._packed_w is not None and lin._packed_w[0][0] == "bf16"
+        wb = lin._packed_weight("bf16")
+        wq = ops.float_to_bfp_blocked(lin.weight.detach(), **a, identifier="w")
+        assert torch.equal(wb[:, :1000].float(), wq.float()) and (wb[:, 1000:] == 0).all()
+        assert abs(float((wq == 0).float().mean()) - 0.5) < 0.02
+        monkeypatch.setenv("BFP_LINEAR_PATH", "fakequant")
+        y_fq = lin(x)
+        monkeypatch.setenv("BFP_LINEAR_PATH", "tc")
+    xq = ops.float_to_bfp_blocked(x, **a, identifier="in").double()
+    exact = xq @ wq.double().t() + lin.bias.detach().double()
+    tol = 1e-5 if dt == torch.float32 else 2.0 ** -10
+    for got in (y, y_fq):
+        assert float((got.double() - exact).norm() / exact.norm()) <= tol
+    # F_matmul_bfp with a broadcast weight: the global threshold is taken over the weight's own shape
+    mm = ops.F_matmul_bfp(**dict(kw))
+    xb, w2 = torch.randn(3, 40, 256, device="cuda").to(dt), (torch.randn(256, 72, device="cuda") * 0.1).to(dt)
+    w3 = w2.unsqueeze(0)                                                        # [1, K, N] -> broadcast over the batch of 3
+    with torch.no_grad():
+        y2, y3 = mm(xb, w2), mm(xb, w3)
+        wq2 = ops.float_to_bfp_blocked(w2.t().contiguous(), **a, identifier="w").t().double()
+        e2 = ops.float_to_bfp_blocked(xb, **a, identifier="in").double() @ wq2
+    for got in (y2, y3):
+        assert got.shape == (3, 40, 72) and float((got.double() - e2).norm() / e2.norm()) <= tol

@@ -85,3 +85,33 @@ def test_int_format_with_sparsity_and_live_reference(ops, oracle):
     # sgd_update switches to weight_mant_bits (bfp_ops.py:113-114)
     y = ops.float_to_bfp_blocked(w.cuda(), **_args(ops, 4), identifier="w", sgd_update=True).cpu().numpy()
     assert _golden.mismatches(y, oracle.int_quantize(w.numpy(), 15, True), "f32") == 0
+
+
+@pytest.mark.parametrize("dt", ["f32", "bf16", "f16"])
+def test_int_with_n4_sparsity_single_pass_equals_composition(ops, oracle, dt):
+    """2-D weights take one fused kernel (bfp_int_quantize_nm); it must equal the two stand-alone kernels composed the way
+    bfp_ops.py:143-149 composes them, and the oracle, bit for bit -- including the heavy ties of 2- and 4-bit grids."""
+    from oracle import bfp_oracle as O
+    g = torch.Generator().manual_seed(9)
+    for (rows, K), bits, N, first in itertools.product([(40, 64), (33, 4096), (9, 11008), (5, 16384)], (8, 4, 2), (1, 2, 3), ("s", "q")):
+        w = (torch.randn(rows, K, generator=g) * 0.05).to(TORCH_DT[dt])
+        w.view(-1)[::7] = 0
+        w[1] = w[1].abs()
+        w[2] = 0
+        a = _args(ops, bits, w_sparsity=True, N=N, M=4, first=first, sparsity_mode="structured")
+        assert ops._int_nm_fusable(w, N, 4)
+        y = ops.float_to_bfp_blocked(w.cuda(), **a, identifier="w")
+        assert y.dtype == torch.float32 and y.shape == w.shape
+        if first == "s":
+            c = ops._int_quantize(ops._structured_N_M_sparsity(w.cuda(), "cuda", N, 4), bits, weight=True)
+        else:
+            c = ops._structured_N_M_sparsity(ops._int_quantize(w.cuda(), bits, weight=True), "cuda", N, 4)
+        assert torch.equal(y.view(torch.int32), c.view(torch.int32)), (rows, K, bits, N, first)
+        if K <= 4096:
+            x = O.from_torch(w)[0]
+            o = (oracle.int_quantize(oracle.nm_sparsify(x, N, 4, dt=dt), bits, True, dt=dt) if first == "s"
+                 else oracle.nm_sparsify(oracle.int_quantize(x, bits, True, dt=dt), N, 4))
+            assert _golden.mismatches(y.cpu().numpy(), o, "f32") == 0, (rows, K, bits, N, first, "oracle")
+    # shapes outside the fused kernel's reach keep composing
+    assert not ops._int_nm_fusable(torch.zeros(4, 6), 2, 4) and not ops._int_nm_fusable(torch.zeros(2, 3, 8), 2, 4)
+    assert not ops._int_nm_fusable(torch.zeros(4, 8), 2, 8)
