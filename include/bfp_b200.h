@@ -124,6 +124,17 @@ size_t bfp_int_workspace_bytes(int64_t C);
 int bfp_int_quantize(const void* in, float* out, int64_t A, int64_t C, int64_t inner, int dtype, int bits,
                      void* workspace, void* stream);
 
+/* Activations [A, C] (channel = last dim, int_ops.py:47-50) quantised like bfp_int_quantize and written as three bf16
+ * planes whose sum is the fp32 fake-quantised value: the operands of bf16 tensor-core GEMMs against the weight's integer
+ * grid (BFPLinear with sparsity_num_format == 'int').  out_bf16 holds 3 A C elements:
+ *   hi     column segments of width kseg, segment-major: segment s is a contiguous [A, min(kseg, C - s kseg)] matrix at
+ *          element offset s * A * kseg;
+ *   mid|lo one [A, 2C] matrix at element offset A * C.
+ * The contraction is chunked accordingly (mid|lo first, then one bfp_gemm_bf16_acc per hi segment).  C and kseg must be
+ * multiples of 8; workspace as for bfp_int_quantize, 16-byte aligned. */
+int bfp_int_quantize_split3(const void* in, void* out_bf16, int64_t A, int64_t C, int64_t kseg, int dtype, int bits,
+                            void* workspace, void* stream);
+
 /* 2-D weights [C, K] with N:4 structured sparsity and the 'int' format in ONE pass (float_to_bfp_blocked with
  * sparsity_num_format == 'int', sparsity_mode == 'structured', bfp_ops.py:143-149): order BFP_ORDER_SPARSIFY_QUANT =
  * _quantize(_sparsify(t)), BFP_ORDER_QUANT_SPARSIFY = _sparsify(_quantize(t)).  torch-CUDA tie rule.  Needs M == 4,
@@ -196,6 +207,15 @@ int bfp_gemm_bf16(const void* a_bf16, const void* b_bf16, const float* bias, flo
 /* ... with the output dtype chosen: BFP_DT_F32, or BFP_DT_F16 / BFP_DT_BF16 (accumulator + bias rounded once in the epilogue). */
 int bfp_gemm_bf16_ex(const void* a_bf16, const void* b_bf16, const float* bias, void* out, int out_dtype, int64_t T, int64_t N,
                      int64_t K, void* stream);
+/* out[T,N] (fp32) += A . B^T: the K-chunked contraction.  The tensor cores truncate (round toward zero) each time a group
+ * of products joins the fp32 accumulator, so a long contraction whose partial sums are not exactly representable drifts by
+ * about 2^-25 per MMA step (measured: 1.7e-5 relative at K = 12288).  BFP operands normally sum exactly; operands that do
+ * not (the 'int' format's three-plane activations, bfp_int_quantize_split3) are contracted in chunks of K: the first chunk
+ * through bfp_gemm_bf16 / bfp_gemm_bf16_sp, the rest through these, whose epilogue adds the tile into `out` with TMA
+ * reduce-add (one correctly rounded fp32 add per chunk).  Needs N % 4 == 0 and a 16-byte aligned `out`. */
+int bfp_gemm_bf16_acc(const void* a_bf16, const void* b_bf16, float* out, int64_t T, int64_t N, int64_t K, void* stream);
+int bfp_gemm_bf16_sp_acc(const void* x_bf16, const void* w_comp, const void* w_meta, float* out, int64_t T, int64_t N, int64_t K,
+                         void* stream);
 
 /* 2:4 structured-sparse variant of the BFP linear for weights pruned by _structured_N_M_sparsity with N=2, M=4
  * (bfp_ops.py:73-91; the reference then multiplies the zero-filled dense tensor, bfp_ops.py:187-190).  The pruned

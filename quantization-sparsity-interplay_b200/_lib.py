@@ -45,6 +45,7 @@ SIGNATURES = {
     "bfp_nm_sparsify": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp]),
     "bfp_int_workspace_bytes": (ctypes.c_size_t, [_i64]),
     "bfp_int_quantize": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp]),
+    "bfp_int_quantize_split3": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp]),
     "bfp_int_quantize_nm": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     "bfp_unstructured_workspace_bytes": (ctypes.c_size_t, []),
     "bfp_unstructured_sparsify": (_i32, [_vp, _vp, _i64, _i32, _u64, _vp, _vp]),
@@ -59,6 +60,8 @@ SIGNATURES = {
     "bfp_quantize_pack_bf16": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _i32, _u64, _u64, _i32, _i32, _i32, _vp]),
     "bfp_gemm_bf16": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "bfp_gemm_bf16_ex": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp]),
+    "bfp_gemm_bf16_acc": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "bfp_gemm_bf16_sp_acc": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "bfp_sp_layout": (_i32, [_i64, _i64] + [ctypes.POINTER(_i64)] * 2),
     "bfp_compress_2to4_bf16": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "bfp_gemm_bf16_sp": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),

@@ -774,6 +774,97 @@ class _BFPLinearTC(torch.autograd.Function):
         return grad_x, grad_w, grad_b, None, None, None
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# Row f2 on the tensor cores: BFPLinear with sparsity_num_format == 'int' (inference, fp32 modules).
+#   w_q[n, k] = s_n * j_w[n, k]       per-row scale, |j_w| <= 2^(bits-1): the integer grid is exact in bf16
+#   x_q[t, k] = s_k * j_x[t, k]       per-COLUMN scale (int_ops.py:47-50 reduces activations over rows): the scale runs along
+#                                     the contraction, so this is not an integer GEMM.  x_q (an fp32 value) is written as
+#                                     three bf16 planes that sum to it, and
+#   y[t, n]   = s_n * sum_k (hi + mid + lo)[t, k] * j_w[n, k] + bias[n]
+# is a bf16 contraction over K' = 3K (dense, or 2:4 when the weight is pruned that way), then a per-column scale: the
+# reference's F.linear(x_q, w_q, bias) up to the rounding of s_n * j_w (relative 2^-24).  Unlike BFP operands these sums are
+# not exactly representable, and the tensor cores truncate at every accumulation step, so the contraction is chunked along
+# K (include/bfp_b200.h bfp_gemm_bf16_acc): one launch for the small mid|lo planes, one accumulating launch per 1024 columns
+# of the hi plane.
+# ---------------------------------------------------------------------------------------------------------------
+def _int_tc_eligible(x, w, bfp_args):
+    if os.environ.get("BFP_LINEAR_PATH", "tc") != "tc":
+        return False
+    training = torch.is_grad_enabled() and (x.requires_grad or w.requires_grad)
+    return (not training and x.is_cuda and w.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32
+            and bfp_args['num_format'] == 'bfp' and bfp_args['sparsity_num_format'] == 'int' and 1 <= bfp_args['mant_bits'] <= 8
+            and not (bfp_args['in_sparsity'] == True)                                                  # noqa: E712
+            and w.dim() == 2 and x.dim() in (2, 3) and w.shape[1] % 8 == 0 and w.shape[0] % 4 == 0 and x.numel() > 0 and w.numel() > 0)
+
+
+_INT_KSEG = 1024     # hi-plane contraction chunk: 64 dense MMA steps, i.e. ~1e-6 of truncation drift per chunk
+
+
+class _IntPackedWeight:
+    """Integer weight grid in the chunks of the K-chunked contraction: `hi[s]` = columns of hi segment s, `midlo` = the grid
+    twice ([N, 2K]); dense bf16 tensors, or SparseBF16 when the weight is pruned 2:4.  `scale` = per-row s_n."""
+
+    def __init__(self, hi, midlo, scale, sparse):
+        self.hi, self.midlo, self.scale, self.sparse = hi, midlo, scale, sparse
+
+
+def _int_pack_weight(w, bfp_args):
+    """Fake-quantised weight (the reference composition, either order, any sparsity mode) -> integer grid j_w + per-row scale.
+    Returns None -- the caller then keeps the reference's structure -- if s_n * j_w does not reproduce the fake-quantised
+    weight bit for bit."""
+    wq = float_to_bfp_blocked(w, identifier='w', **bfp_args)
+    sparse = bfp_args['w_sparsity'] == True                                                            # noqa: E712
+    seen = _sparsify(w, sparse, bfp_args['sparsity_mode'], w.device, bfp_args['N'], bfp_args['M'], bfp_args['sparsity_frac']) \
+        if (sparse and bfp_args['first'] == 's') else w                    # the tensor Quantizer.find_params saw
+    maxq = torch.tensor(float(2 ** int(bfp_args['mant_bits']) - 1), device=w.device)   # a tensor: IEEE division, not a reciprocal multiply
+    xmin = seen.min(dim=1).values.clamp(max=0.0)                           # int_ops.py:55-56
+    xmax = seen.max(dim=1).values.clamp(min=0.0)
+    xmax = torch.maximum(xmin.abs(), xmax)                                 # :59
+    xmin = torch.where(xmin < 0, -xmax, xmin)                              # :60-62
+    dead = (xmin == 0) & (xmax == 0)                                       # :63-65
+    xmin, xmax = torch.where(dead, -torch.ones_like(xmin), xmin), torch.where(dead, torch.ones_like(xmax), xmax)
+    scale = (xmax - xmin) / maxq                                           # :67
+    grid = torch.round(wq / scale[:, None])
+    if not torch.equal(grid * scale[:, None], wq) or float(grid.abs().max()) > 256:
+        return None
+    grid = grid.to(torch.bfloat16)
+    K = grid.shape[1]
+    fits = sparse and bfp_args['sparsity_mode'] == 'structured' and _nm_fits_2to4(bfp_args['N'], bfp_args['M']) \
+        and os.environ.get("BFP_GEMM_KIND", "") in ("", "sp")
+    form = compress_2to4_bf16 if fits else (lambda t: t)
+    hi = [form(grid[:, k0:k0 + _INT_KSEG].contiguous()) for k0 in range(0, K, _INT_KSEG)]
+    return _IntPackedWeight(hi, form(grid.repeat(1, 2).contiguous()), scale.contiguous(), fits)
+
+
+def _int_tc_linear(x, packed, bias, bfp_args):
+    K = x.shape[-1]
+    T = x.numel() // K
+    N = packed.scale.shape[0]
+    src = x.detach().contiguous()
+    x3 = torch.empty(T * 3 * K, dtype=torch.bfloat16, device=x.device)
+    acc = torch.empty((T, N), dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    with _on(x.device):
+        stream = _stream()
+        ws = torch.empty(L.bfp_int_workspace_bytes(K) // 8 + 2, dtype=torch.int64, device=x.device)
+        _lib.check(L.bfp_int_quantize_split3(src.data_ptr(), x3.data_ptr(), T, K, _INT_KSEG, _DT[src.dtype], int(bfp_args['mant_bits']),
+                                             ws.data_ptr(), stream))
+        # smallest terms first: mid|lo planes in one launch (store), then one accumulating launch per hi segment
+        chunks = [(x3[T * K:], packed.midlo, 2 * K)] + [(x3[k0 * T:], wseg, min(_INT_KSEG, K - k0)) for k0, wseg in zip(range(0, K, _INT_KSEG), packed.hi)]
+        for i, (xc, wc, kc) in enumerate(chunks):
+            if packed.sparse:
+                if i == 0:
+                    _lib.check(L.bfp_gemm_bf16_sp(xc.data_ptr(), wc.comp.data_ptr(), wc.meta.data_ptr(), None, acc.data_ptr(), T, N, kc, stream))
+                else:
+                    _lib.check(L.bfp_gemm_bf16_sp_acc(xc.data_ptr(), wc.comp.data_ptr(), wc.meta.data_ptr(), acc.data_ptr(), T, N, kc, stream))
+            elif i == 0:
+                _lib.check(L.bfp_gemm_bf16(xc.data_ptr(), wc.data_ptr(), None, acc.data_ptr(), T, N, kc, stream))
+            else:
+                _lib.check(L.bfp_gemm_bf16_acc(xc.data_ptr(), wc.data_ptr(), acc.data_ptr(), T, N, kc, stream))
+    acc = acc.view(tuple(x.shape[:-1]) + (N,))
+    return torch.addcmul(bias.detach(), acc, packed.scale) if bias is not None else acc.mul_(packed.scale)
+
+
 class BFPConv2d(torch.nn.Conv2d):
     """bfp_ops.py:247-268: input blocked along W, weight along kw; the convolution itself runs on the dequantised
     operands (conv as im2col + BFP GEMM is "next")."""
@@ -830,7 +921,9 @@ class BFPLinear(torch.nn.Linear):
         key = (kind, w.data_ptr(), w._version, tuple(w.shape), w.device)
         hit = self._packed_by_kind.get(kind)
         if hit is None or hit[0] != key:
-            if kind == 'sp':
+            if kind == 'int':
+                packed = _int_pack_weight(w.detach(), self.bfp_args)
+            elif kind == 'sp':
                 # raises if the pruned weight is not 2:4 (cannot happen for sp_ok configs); the dense form is not kept
                 packed = compress_2to4_bf16(pack_bfp_bf16(w.detach(), identifier='w', **self.bfp_args))
             else:
@@ -847,6 +940,10 @@ class BFPLinear(torch.nn.Linear):
         elif self.num_format == 'bfp':
             determ = self.bfp_args['rounding_mode'] == rounding_modes.DETERM
             training = torch.is_grad_enabled() and (input.requires_grad or self.weight.requires_grad)
+            if _int_tc_eligible(input, self.weight, self.bfp_args):
+                packed = self._packed_weight('int')
+                if packed is not None:
+                    return _int_tc_linear(input, packed, self.bias, self.bfp_args)
             kind = _tensor_core_kind(input, self.weight, self.bfp_args) if (determ or training) else None
             if training and kind is not None and self.bfp_args['mant_bits'] <= 8 and self.bfp_args['grad_sparsity'] != True:   # noqa: E712
                 # training: forward + dgrad + wgrad on the tensor cores.  Stochastic rounding re-quantises the weight on

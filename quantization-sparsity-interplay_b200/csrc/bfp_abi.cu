@@ -178,6 +178,17 @@ int bfp_int_quantize(const void* in, float* out, int64_t A, int64_t C, int64_t i
     return int_quantize_device(in, out, A, C, inner, dtype, bits, workspace, static_cast<cudaStream_t>(stream));
 }
 
+int bfp_int_quantize_split3(const void* in, void* out_bf16, int64_t A, int64_t C, int64_t kseg, int dtype, int bits, void* workspace, void* stream) {
+    if (A < 0 || C < 0 || dtype < 0 || dtype > 2 || kseg <= 0 || kseg % 8) return set_error(BFP_E_ARG, "bad argument (kseg: a positive multiple of 8)");
+    if (bits < 1 || bits > 23) return set_error(BFP_E_ARG, "bits must be in [1, 23]");
+    if (C % 8) return set_error(BFP_E_UNSUPPORTED, "the three-plane form needs C to be a multiple of 8");
+    if (A * C > 0 && (!in || !out_bf16 || !workspace)) return set_error(BFP_E_ARG, "null pointer");
+    if (reinterpret_cast<uintptr_t>(workspace) % 16 || reinterpret_cast<uintptr_t>(out_bf16) % 16)
+        return set_error(BFP_E_ALIGN, "workspace and out_bf16 must be 16-byte aligned");
+    if (int rc = require_device()) return rc;
+    return int_quantize_split3_device(in, out_bf16, A, C, kseg, dtype, bits, workspace, static_cast<cudaStream_t>(stream));
+}
+
 int bfp_int_quantize_nm(const void* in, float* out, int64_t C, int64_t K, int dtype, int bits, int N, int M, int order, void* stream) {
     if (C < 0 || K < 0 || dtype < 0 || dtype > 2) return set_error(BFP_E_ARG, "bad argument");
     if (bits < 1 || bits > 23) return set_error(BFP_E_ARG, "bits must be in [1, 23]");
@@ -262,6 +273,21 @@ int bfp_gemm_bf16_ex(const void* a_bf16, const void* b_bf16, const float* bias, 
     if (T * N > 0 && (!a_bf16 || !b_bf16 || !out)) return set_error(BFP_E_ARG, "null pointer");
     if (int rc = require_device()) return rc;
     return gemm_bf16_ex_device(a_bf16, b_bf16, bias, out, out_dtype, T, N, round_up(K, 8), static_cast<cudaStream_t>(stream));
+}
+
+int bfp_gemm_bf16_acc(const void* a_bf16, const void* b_bf16, float* out, int64_t T, int64_t N, int64_t K, void* stream) {
+    if (T < 0 || N < 0 || K <= 0) return set_error(BFP_E_ARG, "bad argument");
+    if (T * N > 0 && (!a_bf16 || !b_bf16 || !out)) return set_error(BFP_E_ARG, "null pointer");
+    if (int rc = require_device()) return rc;
+    return gemm_bf16_ex_device(a_bf16, b_bf16, nullptr, out, BFP_DT_F32, T, N, round_up(K, 8), static_cast<cudaStream_t>(stream), 1);
+}
+
+int bfp_gemm_bf16_sp_acc(const void* x_bf16, const void* w_comp, const void* w_meta, float* out, int64_t T, int64_t N, int64_t K, void* stream) {
+    if (T < 0 || N < 0 || K <= 0) return set_error(BFP_E_ARG, "bad argument");
+    if (T * N > 0 && (!x_bf16 || !w_comp || !w_meta || !out)) return set_error(BFP_E_ARG, "null pointer");
+    if (int rc = require_device()) return rc;
+    void* outs[1] = {out};
+    return gemm_bf16_sp_multi_device(x_bf16, w_comp, w_meta, nullptr, outs, 1, BFP_DT_F32, N, T, N, round_up(K, 8), static_cast<cudaStream_t>(stream), 1);
 }
 
 int bfp_sp_layout(int64_t rows, int64_t K, int64_t* Kc, int64_t* meta_bytes) { return sp_layout(rows, round_up(K, 8), Kc, meta_bytes); }

@@ -281,6 +281,7 @@ struct ParamsBf16 {
     float* out;
     int out_dtype;              // BFP_DT_F32, or F16 / BF16: accumulator (+ bias) rounded once in the epilogue
     int out_tma;                // 1 = epilogue writes through smem + TMA stores (needs 16-byte aligned rows)
+    int accumulate;             // 1 = out += product (fp32, TMA path only): TMA reduce-add instead of a store
     int T, N;
     int num_k_stages;           // ceil(K / 64)
     int tiles_m, tiles_n;       // tiles_m counts CG * 128 rows
@@ -463,7 +464,7 @@ bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) { tma_store_2d_hint(&map_out, sbuf, n0 + c * 32, (tm * CG + (int)rank) * BM + q * 32, pol); tma_store_commit(); }
+                    if (lane == 0) { tma_store_or_add_2d(&map_out, sbuf, n0 + c * 32, (tm * CG + (int)rank) * BM + q * 32, pol, p.accumulate); tma_store_commit(); }
                 }
                 }
             } else {
@@ -578,7 +579,7 @@ int gemm_bf16_device(const void* a_bf16, const void* b_bf16, const float* bias, 
 }
 
 int gemm_bf16_ex_device(const void* a_bf16, const void* b_bf16, const float* bias, void* out_v, int out_dtype, int64_t T, int64_t N, int64_t Kp,
-                        cudaStream_t st) {
+                        cudaStream_t st, int accumulate) {
     using namespace gemm;
     if (T == 0 || N == 0) return BFP_OK;
     if (out_dtype != BFP_DT_F32 && out_dtype != BFP_DT_F16 && out_dtype != BFP_DT_BF16) return set_error(BFP_E_ARG, "bad output dtype");
@@ -589,7 +590,7 @@ int gemm_bf16_ex_device(const void* a_bf16, const void* b_bf16, const float* bia
     if (reinterpret_cast<uintptr_t>(a_bf16) % 16 || reinterpret_cast<uintptr_t>(b_bf16) % 16)
         return set_error(BFP_E_ALIGN, "bf16 operands must be 16-byte aligned");
     ParamsBf16 p;
-    p.bias = bias; p.out = out; p.out_dtype = out_dtype; p.T = (int)T; p.N = (int)N;
+    p.bias = bias; p.out = out; p.out_dtype = out_dtype; p.T = (int)T; p.N = (int)N; p.accumulate = accumulate;
     p.num_k_stages = (int)((Kp + 63) / 64);
     // tile: CTA pairs on 256x256 (cta_group::2) unless the problem is a single 128-row or 128-column strip; the knobs
     // gemm_bf16_cta_group (1 / 2) and gemm_bf16_tile_n (128 / 256, single-CTA mode only) force a variant.
@@ -609,6 +610,8 @@ int gemm_bf16_ex_device(const void* a_bf16, const void* b_bf16, const float* bia
     CUtensorMap map_out = map_a;
     p.out_tma = ((N * out_es) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 && tuning().gemm_out_tma) ? 1 : 0;
     if (p.out_tma) if (int rc = make_map_out(&map_out, out, out_dtype, T, N, N * out_es, out_es == 4 ? 32 : 64, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (accumulate && (!p.out_tma || out_dtype != BFP_DT_F32 || bias))
+        return set_error(BFP_E_UNSUPPORTED, "accumulating GEMM: fp32 output with 16-byte aligned rows (N % 4 == 0), no bias");
     const int units = std::min(p.tiles_m * p.tiles_n, sms / cg);
     int rc;
     if (cg == 2) rc = launch_bf16<256, 2>(map_a, map_b, map_out, p, units, st);

@@ -74,6 +74,7 @@ struct Params {
     int64_t ld_out;             // row stride of `out` in floats (plain-store path)
     int out_dtype;              // BFP_DT_F32, or BFP_DT_F16 / BFP_DT_BF16: the fp32 accumulator (+ bias) is rounded to it once
     int out_tma;                // 1 = the epilogue stages the tile in smem and writes it with TMA stores (needs N % 4 == 0)
+    int accumulate;             // 1 = out += product (fp32, TMA path, one destination): TMA reduce-add instead of a store
     int debug;                  // timing experiments only (wrong results): bit 0 = every tile loads X tile 0, bit 1 = W tile 0
 };
 
@@ -168,7 +169,7 @@ __device__ __forceinline__ void store_columns(const Params& p, const OutMaps& ou
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-                tma_store_2d_hint(&outs.m[0], buf, n0, t0 + rd * 8, pol);
+                tma_store_or_add_2d(&outs.m[0], buf, n0, t0 + rd * 8, pol, p.accumulate);
                 if (outs.n > 1) {                                 // fused all-gather: the same tile to every peer's buffer
                     for (int g = 1; g < outs.n; ++g) tma_store_2d_hint(&outs.m[g], buf, n0, t0 + rd * 8, pol);
                 }
@@ -748,7 +749,7 @@ int gemm_bf16_sp_device(const void* x_bf16, const void* w_comp, const void* w_me
 }
 
 int gemm_bf16_sp_multi_device(const void* x_bf16, const void* w_comp, const void* w_meta, const float* bias, void* const* out_ptrs, int n_out,
-                              int out_dtype, int64_t ld_out, int64_t T, int64_t N, int64_t Kp, cudaStream_t st) {
+                              int out_dtype, int64_t ld_out, int64_t T, int64_t N, int64_t Kp, cudaStream_t st, int accumulate) {
     using namespace gemm_sp;
     if (T == 0 || N == 0) return BFP_OK;
     if (n_out < 1 || n_out > kMaxDests) return set_error(BFP_E_ARG, "1 to 8 output destinations");
@@ -767,7 +768,7 @@ int gemm_bf16_sp_multi_device(const void* x_bf16, const void* w_comp, const void
     int cg = (N > 128) ? 2 : 1;
     if (tuning().gemm_sp_cta_group == 1 || tuning().gemm_sp_cta_group == 2) cg = tuning().gemm_sp_cta_group;
     Params p;
-    p.bias = bias; p.out = out; p.T = (int)T; p.N = (int)N; p.ld_out = ld_out; p.out_dtype = out_dtype; p.debug = tuning().gemm_sp_debug;
+    p.bias = bias; p.out = out; p.T = (int)T; p.N = (int)N; p.ld_out = ld_out; p.out_dtype = out_dtype; p.debug = tuning().gemm_sp_debug; p.accumulate = accumulate;
     p.num_k_slabs = (int)((Kp + 127) / 128);
     p.e_atoms = (int)(Kc / 64);
     p.tiles_w = (int)((N + 128 * cg - 1) / (128 * cg));
@@ -803,6 +804,8 @@ int gemm_bf16_sp_multi_device(const void* x_bf16, const void* w_comp, const void
     for (int g = 0; g < n_out; ++g) aligned = aligned && out_ptrs[g] && reinterpret_cast<uintptr_t>(out_ptrs[g]) % 16 == 0;
     p.out_tma = (aligned && (tuning().gemm_out_tma || n_out > 1)) ? 1 : 0;
     if (n_out > 1 && !p.out_tma) return set_error(BFP_E_ALIGN, "multi-destination output needs 16-byte aligned slices and a row stride that is a multiple of 16 bytes");
+    if (accumulate && (!p.out_tma || out_dtype != BFP_DT_F32 || bias || n_out != 1))
+        return set_error(BFP_E_UNSUPPORTED, "accumulating GEMM: one fp32 output with 16-byte aligned rows (N % 4 == 0), no bias");
     // each map covers exactly the [T, N] slice (row stride ld_out), so the copy engine clips at the slice's edge
     for (int g = 0; g < (p.out_tma ? n_out : 0); ++g)
         if (int rc = make_map_out(&map_out.m[g], out_ptrs[g], out_dtype, T, N, ld_out * out_es, out_es == 4 ? 32 : 64, 8)) return rc;

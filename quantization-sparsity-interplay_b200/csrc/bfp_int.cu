@@ -86,6 +86,42 @@ __global__ void __launch_bounds__(256) int_apply_kernel(const void* in, float* o
     }
 }
 
+// Activations [A, C] (inner == 1) for the tensor-core contraction: the same per-column quantiser, but the fp32 result
+// x = s_c (q - zero) is written as three bf16 planes with x == hi + mid + lo (8 + 8 + 8 significant bits; the last plane
+// absorbs any remainder to within 2^-25 |x|).  bf16 GEMMs against the integer weight grid then reproduce the fp32 product
+// sum.  Layout (one buffer of 3 A C elements), chosen for the K-chunked contraction of include/bfp_b200.h:
+//   hi   column segments of width kseg, segment-major: segment s is a contiguous [A, w_s] matrix at offset s * A * kseg
+//   mid|lo one [A, 2C] matrix at offset A * C (mid in columns 0 .. C-1, lo in C .. 2C-1)
+// 8 columns per thread (kseg % 8 == 0).
+template <int DT>
+__global__ void __launch_bounds__(256) int_apply_split_kernel(const void* in, __nv_bfloat16* out, int64_t A, int64_t C, int64_t kseg,
+                                                              const float* scale, float maxq, float zero) {
+    const int64_t cv = C / 8, nv = A * cv;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / cv, c0 = (i - row * cv) * 8;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = DType<DT>::load(in, row * C + c0 + e);
+        const float4 s0 = *reinterpret_cast<const float4*>(scale + c0), s1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        __align__(16) __nv_bfloat16 p[3][8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float q = fminf(fmaxf(rintf(__fdiv_rn(v[e], sc[e])) + zero, 0.0f), maxq);   // int_ops.py:7
+            const float x = sc[e] * (q - zero);                                               // :8
+            p[0][e] = __float2bfloat16_rn(x);
+            const float r1 = x - __bfloat162float(p[0][e]);
+            p[1][e] = __float2bfloat16_rn(r1);
+            p[2][e] = __float2bfloat16_rn(r1 - __bfloat162float(p[1][e]));
+        }
+        const int64_t seg = c0 / kseg, ws = min(kseg, C - seg * kseg);
+        *reinterpret_cast<uint4*>(out + seg * A * kseg + row * ws + (c0 - seg * kseg)) = *reinterpret_cast<const uint4*>(p[0]);
+        __nv_bfloat16* ml = out + A * C + row * 2 * C + c0;
+        *reinterpret_cast<uint4*>(ml) = *reinterpret_cast<const uint4*>(p[1]);
+        *reinterpret_cast<uint4*>(ml + C) = *reinterpret_cast<const uint4*>(p[2]);
+    }
+}
+
 // Weights (A == 1: one channel per row of K = inner elements): ONE pass.  A CTA keeps its row in registers (NV 128-bit
 // vectors per thread), reduces min / max across the block, derives the scale and applies it to the registers: 8 B/element of
 // traffic (4 in + 4 out for fp32) instead of the three passes (12 B/element + atomics) of the general path.
@@ -188,11 +224,12 @@ int run_nm(const void* in, float* out, int64_t C, int64_t K, int bits, int N, in
 }
 
 template <int DT>
-int run(const void* in, float* out, int64_t A, int64_t C, int64_t inner, int bits, IntWs ws, cudaStream_t s) {
+int run(const void* in, float* out, int64_t A, int64_t C, int64_t inner, int bits, IntWs ws, cudaStream_t s, __nv_bfloat16* split_out = nullptr,
+        int64_t kseg = 0) {
     const int64_t n = A * C * inner;
     const int sms = device_info().sm_count;
     const float maxq = (float)((1ll << bits) - 1), zero = (float)(((1ll << bits)) / 2.0);
-    if (A == 1 && rows_fusable<DT>(in, out, inner)) return run_rows<DT, 0>(in, out, C, inner, bits, 0, s);
+    if (!split_out && A == 1 && rows_fusable<DT>(in, out, inner)) return run_rows<DT, 0>(in, out, C, inner, bits, 0, s);
     int_init_kernel<<<(int)std::min<int64_t>((C + 255) / 256, 1024), 256, 0, s>>>(ws.mn, ws.mx, C);
     count_launch();
     if (inner >= 32) {
@@ -212,7 +249,8 @@ int run(const void* in, float* out, int64_t A, int64_t C, int64_t inner, int bit
     count_launch();
     int_scale_kernel<<<(int)std::min<int64_t>((C + 255) / 256, 1024), 256, 0, s>>>(ws.mn, ws.mx, ws.scale, C, maxq);
     count_launch();
-    int_apply_kernel<DT><<<(int)std::min<int64_t>((n + 255) / 256, (int64_t)sms * 16), 256, 0, s>>>(in, out, n, C, inner, ws.scale, maxq, zero);
+    if (split_out) int_apply_split_kernel<DT><<<(int)std::min<int64_t>((n / 8 + 255) / 256, (int64_t)sms * 16), 256, 0, s>>>(in, split_out, A, C, kseg, ws.scale, maxq, zero);
+    else int_apply_kernel<DT><<<(int)std::min<int64_t>((n + 255) / 256, (int64_t)sms * 16), 256, 0, s>>>(in, out, n, C, inner, ws.scale, maxq, zero);
     count_launch();
     return check_launch("int quantiser kernels");
 }
@@ -228,6 +266,19 @@ int int_quantize_device(const void* in, float* out, int64_t A, int64_t C, int64_
     case BFP_DT_F32: return run<BFP_DT_F32>(in, out, A, C, inner, bits, ws, s);
     case BFP_DT_F16: return run<BFP_DT_F16>(in, out, A, C, inner, bits, ws, s);
     case BFP_DT_BF16: return run<BFP_DT_BF16>(in, out, A, C, inner, bits, ws, s);
+    }
+    return set_error(BFP_E_ARG, "bad dtype");
+}
+
+int int_quantize_split3_device(const void* in, void* out_bf16, int64_t A, int64_t C, int64_t kseg, int dtype, int bits, void* workspace, cudaStream_t s) {
+    if (A * C == 0) return BFP_OK;
+    IntWs ws;
+    ws.mn = static_cast<int*>(workspace); ws.mx = ws.mn + C; ws.scale = reinterpret_cast<float*>(ws.mx + C);
+    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out_bf16);
+    switch (dtype) {
+    case BFP_DT_F32: return run<BFP_DT_F32>(in, nullptr, A, C, 1, bits, ws, s, o, kseg);
+    case BFP_DT_F16: return run<BFP_DT_F16>(in, nullptr, A, C, 1, bits, ws, s, o, kseg);
+    case BFP_DT_BF16: return run<BFP_DT_BF16>(in, nullptr, A, C, 1, bits, ws, s, o, kseg);
     }
     return set_error(BFP_E_ARG, "bad dtype");
 }

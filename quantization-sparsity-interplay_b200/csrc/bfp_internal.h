@@ -68,7 +68,7 @@ int gemm_bf16_device(const void* a_bf16, const void* b_bf16, const float* bias, 
                      cudaStream_t st);
 
 int gemm_bf16_ex_device(const void* a_bf16, const void* b_bf16, const float* bias, void* out, int out_dtype, int64_t T, int64_t N, int64_t Kp,
-                        cudaStream_t st);
+                        cudaStream_t st, int accumulate = 0);
 
 int sp_layout(int64_t rows, int64_t Kp, int64_t* Kc, int64_t* meta_bytes);
 int compress_2to4_bf16_device(const void* w_bf16, int64_t rows, int64_t Kp, int64_t ld_w, void* comp, void* meta, unsigned int* violations,
@@ -76,10 +76,11 @@ int compress_2to4_bf16_device(const void* w_bf16, int64_t rows, int64_t Kp, int6
 int gemm_bf16_sp_device(const void* x_bf16, const void* w_comp, const void* w_meta, const float* bias, float* out, int64_t T, int64_t N,
                         int64_t Kp, cudaStream_t st);
 int gemm_bf16_sp_multi_device(const void* x_bf16, const void* w_comp, const void* w_meta, const float* bias, void* const* out_ptrs, int n_out,
-                              int out_dtype, int64_t ld_out, int64_t T, int64_t N, int64_t Kp, cudaStream_t st);
+                              int out_dtype, int64_t ld_out, int64_t T, int64_t N, int64_t Kp, cudaStream_t st, int accumulate = 0);
 
 size_t int_workspace_bytes(int64_t C);
 int int_quantize_device(const void* in, float* out, int64_t A, int64_t C, int64_t inner, int dtype, int bits, void* workspace, cudaStream_t s);
+int int_quantize_split3_device(const void* in, void* out_bf16, int64_t A, int64_t C, int64_t kseg, int dtype, int bits, void* workspace, cudaStream_t s);
 int int_quantize_nm_device(const void* in, float* out, int64_t C, int64_t K, int dtype, int bits, int N, int order, cudaStream_t s);
 size_t unstructured_workspace_bytes();
 int unstructured_device(const void* in, void* out, int64_t n, int dtype, unsigned long long k, void* workspace, cudaStream_t s);

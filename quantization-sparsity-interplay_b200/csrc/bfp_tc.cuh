@@ -169,6 +169,16 @@ __device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, const 
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
                  ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(policy) : "memory");
 }
+// out += tile: the copy engine adds the fp32 smem tile into global memory (element-wise RN add at the L2); used by the
+// K-chunked contraction (bfp_gemm_bf16_acc / _sp_acc), where every launch after the first accumulates into the output
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_or_add_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1, uint64_t policy, int accumulate) {
+    if (accumulate) tma_reduce_add_2d(map, smem_src, c0, c1);
+    else tma_store_2d_hint(map, smem_src, c0, c1, policy);
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }

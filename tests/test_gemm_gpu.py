@@ -578,3 +578,38 @@ def test_bfplinear_unstructured_sparsity_runs_on_tensor_cores(ops, dt, first, mo
         e2 = ops.float_to_bfp_blocked(xb, **a, identifier="in").double() @ wq2
     for got in (y2, y3):
         assert got.shape == (3, 40, 72) and float((got.double() - e2).norm() / e2.norm()) <= tol
+
+
+@pytest.mark.parametrize("tile", [0, 256, 480, 240])
+@pytest.mark.parametrize("shape", [(300, 200, 264), (1000, 1536, 1024), (77, 300, 72), (963, 520, 392)])
+def test_gemm_accumulating_variants_add_exactly(ops, shape, tile):
+    """bfp_gemm_bf16_acc / bfp_gemm_bf16_sp_acc: out += A . B^T through the TMA reduce-add epilogue (the K-chunked
+    contraction).  Small-integer operands: two chunks must give the exact integer matmul of the concatenated K."""
+    from qsi_b200 import _lib
+    T, N, K = shape
+    g = torch.Generator().manual_seed(T + N + K)
+    Kp = -(-K // 8) * 8
+    L, st = _lib.lib(), torch.cuda.current_stream().cuda_stream
+    xs = [torch.randint(-15, 16, (T, Kp), generator=g).to(torch.bfloat16).cuda() for _ in range(3)]
+    wd = [torch.randint(-15, 16, (N, Kp), generator=g).to(torch.bfloat16).cuda() for _ in range(3)]
+    wsp = [(_random_2to4(N, Kp, g) * 4).round().clamp(-15, 15).to(torch.bfloat16).cuda() for _ in range(3)]
+    out = torch.empty(T, N, device="cuda")
+    _lib.check(L.bfp_gemm_bf16(xs[0].data_ptr(), wd[0].data_ptr(), None, out.data_ptr(), T, N, Kp, st))
+    for i in (1, 2):
+        _lib.check(L.bfp_gemm_bf16_acc(xs[i].data_ptr(), wd[i].data_ptr(), out.data_ptr(), T, N, Kp, st))
+    ref = sum(x.double() @ w.double().t() for x, w in zip(xs, wd))
+    assert torch.equal(out.double(), ref)
+    _lib.set_option("gemm_sp_tile", tile)
+    try:
+        comp = [ops.compress_2to4_bf16(w) for w in wsp]
+        _lib.check(L.bfp_gemm_bf16_sp(xs[0].data_ptr(), comp[0].comp.data_ptr(), comp[0].meta.data_ptr(), None, out.data_ptr(), T, N, Kp, st))
+        for i in (1, 2):
+            _lib.check(L.bfp_gemm_bf16_sp_acc(xs[i].data_ptr(), comp[i].comp.data_ptr(), comp[i].meta.data_ptr(), out.data_ptr(), T, N, Kp, st))
+    finally:
+        _lib.set_option("gemm_sp_tile", 0)
+    ref = sum(x.double() @ w.double().t() for x, w in zip(xs, wsp))
+    assert torch.equal(out.double(), ref)
+    # no TMA path (N % 4 != 0): the accumulating form refuses instead of silently overwriting
+    if N % 4 == 0:
+        o2 = torch.empty(T, N - 1, device="cuda")
+        assert L.bfp_gemm_bf16_acc(xs[0].data_ptr(), wd[0].data_ptr(), o2.data_ptr(), T, N - 1, Kp, st) == _lib.E_UNSUPPORTED

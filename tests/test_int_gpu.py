@@ -115,3 +115,60 @@ def test_int_with_n4_sparsity_single_pass_equals_composition(ops, oracle, dt):
     # shapes outside the fused kernel's reach keep composing
     assert not ops._int_nm_fusable(torch.zeros(4, 6), 2, 4) and not ops._int_nm_fusable(torch.zeros(2, 3, 8), 2, 4)
     assert not ops._int_nm_fusable(torch.zeros(4, 8), 2, 8)
+
+
+def test_int_activation_three_plane_split(ops):
+    """bfp_int_quantize_split3: hi + mid + lo reproduces the fp32 fake-quantised activation (exactly, up to a last-place
+    remainder the third bf16 plane cannot hold), in the segment-major layout of include/bfp_b200.h."""
+    from qsi_b200 import _lib
+    g = torch.Generator().manual_seed(12)
+    A, C, kseg = 150, 264, 64
+    x = (torch.randn(3, 50, C, generator=g) * torch.rand(C, generator=g) * 4).cuda()
+    x[..., 5] = 0
+    for bits in (8, 4):
+        xq = ops._int_quantize(x, bits, weight=False).view(A, C)
+        x3 = torch.empty(A * 3 * C, dtype=torch.bfloat16, device="cuda")
+        L = _lib.lib()
+        ws = torch.empty(L.bfp_int_workspace_bytes(C) // 8 + 2, dtype=torch.int64, device="cuda")
+        _lib.check(L.bfp_int_quantize_split3(x.data_ptr(), x3.data_ptr(), A, C, kseg, _lib.DT_F32, bits, ws.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream))
+        hi = torch.cat([x3[k0 * A: k0 * A + A * min(kseg, C - k0)].view(A, -1) for k0 in range(0, C, kseg)], dim=1)
+        ml = x3[A * C:].view(A, 2 * C)
+        s = hi.double() + ml[:, :C].double() + ml[:, C:].double()
+        err = (s - xq.double()).abs()
+        assert (err <= xq.double().abs() * 2.0 ** -24).all()
+        assert float((err == 0).double().mean()) > 0.99
+        assert torch.equal(hi, xq.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("cfg", [("structured", "s"), ("structured", "q"), ("unstructured", "s"), ("none", "s")])
+@pytest.mark.parametrize("bits", [8, 4])
+def test_bfplinear_int_format_on_tensor_cores(ops, cfg, bits, monkeypatch):
+    """BFPLinear with sparsity_num_format='int' (inference): three-plane activations x integer weight grid on the bf16 tensor
+    cores (2:4-compressed when the weight is pruned 2:4) against the fp64 contraction of the same fake-quantised operands,
+    and against the reference's structure (fake-quant + F.linear)."""
+    mode, first = cfg
+    kw = dict(num_format="bfp", sparsity_num_format="int", rounding_mode="determ", epsilon=1e-8, mant_bits=bits, block_size=64,
+              w_sparsity=mode != "none", N=2, M=4, first=first, sparsity_mode="structured" if mode == "none" else mode,
+              sparsity_frac=0.5, device="cuda")
+    torch.manual_seed(3)
+    lin = ops.BFPLinear(1096, 520, bias=True, **dict(kw)).cuda()
+    with torch.no_grad():
+        lin.weight[3] = lin.weight[3].abs()                   # a non-negative row: xmin = 0, asymmetric grid
+        lin.weight[4] = 0                                     # a dead row: scale 2 / maxq
+    x = torch.randn(2, 77, 1096, device="cuda") * (torch.rand(1096, device="cuda") * 3 + 0.1)
+    a = ops.unpack_bfp_args(dict(kw))
+    with torch.no_grad():
+        y = lin(x)
+        assert lin._packed_w is not None and lin._packed_w[0][0] == "int" and lin._packed_w[1] is not None
+        assert lin._packed_w[1].sparse == (mode == "structured")
+        monkeypatch.setenv("BFP_LINEAR_PATH", "fakequant")
+        y_fq = lin(x)
+        monkeypatch.setenv("BFP_LINEAR_PATH", "tc")
+    xq = ops.float_to_bfp_blocked(x, **a, identifier="in").double()
+    wq = ops.float_to_bfp_blocked(lin.weight.detach(), **a, identifier="w").double()
+    exact = xq @ wq.t() + lin.bias.detach().double()
+    for got in (y, y_fq):
+        assert got.dtype == torch.float32 and got.shape == (2, 77, 520)
+        assert float((got.double() - exact).norm() / exact.norm()) <= 1e-5
+    assert float((y.double() - exact).norm() / exact.norm()) <= 2e-6
