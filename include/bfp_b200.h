@@ -207,6 +207,14 @@ int bfp_gemm_bf16(const void* a_bf16, const void* b_bf16, const float* bias, flo
 /* ... with the output dtype chosen: BFP_DT_F32, or BFP_DT_F16 / BFP_DT_BF16 (accumulator + bias rounded once in the epilogue). */
 int bfp_gemm_bf16_ex(const void* a_bf16, const void* b_bf16, const float* bias, void* out, int out_dtype, int64_t T, int64_t N,
                      int64_t K, void* stream);
+/* `batch` independent products out[b] = A[b] . B[b]^T in ONE launch (F_matmul_bfp on [..., M, K] x [..., K, N] operands,
+ * bfp_ops.py:240-245: GPT-2 style attention matmuls, modeling_gpt2.py:205-207): A [batch, T, K], B [batch, N, K] bf16
+ * contiguous (K a multiple of 8), out [batch, T, N] of out_dtype.  The operands are read as stacked rows through 2-D tensor
+ * maps and the output is written through a 3-D map that clips each entry's rows, so T and N need not be tile multiples.
+ * Needs N * sizeof(out element) % 16 == 0 and a 16-byte aligned `out`; BFP_E_UNSUPPORTED otherwise. */
+int bfp_gemm_bf16_batched(const void* a_bf16, const void* b_bf16, void* out, int out_dtype, int64_t batch, int64_t T, int64_t N,
+                          int64_t K, void* stream);
+
 /* out[T,N] (fp32) += A . B^T: the K-chunked contraction.  The tensor cores truncate (round toward zero) each time a group
  * of products joins the fp32 accumulator, so a long contraction whose partial sums are not exactly representable drifts by
  * about 2^-25 per MMA step (measured: 1.7e-5 relative at K = 12288).  BFP operands normally sum exactly; operands that do

@@ -527,6 +527,7 @@ def _tensor_core_kind(x, w, bfp_args):
     B, m = bfp_args['block_size'], bfp_args['mant_bits']
     want = os.environ.get("BFP_GEMM_KIND", "")
     unstructured = bfp_args['w_sparsity'] == True and bfp_args['sparsity_mode'] == 'unstructured'            # noqa: E712
+    unstructured = unstructured or (bfp_args['in_sparsity'] == True and bfp_args['sparsity_mode'] == 'unstructured')    # noqa: E712
     i8_ok = B in (32, 64, 128) and 1 <= m <= 7 and not unstructured
     bf16_ok = 1 <= m <= 8 and B >= 4 and (B & (B - 1)) == 0
     sp_ok = (bf16_ok and bfp_args['w_sparsity'] == True and bfp_args['sparsity_mode'] == 'structured'     # noqa: E712
@@ -553,8 +554,7 @@ def _tensor_core_eligible(x, w, bfp_args):
     return (x.is_cuda and w.is_cuda and dtype_ok
             and bfp_args['num_format'] == 'bfp' and bfp_args['sparsity_num_format'] == 'bfp'
             and 1 <= bfp_args['mant_bits'] <= 7 and bfp_args['block_size'] in (32, 64, 128)
-            and not (bfp_args['in_sparsity'] == True)                                                # noqa: E712
-            and (bfp_args['w_sparsity'] != True                                                    # noqa: E712
+            and ((bfp_args['w_sparsity'] != True and bfp_args['in_sparsity'] != True)             # noqa: E712
                  or (bfp_args['sparsity_mode'] == 'unstructured' and 0 < bfp_args['sparsity_frac'] and 1 <= bfp_args['mant_bits'] <= 8)
                  or (bfp_args['sparsity_mode'] == 'structured' and 0 < bfp_args['N'] <= bfp_args['M'] <= 64
                      and (bfp_args['first'] == 's' or bfp_args['block_size'] % bfp_args['M'] == 0))))
@@ -588,10 +588,14 @@ def _tc_matmul(x, w, bfp_args):
     wb = pack_bfp_bf16(w.transpose(-1, -2), identifier='w', **bfp_args)
     wb = wb.view(tuple(w.shape[:-2]) + (N, wb.shape[-1])).expand(batch + (N, wb.shape[-1])).reshape(xe.shape[0], N, -1)   # [b, N, Kp]
     out = torch.empty((xe.shape[0], M, N), dtype=torch.float32, device=x.device)
-    L, stream = _lib.lib(), _stream(x.device)
+    L = _lib.lib()
     with _on(x.device):
-        for b in range(xe.shape[0]):
-            _lib.check(L.bfp_gemm_bf16(xb[b].data_ptr(), wb[b].data_ptr(), None, out[b].data_ptr(), M, N, xb.shape[-1], stream))
+        stream = _stream()
+        if N % 4 == 0:                 # one launch for the whole batch (3-D output map: needs 16-byte aligned output rows)
+            _lib.check(L.bfp_gemm_bf16_batched(xb.data_ptr(), wb.data_ptr(), out.data_ptr(), _lib.DT_F32, xe.shape[0], M, N, xb.shape[-1], stream))
+        else:
+            for b in range(xe.shape[0]):
+                _lib.check(L.bfp_gemm_bf16(xb[b].data_ptr(), wb[b].data_ptr(), None, out[b].data_ptr(), M, N, xb.shape[-1], stream))
     return out.view(batch + (M, N))
 
 
@@ -895,7 +899,8 @@ def _packed_activation(x, bfp_args):
     if os.environ.get("BFP_ACT_CACHE", "1") != "1" or torch.cuda.is_current_stream_capturing():
         return pack_bfp_bf16(x, identifier='in', **bfp_args)
     key = (bfp_args['block_size'], bfp_args['mant_bits'], float(bfp_args['epsilon']), bfp_args['in_sparsity'] == True,   # noqa: E712
-           bfp_args['N'], bfp_args['M'], bfp_args['first'], _stream(x.device))        # same stream: the entry is ordered before its reuse
+           bfp_args['N'], bfp_args['M'], bfp_args['first'], bfp_args['sparsity_mode'], float(bfp_args['sparsity_frac']),
+           _stream(x.device))                                                         # same stream: the entry is ordered before its reuse
     hit = _ACT_CACHE.get(x.device)
     if hit is not None and hit[0] is x and hit[1] == x._version and hit[2] == key:
         return hit[3]
@@ -951,8 +956,8 @@ class BFPLinear(torch.nn.Linear):
                 tkind = kind if kind in ('sp', 'bf16') else 'bf16'
                 cached = self._packed_weight(tkind) if determ else None
                 return _BFPLinearTC.apply(input, self.weight, self.bias, self.bfp_args, (lambda: self._packed_weight('bf16')), cached)
-            if not determ:
-                kind = None
+            if not determ or training:
+                kind = None             # training configurations the autograd Function does not cover keep the reference's structure
             y = None
             if kind == 'i8':
                 # inference fast path: pack activations on the fly, cached packed weight, tcgen05 int8 BFP GEMM

@@ -275,6 +275,16 @@ int bfp_gemm_bf16_ex(const void* a_bf16, const void* b_bf16, const float* bias, 
     return gemm_bf16_ex_device(a_bf16, b_bf16, bias, out, out_dtype, T, N, round_up(K, 8), static_cast<cudaStream_t>(stream));
 }
 
+int bfp_gemm_bf16_batched(const void* a_bf16, const void* b_bf16, void* out, int out_dtype, int64_t batch, int64_t T, int64_t N, int64_t K,
+                          void* stream) {
+    if (batch < 0 || T < 0 || N < 0 || K <= 0) return set_error(BFP_E_ARG, "bad argument");
+    if (batch * T * N == 0) return BFP_OK;
+    if (!a_bf16 || !b_bf16 || !out) return set_error(BFP_E_ARG, "null pointer");
+    if (K % 8) return set_error(BFP_E_ARG, "batched operands are contiguous [batch, rows, K]: K must be a multiple of 8");
+    if (int rc = require_device()) return rc;
+    return gemm_bf16_ex_device(a_bf16, b_bf16, nullptr, out, out_dtype, T, N, K, static_cast<cudaStream_t>(stream), 0, batch);
+}
+
 int bfp_gemm_bf16_acc(const void* a_bf16, const void* b_bf16, float* out, int64_t T, int64_t N, int64_t K, void* stream) {
     if (T < 0 || N < 0 || K <= 0) return set_error(BFP_E_ARG, "bad argument");
     if (T * N > 0 && (!a_bf16 || !b_bf16 || !out)) return set_error(BFP_E_ARG, "null pointer");

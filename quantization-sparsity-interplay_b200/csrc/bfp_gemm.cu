@@ -282,6 +282,8 @@ struct ParamsBf16 {
     int out_dtype;              // BFP_DT_F32, or F16 / BF16: accumulator (+ bias) rounded once in the epilogue
     int out_tma;                // 1 = epilogue writes through smem + TMA stores (needs 16-byte aligned rows)
     int accumulate;             // 1 = out += product (fp32, TMA path only): TMA reduce-add instead of a store
+    int batch;                  // > 1: `batch` independent products; operands are stacked along rows ([batch * T, K], [batch * N, K]),
+                                // T / N / tiles_* are per entry, the output map is 3-D (rows clipped per entry); TMA path only
     int T, N;
     int num_k_stages;           // ceil(K / 64)
     int tiles_m, tiles_n;       // tiles_m counts CG * 128 rows
@@ -327,7 +329,7 @@ bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();
     const int unit = (int)blockIdx.x / CG, num_units = (int)gridDim.x / CG;
-    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int tiles_per = p.tiles_m * p.tiles_n, num_tiles = tiles_per * p.batch;
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStagesBf16; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
@@ -353,9 +355,11 @@ bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             int stage = 0; uint32_t phase = 0;
             const uint64_t pol_keep = l2_policy_evict_last();                 // operands are re-read by other tiles; the output is not
             for (int tile = unit; tile < num_tiles; tile += num_units) {
-                const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
-                const int a_row = (tm * CG + (int)rank) * BM;                 // this CTA's 128 X rows
-                const int b_row = tn * TBN + (int)rank * C::kRowsB;           // this CTA's share of the W tile
+                const int bt = tile / tiles_per, rem = tile - bt * tiles_per;
+                const int tm = rem % p.tiles_m, tn = rem / p.tiles_m;
+                // batched: a tile that runs past its entry's rows reads the next entry's (or zero fill); the output map clips them
+                const int a_row = bt * p.T + (tm * CG + (int)rank) * BM;      // this CTA's 128 X rows
+                const int b_row = bt * p.N + tn * TBN + (int)rank * C::kRowsB;   // this CTA's share of the W tile
                 for (int ks = 0; ks < p.num_k_stages; ++ks) {
                     mbar_wait(&bars->empty[stage], phase ^ 1);
                     if (rank == 0) mbar_expect_tx(&bars->full[stage], (uint32_t)CG * kStageBytesBf16);   // both CTAs' bytes land on the leader
@@ -395,7 +399,8 @@ bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const int row_in_tile = q * 32 + lane;
         int buf = 0; uint32_t buf_phase[2] = {0, 0};
         for (int tile = unit; tile < num_tiles; tile += num_units) {
-            const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
+            const int bt = tile / tiles_per, rem = tile - bt * tiles_per;
+            const int tm = rem % p.tiles_m, tn = rem / p.tiles_m;
             mbar_wait(&bars->tmem_full[buf], buf_phase[buf]);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TBN + half * kCols);
@@ -434,7 +439,11 @@ bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) { tma_store_2d_hint(&map_out, sbuf, n0 + c * 64, (tm * CG + (int)rank) * BM + q * 32, pol); tma_store_commit(); }
+                    if (lane == 0) {
+                        if (p.batch > 1) tma_store_3d_hint(&map_out, sbuf, n0 + c * 64, (tm * CG + (int)rank) * BM + q * 32, bt, pol);
+                        else tma_store_2d_hint(&map_out, sbuf, n0 + c * 64, (tm * CG + (int)rank) * BM + q * 32, pol);
+                        tma_store_commit();
+                    }
                 }
                 } else {
 #pragma unroll
@@ -464,7 +473,11 @@ bfp_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) { tma_store_or_add_2d(&map_out, sbuf, n0 + c * 32, (tm * CG + (int)rank) * BM + q * 32, pol, p.accumulate); tma_store_commit(); }
+                    if (lane == 0) {
+                        if (p.batch > 1) tma_store_3d_hint(&map_out, sbuf, n0 + c * 32, (tm * CG + (int)rank) * BM + q * 32, bt, pol);
+                        else tma_store_or_add_2d(&map_out, sbuf, n0 + c * 32, (tm * CG + (int)rank) * BM + q * 32, pol, p.accumulate);
+                        tma_store_commit();
+                    }
                 }
                 }
             } else {
@@ -579,7 +592,7 @@ int gemm_bf16_device(const void* a_bf16, const void* b_bf16, const float* bias, 
 }
 
 int gemm_bf16_ex_device(const void* a_bf16, const void* b_bf16, const float* bias, void* out_v, int out_dtype, int64_t T, int64_t N, int64_t Kp,
-                        cudaStream_t st, int accumulate) {
+                        cudaStream_t st, int accumulate, int64_t batch) {
     using namespace gemm;
     if (T == 0 || N == 0) return BFP_OK;
     if (out_dtype != BFP_DT_F32 && out_dtype != BFP_DT_F16 && out_dtype != BFP_DT_BF16) return set_error(BFP_E_ARG, "bad output dtype");
@@ -590,7 +603,8 @@ int gemm_bf16_ex_device(const void* a_bf16, const void* b_bf16, const float* bia
     if (reinterpret_cast<uintptr_t>(a_bf16) % 16 || reinterpret_cast<uintptr_t>(b_bf16) % 16)
         return set_error(BFP_E_ALIGN, "bf16 operands must be 16-byte aligned");
     ParamsBf16 p;
-    p.bias = bias; p.out = out; p.out_dtype = out_dtype; p.T = (int)T; p.N = (int)N; p.accumulate = accumulate;
+    p.bias = bias; p.out = out; p.out_dtype = out_dtype; p.T = (int)T; p.N = (int)N; p.accumulate = accumulate; p.batch = (int)batch;
+    if (batch < 1 || batch * T > INT32_MAX || batch * N > INT32_MAX) return set_error(BFP_E_ARG, "bad batch count");
     p.num_k_stages = (int)((Kp + 63) / 64);
     // tile: CTA pairs on 256x256 (cta_group::2) unless the problem is a single 128-row or 128-column strip; the knobs
     // gemm_bf16_cta_group (1 / 2) and gemm_bf16_tile_n (128 / 256, single-CTA mode only) force a variant.
@@ -605,14 +619,20 @@ int gemm_bf16_ex_device(const void* a_bf16, const void* b_bf16, const float* bia
     p.tiles_m = (int)((T + BM * cg - 1) / (BM * cg));
     p.tiles_n = (int)((N + tbn - 1) / tbn);
     CUtensorMap map_a, map_b;
-    if (int rc = make_map(&map_a, a_bf16, T, Kp * 2, BM, true)) return rc;
-    if (int rc = make_map(&map_b, b_bf16, N, Kp * 2, tbn / cg, true)) return rc;
+    if (int rc = make_map(&map_a, a_bf16, batch * T, Kp * 2, BM, true)) return rc;          // batched operands are stacked along rows
+    if (int rc = make_map(&map_b, b_bf16, batch * N, Kp * 2, tbn / cg, true)) return rc;
     CUtensorMap map_out = map_a;
-    p.out_tma = ((N * out_es) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 && tuning().gemm_out_tma) ? 1 : 0;
-    if (p.out_tma) if (int rc = make_map_out(&map_out, out, out_dtype, T, N, N * out_es, out_es == 4 ? 32 : 64, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    p.out_tma = ((N * out_es) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 && (tuning().gemm_out_tma || batch > 1)) ? 1 : 0;
+    if (batch > 1) {
+        if (!p.out_tma || bias || accumulate)
+            return set_error(BFP_E_UNSUPPORTED, "batched GEMM: 16-byte aligned output rows (N * element size % 16 == 0), no bias, no accumulation");
+        if (int rc = make_map_out3(&map_out, out, out_dtype, batch, T, N, out_es == 4 ? 32 : 64, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    } else if (p.out_tma) {
+        if (int rc = make_map_out(&map_out, out, out_dtype, T, N, N * out_es, out_es == 4 ? 32 : 64, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    }
     if (accumulate && (!p.out_tma || out_dtype != BFP_DT_F32 || bias))
         return set_error(BFP_E_UNSUPPORTED, "accumulating GEMM: fp32 output with 16-byte aligned rows (N % 4 == 0), no bias");
-    const int units = std::min(p.tiles_m * p.tiles_n, sms / cg);
+    const int units = (int)std::min<int64_t>((int64_t)p.tiles_m * p.tiles_n * batch, sms / cg);
     int rc;
     if (cg == 2) rc = launch_bf16<256, 2>(map_a, map_b, map_out, p, units, st);
     else if (tbn == 256) rc = launch_bf16<256, 1>(map_a, map_b, map_out, p, units, st);

@@ -68,7 +68,7 @@ int gemm_bf16_device(const void* a_bf16, const void* b_bf16, const float* bias, 
                      cudaStream_t st);
 
 int gemm_bf16_ex_device(const void* a_bf16, const void* b_bf16, const float* bias, void* out, int out_dtype, int64_t T, int64_t N, int64_t Kp,
-                        cudaStream_t st, int accumulate = 0);
+                        cudaStream_t st, int accumulate = 0, int64_t batch = 1);
 
 int sp_layout(int64_t rows, int64_t Kp, int64_t* Kc, int64_t* meta_bytes);
 int compress_2to4_bf16_device(const void* w_bf16, int64_t rows, int64_t Kp, int64_t ld_w, void* comp, void* meta, unsigned int* violations,

@@ -179,6 +179,11 @@ __device__ __forceinline__ void tma_store_or_add_2d(const CUtensorMap* map, cons
     if (accumulate) tma_reduce_add_2d(map, smem_src, c0, c1);
     else tma_store_2d_hint(map, smem_src, c0, c1, policy);
 }
+// batched outputs: the third coordinate selects the batch entry, rows beyond that entry's extent are clipped
+__device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;"
+                 ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
@@ -309,6 +314,23 @@ inline int make_map_out(CUtensorMap* map, const void* ptr, int dtype, int64_t ro
     CUresult r = fn(map, dtype == BFP_DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_errorf(BFP_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return BFP_OK;
+}
+
+// 3-D output map of a batched GEMM: `batch` matrices of [rows, cols], contiguous; box = one [box_rows, box_cols] tile of one matrix
+inline int make_map_out3(CUtensorMap* map, const void* ptr, int dtype, int64_t batch, int64_t rows, int64_t cols, int box_cols, int box_rows,
+                         CUtensorMapSwizzle swz) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return set_error(BFP_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    const int es = dtype == BFP_DT_F32 ? 4 : 2;
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)(cols * es), (cuuint64_t)(rows * cols * es)};
+    cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapDataType dt = dtype == BFP_DT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (dtype == BFP_DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+    CUresult r = fn(map, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_errorf(BFP_E_CUDA, "cuTensorMapEncodeTiled (3-D) failed (%d)", (int)r);
     return BFP_OK;
 }
 

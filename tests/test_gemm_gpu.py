@@ -613,3 +613,88 @@ def test_gemm_accumulating_variants_add_exactly(ops, shape, tile):
     if N % 4 == 0:
         o2 = torch.empty(T, N - 1, device="cuda")
         assert L.bfp_gemm_bf16_acc(xs[0].data_ptr(), wd[0].data_ptr(), o2.data_ptr(), T, N - 1, Kp, st) == _lib.E_UNSUPPORTED
+
+
+@pytest.mark.parametrize("mode", ["structured", "unstructured"])
+def test_bfplinear_input_sparsity_on_tensor_cores(ops, mode, monkeypatch):
+    """in_sparsity (activations pruned too): the pack kernel applies the N:M mask to x as well (or composes the global
+    pruning), and the contraction still runs on the tensor cores -- same function as fake-quant + F.linear."""
+    kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=7, block_size=32,
+              in_sparsity=True, w_sparsity=True, N=2, M=4, first="s", sparsity_mode=mode, sparsity_frac=0.4, device="cuda")
+    torch.manual_seed(11)
+    lin = ops.BFPLinear(512, 264, bias=True, **dict(kw)).cuda()
+    x = torch.randn(5, 40, 512, device="cuda")
+    a = ops.unpack_bfp_args(dict(kw))
+    with torch.no_grad():
+        y = lin(x)
+        assert lin._packed_w is not None and lin._packed_w[0][0] == ("sp" if mode == "structured" else "bf16")
+        monkeypatch.setenv("BFP_LINEAR_PATH", "fakequant")
+        y_fq = lin(x)
+        monkeypatch.setenv("BFP_LINEAR_PATH", "tc")
+    xq = ops.float_to_bfp_blocked(x, **a, identifier="in")
+    assert abs(float((xq == 0).float().mean()) - (0.5 if mode == "structured" else 0.4)) < 0.03
+    exact = xq.double() @ ops.float_to_bfp_blocked(lin.weight.detach(), **a, identifier="w").double().t() + lin.bias.detach().double()
+    for got in (y, y_fq):
+        assert float((got.double() - exact).norm() / exact.norm()) <= 1e-5
+
+
+def test_bfplinear_training_with_grad_sparsity_keeps_autograd(ops, monkeypatch):
+    """grad_sparsity is not covered by the tensor-core autograd Function: the module must fall back to the reference's
+    structure (and still produce gradients), never to the inference kernels."""
+    kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=7, block_size=64,
+              w_sparsity=True, grad_sparsity=True, N=2, M=4, first="s", sparsity_mode="structured", device="cuda")
+    torch.manual_seed(2)
+    lin = ops.BFPLinear(256, 128, bias=True, **dict(kw)).cuda()
+    x = torch.randn(64, 256, device="cuda", requires_grad=True)
+    y = lin(x)
+    assert y.requires_grad
+    y.square().sum().backward()
+    gx, gw = x.grad.clone(), lin.weight.grad.clone()
+    x.grad = None; lin.weight.grad = None
+    monkeypatch.setenv("BFP_LINEAR_PATH", "fakequant")
+    lin(x).square().sum().backward()
+    assert torch.allclose(gx, x.grad, rtol=1e-5, atol=1e-6) and torch.allclose(gw, lin.weight.grad, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("shape", [(5, 200, 136, 72), (12, 512, 512, 64), (7, 300, 64, 512), (3, 1, 8, 8), (2, 1000, 520, 264)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16])
+def test_gemm_bf16_batched_exact_products(ops, shape, dt):
+    """bfp_gemm_bf16_batched: every entry of the batch is the exact integer matmul of its own operands -- also when tiles run
+    past an entry's rows (T, N not tile multiples): the 3-D output map clips them, nothing leaks into the next entry."""
+    from qsi_b200 import _lib
+    b, T, N, K = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    xs = torch.randint(-15, 16, (b, T, K), generator=g).to(torch.bfloat16).cuda()
+    ws = torch.randint(-15, 16, (b, N, K), generator=g).to(torch.bfloat16).cuda()
+    out = torch.full((b, T, N), float("nan"), dtype=dt, device="cuda")
+    guard = torch.full((1 << 16,), 7.0, dtype=dt, device="cuda")              # likely right behind `out` in the allocator's block
+    _lib.check(_lib.lib().bfp_gemm_bf16_batched(xs.data_ptr(), ws.data_ptr(), out.data_ptr(), _lib.DT_F32 if dt == torch.float32 else _lib.DT_F16,
+                                                b, T, N, K, torch.cuda.current_stream().cuda_stream))
+    ref = torch.bmm(xs.double(), ws.double().transpose(1, 2))
+    assert torch.equal(out.double(), ref.to(dt).double())
+    assert (guard == 7.0).all()
+
+
+def test_f_matmul_bfp_attention_shapes_one_launch(ops):
+    """GPT-2 style attention products (modeling_gpt2.py:205-207, :295): [B, H, S, D] x [B, H, D, S] and [B, H, S, S] x [B, H, S, D]
+    through F_matmul_bfp -- one batched launch each, equal to the per-entry contraction of the same quantised operands."""
+    from qsi_b200 import _lib
+    kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=7, block_size=64, device="cuda")
+    mm = ops.F_matmul_bfp(**dict(kw))
+    a = ops.unpack_bfp_args(dict(kw))
+    torch.manual_seed(4)
+    q, k, v = (torch.randn(2, 12, 200, 64, device="cuda") for _ in range(3))
+    with torch.no_grad():
+        n0 = _lib.lib().bfp_launch_count()
+        s = mm(q, k.transpose(-1, -2))
+        n1 = _lib.lib().bfp_launch_count()
+        assert n1 - n0 == 3                                                   # two packs + ONE GEMM for 24 heads
+        p = torch.softmax(s / 8.0, dim=-1)
+        o = mm(p, v)
+    qq = ops.float_to_bfp_blocked(q, **a, identifier="in").double()
+    kq = ops.float_to_bfp_blocked(k, **a, identifier="w").double()            # blocked along D, the contraction
+    assert s.shape == (2, 12, 200, 200) and float((s.double() - qq @ kq.transpose(-1, -2)).abs().max()) <= 1e-4
+    pq = ops.float_to_bfp_blocked(p, **a, identifier="in").double()
+    vq = ops.float_to_bfp_blocked(v.transpose(-1, -2).contiguous(), **a, identifier="w").double().transpose(-1, -2)
+    e = pq @ vq
+    assert o.shape == (2, 12, 200, 64) and float((o.double() - e).norm() / e.norm()) <= 1e-5
