@@ -586,7 +586,7 @@ def _tc_matmul(x, w, bfp_args):
     xb = pack_bfp_bf16(xe, identifier='in', **bfp_args).view(xe.shape[0], M, -1)       # [b, M, Kp]
     # the weight is quantised in its OWN shape (a global magnitude threshold must not see broadcast copies), then broadcast
     wb = pack_bfp_bf16(w.transpose(-1, -2), identifier='w', **bfp_args)
-    wb = wb.view(tuple(w.shape[:-2]) + (N, wb.shape[-1])).expand(batch + (N, wb.shape[-1])).reshape(xe.shape[0], N, -1)   # [b, N, Kp]
+    wb = wb.view(tuple(w.shape[:-2]) + (N, wb.shape[-1])).expand(batch + (N, wb.shape[-1])).reshape(xe.shape[0], N, -1).contiguous()   # [b, N, Kp], materialised
     out = torch.empty((xe.shape[0], M, N), dtype=torch.float32, device=x.device)
     L = _lib.lib()
     with _on(x.device):
@@ -973,3 +973,32 @@ class BFPLinear(torch.nn.Linear):
                 return y if input.dtype == torch.float32 else y.to(input.dtype)     # fp32 accumulation, one rounding to the dtype
             return self.linear_op(input, self.weight, self.bias)
         raise NotImplementedError('NumFormat not implemented')
+
+
+class BFPConv1D(torch.nn.Module):
+    """A name the reference's callers import but bfp_ops.py never defines (modeling_gpt2.py:58 imports it; :173-181 and
+    :580-581 construct `BFPConv1D(nf, nx, **bfp_args)`, so the reference's GPT-2 cannot be imported as published).  Provided
+    as the repair SURVEY.md section 8(b) lists: Hugging Face's Conv1D -- weight [nx, nf], y = x @ weight + bias -- with the
+    product taken by F_matmul_bfp (bfp_ops.py:240-245), i.e. both operands BFP-quantised along the contraction exactly like
+    BFPLinear does for the transposed weight; 'fp32' format = plain Conv1D.  The bias is never quantised."""
+
+    def __init__(self, nf, nx, **kwargs):
+        super().__init__()
+        self.bfp_args = unpack_bfp_args(kwargs)
+        self.num_format = self.bfp_args['num_format']
+        self.nf = nf
+        self.weight = torch.nn.Parameter(torch.empty(nx, nf))
+        self.bias = torch.nn.Parameter(torch.zeros(nf))
+        torch.nn.init.normal_(self.weight, std=0.02)
+        self.matmul_op = _get_bfp_op(torch.matmul, 'matmul', self.bfp_args, transpose=True)
+
+    def forward(self, x):
+        size_out = x.size()[:-1] + (self.nf,)
+        x2 = x.reshape(-1, x.size(-1))
+        if self.num_format == 'fp32':
+            y = torch.addmm(self.bias, x2, self.weight)
+        elif self.num_format == 'bfp':
+            y = self.matmul_op(x2, self.weight) + self.bias
+        else:
+            raise NotImplementedError('NumFormat not implemented')
+        return y.view(size_out)

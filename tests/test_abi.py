@@ -85,7 +85,7 @@ def test_python_surface_matches_reference_names():
     names = ["rounding_modes", "round_tensor", "get_exponent", "_convert_blocked_float_to_bfp",
              "_no_sparsity_float_to_bfp", "_unstructured_sparsity", "_structured_N_M_sparsity", "_sparsify", "_quantize",
              "float_to_bfp_blocked", "MxM_pre_processing", "_get_op_name", "_gen_bfp_op", "_get_bfp_op",
-             "unpack_bfp_args", "F_linear_bfp", "F_matmul_bfp", "BFPConv2d", "BFPLinear", "float_to_bfp_tiled"]
+             "unpack_bfp_args", "F_linear_bfp", "F_matmul_bfp", "BFPConv2d", "BFPLinear", "float_to_bfp_tiled", "BFPConv1D"]
     for n in names:
         assert hasattr(bfp_ops, n), n
     # signature parity with the reference where it is present

@@ -698,3 +698,26 @@ def test_f_matmul_bfp_attention_shapes_one_launch(ops):
     vq = ops.float_to_bfp_blocked(v.transpose(-1, -2).contiguous(), **a, identifier="w").double().transpose(-1, -2)
     e = pq @ vq
     assert o.shape == (2, 12, 200, 64) and float((o.double() - e).norm() / e.norm()) <= 1e-5
+
+
+def test_bfpconv1d_repair_equals_bfplinear_on_the_transposed_weight(ops):
+    """BFPConv1D (imported by the reference's GPT-2, never defined there): weight [nx, nf], quantised along the contraction --
+    the same function as BFPLinear holding weight^T; inference on the tensor cores, training through autograd."""
+    kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=7, block_size=64,
+              w_sparsity=True, N=2, M=4, first="s", sparsity_mode="structured", device="cuda")
+    torch.manual_seed(8)
+    c1 = ops.BFPConv1D(384, 256, **dict(kw)).cuda()
+    lin = ops.BFPLinear(256, 384, bias=True, **dict(kw)).cuda()
+    with torch.no_grad():
+        c1.bias.normal_()
+        lin.weight.copy_(c1.weight.t()); lin.bias.copy_(c1.bias)
+    x = torch.randn(4, 50, 256, device="cuda")
+    with torch.no_grad():
+        y, yl = c1(x), lin(x)
+    assert y.shape == (4, 50, 384) and torch.allclose(y, yl, rtol=1e-5, atol=1e-5)
+    xg = x.clone().requires_grad_(True)
+    c1(xg).square().sum().backward()
+    assert xg.grad is not None and c1.weight.grad is not None and c1.weight.grad.shape == (256, 384)
+    plain = ops.BFPConv1D(384, 256).cuda()                                    # default num_format 'fp32': plain Conv1D
+    with torch.no_grad():
+        assert torch.allclose(plain(x), x @ plain.weight + plain.bias, rtol=1e-5, atol=1e-5)
