@@ -602,21 +602,45 @@ def _tc_matmul(x, w, bfp_args):
 def _tc_conv2d(x, w, bias, stride, padding, dilation, groups, bfp_args):
     """F.conv2d(Q_in(x), Q_w(w), ...) as im2col + BFP GEMM (BFPConv2d, bfp_ops.py:247-268): the input is blocked along W and the
     weight along kw exactly like the reference (quantise FIRST, then unfold -- zero padding is applied to the quantised tensor
-    as F.conv2d does)."""
+    as F.conv2d does).  The result is returned in channels-last memory format (a view of the GEMM's [B*L, O] output: no
+    transposing copy; ViT flattens it straight back to [B, L, O])."""
     B, C, H, W = x.shape
     O, _, kh, kw = w.shape
-    xq = pack_bfp_bf16(x, identifier='in', **bfp_args)[:, :W].reshape(B, C, H, W)       # exact bf16 values of Q_in(x)
-    cols = F.unfold(xq, (kh, kw), dilation=dilation, padding=padding, stride=stride)    # [B, C*kh*kw, L]
-    Lout = cols.shape[-1]
     Kc = C * kh * kw
     Kp = -(-Kc // 8) * 8
-    a = torch.zeros((B * Lout, Kp), dtype=torch.bfloat16, device=x.device) if Kp != Kc else torch.empty((B * Lout, Kp), dtype=torch.bfloat16, device=x.device)
-    a.view(B, Lout, Kp)[:, :, :Kc] = cols.transpose(1, 2)
-    wq = _pad_cols(pack_bfp_bf16(w, identifier='w', **bfp_args)[:, :kw].reshape(O, Kc), Kp)
-    y = bfp_linear_bf16(a, wq, bias)                                                    # [B*L, O]
     Ho = (H + 2 * padding[0] - dilation[0] * (kh - 1) - 1) // stride[0] + 1
     Wo = (W + 2 * padding[1] - dilation[1] * (kw - 1) - 1) // stride[1] + 1
-    return y.view(B, Lout, O).permute(0, 2, 1).reshape(B, O, Ho, Wo)
+    xq = pack_bfp_bf16(x, identifier='in', **bfp_args)[:, :W].reshape(B, C, H, W)       # exact bf16 values of Q_in(x)
+    if _is_patch_embedding(x, w, stride, padding, dilation) and Kp == Kc:
+        # kernel == stride: the windows tile the image, im2col is ONE permuting copy
+        a = xq.view(B, C, Ho, kh, Wo, kw).permute(0, 2, 4, 1, 3, 5).reshape(B * Ho * Wo, Kc)
+    else:
+        cols = F.unfold(xq, (kh, kw), dilation=dilation, padding=padding, stride=stride)    # [B, C*kh*kw, L]
+        Lout = cols.shape[-1]
+        a = torch.zeros((B * Lout, Kp), dtype=torch.bfloat16, device=x.device) if Kp != Kc else torch.empty((B * Lout, Kp), dtype=torch.bfloat16, device=x.device)
+        a.view(B, Lout, Kp)[:, :, :Kc] = cols.transpose(1, 2)
+    wq = _pad_cols(pack_bfp_bf16(w, identifier='w', **bfp_args)[:, :kw].reshape(O, Kc), Kp)
+    y = bfp_linear_bf16(a, wq, bias)                                                    # [B*L, O]
+    return y.view(B, Ho, Wo, O).permute(0, 3, 1, 2)
+
+
+def _is_patch_embedding(x, w, stride, padding, dilation):
+    kh, kw = w.shape[-2], w.shape[-1]
+    return (tuple(stride) == (kh, kw) and tuple(padding) == (0, 0) and tuple(dilation) == (1, 1)
+            and x.shape[-2] % kh == 0 and x.shape[-1] % kw == 0)
+
+
+def _im2col_pays(x, w, stride, padding, dilation):
+    """Measured (tools/bench_conv.py, profiles/r01_conv_paths.json): with torch's unfold / transposing copies as the im2col,
+    the tensor-core path only wins where im2col is a single permuting copy -- patch embeddings (kernel == stride, ViT).  For
+    overlapping windows (3x3, 7x7) and 1x1 convolutions over NCHW the fused quantiser + the library convolution -- the
+    reference's own structure, exact here too because BFP values fit TF32 -- is 5-10x faster, so that is the default.
+    BFP_CONV_IM2COL_MAX_EXPANSION=<kh*kw / (sh*sw) limit> forces the im2col path for other shapes (tests, experiments)."""
+    limit = os.environ.get("BFP_CONV_IM2COL_MAX_EXPANSION")
+    if limit is not None:
+        return w.shape[-2] * w.shape[-1] <= float(limit) * stride[0] * stride[1]
+    return (_is_patch_embedding(x, w, stride, padding, dilation) and w.shape[-2] * w.shape[-1] > 1      # 1x1: the library wins (0.32 vs 0.65 ms)
+            and (w.shape[1] * w.shape[2] * w.shape[3]) % 8 == 0)
 
 
 def _pair(v):
@@ -675,7 +699,7 @@ def _gen_bfp_op(op, name, bfp_args, transpose=False):
                 return bfp_linear_bf16(pack_bfp_bf16(x, identifier='in', **bfp_args), pack_bfp_bf16(w, identifier='w', **bfp_args),
                                        args[0] if args else None, out_shape=tuple(x.shape[:-1]) + (w.shape[0],)).to(x.dtype)
             if op is F.conv2d and x.dim() == 4 and w.dim() == 4 and not kwargs and len(args) == 5 and args[4] == 1 \
-                    and not isinstance(args[2], str):
+                    and not isinstance(args[2], str) and _im2col_pays(x, w, _pair(args[1]), _pair(args[2]), _pair(args[3])):
                 return _tc_conv2d(x, w, args[0], _pair(args[1]), _pair(args[2]), _pair(args[3]), 1, bfp_args).to(x.dtype)
         x, w = NewOpIn.apply(x, w)
         out = op(x, w, *args, **kwargs)

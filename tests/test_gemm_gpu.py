@@ -428,8 +428,14 @@ def test_bfpconv2d_im2col_tensor_core_path(ops, cfg, w_sparse, monkeypatch):
     conv = ops.BFPConv2d(cfg["C"], cfg["O"], cfg["k"], cfg["stride"], cfg["padding"], cfg["dilation"], 1, True, **dict(kw)).cuda()
     x = torch.randn(cfg["B"], cfg["C"], cfg["H"], cfg["W"], device="cuda")
     a = ops.unpack_bfp_args(dict(kw))
+    patch = cfg["k"] == cfg["stride"]
+    if not patch:
+        monkeypatch.setenv("BFP_CONV_IM2COL_MAX_EXPANSION", "1e9")                  # overlapping windows: im2col is opt-in
+    from qsi_b200 import _lib
     with torch.no_grad():
+        n0 = _lib.lib().bfp_launch_count()
         y = conv(x)
+        assert _lib.lib().bfp_launch_count() - n0 == 3                              # two packs + one tcgen05 GEMM
         monkeypatch.setenv("BFP_LINEAR_PATH", "fakequant")
         y_fq = conv(x)                                                              # the reference's structure (cuDNN on fake-quant)
         monkeypatch.setenv("BFP_LINEAR_PATH", "tc")
