@@ -207,6 +207,12 @@ int bfp_gemm_bf16(const void* a_bf16, const void* b_bf16, const float* bias, flo
 /* ... with the output dtype chosen: BFP_DT_F32, or BFP_DT_F16 / BFP_DT_BF16 (accumulator + bias rounded once in the epilogue). */
 int bfp_gemm_bf16_ex(const void* a_bf16, const void* b_bf16, const float* bias, void* out, int out_dtype, int64_t T, int64_t N,
                      int64_t K, void* stream);
+/* Transposed copy of a 16-bit matrix with zero padding: out[c][r] = in[r][c] for r < rows, c < cols; out columns
+ * rows .. ld_out-1 are zero.  in has row stride ld_in (>= cols), out [cols, ld_out] with ld_out even and >= rows.  The
+ * backward contractions of the BFP linear (bfp_ops.py:168-185: dgrad over N, wgrad over T) take their operands from the
+ * packed bf16 tensors through this. */
+int bfp_transpose_pad_16(const void* in, void* out, int64_t rows, int64_t cols, int64_t ld_in, int64_t ld_out, void* stream);
+
 /* `batch` independent products out[b] = A[b] . B[b]^T in ONE launch (F_matmul_bfp on [..., M, K] x [..., K, N] operands,
  * bfp_ops.py:240-245: GPT-2 style attention matmuls, modeling_gpt2.py:205-207): A [batch, T, K], B [batch, N, K] bf16
  * contiguous (K a multiple of 8), out [batch, T, N] of out_dtype.  The operands are read as stacked rows through 2-D tensor

@@ -60,6 +60,7 @@ SIGNATURES = {
     "bfp_quantize_pack_bf16": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _i32, _u64, _u64, _i32, _i32, _i32, _vp]),
     "bfp_gemm_bf16": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "bfp_gemm_bf16_ex": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp]),
+    "bfp_transpose_pad_16": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _vp]),
     "bfp_gemm_bf16_batched": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _i64, _vp]),
     "bfp_gemm_bf16_acc": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "bfp_gemm_bf16_sp_acc": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),

@@ -757,6 +757,19 @@ def _pad_cols(t, cols):
     return out
 
 
+def _transpose_pad(t, rows, cols, ld_out):
+    """bf16 / fp16 t [>= rows, >= cols] (row-major, any row stride) -> contiguous [cols, ld_out] = t[:rows, :cols]^T, zero-padded
+    (csrc/bfp_pack.cu transpose16_kernel: torch's transposing copy runs at about a quarter of this kernel's bandwidth)."""
+    assert t.dim() == 2 and t.stride(1) == 1 and t.element_size() == 2 and ld_out % 2 == 0 and ld_out >= rows
+    out = torch.empty((cols, ld_out), dtype=t.dtype, device=t.device)
+    if rows and cols:
+        with _on(t.device):
+            _lib.check(_lib.lib().bfp_transpose_pad_16(t.data_ptr(), out.data_ptr(), rows, cols, t.stride(0), ld_out, _stream()))
+    elif out.numel():
+        out.zero_()
+    return out
+
+
 class _BFPLinearTC(torch.autograd.Function):
     """BFPLinear forward AND backward on the tensor cores.  Same function as the reference's
     new_op (bfp_ops.py:160-192): forward F.linear(Q_in(x), Q_w(w), bias); backward = F.linear's backward applied to the
@@ -790,15 +803,15 @@ class _BFPLinearTC(torch.autograd.Function):
         grad_x = grad_w = grad_b = None
         if need_x:
             wb = ctx.wb_dense() if callable(ctx.wb_dense) else ctx.wb_dense     # dgrad contracts over N: the dense form
-            wbT = _pad_cols(wb[:, :K].t(), Np)                                  # [K, Np]
+            wbT = _transpose_pad(wb, N, K, Np)                                  # [K, Np]
             grad_x = bfp_linear_bf16(gq, wbT).view(ctx.x_shape)
         if need_w:
             Tp = -(-T // 8) * 8
-            gqT = _pad_cols(gq[:, :N].t(), Tp)                                  # [N, Tp]
-            xbT = _pad_cols(xb[:, :K].t(), Tp)                                  # [K, Tp]
+            gqT = _transpose_pad(gq, T, N, Tp)                                  # [N, Tp]
+            xbT = _transpose_pad(xb, T, K, Tp)                                  # [K, Tp]
             grad_w = bfp_linear_bf16(gqT, xbT)                                  # [N, K]
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            grad_b = gq[:, :N].float().sum(0)
+            grad_b = gq[:, :N].sum(0, dtype=torch.float32)
         return grad_x, grad_w, grad_b, None, None, None
 
 

@@ -275,6 +275,13 @@ int bfp_gemm_bf16_ex(const void* a_bf16, const void* b_bf16, const float* bias, 
     return gemm_bf16_ex_device(a_bf16, b_bf16, bias, out, out_dtype, T, N, round_up(K, 8), static_cast<cudaStream_t>(stream));
 }
 
+int bfp_transpose_pad_16(const void* in, void* out, int64_t rows, int64_t cols, int64_t ld_in, int64_t ld_out, void* stream) {
+    if (rows < 0 || cols < 0) return set_error(BFP_E_ARG, "bad argument");
+    if (rows * cols > 0 && (!in || !out)) return set_error(BFP_E_ARG, "null pointer");
+    if (int rc = require_device()) return rc;
+    return transpose16_device(in, out, rows, cols, ld_in, ld_out, static_cast<cudaStream_t>(stream));
+}
+
 int bfp_gemm_bf16_batched(const void* a_bf16, const void* b_bf16, void* out, int out_dtype, int64_t batch, int64_t T, int64_t N, int64_t K,
                           void* stream) {
     if (batch < 0 || T < 0 || N < 0 || K <= 0) return set_error(BFP_E_ARG, "bad argument");

@@ -81,6 +81,7 @@ int gemm_bf16_sp_multi_device(const void* x_bf16, const void* w_comp, const void
 size_t int_workspace_bytes(int64_t C);
 int int_quantize_device(const void* in, float* out, int64_t A, int64_t C, int64_t inner, int dtype, int bits, void* workspace, cudaStream_t s);
 int int_quantize_split3_device(const void* in, void* out_bf16, int64_t A, int64_t C, int64_t kseg, int dtype, int bits, void* workspace, cudaStream_t s);
+int transpose16_device(const void* in, void* out, int64_t R, int64_t C, int64_t ld_in, int64_t ld_out, cudaStream_t s);
 int int_quantize_nm_device(const void* in, float* out, int64_t C, int64_t K, int dtype, int bits, int N, int order, cudaStream_t s);
 size_t unstructured_workspace_bytes();
 int unstructured_device(const void* in, void* out, int64_t n, int dtype, unsigned long long k, void* workspace, cudaStream_t s);

@@ -315,4 +315,55 @@ int unpack_device(const int8_t* mant, const float* scale_t, float* out, int64_t 
     return check_launch("unpack_kernel");
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// 16-bit transpose with zero padding: in [R, C] (row stride ld_in) -> out [C, ld_out], out[c][r] = in[r][c], columns R .. ld_out-1
+// zero.  The backward contractions of the BFP linear run over T (wgrad) and N (dgrad): their operands are the transposes
+// of the packed bf16 tensors (bfp_ops._BFPLinearTC.backward).  64 x 64 tiles through shared memory, 128-byte rows both ways.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) transpose16_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int64_t R, int64_t C,
+                                                          int64_t ld_in, int64_t ld_out) {
+    __shared__ uint16_t tile[64][66];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.y * 64, c0 = (int64_t)blockIdx.x * 64;
+    const bool vec_in = (ld_in % 2 == 0) && (reinterpret_cast<uintptr_t>(in) % 4 == 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = ty + 8 * i;
+        const int64_t gr = r0 + r, gc = c0 + 2 * tx;
+        uint32_t v = 0;
+        if (gr < R) {
+            if (vec_in && gc + 1 < C) v = *reinterpret_cast<const uint32_t*>(in + gr * ld_in + gc);
+            else {
+                if (gc < C) v = in[gr * ld_in + gc];
+                if (gc + 1 < C) v |= (uint32_t)in[gr * ld_in + gc + 1] << 16;
+            }
+        }
+        tile[r][2 * tx] = (uint16_t)(v & 0xffffu);
+        tile[r][2 * tx + 1] = (uint16_t)(v >> 16);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = ty + 8 * i;
+        const int64_t gc = c0 + c, gr = r0 + 2 * tx;                  // out row gc, out columns gr, gr + 1 (ld_out is even)
+        if (gc < C && gr < ld_out) {
+            const uint32_t v = (uint32_t)tile[2 * tx][c] | ((uint32_t)tile[2 * tx + 1][c] << 16);   // rows >= R were loaded as zero
+            *reinterpret_cast<uint32_t*>(out + gc * ld_out + gr) = v;
+        }
+    }
+}
+}  // namespace
+
+int transpose16_device(const void* in, void* out, int64_t R, int64_t C, int64_t ld_in, int64_t ld_out, cudaStream_t s) {
+    if (R == 0 || C == 0) return BFP_OK;
+    if (ld_out % 2 || ld_out < R || ld_in < C) return set_error(BFP_E_ARG, "transpose: ld_out must be even and >= R, ld_in >= C");
+    if (reinterpret_cast<uintptr_t>(out) % 4) return set_error(BFP_E_ALIGN, "transpose: out must be 4-byte aligned");
+    const int64_t gx = (C + 63) / 64, gy = (ld_out + 63) / 64;
+    if (gy > 65535) return set_error(BFP_E_ARG, "transpose: too many rows");
+    transpose16_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, s>>>(static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), R, C, ld_in, ld_out);
+    count_launch();
+    return check_launch("transpose16_kernel");
+}
+
 }  // namespace bfp

@@ -727,3 +727,14 @@ def test_bfpconv1d_repair_equals_bfplinear_on_the_transposed_weight(ops):
     plain = ops.BFPConv1D(384, 256).cuda()                                    # default num_format 'fp32': plain Conv1D
     with torch.no_grad():
         assert torch.allclose(plain(x), x @ plain.weight + plain.bias, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(4096, 4096, 4096), (100, 37, 40), (1, 8, 8), (65, 129, 136), (1000, 520, 520), (63, 64, 70)])
+def test_transpose_pad_16(ops, shape):
+    """bfp_transpose_pad_16: out[c][r] = in[r][c] with zero padding, for strided inputs and ragged edges."""
+    R, C, ld_in = shape
+    ld_out = -(-R // 8) * 8
+    g = torch.Generator().manual_seed(R + C)
+    src = torch.randn(R, ld_in, generator=g).to(torch.bfloat16).cuda()
+    out = ops._transpose_pad(src, R, C, ld_out)
+    assert out.shape == (C, ld_out) and torch.equal(out[:, :R], src[:, :C].t()) and (out[:, R:] == 0).all()
