@@ -148,6 +148,7 @@ def test_bfplinear_int_format_on_tensor_cores(ops, cfg, bits, monkeypatch):
     cores (2:4-compressed when the weight is pruned 2:4) against the fp64 contraction of the same fake-quantised operands,
     and against the reference's structure (fake-quant + F.linear)."""
     mode, first = cfg
+    monkeypatch.setenv("BFP_INT_LINEAR", "tc")                    # opt-in: the default keeps the library GEMM (bit-identical logits)
     kw = dict(num_format="bfp", sparsity_num_format="int", rounding_mode="determ", epsilon=1e-8, mant_bits=bits, block_size=64,
               w_sparsity=mode != "none", N=2, M=4, first=first, sparsity_mode="structured" if mode == "none" else mode,
               sparsity_frac=0.5, device="cuda")
@@ -172,3 +173,19 @@ def test_bfplinear_int_format_on_tensor_cores(ops, cfg, bits, monkeypatch):
         assert got.dtype == torch.float32 and got.shape == (2, 77, 520)
         assert float((got.double() - exact).norm() / exact.norm()) <= 1e-5
     assert float((y.double() - exact).norm() / exact.norm()) <= 2e-6
+
+
+def test_bfplinear_int_format_default_is_the_library_gemm(ops):
+    """Without BFP_INT_LINEAR=tc the INT-format module keeps the reference's structure (fused quantiser + F.linear): its output is
+    bit-identical to F.linear on the fake-quantised operands, which is what keeps whole-model logits equal to the reference's."""
+    kw = dict(num_format="bfp", sparsity_num_format="int", rounding_mode="determ", epsilon=1e-8, mant_bits=8, block_size=64,
+              w_sparsity=True, N=2, M=4, first="s", sparsity_mode="structured", device="cuda")
+    torch.manual_seed(3)
+    lin = ops.BFPLinear(512, 256, bias=True, **dict(kw)).cuda()
+    x = torch.randn(4, 33, 512, device="cuda")
+    a = ops.unpack_bfp_args(dict(kw))
+    with torch.no_grad():
+        y = lin(x)
+        ref = torch.nn.functional.linear(ops.float_to_bfp_blocked(x, **a, identifier="in"),
+                                         ops.float_to_bfp_blocked(lin.weight.detach(), **a, identifier="w"), lin.bias)
+    assert lin._packed_w is None and torch.equal(y, ref)

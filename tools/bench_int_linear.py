@@ -3,6 +3,7 @@
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+os.environ["BFP_INT_LINEAR"] = "tc"        # the path under test is opt-in (see bfp_ops._int_tc_eligible)
 import torch
 from qsi_b200 import bfp_ops as ours
 from _refload import load_reference
