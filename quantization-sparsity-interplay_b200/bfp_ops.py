@@ -575,26 +575,28 @@ def _tc_inference_ok(x, w, bfp_args):
 
 def _tc_matmul(x, w, bfp_args):
     """torch.matmul(Q_in(x), Q_w(w^T)^T) for x [..., M, K], w [..., K, N] (F_matmul_bfp, bfp_ops.py:240-245 with transpose=True):
-    one GEMM when w is a matrix, one per broadcast batch entry otherwise."""
+    one GEMM when w is a matrix, ONE batched launch over the broadcast batch otherwise (bfp_gemm_bf16_batched)."""
     K, N = w.shape[-2], w.shape[-1]
     if w.dim() == 2:
         wb = pack_bfp_bf16(w.t(), identifier='w', **bfp_args)                          # [N, Kp], blocked along K
         return bfp_linear_bf16(pack_bfp_bf16(x, identifier='in', **bfp_args), wb, None, out_shape=tuple(x.shape[:-1]) + (N,))
     batch = torch.broadcast_shapes(x.shape[:-2], w.shape[:-2])
-    xe = x.expand(batch + x.shape[-2:]).reshape((-1,) + tuple(x.shape[-2:]))
+    nb = math.prod(batch)
     M = x.shape[-2]
-    xb = pack_bfp_bf16(xe, identifier='in', **bfp_args).view(xe.shape[0], M, -1)       # [b, M, Kp]
-    # the weight is quantised in its OWN shape (a global magnitude threshold must not see broadcast copies), then broadcast
+    # both operands are quantised in their OWN shape (a global magnitude threshold must not see broadcast copies), then
+    # broadcast and materialised as contiguous [b, rows, Kp] stacks (no copy when nothing is broadcast)
+    xb = pack_bfp_bf16(x, identifier='in', **bfp_args)
+    xb = xb.view(tuple(x.shape[:-2]) + (M, xb.shape[-1])).expand(batch + (M, xb.shape[-1])).reshape(nb, M, -1).contiguous()
     wb = pack_bfp_bf16(w.transpose(-1, -2), identifier='w', **bfp_args)
-    wb = wb.view(tuple(w.shape[:-2]) + (N, wb.shape[-1])).expand(batch + (N, wb.shape[-1])).reshape(xe.shape[0], N, -1).contiguous()   # [b, N, Kp], materialised
-    out = torch.empty((xe.shape[0], M, N), dtype=torch.float32, device=x.device)
+    wb = wb.view(tuple(w.shape[:-2]) + (N, wb.shape[-1])).expand(batch + (N, wb.shape[-1])).reshape(nb, N, -1).contiguous()
+    out = torch.empty((nb, M, N), dtype=torch.float32, device=x.device)
     L = _lib.lib()
     with _on(x.device):
         stream = _stream()
         if N % 4 == 0:                 # one launch for the whole batch (3-D output map: needs 16-byte aligned output rows)
-            _lib.check(L.bfp_gemm_bf16_batched(xb.data_ptr(), wb.data_ptr(), out.data_ptr(), _lib.DT_F32, xe.shape[0], M, N, xb.shape[-1], stream))
+            _lib.check(L.bfp_gemm_bf16_batched(xb.data_ptr(), wb.data_ptr(), out.data_ptr(), _lib.DT_F32, nb, M, N, xb.shape[-1], stream))
         else:
-            for b in range(xe.shape[0]):
+            for b in range(nb):
                 _lib.check(L.bfp_gemm_bf16(xb[b].data_ptr(), wb[b].data_ptr(), None, out[b].data_ptr(), M, N, xb.shape[-1], stream))
     return out.view(batch + (M, N))
 
