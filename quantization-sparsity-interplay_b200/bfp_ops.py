@@ -569,7 +569,8 @@ def _tensor_core_eligible(x, w, bfp_args):
 # fp32 accumulation in TMEM.
 # ---------------------------------------------------------------------------------------------------------------
 def _tc_inference_ok(x, w, bfp_args):
-    return (bfp_args['rounding_mode'] == rounding_modes.DETERM and not (torch.is_grad_enabled() and (x.requires_grad or w.requires_grad))
+    return ((bfp_args['rounding_mode'] == rounding_modes.DETERM or (x.dtype == torch.float32 and w.dtype == torch.float32))
+            and not (torch.is_grad_enabled() and (x.requires_grad or w.requires_grad))
             and _tensor_core_kind(x, w, bfp_args) is not None and 1 <= bfp_args['mant_bits'] <= 8)
 
 
@@ -983,6 +984,19 @@ class BFPLinear(torch.nn.Linear):
         self._packed_w = hit
         return hit[1]
 
+    def _stochastic_forward(self, input):
+        """Inference with rounding_mode='stoc' -- what every script of the reference sets (bfp_config.yaml:4) -- on the tensor
+        cores: like the reference, BOTH operands are re-quantised with fresh uniforms on every call (no weight cache, no
+        activation cache), then contracted as exact-bf16 operands; a 2:4-pruned weight is re-compressed per call (the mask
+        is applied before rounding in either order, so the pattern holds whatever the draw).  fp32 modules only: with
+        half-precision inputs the reference's quantiser returns fp32 and the model changes dtype."""
+        xb = pack_bfp_bf16(input, identifier='in', **self.bfp_args)
+        wb = pack_bfp_bf16(self.weight.detach(), identifier='w', **self.bfp_args)
+        out_shape = tuple(input.shape[:-1]) + (self.out_features,)
+        if _tensor_core_kind(input, self.weight, self.bfp_args) == 'sp':
+            return bfp_linear_bf16_sp(xb, compress_2to4_bf16(wb, check=False), self.bias, out_shape=out_shape)
+        return bfp_linear_bf16(xb, wb, self.bias, out_shape=out_shape)
+
     def forward(self, input):
         if self.num_format == 'fp32':
             return F.linear(input, self.weight, self.bias)
@@ -1000,6 +1014,9 @@ class BFPLinear(torch.nn.Linear):
                 tkind = kind if kind in ('sp', 'bf16') else 'bf16'
                 cached = self._packed_weight(tkind) if determ else None
                 return _BFPLinearTC.apply(input, self.weight, self.bias, self.bfp_args, (lambda: self._packed_weight('bf16')), cached)
+            if (not determ and not training and input.dtype == torch.float32 and self.bfp_args['mant_bits'] <= 8
+                    and _tensor_core_kind(input, self.weight, self.bfp_args) is not None):
+                return self._stochastic_forward(input)
             if not determ or training:
                 kind = None             # training configurations the autograd Function does not cover keep the reference's structure
             y = None

@@ -738,3 +738,32 @@ def test_transpose_pad_16(ops, shape):
     src = torch.randn(R, ld_in, generator=g).to(torch.bfloat16).cuda()
     out = ops._transpose_pad(src, R, C, ld_out)
     assert out.shape == (C, ld_out) and torch.equal(out[:, :R], src[:, :C].t()) and (out[:, R:] == 0).all()
+
+
+@pytest.mark.parametrize("w_sparse", [True, False])
+def test_bfplinear_stochastic_inference_on_tensor_cores(ops, w_sparse, monkeypatch):
+    """rounding_mode='stoc' at inference (what the reference's scripts set): both operands are re-quantised per call with fresh
+    uniforms and contracted on the tensor cores.  Same distribution as the fake-quant path: fresh draws per call, the 2:4 mask
+    exact, the mean over draws converging to the same limit with the same per-draw error."""
+    from qsi_b200 import _lib
+    kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="stoc", epsilon=1e-8, mant_bits=5, block_size=64,
+              w_sparsity=w_sparse, N=2, M=4, first="s", sparsity_mode="structured", device="cuda")
+    torch.manual_seed(6)
+    lin = ops.BFPLinear(512, 256, bias=True, **dict(kw)).cuda()
+    x = torch.randn(3, 40, 512, device="cuda")
+    with torch.no_grad():
+        n0 = _lib.lib().bfp_launch_count()
+        y0 = lin(x)
+        assert _lib.lib().bfp_launch_count() - n0 == (4 if w_sparse else 3)   # pack x, pack w, (compress,) one tcgen05 GEMM
+        assert lin._packed_w is None                                           # nothing cached: every call re-quantises the weight
+        ys = torch.stack([lin(x) for _ in range(64)])
+        monkeypatch.setenv("BFP_LINEAR_PATH", "fakequant")
+        fs = torch.stack([lin(x) for _ in range(64)])
+        monkeypatch.setenv("BFP_LINEAR_PATH", "tc")
+    assert y0.shape == (3, 40, 256) and not torch.equal(ys[0], ys[1])
+    a = ops.unpack_bfp_args(dict(kw, rounding_mode="determ"))
+    w_lim = ops._structured_N_M_sparsity(lin.weight.detach(), "cuda", 2, 4) if w_sparse else lin.weight.detach()
+    limit = x @ w_lim.t() + lin.bias.detach()                                  # stochastic rounding is unbiased around this
+    e_tc, e_fq = (ys[0] - limit).norm() / limit.norm(), (fs[0] - limit).norm() / limit.norm()
+    m_tc, m_fq = (ys.mean(0) - limit).norm() / limit.norm(), (fs.mean(0) - limit).norm() / limit.norm()
+    assert 0.7 < float(e_tc / e_fq) < 1.4 and float(m_tc) < 0.35 * float(e_tc) and float(m_fq) < 0.35 * float(e_fq)

@@ -56,15 +56,15 @@ def main():
     ap.add_argument("--dtype", default="", choices=["", "fp32", "fp16", "bf16"])
     ap.add_argument("--layers", type=int, default=0); ap.add_argument("--batch", type=int, default=0); ap.add_argument("--seq", type=int, default=512)
     ap.add_argument("--mant", type=int, default=0); ap.add_argument("--out", default="")
-    ap.add_argument("--format", default="bfp", choices=["bfp", "int"]); ap.add_argument("--mode", default="structured", choices=["structured", "unstructured"]); ap.add_argument("--first", default="s", choices=["s", "q"])
+    ap.add_argument("--rounding", default="determ", choices=["determ", "stoc"]); ap.add_argument("--format", default="bfp", choices=["bfp", "int"]); ap.add_argument("--mode", default="structured", choices=["structured", "unstructured"]); ap.add_argument("--first", default="s", choices=["s", "q"])
     a = ap.parse_args()
     dev = "cuda"
     m = a.mant or (5 if a.kind == "vit" else 7)            # config 0: HBFP8, config 3: BFP6
     dtn = a.dtype or ("fp16" if a.kind == "llama" else "fp32")
     tdt = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}[dtn]
-    kw = dict(num_format="bfp", sparsity_num_format=a.format, rounding_mode="determ", epsilon=1e-8, mant_bits=m, weight_mant_bits=15,
+    kw = dict(num_format="bfp", sparsity_num_format=a.format, rounding_mode=a.rounding, epsilon=1e-8, mant_bits=m, weight_mant_bits=15,
               block_size=64, w_sparsity=True, N=2, M=4, first=a.first, sparsity_mode=a.mode, sparsity_frac=0.5, device=dev)
-    res = {"model": a.kind, "format": a.format, "mant_bits": m, "block": 64, "sparsity": ("2:4" if a.mode == "structured" else "unstructured 50%") + (" s->q" if a.first == "s" else " q->s"), "dtype": dtn}
+    res = {"model": a.kind, "rounding": a.rounding, "format": a.format, "mant_bits": m, "block": 64, "sparsity": ("2:4" if a.mode == "structured" else "unstructured 50%") + (" s->q" if a.first == "s" else " q->s"), "dtype": dtn}
     outs = {}
     ref = load_reference()
     for tag, impl in (("ours", ours), ("reference", ref)):
@@ -90,6 +90,12 @@ def main():
         outs[tag] = y.float()
         res[tag] = {"swapped_modules": n, "forward_s": dt, "logits_shape": list(y.shape), "finite": bool(torch.isfinite(y).all())}
         print(tag, res[tag], flush=True)
+        if a.rounding == "stoc":
+            # stochastic rounding: two forwards of the SAME implementation differ by their draws; that spread is the yardstick
+            with torch.no_grad():
+                y2 = model(**inp).logits.float()
+            res[tag]["rel_diff_between_two_of_its_own_forwards"] = float((y2 - outs[tag]).norm() / outs[tag].norm())
+            print(tag, "self spread:", res[tag]["rel_diff_between_two_of_its_own_forwards"], flush=True)
         del model
     if "reference" in outs:
         d = (outs["ours"] - outs["reference"])
