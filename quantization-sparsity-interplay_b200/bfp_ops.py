@@ -551,6 +551,9 @@ def _tensor_core_eligible(x, w, bfp_args):
     if training and os.environ.get("BFP_TRAIN_PATH", "tc") != "tc":
         return False
     dtype_ok = x.dtype == w.dtype and (x.dtype == torch.float32 or (x.dtype in (torch.float16, torch.bfloat16) and not training))
+    if bfp_args['rounding_mode'] != rounding_modes.DETERM and not training:
+        # the stochastic quantiser promotes every operand to fp32: any mix of float dtypes is one case
+        dtype_ok = x.dtype in _DT and w.dtype in _DT
     return (x.is_cuda and w.is_cuda and dtype_ok
             and bfp_args['num_format'] == 'bfp' and bfp_args['sparsity_num_format'] == 'bfp'
             and 1 <= bfp_args['mant_bits'] <= 7 and bfp_args['block_size'] in (32, 64, 128)
@@ -988,8 +991,10 @@ class BFPLinear(torch.nn.Linear):
         """Inference with rounding_mode='stoc' -- what every script of the reference sets (bfp_config.yaml:4) -- on the tensor
         cores: like the reference, BOTH operands are re-quantised with fresh uniforms on every call (no weight cache, no
         activation cache), then contracted as exact-bf16 operands; a 2:4-pruned weight is re-compressed per call (the mask
-        is applied before rounding in either order, so the pattern holds whatever the draw).  fp32 modules only: with
-        half-precision inputs the reference's quantiser returns fp32 and the model changes dtype."""
+        is applied before rounding in either order, so the pattern holds whatever the draw).  Half-precision modules (the
+        reference's LLaMA scripts): the reference's stochastic quantiser returns fp32 tensors, so
+        its F.linear is an fp32 SGEMM with an fp32 result -- same here, fp32 out; only bias-free modules (a half bias
+        would not type-check against fp32 operands in the reference either)."""
         xb = pack_bfp_bf16(input, identifier='in', **self.bfp_args)
         wb = pack_bfp_bf16(self.weight.detach(), identifier='w', **self.bfp_args)
         out_shape = tuple(input.shape[:-1]) + (self.out_features,)
@@ -1014,7 +1019,9 @@ class BFPLinear(torch.nn.Linear):
                 tkind = kind if kind in ('sp', 'bf16') else 'bf16'
                 cached = self._packed_weight(tkind) if determ else None
                 return _BFPLinearTC.apply(input, self.weight, self.bias, self.bfp_args, (lambda: self._packed_weight('bf16')), cached)
-            if (not determ and not training and input.dtype == torch.float32 and self.bfp_args['mant_bits'] <= 8
+            if (not determ and not training and self.bfp_args['mant_bits'] <= 8
+                    and (self.bias is None or (input.dtype == torch.float32 and self.weight.dtype == torch.float32))
+                    # ^ stoc promotes both operands to fp32 and returns fp32: a half-precision bias would not type-check
                     and _tensor_core_kind(input, self.weight, self.bfp_args) is not None):
                 return self._stochastic_forward(input)
             if not determ or training:

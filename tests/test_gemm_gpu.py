@@ -767,3 +767,44 @@ def test_bfplinear_stochastic_inference_on_tensor_cores(ops, w_sparse, monkeypat
     e_tc, e_fq = (ys[0] - limit).norm() / limit.norm(), (fs[0] - limit).norm() / limit.norm()
     m_tc, m_fq = (ys.mean(0) - limit).norm() / limit.norm(), (fs.mean(0) - limit).norm() / limit.norm()
     assert 0.7 < float(e_tc / e_fq) < 1.4 and float(m_tc) < 0.35 * float(e_tc) and float(m_fq) < 0.35 * float(e_fq)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16, torch.bfloat16])
+def test_pack_bf16_stochastic_equals_fake_quant_with_the_same_draws(ops, dt):
+    """With the same Philox (seed, offset) the packed bf16 operand is the stochastic fake-quant result value for value (fp32
+    for every input dtype, like the reference's torch.rand promotion) -- so the tensor-core path samples the same
+    distribution as the fused quantiser that the statistical parity tests pin."""
+    from qsi_b200 import _lib
+    for shape, (m, B), first, sparse in itertools.product([(64, 1024), (37, 200)], [(7, 64), (5, 32), (3, 16)], ["s", "q"], [True, False]):
+        g = torch.Generator().manual_seed(m + B)
+        x = (torch.randn(*shape, generator=g) * 0.05).to(dt).cuda()
+        args = ops.unpack_bfp_args(dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="stoc", epsilon=1e-8, mant_bits=m,
+                                        block_size=B, w_sparsity=sparse, N=2, M=4, first=first, sparsity_mode="structured", device="cuda"))
+        order = _lib.ORDER_QUANT_ONLY if not sparse else (_lib.ORDER_SPARSIFY_QUANT if first == "s" else _lib.ORDER_QUANT_SPARSIFY)
+        ph = (1234, 77)
+        fq = ops._fused(x, order, block_size=B, mant_bits=m, epsilon=1e-8, rounding_mode="stoc", N=2, M=4, philox=ph)
+        pb = ops.pack_bfp_bf16(x, identifier="w", philox=ph, **args)
+        assert fq.dtype == torch.float32 and torch.equal(pb[:, : shape[-1]].float(), fq), (shape, m, B, first, sparse)
+
+
+def test_bfplinear_half_precision_stochastic_inference(ops, monkeypatch):
+    """fp16 module, rounding_mode='stoc', no bias (the reference's LLaMA scripts): fp32 result like the reference (its stochastic
+    quantiser promotes to fp32), tensor cores, same distribution as the fake-quant path."""
+    kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="stoc", epsilon=1e-8, mant_bits=5, block_size=64,
+              w_sparsity=True, N=2, M=4, first="s", sparsity_mode="structured", device="cuda")
+    torch.manual_seed(9)
+    lin = ops.BFPLinear(512, 256, bias=False, **dict(kw)).cuda().half()
+    x = torch.randn(3, 40, 512, device="cuda").half()
+    from qsi_b200 import _lib
+    with torch.no_grad():
+        n0 = _lib.lib().bfp_launch_count()
+        y = lin(x)
+        assert _lib.lib().bfp_launch_count() - n0 == 4 and y.dtype == torch.float32
+        ys = torch.stack([lin(x) for _ in range(32)])
+        monkeypatch.setenv("BFP_LINEAR_PATH", "fakequant")
+        f0 = lin(x)
+        fs = torch.stack([lin(x) for _ in range(32)])
+    assert f0.dtype == torch.float32
+    limit = x.float() @ ops._structured_N_M_sparsity(lin.weight.detach(), "cuda", 2, 4).float().t()
+    e_tc, e_fq = (ys[0] - limit).norm() / limit.norm(), (fs[0] - limit).norm() / limit.norm()
+    assert 0.7 < float(e_tc / e_fq) < 1.4 and float((ys.mean(0) - limit).norm() / limit.norm()) < 0.4 * float(e_tc)
