@@ -371,4 +371,9 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    finally:
+        if "torch.distributed" in sys.modules:
+            from qsi_b200 import dist as _qd
+            _qd.shutdown()

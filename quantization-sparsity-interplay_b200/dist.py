@@ -46,6 +46,13 @@ def shard_by_layer(tensors, rank, world):
     return [t for t in tensors if t[0] % world == rank]
 
 
+def shutdown():
+    """Tear the process group down (quietens NCCL's leak warning at exit); a no-op when none was created."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
+
+
 def barrier(device=None):
     if dist.is_initialized():
         if device is not None and device.type == "cuda":
