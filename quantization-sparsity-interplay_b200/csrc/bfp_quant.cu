@@ -119,6 +119,42 @@ __global__ void __launch_bounds__(kStreamThreads) quant_stream_kernel(const Stre
     pdl_launch_dependents();
     pdl_wait();
 
+    if constexpr (STOC && !PADDED) {
+        // Stochastic rounding is ~43 instructions per element, most of them the Philox rounds: a tile's loads are far apart in
+        // time unless the NEXT tile's vectors are requested before this tile's arithmetic starts (software prefetch, one tile
+        // ahead in registers).  Same vectors, same counters, same results as the plain loop below.
+        uint4 nxt[kStreamUnroll];
+        auto fetch = [&](int64_t t) {
+            const int64_t base = t * kTileVecs;
+            const int rem = (int)min((int64_t)kTileVecs, p.n_vec - base);
+#pragma unroll
+            for (int u = 0; u < kStreamUnroll; ++u) {
+                const int li = (int)threadIdx.x + u * kStreamThreads;
+                nxt[u] = (li < rem) ? ld_stream(p.in + base + li) : make_uint4(0u, 0u, 0u, 0u);
+            }
+        };
+        if ((int64_t)blockIdx.x < n_tiles) fetch(blockIdx.x);
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t tile_base = tile * kTileVecs;
+            const int rem = (int)min((int64_t)kTileVecs, p.n_vec - tile_base);
+            uint4 raw[kStreamUnroll];
+#pragma unroll
+            for (int u = 0; u < kStreamUnroll; ++u) raw[u] = nxt[u];
+            if (tile + gridDim.x < n_tiles) fetch(tile + gridDim.x);
+#pragma unroll
+            for (int u = 0; u < kStreamUnroll; ++u) {
+                const int li = (int)threadIdx.x + u * kStreamThreads;
+                uint4 o[kOutVecs];
+                process_vec<DT, ORDER, M, KD, TIE, STOC>(raw[u], p, tile_base + li, o);
+                if (li < rem) {
+                    uint4* dst = p.out + (tile_base + li) * kOutVecs;
+                    st_stream(dst, o[0]);
+                    if (kOutVecs == 2) st_stream(dst + 1, o[kOutVecs - 1]);
+                }
+            }
+        }
+        return;
+    }
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t tile_base = tile * kTileVecs;
         uint4 raw[kStreamUnroll];
