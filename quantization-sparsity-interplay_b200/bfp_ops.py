@@ -987,6 +987,37 @@ class BFPLinear(torch.nn.Linear):
         self._packed_w = hit
         return hit[1]
 
+    def _static_sparse_weight(self):
+        """first == 's': the N:M mask is taken on the unquantised weight, so it does not depend on the rounding draw.  Cached per
+        weight version: the kept values in compressed order [N, Kc] (weight dtype) and the (static) tcgen05 metadata.  A block of B
+        weights is B/2 consecutive compressed values holding the block's maximum, so the per-forward stochastic quantisation
+        runs on the compressed tensor with block size B/2: half the elements, no mask, no re-compression."""
+        w = self.weight
+        key = ('sp_static', w.data_ptr(), w._version, tuple(w.shape), w.device)
+        hit = self._packed_by_kind.get('sp_static')
+        if hit is None or hit[0] != key:
+            a = self.bfp_args
+            ws = _structured_N_M_sparsity(w.detach(), w.device, a['N'], a['M'])       # stays in the weight's dtype: the block
+            # exponent is computed in that dtype's arithmetic (SURVEY.md appendix A.6)
+            n_out, K = ws.shape
+            K128 = -(-K // 128) * 128
+            g = F.pad(ws, (0, K128 - K)).view(n_out, K128 // 4, 4)
+            nz = g != 0
+            cnt = nz.sum(-1)
+            idx = torch.arange(4, device=w.device).expand_as(g)
+            i0 = torch.where(nz, idx, 4).min(-1).values
+            i1 = torch.where(nz & (idx > i0.unsqueeze(-1)), idx, 4).min(-1).values
+            # the compress kernel's padding rule (csrc/bfp_gemm_sp.cu): none -> (0, 1); one -> (i0, 3), or (0, 3) when i0 == 3
+            i0f = torch.where((cnt == 0) | ((cnt == 1) & (i0 == 3)), torch.zeros_like(i0), i0)
+            i1f = torch.where(cnt == 0, torch.ones_like(i1), torch.where(cnt == 1, torch.full_like(i1, 3), i1))
+            kept = torch.stack([g.gather(-1, i0f.unsqueeze(-1)).squeeze(-1), g.gather(-1, i1f.unsqueeze(-1)).squeeze(-1)], -1)
+            comp32 = kept.reshape(n_out, K128 // 2).contiguous()
+            pattern = nz.view(n_out, K128)[:, :-(-K // 8) * 8].to(torch.bfloat16).contiguous()
+            meta = compress_2to4_bf16(pattern).meta                       # raises if the mask is not 2:4 (cannot happen for sp_ok)
+            hit = (key, (comp32, meta))
+            self._packed_by_kind['sp_static'] = hit
+        return hit[1]
+
     def _stochastic_forward(self, input):
         """Inference with rounding_mode='stoc' -- what every script of the reference sets (bfp_config.yaml:4) -- on the tensor
         cores: like the reference, BOTH operands are re-quantised with fresh uniforms on every call (no weight cache, no
@@ -996,9 +1027,14 @@ class BFPLinear(torch.nn.Linear):
         its F.linear is an fp32 SGEMM with an fp32 result -- same here, fp32 out; only bias-free modules (a half bias
         would not type-check against fp32 operands in the reference either)."""
         xb = pack_bfp_bf16(input, identifier='in', **self.bfp_args)
-        wb = pack_bfp_bf16(self.weight.detach(), identifier='w', **self.bfp_args)
         out_shape = tuple(input.shape[:-1]) + (self.out_features,)
-        if _tensor_core_kind(input, self.weight, self.bfp_args) == 'sp':
+        sp = _tensor_core_kind(input, self.weight, self.bfp_args) == 'sp'
+        if sp and self.bfp_args['first'] == 's' and self.bfp_args['block_size'] >= 8 and os.environ.get("BFP_STOC_STATIC_MASK", "1") == "1":
+            comp32, meta = self._static_sparse_weight()
+            wc = pack_bfp_bf16(comp32, identifier='w', **dict(self.bfp_args, w_sparsity=False, block_size=self.bfp_args['block_size'] // 2))
+            return bfp_linear_bf16_sp(xb, SparseBF16(wc, meta, self.out_features, xb.shape[1]), self.bias, out_shape=out_shape)
+        wb = pack_bfp_bf16(self.weight.detach(), identifier='w', **self.bfp_args)
+        if sp:
             return bfp_linear_bf16_sp(xb, compress_2to4_bf16(wb, check=False), self.bias, out_shape=out_shape)
         return bfp_linear_bf16(xb, wb, self.bias, out_shape=out_shape)
 

@@ -752,10 +752,11 @@ def test_bfplinear_stochastic_inference_on_tensor_cores(ops, w_sparse, monkeypat
     lin = ops.BFPLinear(512, 256, bias=True, **dict(kw)).cuda()
     x = torch.randn(3, 40, 512, device="cuda")
     with torch.no_grad():
+        y0 = lin(x)                                                            # (first call builds the static 2:4 structure when w_sparse)
         n0 = _lib.lib().bfp_launch_count()
-        y0 = lin(x)
-        assert _lib.lib().bfp_launch_count() - n0 == (4 if w_sparse else 3)   # pack x, pack w, (compress,) one tcgen05 GEMM
-        assert lin._packed_w is None                                           # nothing cached: every call re-quantises the weight
+        lin(x)
+        assert _lib.lib().bfp_launch_count() - n0 == 3                         # pack x, pack w (compressed form when 2:4), one tcgen05 GEMM
+        assert lin._packed_w is None                                           # no quantised weight is cached: every call re-quantises
         ys = torch.stack([lin(x) for _ in range(64)])
         monkeypatch.setenv("BFP_LINEAR_PATH", "fakequant")
         fs = torch.stack([lin(x) for _ in range(64)])
@@ -797,9 +798,10 @@ def test_bfplinear_half_precision_stochastic_inference(ops, monkeypatch):
     x = torch.randn(3, 40, 512, device="cuda").half()
     from qsi_b200 import _lib
     with torch.no_grad():
-        n0 = _lib.lib().bfp_launch_count()
         y = lin(x)
-        assert _lib.lib().bfp_launch_count() - n0 == 4 and y.dtype == torch.float32
+        n0 = _lib.lib().bfp_launch_count()
+        lin(x)
+        assert _lib.lib().bfp_launch_count() - n0 == 3 and y.dtype == torch.float32
         ys = torch.stack([lin(x) for _ in range(32)])
         monkeypatch.setenv("BFP_LINEAR_PATH", "fakequant")
         f0 = lin(x)
@@ -808,3 +810,29 @@ def test_bfplinear_half_precision_stochastic_inference(ops, monkeypatch):
     limit = x.float() @ ops._structured_N_M_sparsity(lin.weight.detach(), "cuda", 2, 4).float().t()
     e_tc, e_fq = (ys[0] - limit).norm() / limit.norm(), (fs[0] - limit).norm() / limit.norm()
     assert 0.7 < float(e_tc / e_fq) < 1.4 and float((ys.mean(0) - limit).norm() / limit.norm()) < 0.4 * float(e_tc)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16])
+@pytest.mark.parametrize("nm", [(2, 4), (1, 4)])
+def test_static_mask_compressed_weight_equals_regular_sparse_path(ops, dt, nm):
+    """Stochastic inference with first == 's' quantises the cached COMPRESSED weight (block size B/2, static metadata).  With
+    nearest rounding the same machinery must reproduce the regular path -- quantise the full weight, then compress -- exactly."""
+    N_, M_ = nm
+    kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=5, block_size=64,
+              w_sparsity=True, N=N_, M=M_, first="s", sparsity_mode="structured", device="cuda")
+    torch.manual_seed(13)
+    lin = ops.BFPLinear(1000, 264, bias=False, **dict(kw)).cuda().to(dt)      # K = 1000: ragged last block, K padded to 1024
+    with torch.no_grad():
+        lin.weight[5, 1::2] = 0                                                # half the row zero: groups with fewer than two survivors
+        lin.weight[6, ::4] = 0.25                                              # exact powers of two: the exponent's edge case
+    x = torch.randn(70, 1000, device="cuda").to(dt)
+    a = ops.unpack_bfp_args(dict(kw))
+    with torch.no_grad():
+        y = lin(x)
+        assert lin._packed_w[0][0] == "sp"
+        comp, meta = lin._static_sparse_weight()
+        assert comp.dtype == dt and comp.shape == (264, 512)
+        wc = ops.pack_bfp_bf16(comp, identifier="w", **dict(a, w_sparsity=False, block_size=32))
+        xb = ops.pack_bfp_bf16(x, identifier="in", **a)
+        y2 = ops.bfp_linear_bf16_sp(xb, ops.SparseBF16(wc, meta, 264, xb.shape[1]), None, out_dtype=dt)
+    assert torch.equal(y, y2)
