@@ -698,7 +698,8 @@ def _gen_bfp_op(op, name, bfp_args, transpose=False):
 
     def new_op(x, w, *args, **kwargs):
         # inference fast paths on the tensor cores (row f4); anything else runs the reference's structure below
-        if torch.is_tensor(x) and torch.is_tensor(w) and x.dim() >= 2 and w.dim() >= 2 and _tc_inference_ok(x, w, bfp_args):
+        aux_grad = torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in args)     # e.g. a trainable bias
+        if torch.is_tensor(x) and torch.is_tensor(w) and x.dim() >= 2 and w.dim() >= 2 and not aux_grad and _tc_inference_ok(x, w, bfp_args):
             if op is torch.matmul and transpose and not args and not kwargs and x.shape[-1] == w.shape[-2]:
                 return _tc_matmul(x, w, bfp_args).to(x.dtype)
             if op is F.linear and not transpose and w.dim() == 2 and len(args) <= 1 and not kwargs:
@@ -969,54 +970,92 @@ class BFPLinear(torch.nn.Linear):
         self._packed_w = None          # (key, packed weight) of the last kind used: re-packed only when the weight changes
         self._packed_by_kind = {}
 
-    def _packed_weight(self, kind):
+    # ---- packed-weight cache -----------------------------------------------------------------------------------------
+    # The packed / compressed weight is a pure function of (weight values, bfp_args).  torch's version counter sees in-place
+    # ops on the parameter but NOT writes through `.data` (p.data.copy_(), p.data.mul_(mask): the reference's own BFPOptim,
+    # DeepSpeed / apex master-weight copies and pruning scripts all do that), so:
+    #   * nothing is cached while the module is in training mode and the weight requires grad -- every forward re-packs, which
+    #     is one fused kernel and is what the reference does anyway (it re-quantises the weight on every call);
+    #   * in eval mode / for frozen weights the cache is keyed on (storage, version, shape, device, bfp_args) and dropped by
+    #     load_state_dict, .to() / .half() / .cuda() and `invalidate_packed()` -- call that after writing through `.data`;
+    #   * BFP_WEIGHT_CACHE=0 disables caching, BFP_WEIGHT_CACHE=verify re-checks a checksum of the whole weight on every forward
+    #     (one extra read of the weight and a host sync: a debugging aid, not a fast path).
+    def invalidate_packed(self):
+        """Drops every cached packed form of the weight (call after modifying the weight through `.data`)."""
+        self._packed_w = None
+        self._packed_by_kind = {}
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate_packed()
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self.invalidate_packed()
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _args_key(self):
+        a = self.bfp_args
+        return (a['num_format'], a['sparsity_num_format'], a['rounding_mode'], float(a['epsilon']), a['mant_bits'], a['block_size'],
+                a['w_sparsity'] == True, a['N'], a['M'], a['first'], a['sparsity_mode'], float(a['sparsity_frac']))     # noqa: E712
+
+    def _cacheable(self):
+        mode = os.environ.get("BFP_WEIGHT_CACHE", "1")
+        if mode == "0":
+            return False
+        return not (self.training and self.weight.requires_grad)
+
+    def _packed_weight(self, kind, key_prefix=None):
         w = self.weight
-        key = (kind, w.data_ptr(), w._version, tuple(w.shape), w.device)
-        hit = self._packed_by_kind.get(kind)
+        key = (key_prefix or kind, w.data_ptr(), w._version, tuple(w.shape), w.device, w.dtype, self._args_key())
+        if os.environ.get("BFP_WEIGHT_CACHE", "1") == "verify":
+            key = key + (int(w.detach().view(torch.int16 if w.element_size() == 2 else torch.int32).sum(dtype=torch.int64).item()),)
+        hit = self._packed_by_kind.get(kind) if self._cacheable() else None
         if hit is None or hit[0] != key:
             if kind == 'int':
                 packed = _int_pack_weight(w.detach(), self.bfp_args)
             elif kind == 'sp':
                 # raises if the pruned weight is not 2:4 (cannot happen for sp_ok configs); the dense form is not kept
                 packed = compress_2to4_bf16(pack_bfp_bf16(w.detach(), identifier='w', **self.bfp_args))
+            elif kind == 'sp_static':
+                packed = self._build_static_sparse_weight()
             else:
                 packed = (pack_bfp if kind == 'i8' else pack_bfp_bf16)(w.detach(), identifier='w', **self.bfp_args)
             hit = (key, packed)
-            self._packed_by_kind = {k: v for k, v in self._packed_by_kind.items() if v[0][1:] == key[1:]}   # drop stale kinds
-            self._packed_by_kind[kind] = hit
-        self._packed_w = hit
+            if self._cacheable():
+                self._packed_by_kind = {k: v for k, v in self._packed_by_kind.items() if v[0][1:] == key[1:]}   # drop stale kinds
+                self._packed_by_kind[kind] = hit
+        if kind != 'sp_static':
+            self._packed_w = hit
         return hit[1]
 
     def _static_sparse_weight(self):
-        """first == 's': the N:M mask is taken on the unquantised weight, so it does not depend on the rounding draw.  Cached per
-        weight version: the kept values in compressed order [N, Kc] (weight dtype) and the (static) tcgen05 metadata.  A block of B
-        weights is B/2 consecutive compressed values holding the block's maximum, so the per-forward stochastic quantisation
-        runs on the compressed tensor with block size B/2: half the elements, no mask, no re-compression."""
+        """first == 's': the N:M mask is taken on the unquantised weight, so it does not depend on the rounding draw.  Cached like
+        the other packed forms: the kept values in compressed order [N, Kc] (weight dtype) and the (static) tcgen05 metadata.  A
+        block of B weights is B/2 consecutive compressed values holding the block's maximum, so the per-forward stochastic
+        quantisation runs on the compressed tensor with block size B/2: half the elements, no mask, no re-compression."""
+        return self._packed_weight('sp_static')
+
+    def _build_static_sparse_weight(self):
         w = self.weight
-        key = ('sp_static', w.data_ptr(), w._version, tuple(w.shape), w.device)
-        hit = self._packed_by_kind.get('sp_static')
-        if hit is None or hit[0] != key:
-            a = self.bfp_args
-            ws = _structured_N_M_sparsity(w.detach(), w.device, a['N'], a['M'])       # stays in the weight's dtype: the block
-            # exponent is computed in that dtype's arithmetic (SURVEY.md appendix A.6)
-            n_out, K = ws.shape
-            K128 = -(-K // 128) * 128
-            g = F.pad(ws, (0, K128 - K)).view(n_out, K128 // 4, 4)
-            nz = g != 0
-            cnt = nz.sum(-1)
-            idx = torch.arange(4, device=w.device).expand_as(g)
-            i0 = torch.where(nz, idx, 4).min(-1).values
-            i1 = torch.where(nz & (idx > i0.unsqueeze(-1)), idx, 4).min(-1).values
-            # the compress kernel's padding rule (csrc/bfp_gemm_sp.cu): none -> (0, 1); one -> (i0, 3), or (0, 3) when i0 == 3
-            i0f = torch.where((cnt == 0) | ((cnt == 1) & (i0 == 3)), torch.zeros_like(i0), i0)
-            i1f = torch.where(cnt == 0, torch.ones_like(i1), torch.where(cnt == 1, torch.full_like(i1, 3), i1))
-            kept = torch.stack([g.gather(-1, i0f.unsqueeze(-1)).squeeze(-1), g.gather(-1, i1f.unsqueeze(-1)).squeeze(-1)], -1)
-            comp32 = kept.reshape(n_out, K128 // 2).contiguous()
-            pattern = nz.view(n_out, K128)[:, :-(-K // 8) * 8].to(torch.bfloat16).contiguous()
-            meta = compress_2to4_bf16(pattern).meta                       # raises if the mask is not 2:4 (cannot happen for sp_ok)
-            hit = (key, (comp32, meta))
-            self._packed_by_kind['sp_static'] = hit
-        return hit[1]
+        a = self.bfp_args
+        ws = _structured_N_M_sparsity(w.detach(), w.device, a['N'], a['M'])       # stays in the weight's dtype: the block
+        # exponent is computed in that dtype's arithmetic (SURVEY.md appendix A.6)
+        n_out, K = ws.shape
+        K128 = -(-K // 128) * 128
+        g = F.pad(ws, (0, K128 - K)).view(n_out, K128 // 4, 4)
+        nz = g != 0
+        cnt = nz.sum(-1)
+        idx = torch.arange(4, device=w.device).expand_as(g)
+        i0 = torch.where(nz, idx, 4).min(-1).values
+        i1 = torch.where(nz & (idx > i0.unsqueeze(-1)), idx, 4).min(-1).values
+        # the compress kernel's padding rule (csrc/bfp_gemm_sp.cu): none -> (0, 1); one -> (i0, 3), or (0, 3) when i0 == 3
+        i0f = torch.where((cnt == 0) | ((cnt == 1) & (i0 == 3)), torch.zeros_like(i0), i0)
+        i1f = torch.where(cnt == 0, torch.ones_like(i1), torch.where(cnt == 1, torch.full_like(i1, 3), i1))
+        kept = torch.stack([g.gather(-1, i0f.unsqueeze(-1)).squeeze(-1), g.gather(-1, i1f.unsqueeze(-1)).squeeze(-1)], -1)
+        comp32 = kept.reshape(n_out, K128 // 2).contiguous()
+        pattern = nz.view(n_out, K128)[:, :-(-K // 8) * 8].to(torch.bfloat16).contiguous()
+        meta = compress_2to4_bf16(pattern).meta                       # raises if the mask is not 2:4 (cannot happen for sp_ok)
+        return (comp32, meta)
 
     def _stochastic_forward(self, input):
         """Inference with rounding_mode='stoc' -- what every script of the reference sets (bfp_config.yaml:4) -- on the tensor
@@ -1043,13 +1082,16 @@ class BFPLinear(torch.nn.Linear):
             return F.linear(input, self.weight, self.bias)
         elif self.num_format == 'bfp':
             determ = self.bfp_args['rounding_mode'] == rounding_modes.DETERM
-            training = torch.is_grad_enabled() and (input.requires_grad or self.weight.requires_grad)
-            if _int_tc_eligible(input, self.weight, self.bfp_args):
+            # a trainable bias alone (BitFit, frozen backbones) also needs the autograd path: the inference kernels take bias.detach()
+            training = torch.is_grad_enabled() and (input.requires_grad or self.weight.requires_grad
+                                                    or (self.bias is not None and self.bias.requires_grad))
+            if not training and _int_tc_eligible(input, self.weight, self.bfp_args):
                 packed = self._packed_weight('int')
                 if packed is not None:
                     return _int_tc_linear(input, packed, self.bias, self.bfp_args)
             kind = _tensor_core_kind(input, self.weight, self.bfp_args) if (determ or training) else None
-            if training and kind is not None and self.bfp_args['mant_bits'] <= 8 and self.bfp_args['grad_sparsity'] != True:   # noqa: E712
+            if (training and kind is not None and self.bfp_args['mant_bits'] <= 8 and self.bfp_args['grad_sparsity'] != True   # noqa: E712
+                    and input.dtype == torch.float32 and self.weight.dtype == torch.float32):
                 # training: forward + dgrad + wgrad on the tensor cores.  Stochastic rounding re-quantises the weight on
                 # every forward like the reference (no cache), and keeps it dense for the backward contraction over N.
                 tkind = kind if kind in ('sp', 'bf16') else 'bf16'

@@ -836,3 +836,68 @@ def test_static_mask_compressed_weight_equals_regular_sparse_path(ops, dt, nm):
         xb = ops.pack_bfp_bf16(x, identifier="in", **a)
         y2 = ops.bfp_linear_bf16_sp(xb, ops.SparseBF16(wc, meta, 264, xb.shape[1]), None, out_dtype=dt)
     assert torch.equal(y, y2)
+
+
+_KW = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=7, block_size=64,
+           w_sparsity=True, N=2, M=4, first="s", sparsity_mode="structured", device="cuda")
+
+
+def test_weight_written_through_data_is_never_served_stale(ops, monkeypatch):
+    """Writes through `.data` do not bump torch's version counter (the reference's BFPOptim, DeepSpeed / apex master-weight
+    copies and pruning scripts all write that way).  Training-mode modules with trainable weights therefore never cache the
+    packed weight; eval-mode modules cache it and are refreshed by invalidate_packed() / load_state_dict / .to(); the
+    BFP_WEIGHT_CACHE=verify mode catches the write by checksum."""
+    torch.manual_seed(0)
+    x = torch.randn(96, 256, device="cuda")
+    lin = ops.BFPLinear(256, 128, bias=False, **dict(_KW)).cuda()           # nn.Module default: training mode
+    with torch.no_grad():
+        y0 = lin(x)
+        v = lin.weight._version
+        lin.weight.data.mul_(0.5)
+        assert lin.weight._version == v                                      # the write is invisible to the version counter
+        y1 = lin(x)
+    assert torch.allclose(y1, 0.5 * y0, rtol=1e-6, atol=1e-7) and not torch.equal(y1, y0)
+    lin.eval()
+    with torch.no_grad():
+        y2 = lin(x)
+        assert torch.equal(y2, y1)
+        lin.weight.data.mul_(2.0)
+        lin.invalidate_packed()
+        assert torch.equal(lin(x), y0)
+        sd = {k: t.clone() for k, t in lin.state_dict().items()}
+        sd["weight"] = sd["weight"] * 0.5
+        lin(x)                                                               # packed form of the current weight is cached ...
+        lin.load_state_dict(sd)                                              # ... and dropped by load_state_dict (copy_ also bumps the version)
+        assert torch.equal(lin(x), y1)
+        monkeypatch.setenv("BFP_WEIGHT_CACHE", "verify")
+        lin(x)
+        lin.weight.data.mul_(2.0)
+        assert torch.equal(lin(x), y0)                                       # caught by the checksum, no invalidate call
+    # the key also covers the quantiser arguments
+    monkeypatch.delenv("BFP_WEIGHT_CACHE")
+    with torch.no_grad():
+        ya = lin(x)
+        lin.bfp_args['mant_bits'] = 3
+        yb = lin(x)
+    assert not torch.equal(ya, yb)
+
+
+def test_trainable_bias_alone_gets_its_gradient(ops):
+    """BitFit / frozen backbones: only the bias requires grad.  The reference's F.linear(xq, wq, bias) back-propagates to it."""
+    torch.manual_seed(1)
+    for dt in (torch.float32, torch.float16):
+        lin = ops.BFPLinear(256, 128, bias=True, **dict(_KW)).cuda().to(dt)
+        lin.weight.requires_grad_(False)
+        x = torch.randn(40, 256, device="cuda", dtype=dt)
+        y = lin(x)
+        assert y.requires_grad and y.dtype == dt
+        y.float().sum().backward()
+        assert lin.bias.grad is not None and lin.weight.grad is None
+        # d(sum y)/d bias = number of rows, after the output-gradient quantiser (ones are BFP-exact)
+        assert torch.allclose(lin.bias.grad.float(), torch.full((128,), 40.0, device="cuda"))
+        op = ops.F_linear_bfp(**dict(_KW))
+        b = torch.zeros(128, device="cuda", dtype=dt, requires_grad=True)
+        y2 = op(x, lin.weight, b)
+        assert y2.requires_grad
+        y2.float().sum().backward()
+        assert torch.allclose(b.grad.float(), torch.full((128,), 40.0, device="cuda"))

@@ -14,7 +14,7 @@ def t(fn, n=10):
     e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1) / n
 for dt in (torch.float16, torch.bfloat16):
     for (N, K) in ((4096, 4096), (11008, 4096), (4096, 11008)):
-        lin = ops.BFPLinear(K, N, bias=False, **dict(kw)).cuda().to(dt)
+        lin = ops.BFPLinear(K, N, bias=False, **dict(kw)).cuda().to(dt).eval()
         xs = [torch.randn(4096, K, device="cuda").to(dt) for _ in range(3)]
         i = [0]
         def f():

@@ -20,7 +20,7 @@ for mode in ("structured", "unstructured"):
               N=2, M=4, first="s", sparsity_mode=mode, sparsity_frac=0.5, device="cuda")
     for N, K in [(4096, 4096), (11008, 4096), (4096, 11008)]:
         torch.manual_seed(0)
-        lin = ours.BFPLinear(K, N, bias=True, **dict(kw)).cuda()
+        lin = ours.BFPLinear(K, N, bias=True, **dict(kw)).cuda().eval()
         x = torch.randn(4096, K, device="cuda")
         with torch.no_grad():
             ms = t(lambda: lin(x)); y = lin(x)

@@ -23,10 +23,10 @@ for name, (N, K) in SHAPES:
     g = torch.Generator(device=dev).manual_seed(5)
     w = (torch.randn(N, K, device=dev, generator=g) * 0.02).to(DT)
     x = torch.randn(T, K, device=dev, generator=g).to(DT)
-    cp = qd.ColumnParallelBFPLinear(K, N, bias=False, **dict(kw)).to(dev).to(DT).load_full(w)
+    cp = qd.ColumnParallelBFPLinear(K, N, bias=False, **dict(kw)).to(dev).to(DT).eval().load_full(w)
     with torch.no_grad():
         y = cp(x)
-        full = ops.BFPLinear(K, N, bias=False, **dict(kw)).to(dev).to(DT)
+        full = ops.BFPLinear(K, N, bias=False, **dict(kw)).to(dev).to(DT).eval()
         full.weight.copy_(w)
         y_ref = full(x)
         ok = torch.equal(y, y_ref)
@@ -38,7 +38,7 @@ for name, (N, K) in SHAPES:
             for _ in range(n): fn()
             e1.record(); torch.cuda.synchronize()
             return qd.max_over_ranks(e0.elapsed_time(e1) / n, dev)
-        fused = cp._fused_ok(x) and cp._fused_failed is None
+        fused = cp._path == 'fused'
         ms_fwd = timed(lambda: cp(x)); ms_alias = timed(lambda: cp(x, alias_output=True)); ms_local = timed(lambda: cp.local(x)); ms_full = timed(lambda: full(x))
         os.environ["BFP_COLUMN_PARALLEL"] = "nccl"
         y_nccl = cp(x); ok_nccl = torch.equal(y_nccl, y_ref)

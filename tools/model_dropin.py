@@ -25,11 +25,13 @@ def swap(model, impl, kw, targets=None, conv_name="projection"):
             if isinstance(ch, torch.nn.Linear) and (targets is None or name in targets):
                 new = impl.BFPLinear(ch.in_features, ch.out_features, bias=ch.bias is not None, **dict(kw))
                 new.weight, new.bias = ch.weight, ch.bias
+                new.train(ch.training)
                 setattr(parent, name, new); n += 1
             elif isinstance(ch, torch.nn.Conv2d) and name == conv_name:
                 new = impl.BFPConv2d(ch.in_channels, ch.out_channels, ch.kernel_size, ch.stride, ch.padding, ch.dilation, ch.groups,
                                      bias=ch.bias is not None, **dict(kw))
                 new.weight, new.bias = ch.weight, ch.bias
+                new.train(ch.training)
                 setattr(parent, name, new); n += 1
     return n
 
