@@ -499,13 +499,14 @@ def leg_gemm(torch, dev, g, peaks):
 
 
 def measure_traffic(timeout_s=150):
-    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (4096x11008 fp32, HBFP8 B=64, s->q),
-    measured now by an ncu child process of this script (--traffic-child).  Returns (bytes or None, provenance)."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, averaged over the sweep's launch mix (both
+    shapes, HBFP8 B=64, s->q), measured now by an ncu child process of this script (--traffic-child).
+    Returns (bytes or None, provenance)."""
     ncu = shutil.which("ncu") or ("/usr/local/cuda/bin/ncu" if os.path.exists("/usr/local/cuda/bin/ncu") else None)
     if ncu is None:
         return None, "ncu not found"
     cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:quant_stream_kernel",
-           "-s", "4", "-c", "2", "--csv", sys.executable, os.path.abspath(__file__), "--traffic-child"]
+           "-s", "4", "-c", "4", "--csv", sys.executable, os.path.abspath(__file__), "--traffic-child"]
     try:
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, cwd=ROOT)
     except Exception as e:                                  # noqa: BLE001
@@ -526,20 +527,23 @@ def measure_traffic(timeout_s=150):
         return None, ("ncu produced no dram counters (rc %d): " % r.returncode + (r.stderr or r.stdout)[-160:].replace("\n", " "))
     rd = sum(vals["dram__bytes_read.sum"]) / len(vals["dram__bytes_read.sum"])
     wr = sum(vals["dram__bytes_write.sum"]) / len(vals["dram__bytes_write.sum"])
-    return rd + wr, f"ncu child in this run: {len(vals['dram__bytes_read.sum'])} launches of 4096x11008 fp32, read {rd / 1e6:.1f} MB + write {wr / 1e6:.1f} MB per launch"
+    return rd + wr, (f"ncu child in this run: mean of {len(vals['dram__bytes_read.sum'])} launches alternating 4096x4096 and 4096x11008 fp32 (the sweep's "
+                     f"launch mix), read {rd / 1e6:.1f} MB + write {wr / 1e6:.1f} MB per launch")
 
 
 def traffic_child():
+    """Launches the two shapes of the sweep alternately (m = 7, B = 64, s->q); the parent captures 2 launches of each."""
     import torch
     from qsi_b200 import _lib
     L = _lib.lib()
     dev = torch.device("cuda", 0)
-    xs = [torch.randn(4096, 11008, device=dev) * 0.02 for _ in range(2)]
-    y = torch.empty(4096, 11008, device=dev)
+    xs = {s: [torch.randn(*s, device=dev) * 0.02 for _ in range(2)] for s in SHAPES}
+    ys = {s: torch.empty(*s, device=dev) for s in SHAPES}
     st = torch.cuda.current_stream().cuda_stream
-    for i in range(8):
-        _lib.check(L.bfp_quantize(xs[i % 2].data_ptr(), y.data_ptr(), 4096, 11008, _lib.DT_F32, _lib.DT_F32, 64, 7, 1e-8, _lib.ROUND_NEAREST, 0, 0,
-                                  N_, M_, _lib.ORDER_SPARSIFY_QUANT, _lib.TIE_TORCH_CUDA, st))
+    for i in range(6):
+        for s in SHAPES:
+            _lib.check(L.bfp_quantize(xs[s][i % 2].data_ptr(), ys[s].data_ptr(), s[0], s[1], _lib.DT_F32, _lib.DT_F32, 64, 7, 1e-8, _lib.ROUND_NEAREST,
+                                      0, 0, N_, M_, _lib.ORDER_SPARSIFY_QUANT, _lib.TIE_TORCH_CUDA, st))
     torch.cuda.synchronize()
 
 

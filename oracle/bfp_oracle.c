@@ -107,11 +107,21 @@ static inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
 }
-/* uniform for flat (padded-layout-free) element index i: 24-bit, in [0,1). */
-float oracle_philox_uniform(uint64_t seed, uint64_t offset, uint64_t i) {
+/* 32-bit word of the stream for flat element index i: word (i & 3) of the block with counter (i >> 2, offset), key = seed */
+uint32_t oracle_philox_word(uint64_t seed, uint64_t offset, uint64_t i) {
     uint32_t c[4] = { (uint32_t)(i >> 2), (uint32_t)((i >> 2) >> 32), (uint32_t)offset, (uint32_t)(offset >> 32) };
     philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-    return (float)(c[i & 3] >> 8) * 5.9604644775390625e-08f;
+    return c[i & 3];
+}
+/* uniform in [0,1): the word truncated (round toward zero) to 24 significant bits, times 2^-32 -- what the kernel's
+ * cvt.rz.f32.u32 followed by an exact power-of-two scale gives.  Words >= 2^31 yield (w >> 8) * 2^-24. */
+float oracle_philox_uniform(uint64_t seed, uint64_t offset, uint64_t i) {
+    uint32_t w = oracle_philox_word(seed, offset, i);
+    if (w) {
+        int drop = 32 - __builtin_clz(w) - 24;
+        if (drop > 0) w &= ~((1u << drop) - 1u);
+    }
+    return (float)w * 2.3283064365386963e-10f;            /* exact: <= 24 significant bits, power-of-two scale */
 }
 void oracle_philox_fill(float *u, int64_t n, uint64_t seed, uint64_t offset) {
 #pragma omp parallel for schedule(static)

@@ -4,7 +4,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbfp_b200.so")
+LIB_PATH = os.environ.get("BFP_B200_LIB") or os.path.join(_HERE, "libbfp_b200.so")     # the override is for A/B runs of kernel variants (tools/)
 CSRC = os.path.join(_HERE, "csrc")
 
 DT_F32, DT_F16, DT_BF16 = 0, 1, 2

@@ -1015,7 +1015,8 @@ class BFPLinear(torch.nn.Linear):
                 packed = _int_pack_weight(w.detach(), self.bfp_args)
             elif kind == 'sp':
                 # raises if the pruned weight is not 2:4 (cannot happen for sp_ok configs); the dense form is not kept
-                packed = compress_2to4_bf16(pack_bfp_bf16(w.detach(), identifier='w', **self.bfp_args))
+                # (the violation count is read back -- one sync -- only when the result is going to be cached)
+                packed = compress_2to4_bf16(pack_bfp_bf16(w.detach(), identifier='w', **self.bfp_args), check=self._cacheable())
             elif kind == 'sp_static':
                 packed = self._build_static_sparse_weight()
             else:

@@ -73,7 +73,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint64_t ctr, uint64_t offset, ui
     }
     return make_uint4(c0, c1, c2, c3);
 }
-__device__ __forceinline__ float u01(uint32_t w) { return (float)(w >> 8) * 5.9604644775390625e-08f; }  // [0,1), 24 bit
+// uniform in [0,1): the 32-bit word truncated to 24 significant bits (round toward zero), times 2^-32 -- one conversion, no shift.
+// Words >= 2^31 give exactly (w >> 8) * 2^-24; smaller words keep proportionally finer steps.  Never 1.0.
+__device__ __forceinline__ float u32_rz(uint32_t w) { return __uint2float_rz(w); }
+__device__ __forceinline__ float u01(uint32_t w) { return u32_rz(w) * 2.3283064365386963e-10f; }
+// fl(u - 0.5): the sample the reference adds to t / interval (bfp_ops.py:22), in one fused operation (u itself is exact)
+__device__ __forceinline__ float u01_centered(uint32_t w) { return __fmaf_rn(u32_rz(w), 2.3283064365386963e-10f, -0.5f); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // block scale: everything derived from the block's max |t|   (bfp_ops.py:29-33, :38-39)
@@ -83,6 +88,7 @@ struct BlockScale {
     float delta;   // 2^(e-m)  (interval, bfp_ops.py:38)
     float vmax;    // fast path: 2^m - 1 (clamp on the integer grid); slow path: 2^e - interval (max_v, bfp_ops.py:39)
     float e;       // block exponent as torch holds it (float in the tensor dtype)
+    int p;         // e - m (fast path only)
     bool fast;
 };
 
@@ -184,36 +190,37 @@ __device__ __forceinline__ BlockScale make_scale(uint32_t amax_bits, int m, floa
         sc.inv = __uint_as_float((uint32_t)(127 - p) << 23);
         sc.vmax = (float)((1 << m) - 1);
         sc.e = (float)e;
+        sc.p = p;
         sc.fast = true;
     } else {
         const float3 r = make_scale_slow<DT>(s, m);
-        sc.delta = r.x; sc.vmax = r.y; sc.e = r.z; sc.inv = 0.0f; sc.fast = false;
+        sc.delta = r.x; sc.vmax = r.y; sc.e = r.z; sc.inv = 0.0f; sc.p = 0; sc.fast = false;
     }
     return sc;
 }
 
-// one element, fast path: bfp_ops.py:40-44 with every product exact.  STOC: u is the element's uniform in [0,1).
+// one element, fast path: bfp_ops.py:40-44 with every product exact.  STOC: smp = fl(u - 0.5), u the element's uniform in [0,1).
 template <bool STOC>
-__device__ __forceinline__ float quant_elt_fast(float t, const BlockScale& sc, float u) {
+__device__ __forceinline__ float quant_elt_fast(float t, const BlockScale& sc, float smp) {
     const float x = t * sc.inv;                                   // exact (power-of-two scale)
-    const float r = STOC ? rintf((u - 0.5f) + x) : rintf(x);      // bfp_ops.py:22-25
+    const float r = STOC ? rintf(smp + x) : rintf(x);             // bfp_ops.py:22-25
     return fminf(fmaxf(r, -sc.vmax), sc.vmax) * sc.delta;         // clamp on the grid, exact product
 }
 
 // one element, literal evaluation (out of line; see make_scale_slow)
 template <int DT, bool STOC>
-__device__ __noinline__ float quant_elt_slow(float t, float delta, float vmax, float u) {
+__device__ __noinline__ float quant_elt_slow(float t, float delta, float vmax, float smp) {
     using D = DType<DT>;
     const float x = D::rnd(t / delta);
     float y;
-    if (STOC) y = rintf((u - 0.5f) + x) * delta;                  // fp32 from here on (type promotion)
+    if (STOC) y = rintf(smp + x) * delta;                         // fp32 from here on (type promotion)
     else y = D::rnd(rintf(x) * delta);
     return t_min(t_max(y, -vmax), vmax);
 }
 
 template <int DT, bool STOC>
-__device__ __forceinline__ float quant_elt(float t, const BlockScale& sc, float u) {
-    return sc.fast ? quant_elt_fast<STOC>(t, sc, u) : quant_elt_slow<DT, STOC>(t, sc.delta, sc.vmax, u);
+__device__ __forceinline__ float quant_elt(float t, const BlockScale& sc, float smp) {
+    return sc.fast ? quant_elt_fast<STOC>(t, sc, smp) : quant_elt_slow<DT, STOC>(t, sc.delta, sc.vmax, smp);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -299,6 +306,66 @@ __device__ __forceinline__ void nm_mask_group(float* v, int kdrop) {
         }
         if (rank < kdrop) v[i] = 0.0f;
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// 2:4-style masks (M = 4, torch-CUDA rule) on sign bits instead of predicates.
+// For i < j let s_ij = sign(k_j - k_i) = (k_j < k_i) = "j precedes i" (j > i needs a strictly smaller key); "i precedes j" is
+// its negation.  Element i is dropped iff fewer than KD of the other three precede it: one LOP3 per element on the three
+// difference words (only bit 31 matters), with the negations folded into the look-up table.
+// ---------------------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr uint32_t drop_lut(int kdrop, int na, int nb, int nc) {
+    uint32_t lut = 0;
+    for (int i = 0; i < 8; ++i) {
+        const int a = (i >> 2) & 1, b = (i >> 1) & 1, c = i & 1;
+        if ((a ^ na) + (b ^ nb) + (c ^ nc) < kdrop) lut |= 1u << i;
+    }
+    return lut;
+}
+template <uint32_t LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return d;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+// four fp32 values (any bit patterns): dropped entries become +0.0, kept entries keep their bits
+template <int KD>
+__device__ __forceinline__ void nm_mask4_bits(uint32_t* w) {
+    const uint32_t k0 = w[0] & 0x7fffffffu, k1 = w[1] & 0x7fffffffu, k2 = w[2] & 0x7fffffffu, k3 = w[3] & 0x7fffffffu;
+    const uint32_t s01 = k1 - k0, s02 = k2 - k0, s03 = k3 - k0, s12 = k2 - k1, s13 = k3 - k1, s23 = k3 - k2;   // keys < 2^31: no wrap
+    const uint32_t d0 = lop3<drop_lut(KD, 0, 0, 0)>(s01, s02, s03);
+    const uint32_t d1 = lop3<drop_lut(KD, 1, 0, 0)>(s01, s12, s13);
+    const uint32_t d2 = lop3<drop_lut(KD, 1, 1, 0)>(s02, s12, s23);
+    const uint32_t d3 = lop3<drop_lut(KD, 1, 1, 1)>(s03, s13, s23);
+    w[0] &= ~(uint32_t)((int32_t)d0 >> 31); w[1] &= ~(uint32_t)((int32_t)d1 >> 31);
+    w[2] &= ~(uint32_t)((int32_t)d2 >> 31); w[3] &= ~(uint32_t)((int32_t)d3 >> 31);
+}
+
+// four 16-bit floats (fp16 or bf16 bit patterns) packed as w0 = (e0 | e1 << 16), w1 = (e2 | e3 << 16).  Per 16-bit lane,
+// bit 15 of (k_j | 0x8000) - k_i is (k_j >= k_i); lanes never borrow from each other because the minuend has bit 15 set.
+template <int KD>
+__device__ __forceinline__ void nm_mask4_packed16(uint32_t& w0, uint32_t& w1) {
+    constexpr uint32_t H = 0x80008000u;
+    const uint32_t a0 = w0 & ~H, a1 = w1 & ~H;                    // keys
+    const uint32_t x0 = prmt(w0 | H, 0u, 0x1032u), x1 = prmt(w1 | H, 0u, 0x1032u);   // halves swapped, bit 15 forced
+    const uint32_t X = (w1 | H) - a0;                             // lo: k2 >= k0      hi: k3 >= k1
+    const uint32_t Y = x1 - a0;                                   // lo: k3 >= k0      hi: k2 >= k1
+    const uint32_t R0 = x0 - a0 - 0x10000u;                       // lo: k1 >= k0      hi: k0 >  k1
+    const uint32_t R1 = x1 - a1 - 0x10000u;                       // lo: k3 >= k2      hi: k2 >  k3
+    const uint32_t Ys = prmt(Y, 0u, 0x1032u);                     // lo: k2 >= k1      hi: k3 >= k0
+    // element 0 (lo) is preceded by j iff k_j < k_0: !R0, !X, !Y.  element 1 (hi): by 0 iff k0 <= k1 = !R0.hi, by 3 iff !X.hi, by 2 iff !Y.hi
+    const uint32_t d01 = lop3<drop_lut(KD, 1, 1, 1)>(R0, X, Y);
+    // element 2 (lo): by 0 iff k0 <= k2 = X.lo, by 1 iff k1 <= k2 = Ys.lo, by 3 iff k3 < k2 = !R1.lo.  element 3 (hi): X.hi, Ys.hi, !R1.hi
+    const uint32_t d23 = lop3<drop_lut(KD, 0, 0, 1)>(X, Ys, R1);
+    w0 &= ~prmt(d01, 0u, 0xBB99u);                                // bit 15 / bit 31 replicated over their 16-bit lane
+    w1 &= ~prmt(d23, 0u, 0xBB99u);
 }
 
 }  // namespace bfp

@@ -81,7 +81,7 @@ __device__ __forceinline__ void process_vec(const uint4& raw, const StreamParams
 #pragma unroll
             for (int q = 0; q < V / 4; ++q) {
                 const uint4 r = philox4x32_10((uint64_t)(p.ctr_base + vec_index * (V / 4) + q), p.offset, p.seed);
-                un[4 * q] = u01(r.x); un[4 * q + 1] = u01(r.y); un[4 * q + 2] = u01(r.z); un[4 * q + 3] = u01(r.w);
+                un[4 * q] = u01_centered(r.x); un[4 * q + 1] = u01_centered(r.y); un[4 * q + 2] = u01_centered(r.z); un[4 * q + 3] = u01_centered(r.w);
             }
         }
         if (sc.fast) {                                 // one branch per vector, uniform across the block's lanes
@@ -101,9 +101,266 @@ __device__ __forceinline__ void process_vec(const uint4& raw, const StreamParams
     }
 }
 
-// ORDER: BFP_ORDER_*.  M / KD / TIE: see mask_vec.  STOC: stochastic rounding (fp32 output).
+// ---------------------------------------------------------------------------------------------------------------
+// Tile path (the common configurations: no mask or an N:4 mask with the torch-CUDA tie rule).  A thread's kStreamUnroll
+// vectors go through the phases TOGETHER -- mask / block max of all, one butterfly (the shuffle latencies of the vectors
+// overlap and the lanes_per_block test is taken once per step, not once per vector), scales, Philox for all, rounding --
+// and the arithmetic is laid out for the pipes the kernel is short of: it is bound by the ALU pipe (logic, compares,
+// min/max: 16 lanes/clk/SMSP), so work is moved to the FMA pipe wherever that is exact.
+//   * nearest rounding never divides or multiplies: with C = 2^(p + MB) (p = e - m, MB = explicit mantissa bits of the
+//     arithmetic type) fl(|t| + C) - C is |t| rounded half-to-even to a multiple of 2^p, exactly, because |t| <= 2^e <= C
+//     keeps the sum inside [C, 2C] where the spacing is 2^p; then min(., (2^m - 1) 2^p) and the sign of t.  For fp16 / bf16
+//     tensors this runs on packed pairs (HADD2 / HMNMX2), no unpacking: 3 FMA-pipe + 1 logic instruction per TWO elements.
+//   * stochastic rounding keeps the reference's order of operations, rint(fl(fl(u - 0.5) + t / 2^p)) (bfp_ops.py:22-23); the
+//     clamp to +-(2^m - 1) -- only r = +-2^m can exceed it -- is r - ((r K1 + 1.5 2^23) - 1.5 2^23) with
+//     K1 = 2^-m (1/2 + 2^-(m+2)): the bracket rounds to +-1 exactly when |r| = 2^m and to 0 otherwise (three FMA-pipe
+//     instructions instead of two FMNMX), and keeps -0.0.
+//   * the N:4 mask works on sign bits of key differences (nm_mask4_bits / nm_mask4_packed16 in bfp_common.cuh).
+// Blocks outside the exact range (all-zero fp16, Inf / NaN, denormal scale, huge values) fall back, per vector, to the literal
+// evaluation in quant_elt_slow.  Results are bit-identical to process_vec (tests run both against the oracle and golden files).
+// ---------------------------------------------------------------------------------------------------------------
+template <int DT> struct PackedLimits;          // exponent range of p = e - m for which C = 2^(p + MB) is a normal number of the type
+template <> struct PackedLimits<BFP_DT_F32> { static constexpr int kMB = 23, kPMax = 100, kMMax = 23; };
+template <> struct PackedLimits<BFP_DT_F16> { static constexpr int kMB = 10, kPMax = 5, kMMax = 10; };
+template <> struct PackedLimits<BFP_DT_BF16> { static constexpr int kMB = 7, kPMax = 119, kMMax = 7; };
+
+__device__ __forceinline__ uint32_t hadd2_bits(uint32_t a, uint32_t b, bool bf16) {
+    uint32_t d;
+    if (bf16) asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    else asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t hsub2_bits(uint32_t a, uint32_t b, bool bf16) {
+    uint32_t d;
+    if (bf16) asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    else asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t hmin2_bits(uint32_t a, uint32_t b, bool bf16) {
+    uint32_t d;
+    if (bf16) asm("min.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    else asm("min.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+
+template <int DT, int ORDER, int M, int KD, int TIE, bool STOC>
+struct TilePath {
+    static constexpr bool kMaskOk = (ORDER == BFP_ORDER_QUANT_ONLY) || (M == 4 && KD > 0 && TIE == BFP_TIE_TORCH_CUDA);
+    // fp32 with nearest rounding keeps the per-vector code: it is already at the copy roofline with 32 registers and 8 CTAs per SM,
+    // and measured 9 % faster back to back than the tile path (40 registers, 6 CTAs): profiles/r02_tune_quant_variants.log
+    static constexpr bool kEnabled = kMaskOk && (STOC || DT != BFP_DT_F32);
+};
+
+// General (rare) blocks of the tile path: exponent needs the real log2 / the literal half-precision formulas, all-zero or
+// non-finite blocks, scales outside the exact range.  One vector (already masked when the mask comes first), out of line.
+struct VecOut { uint4 a, b; };
+template <int DT, bool STOC>
+__device__ __noinline__ VecOut quant_vec_general(uint4 wv, uint32_t abits, int m, float eps, uint4 smp_lo, uint4 smp_hi) {
+    using D = DType<DT>;
+    constexpr int V = D::kVec;
+    float v[V];
+    unpack_vec<DT>(wv, v);
+    const BlockScale sc = make_scale<DT>(abits, m, eps);
+    float smp[8] = {__uint_as_float(smp_lo.x), __uint_as_float(smp_lo.y), __uint_as_float(smp_lo.z), __uint_as_float(smp_lo.w),
+                    __uint_as_float(smp_hi.x), __uint_as_float(smp_hi.y), __uint_as_float(smp_hi.z), __uint_as_float(smp_hi.w)};
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = quant_elt<DT, STOC>(v[i], sc, STOC ? smp[i] : 0.0f);
+    VecOut o;
+    if (STOC) { o.a = pack_vec<BFP_DT_F32>(v); o.b = pack_vec<BFP_DT_F32>(v + (V == 8 ? 4 : 0)); }
+    else { o.a = pack_vec<DT>(v); o.b = o.a; }
+    return o;
+}
+
+// Per-launch constants of the simple path (uniform: functions of mant_bits only).
+//   A block is "simple" when its exponent is e = k + 1 with k = floor(log2 s), s = max|t| + eps, WITHOUT evaluating a
+//   logarithm -- fp32: the mantissa of s is more than 128 ulp above 2^k (bfp_common.cuh make_scale); fp16 / bf16: the mantissa
+//   is at or above the tabulated step of k -- and k lies in the range where every constant below is an exact normal number.
+//   Then p = k + 1 - m and max|t| < 2^e, so |t / 2^p| < 2^m for every element of the block.
+template <int DT, bool STOC>
+struct SimpleConsts {
+    uint32_t lo_bits, span_bits;   // simple iff bits(s) - lo_bits < span_bits  (s > 0: its bit pattern is monotone in s)
+    __device__ __forceinline__ SimpleConsts(int m) {
+        using PL = PackedLimits<DT>;
+        using D = DType<DT>;
+        int klo = max(D::kMinExp, D::kMinScaleExp + m - 1);                       // p = k + 1 - m >= kMinScaleExp
+        int khi = min(D::kMaxExp - 1, PL::kPMax + m - 1);                         // e = k + 1 <= kMaxExp, p <= kPMax
+        const bool m_ok = m >= 1 && m <= (STOC ? min(20, D::kMaxMant) : PL::kMMax);
+        if (!m_ok || khi < klo) { klo = 0; khi = -1; }
+        lo_bits = (uint32_t)(klo + 127) << 23;
+        span_bits = (uint32_t)(khi + 1 - klo) << 23;                              // 0 = never simple
+    }
+};
+
+template <int DT, int ORDER, int M, int KD, int TIE, bool STOC, class Store>
+__device__ __forceinline__ void process_tile(const uint4* raw, const StreamParams& p, const int64_t* vidx, Store&& store) {
+    using D = DType<DT>;
+    using PL = PackedLimits<DT>;
+    constexpr int V = D::kVec;
+    constexpr int U = kStreamUnroll;
+    constexpr bool kQuant = ORDER != BFP_ORDER_SPARSIFY_ONLY;
+    constexpr bool kSparseFirst = ORDER == BFP_ORDER_SPARSIFY_QUANT || ORDER == BFP_ORDER_SPARSIFY_ONLY;
+    constexpr bool kSparseLast = ORDER == BFP_ORDER_QUANT_SPARSIFY;
+    constexpr bool kHalf = DT != BFP_DT_F32;
+    constexpr bool kBf16 = DT == BFP_DT_BF16;
+    constexpr int kOutVecs = (STOC && V == 8) ? 2 : 1;
+    constexpr int KDD = KD > 0 ? KD : 1;
+    uint32_t w[U][4];
+    uint32_t amax[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        w[u][0] = raw[u].x; w[u][1] = raw[u].y; w[u][2] = raw[u].z; w[u][3] = raw[u].w;
+        if (kQuant) {
+            // block max over the UNMASKED keys: the maximum always survives an N:M mask with N >= 1 (SURVEY.md appendix A.4 i)
+            if (kHalf) {
+                const uint32_t a01 = __vmaxu2(w[u][0] & 0x7fff7fffu, w[u][1] & 0x7fff7fffu), a23 = __vmaxu2(w[u][2] & 0x7fff7fffu, w[u][3] & 0x7fff7fffu);
+                amax[u] = __vmaxu2(a01, a23);                     // (max of the even elements | max of the odd elements << 16)
+            } else {
+                amax[u] = max(max(w[u][0] & 0x7fffffffu, w[u][1] & 0x7fffffffu), max(w[u][2] & 0x7fffffffu, w[u][3] & 0x7fffffffu));
+            }
+        }
+        if (kSparseFirst && M == 4) {
+            if (kHalf) { nm_mask4_packed16<KDD>(w[u][0], w[u][1]); nm_mask4_packed16<KDD>(w[u][2], w[u][3]); }
+            else nm_mask4_bits<KDD>(w[u]);
+        }
+    }
+    if (kQuant) {
+        // butterfly over the lanes that share a block; every lane of the warp executes every shuffle
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            if (off < p.lanes_per_block) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t o = __shfl_xor_sync(0xffffffffu, amax[u], off);
+                    amax[u] = kHalf ? __vmaxu2(amax[u], o) : max(amax[u], o);
+                }
+            }
+        }
+        const SimpleConsts<DT, STOC> sk(p.m);
+        const int m = p.m;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            // the vector's uniforms, fl(u - 0.5): generated here, not for the whole tile up front -- 8 (not 32) live registers for
+            // 16-bit inputs; the scheduler still overlaps this vector's Philox rounds with the previous vector's rounding
+            float un[STOC ? V : 1];
+            if (STOC) {
+#pragma unroll
+                for (int q = 0; q < V / 4; ++q) {
+                    const uint4 r = philox4x32_10((uint64_t)(p.ctr_base + vidx[u] * (V / 4) + q), p.offset, p.seed);
+                    un[4 * q] = u01_centered(r.x); un[4 * q + 1] = u01_centered(r.y);
+                    un[4 * q + 2] = u01_centered(r.z); un[4 * q + 3] = u01_centered(r.w);
+                }
+            }
+            uint32_t abits;
+            if (kHalf) {
+                const uint32_t a16 = max(amax[u] & 0xffffu, amax[u] >> 16);
+                abits = kBf16 ? (a16 << 16) : __float_as_uint(__half2float(__ushort_as_half((unsigned short)a16)));
+            } else {
+                abits = amax[u];
+            }
+            const uint32_t sb = __float_as_uint(D::rnd(__uint_as_float(abits) + p.eps));      // bfp_ops.py:33  max_v + epsilon
+            bool simple = (sb - sk.lo_bits) < sk.span_bits;
+            if (kHalf) {
+                constexpr int MB = HalfBits<kHalf ? DT : BFP_DT_F16>::kMant;
+                const uint32_t step1 = g_exp_step[HalfBits<kHalf ? DT : BFP_DT_F16>::kTable][((sb >> 23) + 1u) & 0xffu];   // index k + 128 = biased exponent + 1 (Inf / NaN wrap to entry 0 = not tabulated)
+                const uint32_t f = (sb >> (23 - MB)) & ((1u << MB) - 1u);
+                simple = simple && step1 != 0u && f + 1u >= step1;
+            } else {
+                simple = simple && (sb & 0x7fffffu) > 128u;
+            }
+            const uint32_t ebits = sb & 0x7f800000u;                                  // 2^k
+            uint4 o0, o1;
+            if (simple) {
+                if (!STOC && kHalf) {
+                    // packed pairs: C = 2^(p + MB) and (2^m - 1) 2^p in the tensor's own 16-bit format, both halves
+                    uint32_t c16;
+                    if (kBf16) c16 = (ebits >> 16) + (uint32_t)((1 - m + PL::kMB) << 7);
+                    else c16 = (((ebits >> 23) - 127u + 15u + (uint32_t)(1 - m + PL::kMB)) << 10);
+                    const uint32_t c2 = c16 * 0x00010001u;
+                    // (2^m - 1) 2^p = C (2^m - 1) 2^-MB, the factor exact in the type (m <= MB significant bits)
+                    const float vf = (float)((1 << m) - 1) * (kBf16 ? 0.0078125f : 0.0009765625f);
+                    const uint32_t vk16 = kBf16 ? (__float_as_uint(vf) >> 16) : (uint32_t)__half_as_ushort(__float2half_rn(vf));
+                    uint32_t v2;
+                    {
+                        const uint32_t vk2 = vk16 * 0x00010001u;
+                        if (kBf16) asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(v2) : "r"(c2), "r"(vk2));
+                        else asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(v2) : "r"(c2), "r"(vk2));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t a = w[u][i] & 0x7fff7fffu;
+                        const uint32_t r = hmin2_bits(hsub2_bits(hadd2_bits(a, c2, kBf16), c2, kBf16), v2, kBf16);
+                        w[u][i] = r | (w[u][i] & 0x80008000u);
+                    }
+                    o0 = make_uint4(w[u][0], w[u][1], w[u][2], w[u][3]); o1 = o0;
+                } else if (!STOC) {
+                    const float c = __uint_as_float(ebits + (uint32_t)((1 - m + PL::kMB) << 23));
+                    const float vd = c * ((float)((1 << m) - 1) * 1.1920928955078125e-07f);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float t = __uint_as_float(w[u][i]);
+                        const float r = fminf((fabsf(t) + c) - c, vd);
+                        w[u][i] = __float_as_uint(r) | (w[u][i] & 0x80000000u);
+                    }
+                    o0 = make_uint4(w[u][0], w[u][1], w[u][2], w[u][3]); o1 = o0;
+                } else {
+                    // stochastic rounding: fp32 arithmetic and fp32 output for every input type (torch promotion, bfp_ops.py:22-23).
+                    // |t / 2^p| < 2^m here, so |r| <= 2^m and the FMA-pipe clamp is exact.
+                    float v[V];
+                    unpack_vec<DT>(make_uint4(w[u][0], w[u][1], w[u][2], w[u][3]), v);
+                    const uint32_t dbits = ebits + (uint32_t)((1 - m) << 23);       // 2^p
+                    const float delta = __uint_as_float(dbits), inv = __uint_as_float(0x7f000000u - dbits);
+                    const float k1 = __uint_as_float((uint32_t)(127 - m - 1) << 23) + __uint_as_float((uint32_t)(127 - 2 * m - 2) << 23);
+#pragma unroll
+                    for (int i = 0; i < V; ++i) {
+                        const float r = rintf(__fmaf_rn(v[i], inv, un[i]));      // = fl(fl(u - 0.5) + t / 2^p): the product is exact
+                        const float c = __fmaf_rn(r, k1, 12582912.0f) - 12582912.0f;
+                        v[i] = (r - c) * delta;
+                    }
+                    o0 = pack_vec<BFP_DT_F32>(v); o1 = pack_vec<BFP_DT_F32>(v + (V == 8 ? 4 : 0));
+                }
+            } else {
+                uint4 s0 = make_uint4(0u, 0u, 0u, 0u), s1 = s0;
+                if (STOC) {
+                    s0 = make_uint4(__float_as_uint(un[0]), __float_as_uint(un[1]), __float_as_uint(un[2]), __float_as_uint(un[3]));
+                    if (V == 8) s1 = make_uint4(__float_as_uint(un[V - 4]), __float_as_uint(un[V - 3]), __float_as_uint(un[V - 2]), __float_as_uint(un[V - 1]));
+                }
+                const VecOut g = quant_vec_general<DT, STOC>(make_uint4(w[u][0], w[u][1], w[u][2], w[u][3]), abits, m, p.eps, s0, s1);
+                o0 = g.a; o1 = g.b;
+            }
+            if (kSparseLast && M == 4) {
+                if (STOC || !kHalf) {
+                    uint32_t b[4] = {o0.x, o0.y, o0.z, o0.w};
+                    nm_mask4_bits<KDD>(b);
+                    o0 = make_uint4(b[0], b[1], b[2], b[3]);
+                    if (kOutVecs == 2) {
+                        uint32_t c[4] = {o1.x, o1.y, o1.z, o1.w};
+                        nm_mask4_bits<KDD>(c);
+                        o1 = make_uint4(c[0], c[1], c[2], c[3]);
+                    }
+                } else {
+                    nm_mask4_packed16<KDD>(o0.x, o0.y); nm_mask4_packed16<KDD>(o0.z, o0.w);
+                }
+            }
+            uint4 o[kOutVecs];
+            o[0] = o0;
+            if (kOutVecs == 2) o[kOutVecs - 1] = o1;
+            store(u, o);
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            uint4 o[kOutVecs];
+            o[0] = make_uint4(w[u][0], w[u][1], w[u][2], w[u][3]);
+            store(u, o);
+        }
+    }
+}
+
+// The per-vector streaming loop (round 1's kernel body, unchanged): every vector is loaded up front, then processed and stored one
+// after the other with 32-bit in-tile indexing -- 32 registers, 8 CTAs per SM.  Used where the tile path is not (fp32 with nearest
+// rounding, exotic group sizes, the torch-CPU tie rule).
 template <int DT, int ORDER, int M, int KD, int TIE, bool STOC, bool PADDED>
-__global__ void __launch_bounds__(kStreamThreads) quant_stream_kernel(const StreamParams p) {
+__device__ __forceinline__ void stream_body_per_vector(const StreamParams& p) {
     using D = DType<DT>;
     constexpr int V = D::kVec;
     constexpr bool kQuant = ORDER != BFP_ORDER_SPARSIFY_ONLY;
@@ -195,6 +452,121 @@ __global__ void __launch_bounds__(kStreamThreads) quant_stream_kernel(const Stre
                     if (kOutVecs == 2) st_stream(dst + 1, o[kOutVecs - 1]);
                 }
             }
+        }
+    }
+}
+
+// kStreamUnroll vectors of one thread: the tile path where it applies, else vector by vector.  store(u, o) receives vector u's
+// kOutVecs output vectors as soon as they are final.
+template <int DT, int ORDER, int M, int KD, int TIE, bool STOC, class Store>
+__device__ __forceinline__ void process_vectors(const uint4* raw, const StreamParams& p, const int64_t* vidx, Store&& store) {
+    constexpr int kOutVecs = (STOC && DType<DT>::kVec == 8) ? 2 : 1;
+    if constexpr (TilePath<DT, ORDER, M, KD, TIE, STOC>::kEnabled) {
+        process_tile<DT, ORDER, M, KD, TIE, STOC>(raw, p, vidx, store);
+    } else {
+#pragma unroll
+        for (int u = 0; u < kStreamUnroll; ++u) {
+            uint4 o[kOutVecs];
+            process_vec<DT, ORDER, M, KD, TIE, STOC>(raw[u], p, vidx[u], o);
+            store(u, o);
+        }
+    }
+}
+
+// ORDER: BFP_ORDER_*.  M / KD / TIE: see mask_vec.  STOC: stochastic rounding (fp32 output).
+#ifndef BFP_STOC_MIN_CTAS
+#define BFP_STOC_MIN_CTAS 3
+#endif
+#ifndef BFP_HALF_MIN_CTAS
+#define BFP_HALF_MIN_CTAS 4
+#endif
+template <int DT, bool STOC> struct StreamOcc { static constexpr int kMinCtas = STOC ? BFP_STOC_MIN_CTAS : (DT == BFP_DT_F32 ? 1 : BFP_HALF_MIN_CTAS); };
+template <int DT, int ORDER, int M, int KD, int TIE, bool STOC, bool PADDED>
+__global__ void __launch_bounds__(kStreamThreads, StreamOcc<DT, STOC>::kMinCtas) quant_stream_kernel(const StreamParams p) {
+    using D = DType<DT>;
+    constexpr int V = D::kVec;
+    constexpr int kOutVecs = (STOC && V == 8) ? 2 : 1;     // fp32 output of 8 half inputs = two 16-B stores
+    constexpr int kTileVecs = kStreamThreads * kStreamUnroll;
+
+    if constexpr (!TilePath<DT, ORDER, M, KD, TIE, STOC>::kEnabled) {
+        stream_body_per_vector<DT, ORDER, M, KD, TIE, STOC, PADDED>(p);
+        return;
+    }
+    const int64_t n_tiles = (p.n_vec + kTileVecs - 1) / kTileVecs;
+
+    // Programmatic dependent launch: let the next kernel on the stream get its CTAs resident while this one drains, and
+    // do not touch global memory before everything earlier on the stream has completed (stream order is preserved).
+    pdl_launch_dependents();
+    pdl_wait();
+
+    if constexpr (STOC && !PADDED) {
+        // Stochastic rounding is instruction-heavy (Philox4x32-10): a tile's loads are far apart in time unless the NEXT tile's
+        // vectors are requested before this tile's arithmetic starts (software prefetch, one tile ahead in registers).
+        uint4 nxt[kStreamUnroll];
+        auto fetch = [&](int64_t t) {
+            const int64_t base = t * kTileVecs;
+            const int rem = (int)min((int64_t)kTileVecs, p.n_vec - base);
+#pragma unroll
+            for (int u = 0; u < kStreamUnroll; ++u) {
+                const int li = (int)threadIdx.x + u * kStreamThreads;
+                nxt[u] = (li < rem) ? ld_stream(p.in + base + li) : make_uint4(0u, 0u, 0u, 0u);
+            }
+        };
+        if ((int64_t)blockIdx.x < n_tiles) fetch(blockIdx.x);
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t tile_base = tile * kTileVecs;
+            const int rem = (int)min((int64_t)kTileVecs, p.n_vec - tile_base);
+            uint4 raw[kStreamUnroll];
+            int64_t vidx[kStreamUnroll];
+#pragma unroll
+            for (int u = 0; u < kStreamUnroll; ++u) { raw[u] = nxt[u]; vidx[u] = tile_base + (int)threadIdx.x + u * kStreamThreads; }
+            if (tile + gridDim.x < n_tiles) fetch(tile + gridDim.x);
+            process_vectors<DT, ORDER, M, KD, TIE, STOC>(raw, p, vidx, [&](int u, const uint4* o) {
+                const int li = (int)threadIdx.x + u * kStreamThreads;
+                if (li < rem) {
+                    uint4* dst = p.out + (tile_base + li) * kOutVecs;
+                    st_stream(dst, o[0]);
+                    if (kOutVecs == 2) st_stream(dst + 1, o[kOutVecs - 1]);
+                }
+            });
+        }
+        return;
+    }
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t tile_base = tile * kTileVecs;
+        uint4 raw[kStreamUnroll];
+        int64_t vidx[kStreamUnroll];
+        if constexpr (!PADDED) {
+            // flat mode: 32-bit in-tile indexing, one bounds compare per vector
+            const int rem = (int)min((int64_t)kTileVecs, p.n_vec - tile_base);   // vectors of this tile that exist
+            const uint4* src = p.in + tile_base;
+#pragma unroll
+            for (int u = 0; u < kStreamUnroll; ++u) {
+                const int li = (int)threadIdx.x + u * kStreamThreads;
+                raw[u] = (li < rem) ? ld_stream(src + li) : make_uint4(0u, 0u, 0u, 0u);
+                vidx[u] = tile_base + li;
+            }
+            process_vectors<DT, ORDER, M, KD, TIE, STOC>(raw, p, vidx, [&](int u, const uint4* o) {
+                const int li = (int)threadIdx.x + u * kStreamThreads;
+                if (li < rem) {
+                    uint4* dst = p.out + (tile_base + li) * kOutVecs;
+                    st_stream(dst, o[0]);
+                    if (kOutVecs == 2) st_stream(dst + 1, o[kOutVecs - 1]);
+                }
+            });
+        } else {
+#pragma unroll
+            for (int u = 0; u < kStreamUnroll; ++u) {
+                vidx[u] = real_vec(p, tile_base + (int)threadIdx.x + u * kStreamThreads);     // -1 = padding / out of range
+                raw[u] = vidx[u] >= 0 ? ld_stream(p.in + vidx[u]) : make_uint4(0u, 0u, 0u, 0u);
+            }
+            process_vectors<DT, ORDER, M, KD, TIE, STOC>(raw, p, vidx, [&](int u, const uint4* o) {
+                if (vidx[u] >= 0) {
+                    uint4* dst = p.out + vidx[u] * kOutVecs;
+                    st_stream(dst, o[0]);
+                    if (kOutVecs == 2) st_stream(dst + 1, o[kOutVecs - 1]);
+                }
+            });
         }
     }
 }
@@ -317,7 +689,7 @@ __global__ void __launch_bounds__(128) quant_generic_kernel(const GenericParams 
             const uint64_t flat = (uint64_t)(p.index_base + row * p.K + c);
             const uint4 r = philox4x32_10(flat >> 2, p.offset, p.seed);
             const uint32_t w = (flat & 3) == 0 ? r.x : ((flat & 3) == 1 ? r.y : ((flat & 3) == 2 ? r.z : r.w));
-            return u01(w);
+            return u01_centered(w);
         };
         if (ORDER == BFP_ORDER_SPARSIFY_ONLY) {
             for (int64_t c = idx * p.M; c < min(p.K, idx * p.M + p.M); ++c)

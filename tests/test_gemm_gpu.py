@@ -478,7 +478,7 @@ def test_bfplinear_forward_is_cuda_graph_capturable(ops):
     kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=7, block_size=64,
               w_sparsity=True, N=2, M=4, first="s", sparsity_mode="structured", device="cuda")
     torch.manual_seed(11)
-    lins = [ops.BFPLinear(512, 768, bias=True, **dict(kw)).cuda(), ops.BFPLinear(768, 256, bias=False, **dict(dict(kw), w_sparsity=False)).cuda()]
+    lins = [ops.BFPLinear(512, 768, bias=True, **dict(kw)).cuda().eval(), ops.BFPLinear(768, 256, bias=False, **dict(dict(kw), w_sparsity=False)).cuda().eval()]
     x = torch.randn(300, 512, device="cuda")
     with torch.no_grad():
         ref = lins[1](lins[0](x))                       # also packs + caches the weights outside the capture
@@ -503,7 +503,7 @@ def test_packed_activation_cache_is_safe(ops):
     kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=7, block_size=64, device="cuda")
     from qsi_b200 import _lib
     torch.manual_seed(2)
-    q, k = ops.BFPLinear(256, 128, bias=False, **dict(kw)).cuda(), ops.BFPLinear(256, 64, bias=False, **dict(kw)).cuda()
+    q, k = ops.BFPLinear(256, 128, bias=False, **dict(kw)).cuda().eval(), ops.BFPLinear(256, 64, bias=False, **dict(kw)).cuda().eval()
     x = torch.randn(96, 256, device="cuda")
     with torch.no_grad():
         q(x); k(x)                                           # weights packed, x's packed form cached
@@ -749,7 +749,7 @@ def test_bfplinear_stochastic_inference_on_tensor_cores(ops, w_sparse, monkeypat
     kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="stoc", epsilon=1e-8, mant_bits=5, block_size=64,
               w_sparsity=w_sparse, N=2, M=4, first="s", sparsity_mode="structured", device="cuda")
     torch.manual_seed(6)
-    lin = ops.BFPLinear(512, 256, bias=True, **dict(kw)).cuda()
+    lin = ops.BFPLinear(512, 256, bias=True, **dict(kw)).cuda().eval()
     x = torch.randn(3, 40, 512, device="cuda")
     with torch.no_grad():
         y0 = lin(x)                                                            # (first call builds the static 2:4 structure when w_sparse)
@@ -794,7 +794,7 @@ def test_bfplinear_half_precision_stochastic_inference(ops, monkeypatch):
     kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="stoc", epsilon=1e-8, mant_bits=5, block_size=64,
               w_sparsity=True, N=2, M=4, first="s", sparsity_mode="structured", device="cuda")
     torch.manual_seed(9)
-    lin = ops.BFPLinear(512, 256, bias=False, **dict(kw)).cuda().half()
+    lin = ops.BFPLinear(512, 256, bias=False, **dict(kw)).cuda().half().eval()
     x = torch.randn(3, 40, 512, device="cuda").half()
     from qsi_b200 import _lib
     with torch.no_grad():
@@ -893,11 +893,11 @@ def test_trainable_bias_alone_gets_its_gradient(ops):
         assert y.requires_grad and y.dtype == dt
         y.float().sum().backward()
         assert lin.bias.grad is not None and lin.weight.grad is None
-        # d(sum y)/d bias = number of rows, after the output-gradient quantiser (ones are BFP-exact)
-        assert torch.allclose(lin.bias.grad.float(), torch.full((128,), 40.0, device="cuda"))
+        # d(sum y)/d bias = sum over rows of Q_grad(1.0); a block of ones has e = 0 and 1.0 saturates to (2^7 - 1) / 2^7
+        assert torch.allclose(lin.bias.grad.float(), torch.full((128,), 40.0 * 127 / 128, device="cuda"))
         op = ops.F_linear_bfp(**dict(_KW))
         b = torch.zeros(128, device="cuda", dtype=dt, requires_grad=True)
         y2 = op(x, lin.weight, b)
         assert y2.requires_grad
         y2.float().sum().backward()
-        assert torch.allclose(b.grad.float(), torch.full((128,), 40.0, device="cuda"))
+        assert torch.allclose(b.grad.float(), torch.full((128,), 40.0 * 127 / 128, device="cuda"))

@@ -130,10 +130,18 @@ def test_stochastic_rounding_statistics(oracle):
 
 def test_philox_known_answer(oracle):
     """Philox4x32-10 KAT from the Random123 distribution (kat_vectors): counter=key=0 -> 6627e8d5 e169c58d bc57ac4c 9b00dbd8."""
+    import ctypes
     L = oracle.lib()
-    # uniform i uses word (i & 3) of the block for counter (i>>2, 0, offset, 0), key = seed
-    words = [int(round(L.oracle_philox_uniform(0, 0, i) * (1 << 24))) for i in range(4)]
-    assert words == [0x6627e8d5 >> 8, 0xe169c58d >> 8, 0xbc57ac4c >> 8, 0x9b00dbd8 >> 8]
+    L.oracle_philox_word.argtypes = [ctypes.c_uint64] * 3
+    L.oracle_philox_word.restype = ctypes.c_uint32
+    kat = [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    # element i uses word (i & 3) of the block for counter (i>>2, 0, offset, 0), key = seed
+    assert [L.oracle_philox_word(0, 0, i) for i in range(4)] == kat
+    # the uniform is that word truncated to 24 significant bits, times 2^-32 (the kernel's cvt.rz.f32.u32 and an exact scale)
+    for i, w in enumerate(kat):
+        drop = max(0, w.bit_length() - 24)
+        assert L.oracle_philox_uniform(0, 0, i) == np.float32((w >> drop << drop) * 2.0 ** -32)
+    assert L.oracle_philox_uniform(0, 0, 1) == np.float32((0xe169c58d >> 8) * 2.0 ** -24)       # words >= 2^31: (w >> 8) * 2^-24
 
 
 # ---------------------------------------------------------------------------------------------------------------
