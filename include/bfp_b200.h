@@ -76,7 +76,9 @@ uint64_t bfp_launch_count(void);
  *   "gemm_bf16_cta_group" 0 = dense bf16 GEMM uses CTA pairs when T > 128 and N > 128; 1 / 2 forces the mode
  *   "pdl"                 1 (default) = the streaming kernels are launched with programmatic stream serialization
  *   "gemm_sp_cta_group"   0 = bfp_gemm_bf16_sp uses CTA pairs (cta_group::2) when N > 128; 1 / 2 forces the mode
- *   "gemm_bf16_tile_n"    0 = bfp_gemm_bf16 uses its 128x256 tile (128x128 when N <= 128); 128 / 256 forces one */
+ *   "gemm_bf16_tile_n"    0 = bfp_gemm_bf16 uses its 128x256 tile (128x128 when N <= 128); 128 / 256 forces one
+ *   "unstructured_force_fallback" 1 = bfp_unstructured_quantize takes its whole-tensor radix select (the path for a missed
+ *                         bracket or massive ties on a non-round value); for tests */
 int bfp_set_option(const char* name, int64_t value);
 
 /* sm count, compute capability, L2 bytes of the current device. */
@@ -111,6 +113,21 @@ int bfp_nm_sparsify(const void* in, void* out, int64_t rows, int64_t K, int dtyp
 size_t bfp_unstructured_workspace_bytes(void);
 int bfp_unstructured_sparsify(const void* in, void* out, int64_t numel, int dtype, uint64_t k, void* workspace,
                               void* stream);
+
+/* float_to_bfp_blocked (bfp_ops.py:124-149) with sparsity_mode == 'unstructured' and sparsity_num_format in {'bfp','fp32'}:
+ * global magnitude pruning (_unstructured_sparsity, :61-71) and the BFP quantiser (_no_sparsity_float_to_bfp, :46-59) in the
+ * order `order` -- BFP_ORDER_SPARSIFY_QUANT (first == 's'), BFP_ORDER_QUANT_SPARSIFY (the k smallest magnitudes of the QUANTISED
+ * tensor go) or BFP_ORDER_SPARSIFY_ONLY -- in two reads and one write of the tensor: a sampled bracket of the k-th magnitude, one
+ * counting pass, one masking + quantising pass (csrc/bfp_unstructured_fused.cu).  Same results as composing
+ * bfp_unstructured_sparsify and bfp_quantize (same Philox counters for stochastic rounding).  k in (0, numel).
+ * Needs 16-byte aligned buffers, numel a multiple of 4 (fp32) / 8 (half) and, when quantising, K a multiple of a power-of-two
+ * block_size of 4..128 (fp32) / 8..256 (half) elements: BFP_E_UNSUPPORTED otherwise (compose the two calls).  out must not alias
+ * in.  `workspace`: bfp_unstructured_quantize_workspace_bytes(numel, in_dtype) bytes of caller-owned device scratch
+ * (about numel / 2 bytes), 16-byte aligned; no allocation and no host synchronisation inside. */
+size_t bfp_unstructured_quantize_workspace_bytes(int64_t numel, int dtype);
+int bfp_unstructured_quantize(const void* in, void* out, int64_t rows, int64_t K, int in_dtype, int out_dtype, uint64_t k,
+                              int order, int block_size, int mant_bits, float eps, int rounding, uint64_t seed, uint64_t offset,
+                              void* workspace, size_t workspace_bytes, void* stream);
 
 /* The 'int' number format (_quantize with sparsity_num_format == 'int', bfp_ops.py:111-120): SparseGPT's per-channel
  * symmetric min/max INT-`bits` fake quantiser (int_ops.py Quantizer.configure/find_params/quantize, perchannel, sym).

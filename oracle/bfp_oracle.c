@@ -288,7 +288,8 @@ int oracle_unstructured_sparsify(const void *in, void *out, int64_t n, int dt, i
     if (k < 0) return 1;
     if (k > n) k = n;
     kv_t *kv = (kv_t *)malloc(sizeof(kv_t) * (size_t)(n > 0 ? n : 1));
-    for (int64_t i = 0; i < n; ++i) { kv[i].key = order_key(fabsf(load_elt(in, dt, i))); kv[i].idx = i; }
+    /* torch's CUDA radix select maps every NaN to one all-ones key (TopKTypeConfig::convert): NaNs tie, index order decides */
+    for (int64_t i = 0; i < n; ++i) { uint32_t key = order_key(fabsf(load_elt(in, dt, i))); kv[i].key = key > 0x7f800000u ? 0x7f800001u : key; kv[i].idx = i; }
     qsort(kv, (size_t)n, sizeof(kv_t), kv_cmp);
     for (int64_t i = 0; i < n; ++i) store_elt(out, dt, i, load_elt(in, dt, i));
     for (int64_t j = 0; j < k; ++j) store_elt(out, dt, kv[j].idx, 0.0f);

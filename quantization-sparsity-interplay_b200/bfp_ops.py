@@ -176,13 +176,50 @@ def _no_sparsity_float_to_bfp(t, block_size, mant_bits, epsilon, rounding_mode, 
 # ---------------------------------------------------------------------------------------------------------------
 # bfp_ops.py:61-102: sparsity
 # ---------------------------------------------------------------------------------------------------------------
+def _unstructured_fused(t, sparsity_frac, order, block_size=0, mant_bits=0, epsilon=0.0, rounding_mode=rounding_modes.DETERM,
+                        philox=None):
+    """Global magnitude pruning fused with the BFP quantiser (csrc/bfp_unstructured_fused.cu): a sampled bracket of the k-th
+    magnitude, one counting read, one masking + quantising read/write.  Returns None when the call does not fit that path
+    (CPU tensor, ragged block structure, k == 0 or k == numel): the caller then composes the stand-alone kernels."""
+    if os.environ.get("BFP_UNSTRUCTURED_FUSED", "1") == "0" or not t.is_cuda or t.dtype not in _DT or t.dim() == 0:
+        return None
+    src = t.detach().contiguous()
+    n = src.numel()
+    k = int(n * sparsity_frac)                                   # bfp_ops.py:66
+    vec = 4 if src.dtype == torch.float32 else 8
+    if n == 0 or k <= 0 or k >= n or n % vec or src.data_ptr() % 16:
+        return None
+    K = src.shape[-1]
+    quant = order != _lib.ORDER_SPARSIFY_ONLY
+    if quant:
+        B = int(block_size)
+        if B < vec or B & (B - 1) or B // vec > 32 or K % B:
+            return None
+    rounding = _rounding_code(rounding_mode) if quant else _lib.ROUND_NEAREST
+    stoc = rounding == _lib.ROUND_STOCHASTIC
+    out = torch.empty(src.shape, dtype=torch.float32 if stoc else src.dtype, device=src.device)
+    seed, offset = (philox if philox is not None else _PhiloxState.next()) if stoc else (0, 0)
+    L = _lib.lib()
+    with _on(src.device):
+        nbytes = L.bfp_unstructured_quantize_workspace_bytes(n, _DT[src.dtype])
+        ws = torch.empty(nbytes // 8 + 1, dtype=torch.int64, device=src.device)
+        _lib.check(L.bfp_unstructured_quantize(src.data_ptr(), out.data_ptr(), n // K, K, _DT[src.dtype], _DT[out.dtype], k, order,
+                                               int(block_size), int(mant_bits), float(epsilon), rounding, seed, offset,
+                                               ws.data_ptr(), nbytes, _stream()))
+    return out
+
+
 def _unstructured_sparsity(t, device, sparsity_frac=0):
     """bfp_ops.py:61-71: global magnitude pruning -- the k = int(numel * frac) smallest |t| of the whole tensor become
-    +0.0 (ties at the threshold in index order, like torch-CUDA's topk).  Multi-pass radix select on the GPU
+    +0.0 (ties at the threshold in index order, like torch-CUDA's topk).  Two reads + one write through the sampled-bracket
+    pipeline (csrc/bfp_unstructured_fused.cu); shapes it does not take go through the multi-pass radix select
     (csrc/bfp_unstructured.cu); CPU tensors are staged through the GPU."""
     assert (sparsity_frac > 0)
     if t.dtype not in _DT:
         raise TypeError(f"bfp_b200 supports float32 / float16 / bfloat16 tensors, got {t.dtype}")
+    fused = _unstructured_fused(t, sparsity_frac, _lib.ORDER_SPARSIFY_ONLY)
+    if fused is not None:
+        return fused
     src = t.detach().contiguous()
     n = src.numel()
     k = int(n * sparsity_frac)                                   # bfp_ops.py:66
@@ -313,6 +350,15 @@ def float_to_bfp_blocked(t, mant_bits, epsilon, rounding_mode, device, block_siz
             and _int_nm_fusable(t, N, M)):
         bits = weight_mant_bits if sgd_update else mant_bits                            # bfp_ops.py:113-114
         return _int_quantize_nm(t, bits, N, M, _lib.ORDER_SPARSIFY_QUANT if first == 's' else _lib.ORDER_QUANT_SPARSIFY)
+
+    if sparsity and sparsity_mode == 'unstructured' and sparsity_num_format == 'bfp':
+        # global magnitude pruning and the BFP quantiser in two reads + one write (either order)
+        assert (sparsity_frac > 0)                                                      # bfp_ops.py:62
+        m = weight_mant_bits if sgd_update else mant_bits                               # bfp_ops.py:108-109
+        y = _unstructured_fused(t, sparsity_frac, _lib.ORDER_SPARSIFY_QUANT if first == 's' else _lib.ORDER_QUANT_SPARSIFY,
+                                block_size=block_size, mant_bits=m, epsilon=epsilon, rounding_mode=rounding_mode)
+        if y is not None:
+            return y
 
     if first == 's':
         sparse_t = _sparsify(t, sparsity, sparsity_mode, device, N, M, sparsity_frac)

@@ -135,6 +135,7 @@ int bfp_set_option(const char* name, int64_t value) {
     else if (!strcmp(name, "gemm_sp_tile") && (value == 0 || value == 240 || value == 256 || value == 480)) t.gemm_sp_tile = (int)value;
     else if (!strcmp(name, "gemm_sp_cta_group") && value >= 0 && value <= 2) t.gemm_sp_cta_group = (int)value;
     else if (!strcmp(name, "gemm_bf16_tile_n") && (value == 0 || value == 128 || value == 256)) t.gemm_bf16_tile_n = (int)value;
+    else if (!strcmp(name, "unstructured_force_fallback") && (value == 0 || value == 1)) t.unstructured_force_fallback = (int)value;
     else return set_errorf(BFP_E_ARG, "unknown option or bad value: %s", name);
     return BFP_OK;
 }
@@ -207,6 +208,35 @@ int bfp_unstructured_sparsify(const void* in, void* out, int64_t numel, int dtyp
     if (reinterpret_cast<uintptr_t>(workspace) % 8) return set_error(BFP_E_ALIGN, "workspace must be 8-byte aligned");
     if (int rc = require_device()) return rc;
     return unstructured_device(in, out, numel, dtype, k, workspace, static_cast<cudaStream_t>(stream));
+}
+
+size_t bfp_unstructured_quantize_workspace_bytes(int64_t numel, int dtype) { return unstructured_fused_workspace_bytes(numel, dtype); }
+
+int bfp_unstructured_quantize(const void* in, void* out, int64_t rows, int64_t K, int in_dtype, int out_dtype, uint64_t k, int order,
+                              int block_size, int mant_bits, float eps, int rounding, uint64_t seed, uint64_t offset, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    if (rows < 0 || K < 0 || in_dtype < 0 || in_dtype > 2 || out_dtype < 0 || out_dtype > 2) return set_error(BFP_E_ARG, "bad argument");
+    if (order != BFP_ORDER_SPARSIFY_ONLY && order != BFP_ORDER_SPARSIFY_QUANT && order != BFP_ORDER_QUANT_SPARSIFY)
+        return set_error(BFP_E_ARG, "order must be SPARSIFY_ONLY, SPARSIFY_QUANT or QUANT_SPARSIFY");
+    const bool quant = order != BFP_ORDER_SPARSIFY_ONLY;
+    if (rounding != BFP_ROUND_NEAREST && rounding != BFP_ROUND_STOCHASTIC) return set_error(BFP_E_ARG, "Rounding mode is not implemented");   // bfp_ops.py:27
+    if (quant && block_size <= 0) return set_error(BFP_E_ARG, "block_size must be > 0 for the bfp format");                         // bfp_ops.py:130
+    if (quant && (mant_bits < 0 || mant_bits > 23)) return set_error(BFP_E_ARG, "mant_bits must be in [0, 23]");
+    const int want_out = (quant && rounding == BFP_ROUND_STOCHASTIC) ? BFP_DT_F32 : in_dtype;
+    if (out_dtype != want_out) return set_error(BFP_E_ARG, "out_dtype must equal in_dtype for nearest rounding and be fp32 for stochastic rounding");
+    const int64_t n = rows * K;
+    if (n == 0) return BFP_OK;
+    if (!in || !out || !workspace) return set_error(BFP_E_ARG, "null pointer");
+    if (in == out) return set_error(BFP_E_ARG, "out must not alias in");
+    if (k == 0 || k >= (uint64_t)n) return set_error(BFP_E_ARG, "k must be in (0, numel): nothing or everything dropped needs no selection");
+    if (workspace_bytes < unstructured_fused_workspace_bytes(n, in_dtype)) return set_error(BFP_E_ARG, "workspace smaller than bfp_unstructured_quantize_workspace_bytes()");
+    UnstructuredArgs a{in, out, workspace, n, K, in_dtype, (unsigned long long)k, order, block_size, mant_bits, eps,
+                       quant ? rounding : BFP_ROUND_NEAREST, seed, offset};
+    if (!unstructured_fused_supported(a))
+        return set_error(BFP_E_UNSUPPORTED, "fused unstructured pruning needs 16-byte aligned buffers, numel a multiple of the 128-bit vector and K a "
+                                            "multiple of a power-of-two block_size; compose bfp_unstructured_sparsify and bfp_quantize otherwise");
+    if (int rc = require_device()) return rc;
+    return unstructured_fused_device(a, static_cast<cudaStream_t>(stream));
 }
 
 int bfp_block_exponent(const void* in, float* exp_out, int64_t rows, int64_t K, int dtype, int block_size, float eps, void* stream) {

@@ -53,6 +53,9 @@ template <> struct DType<BFP_DT_BF16> {
 };
 
 __device__ __forceinline__ uint32_t abs_bits(float x) { return __float_as_uint(x) & 0x7fffffffu; }
+// Order key of torch.topk over |x| on CUDA (bfp_ops.py:66): the bit pattern of |x|, with every NaN mapped to ONE key above
+// +inf -- torch's radix select converts all NaNs to the same all-ones pattern, so NaNs tie with each other (index order).
+__device__ __forceinline__ uint32_t topk_key(float x) { return min(abs_bits(x), 0x7f800001u); }
 
 // torch.maximum / torch.minimum: NaN in either operand propagates.
 __device__ __forceinline__ float t_max(float a, float b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }

@@ -29,7 +29,8 @@ struct Tuning {
     int gemm_out_tma = 1;                 // GEMM epilogues write the output tile with TMA stores (0 = plain st.global)
     int gemm_sp_tile = 0;                 // sparse kind on CTA pairs: 0 = pick 256- or 480-token tiles by cost; 256 / 480 forces one
     int gemm_sp_cta_group = 0;            // 0 = CTA pairs (cta_group::2) when N > 128; 1 or 2 forces the mode
-    int gemm_bf16_tile_n = 0;             // 0 = default tile (128x256); 128 or 256 forces the width  // bfp_quantize_host: input bytes per pipelined chunk
+    int gemm_bf16_tile_n = 0;             // 0 = default tile (128x256); 128 or 256 forces the width
+    int unstructured_force_fallback = 0;  // tests: the fused unstructured pipeline selects over the whole tensor (its rare path)
 };
 Tuning& tuning();
 
@@ -85,6 +86,22 @@ int transpose16_device(const void* in, void* out, int64_t R, int64_t C, int64_t 
 int int_quantize_nm_device(const void* in, float* out, int64_t C, int64_t K, int dtype, int bits, int N, int order, cudaStream_t s);
 size_t unstructured_workspace_bytes();
 int unstructured_device(const void* in, void* out, int64_t n, int dtype, unsigned long long k, void* workspace, cudaStream_t s);
+struct UnstructuredArgs {           // global magnitude pruning fused with the BFP quantiser (bfp_unstructured_fused.cu)
+    const void* in;
+    void* out;
+    void* workspace;
+    int64_t n, K;                   // numel, last dim
+    int dtype;
+    unsigned long long k;           // entries to drop
+    int order;                      // BFP_ORDER_SPARSIFY_ONLY / SPARSIFY_QUANT / QUANT_SPARSIFY
+    int B, m;
+    float eps;
+    int rounding;
+    uint64_t seed, offset;
+};
+size_t unstructured_fused_workspace_bytes(int64_t n, int dtype);
+bool unstructured_fused_supported(const UnstructuredArgs& a);
+int unstructured_fused_device(const UnstructuredArgs& a, cudaStream_t s);
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline int64_t packed_kp(int64_t K) { return round_up(K, 16); }

@@ -35,7 +35,7 @@ struct SelectState {          // lives in the caller's workspace
 };
 
 template <int DT>
-__device__ __forceinline__ uint32_t key_at(const void* in, int64_t i) { return abs_bits(DType<DT>::load(in, i)); }
+__device__ __forceinline__ uint32_t key_at(const void* in, int64_t i) { return topk_key(DType<DT>::load(in, i)); }
 
 // keys of one 128-bit vector (4 fp32 / 8 half values)
 template <int DT>
@@ -43,7 +43,7 @@ __device__ __forceinline__ void keys_of(const uint4& raw, uint32_t* k) {
     float v[DType<DT>::kVec];
     unpack_vec<DT>(raw, v);
 #pragma unroll
-    for (int i = 0; i < DType<DT>::kVec; ++i) k[i] = abs_bits(v[i]);
+    for (int i = 0; i < DType<DT>::kVec; ++i) k[i] = topk_key(v[i]);
 }
 
 template <int DT>
@@ -234,14 +234,14 @@ __global__ void __launch_bounds__(kThreadsU) apply_kernel(const void* in, void* 
                 float v[V];
                 unpack_vec<DT>(ld_stream(src + j), v);
 #pragma unroll
-                for (int e = 0; e < V; ++e) v[e] = abs_bits(v[e]) < lim ? 0.0f : v[e];
+                for (int e = 0; e < V; ++e) v[e] = topk_key(v[e]) < lim ? 0.0f : v[e];
                 st_stream(dst + j, pack_vec<DT>(v));
             }
             i0 = lo + nv * V;
         }
         for (int64_t i = i0 + threadIdx.x; i < hi; i += kThreadsU) {
             const float v = D::load(in, i);
-            D::store(out, i, abs_bits(v) < lim ? 0.0f : v);
+            D::store(out, i, topk_key(v) < lim ? 0.0f : v);
         }
         return;
     }
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kThreadsU) apply_kernel(const void* in, void* 
         }
         unsigned int ties = 0;                               // bit e: element e equals tau
 #pragma unroll
-        for (int e = 0; e < V; ++e) ties |= (i0 + e < hi && abs_bits(v[e]) == tau) ? (1u << e) : 0u;
+        for (int e = 0; e < V; ++e) ties |= (i0 + e < hi && topk_key(v[e]) == tau) ? (1u << e) : 0u;
         if (__syncthreads_or(ties != 0u)) {
             // exclusive prefix of the tie counts over the threads of the tile (thread order = index order)
             const unsigned int cnt = __popc(ties);
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kThreadsU) apply_kernel(const void* in, void* 
             __syncthreads();                                  // s_warp is reused by the next tile with ties
         }
 #pragma unroll
-        for (int e = 0; e < V; ++e) v[e] = (abs_bits(v[e]) < tau) ? 0.0f : v[e];
+        for (int e = 0; e < V; ++e) v[e] = (topk_key(v[e]) < tau) ? 0.0f : v[e];
         if (full) {
             st_stream(reinterpret_cast<uint4*>(static_cast<char*>(out) + i0 * sizeof(typename D::T)), pack_vec<DT>(v));
         } else {
