@@ -20,6 +20,7 @@ the single-GPU result checked on rank 0) is reported as `column_parallel`.
   roofline  the stream kernel against the measured HBM copy peak (MEASURED_PEAKS.json); `traffic` is measured in the run by an
             ncu child process (dram bytes of one launch) when ncu is available, else null
   quant_modes   the reference's real operating modes (stochastic rounding, fp16 / bf16 tensors) on the same shapes
+  unstructured  global magnitude pruning fused with the quantiser (the other sparsity mode of the reference's scripts)
   gemm      BFP GEMM TOPS at the LLaMA-7B shapes, burst and sustained (>= 2 s), with its own roofline block
   cpu_baseline  the CPU implementation (reference if baseline/_ref is present, else the oracle port) on a bounded sample
 """
@@ -408,6 +409,49 @@ def leg_quant_modes(torch, dev, peak):
     return out
 
 
+def leg_unstructured(torch, dev, peak):
+    """Global (unstructured) magnitude pruning at 50 % fused with HBFP8 block 64 -- the sparsity mode of four of the reference's
+    seven LM scripts (bfp_ops.py:61-71 + :46-59) -- through the C ABI: the two-read pipeline (csrc/bfp_unstructured_fused.cu).
+    GB/s = numel x (sizeof(in) + sizeof(out)) / device time; the kernels move 2 reads + 1 write, so 2/3 of the HBM peak is the
+    ceiling of this figure for equal in/out widths."""
+    from qsi_b200 import _lib
+    L = _lib.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    dts = {"f32": (torch.float32, _lib.DT_F32), "bf16": (torch.bfloat16, _lib.DT_BF16)}
+    out = []
+    for shape in SHAPES:
+        n = shape[0] * shape[1]
+        for dname, (tdt, cdt) in dts.items():
+            xs = [(torch.randn(*shape, device=dev) * 0.02).to(tdt) for _ in range(4)]
+            nbytes = L.bfp_unstructured_quantize_workspace_bytes(n, cdt)
+            ws = torch.empty(nbytes // 8 + 1, dtype=torch.int64, device=dev)
+            for order, oname in ((_lib.ORDER_SPARSIFY_QUANT, "s->q"), (_lib.ORDER_QUANT_SPARSIFY, "q->s")):
+                ys = [torch.empty(*shape, device=dev, dtype=tdt) for _ in range(2)]
+
+                def call(i):
+                    rc = L.bfp_unstructured_quantize(xs[i % 4].data_ptr(), ys[i % 2].data_ptr(), shape[0], shape[1], cdt, cdt, n // 2, order,
+                                                     64, 7, 1e-8, _lib.ROUND_NEAREST, 0, 0, ws.data_ptr(), nbytes, stream)
+                    if rc:
+                        _lib.check(rc)
+                for i in range(5):
+                    call(i)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                iters = 30
+                for i in range(iters):
+                    call(i)
+                e1.record(); torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / iters
+                bpe = 2 * xs[0].element_size()
+                gbs = n * bpe / (ms * 1e-3) / 1e9
+                out.append({"shape": list(shape), "dtype": dname, "order": oname, "sparsity_frac": 0.5, "bytes_per_element": bpe, "us": ms * 1e3,
+                            "GBps": gbs, "frac_of_hbm_peak": gbs / peak, "frac_of_two_read_ceiling": gbs / (peak * 2.0 / 3.0), "launches_per_call": 4})
+                del ys
+            del xs, ws
+    return out
+
+
 def leg_gemm(torch, dev, g, peaks):
     """Secondary metric of BASELINE.json: BFP GEMM TOPS at the LLaMA-7B shapes (T = 4096 tokens, HBFP8 B=64, 2:4 s->q weights):
     2:4-sparse exact-bf16 kind (what BFPLinear runs), dense exact-bf16 kind, int8 + per-block rescale kind; burst (10 launches)
@@ -655,6 +699,10 @@ def main():
                 extras["quant_modes"] = leg_quant_modes(torch, dev, peak)
             except Exception as e:          # noqa: BLE001
                 extras["quant_modes"] = {"error": repr(e)[:300]}
+            try:
+                extras["unstructured"] = leg_unstructured(torch, dev, peak)
+            except Exception as e:
+                extras["unstructured"] = {"error": repr(e)[:300]}
             try:
                 extras["gemm"] = leg_gemm(torch, dev, torch.Generator(device=dev).manual_seed(2000), peaks)
             except Exception as e:          # noqa: BLE001

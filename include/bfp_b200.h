@@ -123,7 +123,7 @@ int bfp_unstructured_sparsify(const void* in, void* out, int64_t numel, int dtyp
  * Needs 16-byte aligned buffers, numel a multiple of 4 (fp32) / 8 (half) and, when quantising, K a multiple of a power-of-two
  * block_size of 4..128 (fp32) / 8..256 (half) elements: BFP_E_UNSUPPORTED otherwise (compose the two calls).  out must not alias
  * in.  `workspace`: bfp_unstructured_quantize_workspace_bytes(numel, in_dtype) bytes of caller-owned device scratch
- * (about numel / 2 bytes), 16-byte aligned; no allocation and no host synchronisation inside. */
+ * (numel bytes + 17 MB), 16-byte aligned; numel < 2^32; no allocation and no host synchronisation inside. */
 size_t bfp_unstructured_quantize_workspace_bytes(int64_t numel, int dtype);
 int bfp_unstructured_quantize(const void* in, void* out, int64_t rows, int64_t K, int in_dtype, int out_dtype, uint64_t k,
                               int order, int block_size, int mant_bits, float eps, int rounding, uint64_t seed, uint64_t offset,

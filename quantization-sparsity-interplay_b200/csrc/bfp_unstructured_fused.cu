@@ -4,24 +4,30 @@
 // _no_sparsity_float_to_bfp (:46-59) in either order -- and _unstructured_sparsity alone.  The k = int(numel * frac) entries
 // torch.topk(|t|, k, largest=False) returns on torch-CUDA are dropped: every key strictly below the k-th smallest key tau, and of
 // the keys equal to tau the first (k - #below) in index order.  key = bit pattern of |value| as fp32 (monotone for fp16 / bf16
-// values too; NaN largest).  With first == 'q' the keys are those of the QUANTISED values, recomputed on the fly in every pass.
+// values too; all NaNs share one key above +inf, as in torch's radix select).  With first == 'q' the keys are those of the
+// QUANTISED values, recomputed on the fly in every pass.
 //
 // The multi-pass radix select of bfp_unstructured.cu reads the tensor four times (plus a separate quantiser pass).  Here:
-//   1. sample_kernel   one CTA.  A stratified sample of ~16 K elements goes into a shared-memory histogram of the 16 leading key
-//                      bits; the bins holding the sample quantiles k/n -+ 5.5 sigma bracket tau: a WINDOW of at most 2048 bins
-//                      (a few per cent of the tensor's mass).  Also zeroes the workspace.
-//   2. pass_a_kernel   first full read.  Counts the keys below the window exactly, histograms the keys inside it at 16-bit
-//                      granularity, and appends every in-window key whose 15 trailing bits are not all zero to a candidate list
-//                      (a few per cent of n).  Keys with zero trailing bits -- 0.0, every BFP value with mant_bits <= 8, bf16
-//                      data: where the massive ties are -- are fully described by their bin and never listed.  The last CTA to
-//                      finish picks the bin that holds the k-th key.
-//   3. refine_kernel   the candidates of that bin resolve the 15 trailing bits -> tau, how many keys equal to tau go (`need`) and
-//                      how many there are (`ties_total`).  A cooperative launch: if the bracket missed (probability ~1e-7), the
-//                      window was too wide or the candidate list overflowed (massive ties on a non-round value), the same grid
-//                      runs a three-digit radix select over the whole tensor with grid-wide barriers instead -- no host round trip.
-//   4. apply_kernel    second read + the write: mask (key < tau, or key == tau and tie rank < need), BFP quantisation before or
-//                      after it, 128-bit stores.  When only some of the ties go, tiles are handed out in index order and a chained
-//                      scan with decoupled look-back gives every tile the number of ties before it.
+//   1. sample_kernel   one cluster of 8 CTAs.  A stratified sample of ~64 K elements goes into a histogram of the 16 leading key
+//                      bits spread over the cluster's shared memory; the bins holding the sample quantiles k/n -+ 5.5 sigma
+//                      BRACKET tau (about two per cent of the mass).
+//   2. pass_a_kernel   first full read; CTA b owns the contiguous RANGE b of the tensor.  Counts the keys below the bracket, and
+//                      looks closer at the keys inside it:
+//                        window mode (bracket <= 2048 bins): per-bin counts, kept per range for the keys whose 15 trailing bits
+//                          are zero ("round" keys: 0.0, every BFP value with mant_bits <= 8, bf16 data -- where the massive ties
+//                          are); the other in-bracket keys are appended to a candidate list as (key, range);
+//                        list mode (a wider bracket, e.g. one that straddles the zeros of a ReLU output and its smallest positive
+//                          values): every in-bracket key is listed, except one "hot" round key (the zeros) counted per range.
+//                      The in-bracket keys of a tile go through per-lane queues, so the per-element code is branch-free.
+//   3. refine_kernel   (cooperative launch) window mode: the candidates of the bin that holds the k-th key resolve its 15 trailing
+//                      bits; list mode: a three-digit radix select over the list.  Either way -> tau, how many of the keys equal
+//                      to tau go (`need`) and how many there are, and -- when only some go -- how many of them each range holds
+//                      (from the per-range counts for a round tau, from the list otherwise).  If the bracket missed (probability
+//                      ~1e-7) or the list overflowed (massive ties on a non-round value) the same grid runs the radix select over
+//                      the whole tensor, with grid-wide barriers -- no host round trip.
+//   4. apply_kernel    second read + the write; CTA b owns range b again.  Mask (key < tau; key == tau according to the range:
+//                      all of them, none, or -- in the ONE range where the cut falls -- by a running tie rank), BFP quantisation
+//                      before or after it, 128-bit stores.  No communication between CTAs.
 // = 2 reads + 1 write (12 B / element fp32) for 8 B / element algorithmic.
 #include <cooperative_groups.h>
 
@@ -29,6 +35,7 @@
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "bfp_internal.h"
 #include "bfp_stream.cuh"
@@ -43,31 +50,42 @@ constexpr int kWarps = kT / 32;
 constexpr int kWin = 2048;                 // window bins (16 leading key bits per bin)
 constexpr int kLowBins = 32768;            // the 15 trailing key bits
 constexpr int kSampleThreads = 1024;
-constexpr int kSampleVecs = 4096;          // 128-bit vectors in the sample (16 K fp32 / 32 K half elements)
-constexpr int kWarpBuf = 512;              // candidate keys a warp stages in shared memory between flushes
-constexpr int kFbBins = 2048;              // fallback radix digits: 11 + 10 + 10 bits
-constexpr uint32_t kNoBin = 0xffffffffu;
+constexpr int kSampleCtas = 8;              // the sample kernel is one cluster of eight CTAs
+constexpr int kSampleVecs = 16384;         // 128-bit vectors in the sample (64 K fp32 / 128 K half elements)
+constexpr int kWarpBuf = 256;              // listed keys a warp stages in shared memory between flushes
+constexpr int kQ = 16;                     // elements per thread per tile = slots of a lane's in-bracket queue
+constexpr int kFbBins = 2048;              // radix digits of the list / whole-tensor select: 11 + 10 + 10 bits
+constexpr int kMaxRanges = 2048;
+constexpr uint32_t kNoKey = 0xffffffffu;
 
 enum { MODE_S_ONLY = 0, MODE_SQ = 1, MODE_QS = 2 };
+enum { PATH_TENSOR = 0, PATH_WINDOW = 1, PATH_LIST = 2 };       // FusedState::path
+enum { TIES_ALL = 0, TIES_ROW = 1, TIES_COUNTED = 2 };           // FusedState::tie_src
 
 struct FusedState {
-    uint32_t lo_bin, span;                 // window = bins [lo_bin, lo_bin + span]
-    uint32_t hot_bin;                      // a window bin holding > 1/64 of the sample (counted in registers), or kNoBin
-    uint32_t valid;                        // 1 while the two-read path holds; 0 -> refine_kernel selects over the whole tensor
-    unsigned int done_a, done_r, tile_counter, pad0;
-    unsigned long long below;              // keys in bins below the window
-    unsigned long long cand_count;         // candidate keys appended (may exceed the capacity: then valid = 0)
-    uint32_t bin, pad1;                    // the bin holding the k-th smallest key
-    unsigned long long need_bin, cnt_bin;  // rank of that key inside the bin (1-based), keys in the bin
-    unsigned long long impure_in_bin;      // candidates found in the bin
-    uint32_t tau, pad2;
+    uint32_t lo_bin, span;                 // bracket = bins [lo_bin, lo_bin + span] of the 16 leading key bits
+    uint32_t hot_key;                      // a round key holding > 1/64 of the sample: counted in registers, never queued (kNoKey: none)
+    uint32_t path;                         // PATH_*; pass A / refine downgrade it to PATH_TENSOR when the two-read path does not hold
+    unsigned int done_a, pad0;
+    unsigned long long below;              // keys below the bracket
+    unsigned long long cand_count;         // listed keys (may exceed the capacity: then path = PATH_TENSOR)
+    unsigned long long hot_total;          // list mode: keys equal to hot_key
+    uint32_t bin, pad1;                    // window mode: the bin holding the k-th smallest key ...
+    unsigned long long need_bin, cnt_bin;  // ... its rank inside the bin (1-based), keys in the bin
+    unsigned long long impure_in_bin;      // listed keys found in the bin
+    uint32_t tau;
+    uint32_t tie_src, tie_row;             // where apply_kernel finds the per-range tie counts (TIES_*)
+    uint32_t pad2;
     unsigned long long need, ties_total;   // of the ties_total keys equal to tau the first `need` (index order) are dropped
-    uint32_t prefix_value, prefix_mask;    // fallback radix select
+    uint32_t prefix_value, prefix_mask;    // radix select state
     unsigned long long fb_need;
-    unsigned long long win_hist[kWin];
-    unsigned long long low_hist[kLowBins];
-    unsigned long long fb_hist[3][kFbBins];
+    long long clk[8];                      // sample kernel phase timestamps (BFP_UNSTRUCTURED_TIMING)
+    uint32_t win_hist[kWin];
+    uint32_t fb_hist[3][kFbBins];
+    uint32_t range_count[kMaxRanges];
+    uint32_t low_hist[kLowBins];
 };
+constexpr size_t kStateHeaderWords = offsetof(FusedState, fb_hist) / 4;    // zeroed by the sample kernel (the rest by pass A)
 
 struct UParams {
     const uint4* in;
@@ -78,22 +96,15 @@ struct UParams {
     float eps;
     uint64_t seed, offset;
     FusedState* st;
-    unsigned long long* tile_state;
-    uint32_t* cand;
+    uint32_t* cta_hist;                    // [row][range]: window mode row d = round keys of bin lo_bin + d; list mode row 0 = hot key
+    uint2* cand;                           // (key, range)
     unsigned long long cand_cap;
+    int n_ranges, tiles_per_range;
     int force_fallback;
 };
 
 __device__ __forceinline__ unsigned long long ld_cg64(const unsigned long long* p) { return __ldcg(p); }
 __device__ __forceinline__ uint32_t ld_cg32(const uint32_t* p) { return __ldcg(p); }
-__device__ __forceinline__ unsigned long long ld_volatile64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_volatile64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
 
 // BFP quantisation of one 128-bit vector in place (the arithmetic and Philox counters of process_vec in bfp_quant.cu).  Every lane
 // of the warp must call it: the block maximum is a butterfly over the lanes that share the block.
@@ -152,37 +163,48 @@ __device__ __forceinline__ unsigned long long block_sum(unsigned long long mine,
     return total;
 }
 
-// The bin holding the need-th smallest key (1-based) of a histogram in global memory, by the whole CTA (thread t owns PER
-// consecutive bins).  `extra0` is added to bin 0.  Returns (through smem result) bin, keys before it, keys in it; found = 0 when
-// need is outside [1, total].
+// The bin holding the need-th smallest key (1-based) of a 32-bit histogram in global memory, by the whole CTA.  T threads,
+// T * PER bins: chunk c = bins [c PER, (c + 1) PER).  Chunk sums are formed with coalesced loads, a block scan over the T chunk
+// sums finds the chunk, one warp walks its PER bins: nothing is chained.  `extra_cnt` is added to bin `extra_bin`.
+// found = 0 when need is outside [1, total].
 struct SelectResult { uint32_t bin; int found; unsigned long long before, count; };
-// T threads, T * PER bins: chunk c = bins [c PER, (c + 1) PER).  Chunk sums are formed by warps with coalesced loads, a block scan
-// over the T chunk sums finds the chunk, one warp walks its PER bins.  Every load is coalesced and nothing is chained.
 template <int T, int PER>
-__device__ __forceinline__ SelectResult block_select(const unsigned long long* hist, int nbins, unsigned long long need, unsigned long long extra0,
+__device__ __forceinline__ SelectResult block_select(const uint32_t* hist, int nbins, unsigned long long need, uint32_t extra_bin, unsigned long long extra_cnt,
                                                       unsigned long long* scratch, SelectResult* s_res) {
-    static_assert(PER == 8 || PER % 32 == 0, "chunk = 8 bins (one thread) or a multiple of 32 (one warp pass)");
+    static_assert(PER == 8 || PER == 128, "chunk = 8 bins (one thread) or 128 bins (one 128-bit load per lane)");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ unsigned long long s_chunk[T];
-    auto bin_at = [&](int b) { return (b < nbins ? ld_cg64(hist + b) : 0ull) + (b == 0 ? extra0 : 0ull); };
     unsigned long long c8[PER == 8 ? 8 : 1];
-    if (PER == 8) {
-        unsigned long long mine = 0;
+    // four consecutive bins starting at b (a multiple of 4), as 64-bit counts with the extra key mixed in
+    auto bins4 = [&](int b, unsigned long long* c) {
+        const uint4 w = b < nbins ? __ldcg(reinterpret_cast<const uint4*>(hist + b)) : make_uint4(0u, 0u, 0u, 0u);
+        c[0] = w.x; c[1] = w.y; c[2] = w.z; c[3] = w.w;
+        if ((extra_bin & ~3u) == (uint32_t)b) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { c8[PER == 8 ? j : 0] = bin_at((int)threadIdx.x * 8 + j); mine += c8[PER == 8 ? j : 0]; }
+            for (int j = 0; j < 4; ++j) c[j] += (extra_bin & 3u) == (uint32_t)j ? extra_cnt : 0ull;
+        }
+    };
+    if (PER == 8) {
+        unsigned long long mine = 0, c[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            bins4((int)threadIdx.x * 8 + 4 * h, c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { c8[PER == 8 ? 4 * h + j : 0] = c[j]; mine += c[j]; }
+        }
         s_chunk[threadIdx.x] = mine;
     } else {
-        // warp w sums chunks [32 w, 32 w + 32): lane l reads bins l, l + 32, ... of the chunk
-        for (int c0 = 0; c0 < 32; c0 += 4) {
-            unsigned long long part[4] = {0ull, 0ull, 0ull, 0ull};
+        // warp w sums chunks [32 w, 32 w + 32): one 128-bit load per lane and chunk, eight chunks in flight
+        for (int c0 = 0; c0 < 32; c0 += 8) {
+            unsigned long long part[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int base = (warp * 32 + c0 + q) * PER;
-#pragma unroll
-                for (int j = 0; j < PER / 32; ++j) part[q] += bin_at(base + j * 32 + lane);
+            for (int q = 0; q < 8; ++q) {
+                unsigned long long c[4];
+                bins4((warp * 32 + c0 + q) * 128 + lane * 4, c);
+                part[q] = c[0] + c[1] + c[2] + c[3];
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 8; ++q) {
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) part[q] += __shfl_xor_sync(0xffffffffu, part[q], off);
                 if (lane == 0) s_chunk[warp * 32 + c0 + q] = part[q];
@@ -213,22 +235,20 @@ __device__ __forceinline__ SelectResult block_select(const unsigned long long* h
         if (owner) { s_chunk_sel = (int)threadIdx.x; s_before = before; }
         __syncthreads();
         if (warp == 0 && s_chunk_sel >= 0) {
-            unsigned long long run = s_before;
-            const int base = s_chunk_sel * PER;
-            bool done = false;
-            for (int j = 0; j < PER / 32 && !done; ++j) {
-                const unsigned long long c = bin_at(base + j * 32 + lane);
-                unsigned long long incl = c;
+            unsigned long long c[4];
+            bins4(s_chunk_sel * 128 + lane * 4, c);
+            const unsigned long long sum4 = c[0] + c[1] + c[2] + c[3];
+            unsigned long long incl = sum4;
 #pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, off);
-                    if (lane >= off) incl += o;
-                }
-                const unsigned long long bef = run + incl - c;
-                const bool hit = bef < need && need <= bef + c;
-                if (hit) { s_res->bin = (uint32_t)(base + j * 32 + lane); s_res->before = bef; s_res->count = c; s_res->found = 1; }
-                done = __any_sync(0xffffffffu, hit);
-                run += __shfl_sync(0xffffffffu, incl, 31);
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += o;
+            }
+            unsigned long long bef = s_before + incl - sum4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (bef < need && need <= bef + c[j]) { s_res->bin = (uint32_t)(s_chunk_sel * 128 + lane * 4 + j); s_res->before = bef; s_res->count = c[j]; s_res->found = 1; }
+                bef += c[j];
             }
         }
         __syncthreads();
@@ -242,42 +262,52 @@ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// 1. sample
+// 1. sample: one cluster of eight CTAs.  Every CTA histograms its share of the sample into a private 65536-bin table of 16-bit
+//    counters in its own shared memory; CTA r then owns bins [8192 r, 8192 r + 8192) and sums the eight tables' slices through
+//    distributed shared memory (remote atomics onto the one CTA that owns the populated exponents would serialise).
 // ---------------------------------------------------------------------------------------------------------------
 template <int DT, int MODE, bool STOC>
-__global__ void __launch_bounds__(kSampleThreads) sample_kernel(const UParams p) {
+__global__ void __cluster_dims__(kSampleCtas, 1, 1) __launch_bounds__(kSampleThreads) sample_kernel(const UParams p) {
     pdl_launch_dependents();
     pdl_wait();
     using D = DType<DT>;
     constexpr int V = D::kVec;
-    extern __shared__ unsigned int s_h[];                    // 65536 16-bit counters, two per word
+    constexpr int kOwn = 65536 / kSampleCtas;                // bins per CTA
+    constexpr int kPer = kOwn / kSampleThreads;              // bins per thread
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned int rank = cluster.block_rank();
+    extern __shared__ unsigned int s_h[];                    // 65536 16-bit counters, two per word (this CTA's share of the sample)
     __shared__ unsigned long long s_scr[32];
-    __shared__ uint32_t s_lo, s_hi;
-    __shared__ unsigned int s_best;
+    __shared__ unsigned long long s_tot[kSampleCtas];        // sample keys per owner CTA (every CTA holds a copy)
+    __shared__ uint32_t s_lohi[2];                           // CTA 0's copy is the one that counts
+    __shared__ unsigned long long s_best, s_best_all[kSampleCtas], s_mass_all[kSampleCtas];   // CTA 0 collects the others'
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < 32768; i += kSampleThreads) s_h[i] = 0u;
-    {
+    if (rank == 0) {
         uint32_t* w = reinterpret_cast<uint32_t*>(p.st);
-        for (int i = tid; i < (int)(sizeof(FusedState) / 4); i += kSampleThreads) w[i] = 0u;
+        for (int i = tid; i < (int)kStateHeaderWords; i += kSampleThreads) w[i] = 0u;
     }
-    if (tid == 0) { s_lo = 0u; s_hi = 65535u; s_best = 0u; }
-    __syncthreads();
+    if (tid == 0) { s_lohi[0] = 0u; s_lohi[1] = 65535u; s_best = 0ull; }
+    cluster.sync();
+    long long clk[8];
+    auto stamp = [&](int i) { if (rank == 0 && tid == 0) clk[i] = clock64(); };
+    stamp(0);
 
     // stratified sample: S_u units (a unit = one vector, or one BFP block when the keys are those of quantised values), unit j
     // taken at a hashed position inside the j-th of S_u equal strata
-    const int L = MODE == MODE_QS ? p.lanes_per_block : 1;
-    const int64_t n_units = p.n_vec / L;
-    const int64_t S_u = n_units < (int64_t)(kSampleVecs / L) ? n_units : (int64_t)(kSampleVecs / L);
-    const int64_t stride = n_units / S_u;                    // >= 1
-    const int S_v = (int)(S_u * L);
-    for (int j0 = tid & ~31; j0 < S_v; j0 += kSampleThreads) {
+    const uint32_t L = MODE == MODE_QS ? (uint32_t)p.lanes_per_block : 1u, l_shift = 31 - __clz(L);     // L is a power of two
+    const uint32_t n_units = (uint32_t)(p.n_vec >> l_shift);       // n < 2^32 elements
+    const uint32_t S_u = min(n_units, (uint32_t)kSampleVecs >> l_shift);
+    const uint32_t stride = n_units / S_u;                   // >= 1
+    const int S_v = (int)(S_u << l_shift);
+    for (int j0 = (int)(rank * kSampleThreads) + (tid & ~31); j0 < S_v; j0 += kSampleCtas * kSampleThreads) {
         const int j = j0 + lane;
         const bool active = j < S_v;
         int64_t vec = 0;
         if (active) {
-            const int64_t unit = j / L;
-            const int64_t u = unit * stride + (int64_t)(hash32((uint32_t)unit) % (uint32_t)(stride < 0x7fffffff ? stride : 0x7fffffff));
-            vec = u * L + (j % L);
+            const uint32_t unit = (uint32_t)j >> l_shift;
+            const uint32_t u = unit * stride + hash32(unit) % stride;
+            vec = ((int64_t)u << l_shift) + ((uint32_t)j & (L - 1u));
         }
         float v[V];
         const uint4 raw = active ? ld_stream(p.in + vec) : make_uint4(0u, 0u, 0u, 0u);
@@ -286,10 +316,10 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const UParams p)
 #pragma unroll
         for (int e = 0; e < V; ++e) {
             const uint32_t bin = topk_key(v[e]) >> 15;
-            // up to four rounds of leader aggregation (massive ties: zeros, quantised values), then plain atomics
+            // two rounds of leader aggregation (massive ties: zeros, quantised values), then plain atomics
             bool todo = active;
 #pragma unroll 1
-            for (int r = 0; r < 4; ++r) {
+            for (int r = 0; r < 2; ++r) {
                 const uint32_t act = __ballot_sync(0xffffffffu, todo);
                 if (act == 0u) break;
                 const int leader = __ffs(act) - 1;
@@ -302,60 +332,95 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const UParams p)
             if (todo) atomicAdd(&s_h[bin >> 1], 1u << (16 * (bin & 1u)));
         }
     }
-    __syncthreads();
+    stamp(1);
+    cluster.sync();
+    stamp(2);
 
+    // thread t owns bins [kPer t, kPer t + kPer) of this CTA's slice: one 128-bit read from each of the eight tables
+    static_assert(kPer == 8, "eight 16-bit counters = one uint4");
+    unsigned int c[kPer];
+    unsigned long long mine = 0;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) c[i] = 0u;
+#pragma unroll
+    for (int r = 0; r < kSampleCtas; ++r) {
+        const uint4 w = *reinterpret_cast<const uint4*>(cluster.map_shared_rank(s_h, r) + (rank * kOwn + tid * kPer) / 2);
+        c[0] += w.x & 0xffffu; c[1] += w.x >> 16; c[2] += w.y & 0xffffu; c[3] += w.y >> 16;
+        c[4] += w.z & 0xffffu; c[5] += w.z >> 16; c[6] += w.w & 0xffffu; c[7] += w.w >> 16;
+    }
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) mine += c[i];
+    unsigned long long own_total;
+    const unsigned long long before_cta = block_excl_scan<kSampleThreads>(mine, s_scr, &own_total);
+    if (tid < kSampleCtas) cluster.map_shared_rank(s_tot, tid)[rank] = own_total;
+    stamp(3);
+    cluster.sync();
+    stamp(4);
+    unsigned long long before = before_cta, total = 0;
+#pragma unroll
+    for (int r = 0; r < kSampleCtas; ++r) { const unsigned long long t = s_tot[r]; before += (unsigned int)r < rank ? t : 0ull; total += t; }
     // rank bracket of the k-th smallest key inside the sorted sample
-    const unsigned long long S = (unsigned long long)S_v * V;
+    const unsigned long long S = (unsigned long long)S_v * V;     // == total
     long long r_lo, r_hi;
     if ((unsigned long long)S_v == (unsigned long long)p.n_vec) {
         r_lo = r_hi = (long long)p.k - 1;                    // the sample is the tensor
     } else {
-        const double q = (double)p.k / (double)p.n;
-        const double mean = q * (double)S;
-        const double sd = sqrt((double)S * q * (1.0 - q) * (MODE == MODE_QS ? 4.0 : 1.0));   // design effect: a block shares its scale
-        r_lo = (long long)floor(mean - 5.5 * sd) - 1;
-        r_hi = (long long)ceil(mean + 5.5 * sd) + 1;
+        const float q = (float)p.k / (float)p.n;
+        const float mean = q * (float)S;
+        const float sd = sqrtf((float)S * q * (1.0f - q) * (MODE == MODE_QS ? 4.0f : 1.0f));   // design effect: a block shares its scale
+        r_lo = (long long)floorf(mean - 5.5f * sd) - 2;
+        r_hi = (long long)ceilf(mean + 5.5f * sd) + 2;
     }
-    // thread t owns bins [64 t, 64 t + 64)
-    unsigned long long mine = 0;
-    for (int i = 0; i < 32; ++i) { const unsigned int w = s_h[tid * 32 + ((i + lane) & 31)]; mine += (w & 0xffffu) + (w >> 16); }   // rotated: bank = lane
-    unsigned long long total;
-    const unsigned long long before = block_excl_scan<kSampleThreads>(mine, s_scr, &total);
     for (int which = 0; which < 2; ++which) {
         const long long r = which ? r_hi : r_lo;
         if (r >= 0 && (unsigned long long)r < total && before <= (unsigned long long)r && (unsigned long long)r < before + mine) {
             unsigned long long acc = before;
-            for (int i = 0; i < 64; ++i) {
-                const unsigned int w = s_h[tid * 32 + (i >> 1)];
-                const unsigned int c = (i & 1) ? (w >> 16) : (w & 0xffffu);
-                if ((unsigned long long)r < acc + c) { if (which) s_hi = (uint32_t)(tid * 64 + i); else s_lo = (uint32_t)(tid * 64 + i); break; }
-                acc += c;
+            bool found = false;
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) {
+                if (!found && (unsigned long long)r < acc + c[i]) { cluster.map_shared_rank(s_lohi, 0)[which] = rank * kOwn + tid * kPer + i; found = true; }
+                acc += c[i];
             }
         }
     }
-    __syncthreads();
-    const uint32_t lo = s_lo, hi = max(s_hi, s_lo), span = hi - lo;
-    // hottest window bin of the sample
-    for (uint32_t d = tid; d <= span && d < (uint32_t)kWin; d += kSampleThreads) {
-        const uint32_t b = lo + d;
-        const unsigned int w = s_h[b >> 1];
-        const unsigned int c = (b & 1u) ? (w >> 16) : (w & 0xffffu);
-        if (c) atomicMax(&s_best, (c << 16) | d);           // d < 2048 < 65536; c <= 32768 fits in 16 bits
+    cluster.sync();
+    stamp(5);
+    const uint32_t lo = cluster.map_shared_rank(s_lohi, 0)[0], hi = max(cluster.map_shared_rank(s_lohi, 0)[1], lo), span = hi - lo;
+    // the most populated bracket bin of the sample, and the sample mass of the bracket
+    unsigned long long in_bracket = 0, best = 0;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+        const uint32_t b = rank * kOwn + tid * kPer + i;
+        const unsigned int cc = c[i];
+        if (b >= lo && b <= hi) { in_bracket += cc; best = max(best, ((unsigned long long)cc << 32) | b); }
     }
-    __syncthreads();
-    if (tid == 0) {
+    if (best >> 32) atomicMax(&s_best, best);
+    const unsigned long long mass = block_sum<kSampleThreads>(in_bracket, s_scr);
+    if (tid == 0) { cluster.map_shared_rank(s_best_all, 0)[rank] = s_best; cluster.map_shared_rank(s_mass_all, 0)[rank] = mass; }
+    cluster.sync();
+    if (rank == 0 && tid == 0) {
+        unsigned long long bst = 0, m = 0;
+        for (int r = 0; r < kSampleCtas; ++r) { bst = max(bst, s_best_all[r]); m += s_mass_all[r]; }
+        const unsigned long long best_c = bst >> 32;
         FusedState* st = p.st;
         st->lo_bin = lo; st->span = span;
-        const unsigned int best = s_best;
-        st->hot_bin = ((unsigned long long)(best >> 16) * 64ull > S) ? lo + (best & 0xffffu) : kNoBin;
-        st->valid = (span < (uint32_t)kWin && !p.force_fallback) ? 1u : 0u;
+        const bool hot = best_c * 64ull > S;
+        st->hot_key = hot ? ((uint32_t)(bst & 0xffffffffu) << 15) : kNoKey;
+        uint32_t path = span < (uint32_t)kWin ? PATH_WINDOW : PATH_LIST;
+        // list mode lists everything in the bracket but the hot key: only worth it (and only fits) when that is a small share
+        if (path == PATH_LIST && (m - (hot ? best_c : 0ull)) * 12ull > S) path = PATH_TENSOR;
+        if (p.force_fallback) path = PATH_TENSOR;
+        st->path = path;
+        stamp(6);
+        for (int i = 0; i < 7; ++i) st->clk[i] = clk[i];
     }
+    // (the last remote accesses -- the writes into CTA 0's arrays -- precede the barrier above: no CTA's memory is addressed after it)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // 2. pass A
 // ---------------------------------------------------------------------------------------------------------------
-template <int DT> struct TileCfg { static constexpr int kU = DType<DT>::kVec == 4 ? 4 : 2; };   // 16 elements per thread per tile
+template <int DT> struct TileCfg { static constexpr int kU = kQ / DType<DT>::kVec; };   // 16 elements per thread per tile
 
 template <int DT, int MODE, bool STOC>
 __global__ void __launch_bounds__(kT) pass_a_kernel(const UParams p) {
@@ -365,124 +430,207 @@ __global__ void __launch_bounds__(kT) pass_a_kernel(const UParams p) {
     constexpr int V = D::kVec;
     constexpr int U = TileCfg<DT>::kU;
     constexpr int kTileVecs = kT * U;
-    __shared__ unsigned int s_hist[kWin];
+    __shared__ unsigned int s_pure[kWin], s_imp[kWin];
+    __shared__ uint32_t s_q[kQ][kT];
     __shared__ uint32_t s_buf[kWarps][kWarpBuf];
     __shared__ unsigned long long s_scr[32];
     __shared__ SelectResult s_res;
-    __shared__ int s_last;
+    __shared__ int s_flag;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     FusedState* st = p.st;
-    for (int i = tid; i < kWin; i += kT) s_hist[i] = 0u;
-    // look-back states of apply_kernel's tiles
-    for (int64_t i = (int64_t)blockIdx.x * kT + tid; i < p.n_tiles; i += (int64_t)gridDim.x * kT) p.tile_state[i] = 0ull;
-    if (tid == 0) s_last = (int)ld_cg32(&st->valid);       // one read per CTA: other CTAs may clear the flag while this one runs
+    for (int i = tid; i < kWin; i += kT) { s_pure[i] = 0u; s_imp[i] = 0u; }
+    {   // state that is first used by the refine kernel
+        uint32_t* w = reinterpret_cast<uint32_t*>(st) + kStateHeaderWords;
+        const int words = (int)(sizeof(FusedState) / 4 - kStateHeaderWords);
+        for (int i = blockIdx.x * kT + tid; i < words; i += gridDim.x * kT) w[i] = 0u;
+    }
+    __shared__ uint4 s_head;
+    if (tid == 0) s_head = __ldcg(reinterpret_cast<const uint4*>(st));     // lo_bin, span, hot_key, path: one read per CTA (other CTAs may downgrade the path meanwhile)
     __syncthreads();
-    if (s_last == 0) return;
-    __syncthreads();
-    const uint32_t lo = ld_cg32(&st->lo_bin), span = ld_cg32(&st->span), hot = ld_cg32(&st->hot_bin);
+    const int path = (int)s_head.w;
+    if (path == PATH_TENSOR) return;
+    const bool list = path == PATH_LIST;
+    const uint32_t lo_bin = s_head.x, span = s_head.y, hot_key = s_head.z;
+    const uint32_t lo_key = lo_bin << 15;
+    const uint32_t hi_key = (lo_bin + span + 1u) << 15;                  // exclusive; 2^31 when the bracket reaches the top
     uint32_t below = 0u, hotc = 0u;
     uint32_t used = 0u;                                      // keys staged in this warp's buffer (uniform over the warp)
-    bool dead = false;                                       // the candidate list overflowed: stop listing (valid is already 0)
+    bool dead = false;                                       // the list overflowed: stop listing (path is already PATH_TENSOR)
     auto flush = [&]() {
         if (used == 0u) return;
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(&st->cand_count, (unsigned long long)used);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base + used > p.cand_cap) {
-            if (lane == 0) st->valid = 0u;
+            if (lane == 0) st->path = PATH_TENSOR;
             dead = true;
         } else {
-            for (uint32_t i = lane; i < used; i += 32) p.cand[base + i] = s_buf[warp][i];
+            for (uint32_t i = lane; i < used; i += 32) p.cand[base + i] = make_uint2(s_buf[warp][i], blockIdx.x);
         }
         used = 0u;
         __syncwarp();
     };
-    const int64_t n_tiles = (p.n_vec + kTileVecs - 1) / kTileVecs;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t t0 = (int64_t)blockIdx.x * p.tiles_per_range, t1 = min(p.n_tiles, t0 + p.tiles_per_range);
+    auto range_loop = [&](auto has_hot_c) {
+    constexpr bool has_hot = decltype(has_hot_c)::value;
+    // the next tile's vectors are requested before this tile's arithmetic starts (one tile ahead, in registers)
+    uint4 nxt[U];
+    auto fetch = [&](int64_t t) {
+        const int64_t base = t * kTileVecs;
+        const int r = (int)min((int64_t)kTileVecs, p.n_vec - base);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int li = tid + u * kT;
+            nxt[u] = (li < r) ? ld_stream(p.in + base + li) : make_uint4(0u, 0u, 0u, 0u);
+        }
+    };
+    if (t0 < t1) fetch(t0);
+    for (int64_t tile = t0; tile < t1; ++tile) {
         const int64_t tile_base = tile * kTileVecs;
         const int rem = (int)min((int64_t)kTileVecs, p.n_vec - tile_base);
         uint4 raw[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int li = tid + u * kT;
-            raw[u] = (li < rem) ? ld_stream(p.in + tile_base + li) : make_uint4(0u, 0u, 0u, 0u);
-        }
-        uint32_t key[U * V];
-        uint32_t cm = 0u;                                    // bit j: element j is a candidate
+        for (int u = 0; u < U; ++u) raw[u] = nxt[u];
+        if (tile + 1 < t1) fetch(tile + 1);
+        // phase 1, branch-free: every key goes to this lane's column of s_q; three sign-bit accumulators (one funnel shift per
+        // element each) record key < lo_key, key < hi_key and key == hot_key.  Keys are < 2^31, so a - b is negative iff a < b.
+        uint32_t acc_lo = 0u, acc_hi = 0u, acc_hot = 0u;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int li = tid + u * kT;
             float v[V];
             unpack_vec<DT>(raw[u], v);
             if (MODE == MODE_QS) quantize_vec<DT, STOC>(v, p, tile_base + li);
-            const bool real = li < rem;
 #pragma unroll
             for (int e = 0; e < V; ++e) {
                 const uint32_t kk = topk_key(v[e]);
-                key[u * V + e] = kk;
-                const uint32_t bin = kk >> 15, d = bin - lo;
-                const bool inw = real && d <= span;
-                below += (real && bin < lo) ? 1u : 0u;
-                if (inw) {
-                    if (bin == hot) ++hotc; else atomicAdd(&s_hist[d], 1u);
-                    if (kk & 0x7fffu) cm |= 1u << (u * V + e);
+                s_q[u * V + e][tid] = kk;
+                acc_lo = __funnelshift_l(kk - lo_key, acc_lo, 1);
+                acc_hi = __funnelshift_l(kk - hi_key, acc_hi, 1);
+                if (has_hot) acc_hot = __funnelshift_l((kk ^ hot_key) - 1u, acc_hot, 1);     // x - 1 is negative iff x == 0 (x < 2^31)
+            }
+        }
+        // bit (15 - j) of the accumulators belongs to element j; padding slots of the tensor's last tile are masked out
+        uint32_t real_mask = 0xffffu;
+        if (rem < kTileVecs) {
+            real_mask = 0u;
+#pragma unroll
+            for (int u = 0; u < U; ++u) real_mask |= (tid + u * kT < rem) ? (((1u << V) - 1u) << (kQ - V - u * V)) : 0u;
+        }
+        acc_lo &= real_mask; acc_hot &= real_mask;
+        below += __popc(acc_lo);
+        hotc += __popc(acc_hot);
+        uint32_t inmask = acc_hi & ~acc_lo & ~acc_hot & real_mask;
+        // phase 2: the in-bracket keys (a few per cent of the elements), lanes in step
+        const uint32_t nmax = __reduce_max_sync(0xffffffffu, (uint32_t)__popc(inmask));
+        for (uint32_t it = 0; it < nmax; ++it) {
+            const bool act = inmask != 0u;
+            const int pos = act ? 31 - __clz(inmask) : 0;            // highest set bit = earliest element
+            if (act) inmask ^= 1u << pos;
+            const uint32_t kk = act ? s_q[kQ - 1 - pos][tid] : 0u;
+            bool listed = act;
+            if (!list) {
+                const uint32_t d = (kk >> 15) - lo_bin;
+                const bool pure = (kk & 0x7fffu) == 0u;
+                if (act) atomicAdd(pure ? &s_pure[d] : &s_imp[d], 1u);
+                listed = act && !pure;
+            }
+            const uint32_t mm = __ballot_sync(0xffffffffu, listed);
+            if (mm && !dead) {
+                const uint32_t cnt = __popc(mm);
+                if (used + cnt > (uint32_t)kWarpBuf) flush();
+                if (!dead) {
+                    if (listed) s_buf[warp][used + __popc(mm & ((1u << lane) - 1u))] = kk;
+                    used += cnt;
+                    __syncwarp();
                 }
             }
         }
-        const uint32_t ncand = __popc(cm);
-        if (__any_sync(0xffffffffu, ncand != 0u) && !dead) {
-            uint32_t incl = ncand;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
-                if (lane >= off) incl += o;
-            }
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-            if (used + total > (uint32_t)kWarpBuf) flush();
-            if (total > (uint32_t)kWarpBuf) {                // more than half of a tile is in-window and not round: give up listing
-                if (lane == 0) st->valid = 0u;
-                dead = true;
-            }
-            if (!dead) {
-                uint32_t pos = used + incl - ncand;
-#pragma unroll
-                for (int j = 0; j < U * V; ++j)
-                    if (cm & (1u << j)) s_buf[warp][pos++] = key[j];
-                used += total;
-                __syncwarp();
-            }
-        }
     }
+    };
+    if (hot_key != kNoKey) range_loop(std::true_type{}); else range_loop(std::false_type{});
     if (!dead) flush();
-    __syncthreads();
-    for (int i = tid; i < kWin; i += kT)
-        if (s_hist[i]) atomicAdd(&st->win_hist[i], (unsigned long long)s_hist[i]);
-    const unsigned long long b_sum = block_sum<kT>(below, s_scr);
-    const unsigned long long h_sum = block_sum<kT>(hotc, s_scr);
+    const unsigned long long bh = block_sum<kT>((unsigned long long)below | ((unsigned long long)hotc << 32), s_scr);   // a range holds < 2^32 elements
+    const unsigned long long b_sum = bh & 0xffffffffull, h_sum = bh >> 32;
     if (tid == 0) {
         if (b_sum) atomicAdd(&st->below, b_sum);
-        if (h_sum) atomicAdd(&st->win_hist[hot - lo], h_sum);
+        if (list) {
+            p.cta_hist[blockIdx.x] = (uint32_t)h_sum;
+            if (h_sum) atomicAdd(&st->hot_total, h_sum);
+        } else if (h_sum && hot_key != kNoKey) {
+            s_pure[(hot_key >> 15) - lo_bin] += (uint32_t)h_sum;
+        }
     }
-    // the last CTA to arrive picks the bin
-    __threadfence();
     __syncthreads();
-    if (tid == 0) s_last = atomicAdd(&st->done_a, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const unsigned long long bel = ld_cg64(&st->below);
-    const unsigned long long need_w = p.k > bel ? p.k - bel : 0ull;
-    const SelectResult r = block_select<kT, kWin / kT>(st->win_hist, kWin, need_w, 0ull, s_scr, &s_res);
-    if (tid == 0) {
-        if (!r.found) st->valid = 0u;
-        else { st->bin = lo + r.bin; st->need_bin = need_w - r.before; st->cnt_bin = r.count; }
+    if (!list) {
+        for (uint32_t d = tid; d <= span; d += kT) {
+            const uint32_t pc = s_pure[d], tot = pc + s_imp[d];
+            p.cta_hist[(size_t)d * p.n_ranges + blockIdx.x] = pc;
+            if (tot) atomicAdd(&st->win_hist[d], tot);
+        }
+        // the last CTA to arrive picks the bin
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_flag = atomicAdd(&st->done_a, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (!s_flag) return;
+        __threadfence();
+        const unsigned long long bel = ld_cg64(&st->below);
+        const unsigned long long need_w = p.k > bel ? p.k - bel : 0ull;
+        const SelectResult r = block_select<kT, kWin / kT>(st->win_hist, kWin, need_w, kNoKey, 0ull, s_scr, &s_res);
+        if (tid == 0) {
+            if (!r.found) st->path = PATH_TENSOR;
+            else { st->bin = lo_bin + r.bin; st->need_bin = need_w - r.before; st->cnt_bin = r.count; }
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// 3. refine (cooperative launch): candidates of the selected bin -> tau; or, when the two-read path does not hold, a radix
-//    select over the whole tensor with grid-wide barriers
+// 3. refine (cooperative launch)
 // ---------------------------------------------------------------------------------------------------------------
+// three-digit radix select (11 + 10 + 10 bits) with grid-wide barriers.  count_pass(pv, pm, shift, dm) adds this CTA's keys that
+// match the prefix to the shared histogram s_fb; one extra key value with a known multiplicity can be mixed in.
+template <class CountPass>
+__device__ __forceinline__ bool grid_radix_select(cg::grid_group& grid, FusedState* st, unsigned long long k_init, uint32_t extra_key, unsigned long long extra_cnt,
+                                                  unsigned int* s_fb, unsigned long long* s_scr, SelectResult* s_res, CountPass&& count_pass) {
+    const int tid = threadIdx.x;
+    bool ok = true;
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+        const int sh = pass == 0 ? 20 : (pass == 1 ? 10 : 0), nb = pass == 0 ? 11 : 10;
+        for (int i = tid; i < kFbBins; i += kT) s_fb[i] = 0u;
+        __syncthreads();
+        const uint32_t pv = ld_cg32(&st->prefix_value), pm = ld_cg32(&st->prefix_mask), dm = (1u << nb) - 1u;
+        count_pass(pv, pm, sh, dm);
+        __syncthreads();
+        for (int i = tid; i < kFbBins; i += kT)
+            if (s_fb[i]) atomicAdd(&st->fb_hist[pass][i], s_fb[i]);
+        __threadfence();
+        grid.sync();
+        if (blockIdx.x == 0) {
+            const unsigned long long need = pass == 0 ? k_init : ld_cg64(&st->fb_need);
+            const bool extra_in = extra_cnt != 0ull && (extra_key & pm) == pv;
+            const SelectResult r = block_select<kT, kFbBins / kT>(st->fb_hist[pass], 1 << nb, need, extra_in ? ((extra_key >> sh) & dm) : kNoKey,
+                                                                   extra_in ? extra_cnt : 0ull, s_scr, s_res);
+            if (tid == 0) {
+                if (!r.found) {
+                    st->fb_need = 0ull;                       // need outside the keys counted: the select fails
+                } else {
+                    st->prefix_value = pv | (r.bin << sh);
+                    st->prefix_mask = pm | (dm << sh);
+                    st->fb_need = need - r.before;
+                    if (pass == 2) { st->tau = pv | (r.bin << sh); st->need = need - r.before; st->ties_total = r.count; }
+                }
+            }
+            __threadfence();
+        }
+        grid.sync();
+        if (ld_cg64(&st->fb_need) == 0ull) ok = false;        // uniform over the grid
+        if (!ok) break;
+    }
+    return ok;
+}
+
 template <int DT, int MODE, bool STOC>
 __global__ void __launch_bounds__(kT) refine_kernel(const UParams p) {
     using D = DType<DT>;
@@ -492,87 +640,118 @@ __global__ void __launch_bounds__(kT) refine_kernel(const UParams p) {
     __shared__ unsigned int s_fb[kFbBins];
     __shared__ unsigned long long s_scr[32];
     __shared__ SelectResult s_res;
-    __shared__ int s_last;
+    pdl_launch_dependents();
+    pdl_wait();
+    cg::grid_group grid = cg::this_grid();
     const int tid = threadIdx.x;
     FusedState* st = p.st;
-    if (tid == 0) s_last = (int)ld_cg32(&st->valid);       // stable here: pass A has completed
-    __syncthreads();
-    const bool two_read_path = s_last != 0;
-    __syncthreads();
-    if (two_read_path) {
-        const unsigned long long n_c = min(ld_cg64(&st->cand_count), p.cand_cap);
+    uint32_t path = ld_cg32(&st->path);                      // stable: pass A has completed
+    const unsigned long long n_c = min(ld_cg64(&st->cand_count), p.cand_cap);
+    const unsigned long long gtid = (unsigned long long)blockIdx.x * kT + tid, gthreads = (unsigned long long)gridDim.x * kT;
+
+    // every listed (key, range), four entries (two 128-bit loads) per thread and iteration
+    auto for_each_listed = [&](auto&& fn) {
+        const unsigned long long n4 = n_c / 4;
+        const uint4* c4 = reinterpret_cast<const uint4*>(p.cand);
+#pragma unroll 2
+        for (unsigned long long i = gtid; i < n4; i += gthreads) {
+            const uint4 a = __ldcg(c4 + 2 * i), b = __ldcg(c4 + 2 * i + 1);
+            fn(a.x, a.y); fn(a.z, a.w); fn(b.x, b.y); fn(b.z, b.w);
+        }
+        for (unsigned long long i = n4 * 4 + gtid; i < n_c; i += gthreads) { const uint2 c = __ldcg(p.cand + i); fn(c.x, c.y); }
+    };
+    // the listed keys equal to tau, counted per range
+    auto count_listed_ties = [&](uint32_t tau) {
+        for_each_listed([&](uint32_t kk, uint32_t range) { if (kk == tau) atomicAdd(&st->range_count[range], 1u); });
+    };
+
+    if (path == PATH_WINDOW) {
         const uint32_t bin = ld_cg32(&st->bin);
         unsigned long long impure = 0;
-        for (unsigned long long i = (unsigned long long)blockIdx.x * kT + tid; i < n_c; i += (unsigned long long)gridDim.x * kT) {
-            const uint32_t kk = __ldcg(p.cand + i);
-            if ((kk >> 15) == bin) { atomicAdd(&st->low_hist[kk & 0x7fffu], 1ull); ++impure; }
-        }
+        for_each_listed([&](uint32_t kk, uint32_t) { if ((kk >> 15) == bin) { atomicAdd(&st->low_hist[kk & 0x7fffu], 1u); ++impure; } });
         const unsigned long long i_sum = block_sum<kT>(impure, s_scr);
         if (tid == 0 && i_sum) atomicAdd(&st->impure_in_bin, i_sum);
         __threadfence();
-        __syncthreads();
-        if (tid == 0) s_last = atomicAdd(&st->done_r, 1u) == gridDim.x - 1;
-        __syncthreads();
-        if (!s_last) return;
-        __threadfence();
-        const unsigned long long cnt = ld_cg64(&st->cnt_bin), imp = ld_cg64(&st->impure_in_bin), need_bin = ld_cg64(&st->need_bin);
-        const unsigned long long pure = cnt > imp ? cnt - imp : 0ull;        // keys of the bin with zero trailing bits
-        const SelectResult r = block_select<kT, kLowBins / kT>(st->low_hist, kLowBins, need_bin, pure, s_scr, &s_res);
-        if (tid == 0) {
-            // r.found is guaranteed: need_bin <= cnt_bin = pure + impure
-            st->tau = (bin << 15) | r.bin;
-            st->need = need_bin - r.before;
-            st->ties_total = r.count;
-        }
-        return;
-    }
-    // ---- fallback: 11 + 10 + 10-bit radix select over the whole tensor, every CTA of the grid takes part ----
-    cg::grid_group grid = cg::this_grid();
-    const int lane = tid & 31;
-    (void)lane;
-    const int shifts[3] = {20, 10, 0}, bits[3] = {11, 10, 10};
-    const int64_t n_tiles = (p.n_vec + kTileVecs - 1) / kTileVecs;
-    for (int pass = 0; pass < 3; ++pass) {
-        for (int i = tid; i < kFbBins; i += kT) s_fb[i] = 0u;
-        __syncthreads();
-        const uint32_t pv = ld_cg32(&st->prefix_value), pm = ld_cg32(&st->prefix_mask), dm = (1u << bits[pass]) - 1u;
-        const int sh = shifts[pass];
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int64_t tile_base = tile * kTileVecs;
-            const int rem = (int)min((int64_t)kTileVecs, p.n_vec - tile_base);
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int li = tid + u * kT;
-                const uint4 raw = (li < rem) ? ld_stream(p.in + tile_base + li) : make_uint4(0u, 0u, 0u, 0u);
-                float v[V];
-                unpack_vec<DT>(raw, v);
-                if (MODE == MODE_QS) quantize_vec<DT, STOC>(v, p, tile_base + li);
-                if (li < rem) {
-#pragma unroll
-                    for (int e = 0; e < V; ++e) {
-                        const uint32_t kk = topk_key(v[e]);
-                        if ((kk & pm) == pv) atomicAdd(&s_fb[(kk >> sh) & dm], 1u);
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        for (int i = tid; i < kFbBins; i += kT)
-            if (s_fb[i]) atomicAdd(&st->fb_hist[pass][i], (unsigned long long)s_fb[i]);
-        __threadfence();
         grid.sync();
         if (blockIdx.x == 0) {
-            const unsigned long long need = pass == 0 ? p.k : ld_cg64(&st->fb_need);
-            const SelectResult r = block_select<kT, kFbBins / kT>(st->fb_hist[pass], 1 << bits[pass], need, 0ull, s_scr, &s_res);
+            const unsigned long long cnt = ld_cg64(&st->cnt_bin), imp = ld_cg64(&st->impure_in_bin), need_bin = ld_cg64(&st->need_bin);
+            const unsigned long long pure = cnt > imp ? cnt - imp : 0ull;        // keys of the bin with zero trailing bits
+            const SelectResult r = block_select<kT, kLowBins / kT>(st->low_hist, kLowBins, need_bin, 0u, pure, s_scr, &s_res);
             if (tid == 0) {
-                st->prefix_value = pv | (r.bin << sh);
-                st->prefix_mask = pm | (dm << sh);
-                st->fb_need = need - r.before;
-                if (pass == 2) { st->tau = pv | (r.bin << sh); st->need = need - r.before; st->ties_total = r.count; }
+                // r.found is guaranteed: need_bin <= cnt_bin = pure + impure
+                const unsigned long long need = need_bin - r.before;
+                st->tau = (bin << 15) | r.bin;
+                st->need = need;
+                st->ties_total = r.count;
+                st->tie_src = need == r.count ? TIES_ALL : (r.bin == 0u ? TIES_ROW : TIES_COUNTED);
+                st->tie_row = bin - ld_cg32(&st->lo_bin);
             }
             __threadfence();
         }
         grid.sync();
+        if (ld_cg32(&st->tie_src) == TIES_COUNTED) count_listed_ties(ld_cg32(&st->tau));
+        return;
+    }
+
+    if (path == PATH_LIST) {
+        const unsigned long long bel = ld_cg64(&st->below);
+        const uint32_t hot_key = ld_cg32(&st->hot_key);
+        const unsigned long long hot_total = ld_cg64(&st->hot_total);
+        const bool ok = grid_radix_select(grid, st, p.k > bel ? p.k - bel : 0ull, hot_key, hot_total, s_fb, s_scr, &s_res,
+                                          [&](uint32_t pv, uint32_t pm, int sh, uint32_t dm) {
+                                              for_each_listed([&](uint32_t kk, uint32_t) { if ((kk & pm) == pv) atomicAdd(&s_fb[(kk >> sh) & dm], 1u); });
+                                          });
+        if (ok) {
+            const uint32_t tau = ld_cg32(&st->tau);
+            const bool some = ld_cg64(&st->need) < ld_cg64(&st->ties_total);
+            if (blockIdx.x == 0 && tid == 0) { st->tie_src = !some ? TIES_ALL : (tau == hot_key ? TIES_ROW : TIES_COUNTED); st->tie_row = 0u; }
+            if (some && tau != hot_key) count_listed_ties(tau);
+            return;
+        }
+        // the bracket missed: start over on the whole tensor
+        if (blockIdx.x == 0) {
+            for (int i = tid; i < 3 * kFbBins; i += kT) (&st->fb_hist[0][0])[i] = 0u;
+            if (tid == 0) { st->prefix_value = 0u; st->prefix_mask = 0u; st->fb_need = 0ull; st->path = PATH_TENSOR; }
+            __threadfence();
+        }
+        grid.sync();
+        path = PATH_TENSOR;
+    }
+
+    // ---- whole-tensor select: every CTA of the grid takes part ----
+    const int64_t n_tiles = p.n_tiles;
+    auto for_each_key = [&](int64_t tile, auto&& fn) {
+        const int64_t tile_base = tile * kTileVecs;
+        const int rem = (int)min((int64_t)kTileVecs, p.n_vec - tile_base);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int li = tid + u * kT;
+            const uint4 raw = (li < rem) ? ld_stream(p.in + tile_base + li) : make_uint4(0u, 0u, 0u, 0u);
+            float v[V];
+            unpack_vec<DT>(raw, v);
+            if (MODE == MODE_QS) quantize_vec<DT, STOC>(v, p, tile_base + li);
+            if (li < rem) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) fn(topk_key(v[e]));
+            }
+        }
+    };
+    grid_radix_select(grid, st, p.k, kNoKey, 0ull, s_fb, s_scr, &s_res, [&](uint32_t pv, uint32_t pm, int sh, uint32_t dm) {
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+            for_each_key(tile, [&](uint32_t kk) { if ((kk & pm) == pv) atomicAdd(&s_fb[(kk >> sh) & dm], 1u); });
+    });
+    const uint32_t tau = ld_cg32(&st->tau);
+    const bool some = ld_cg64(&st->need) < ld_cg64(&st->ties_total);
+    if (blockIdx.x == 0 && tid == 0) { st->tie_src = some ? TIES_COUNTED : TIES_ALL; st->tie_row = 0u; }
+    if (some) {
+        // one more read: the keys equal to tau per range
+        for (int r = blockIdx.x; r < p.n_ranges; r += gridDim.x) {
+            unsigned long long c = 0;
+            const int64_t t0 = (int64_t)r * p.tiles_per_range, t1 = min(n_tiles, t0 + p.tiles_per_range);
+            for (int64_t tile = t0; tile < t1; ++tile) for_each_key(tile, [&](uint32_t kk) { c += kk == tau ? 1u : 0u; });
+            const unsigned long long tot = block_sum<kT>(c, s_scr);
+            if (tid == 0) st->range_count[r] = (uint32_t)tot;
+        }
     }
 }
 
@@ -580,24 +759,50 @@ __global__ void __launch_bounds__(kT) refine_kernel(const UParams p) {
 // 4. apply
 // ---------------------------------------------------------------------------------------------------------------
 template <int DT, int MODE, bool STOC>
-__global__ void __launch_bounds__(kT) apply_kernel(const UParams p) {
+__global__ void __launch_bounds__(kT, 3) apply_kernel(const UParams p) {
     pdl_launch_dependents();
     pdl_wait();
     using D = DType<DT>;
     constexpr int V = D::kVec;
-    constexpr int U = TileCfg<DT>::kU;                        // 16 elements per thread per tile
+    constexpr int U = TileCfg<DT>::kU;
     constexpr int kTileVecs = kT * U;
     constexpr int kOutVecs = (STOC && V == 8 && MODE != MODE_S_ONLY) ? 2 : 1;
     __shared__ unsigned int s_w[2][kWarps];
-    __shared__ unsigned long long s_excl;
-    __shared__ int64_t s_tile;
+    __shared__ unsigned long long s_scr[32];
+    __shared__ unsigned char s_keep[kMaxRanges];              // 1: the keys equal to tau of this range stay; 0: they go
+    __shared__ int s_boundary;                                // the range where the cut falls (-1: none)
+    __shared__ unsigned long long s_running;                  // keys equal to tau before that range
+    __shared__ uint4 s_head;
     FusedState* st = p.st;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tau = ld_cg32(&st->tau);
-    const unsigned long long need = ld_cg64(&st->need), ties_total = ld_cg64(&st->ties_total);
-    const bool ranked = need < ties_total;                    // only some of the keys equal to tau go: index order decides
-    const uint32_t lim = tau + (ranked ? 0u : 1u);            // drop key < lim (keys <= 0x7fffffff: no overflow)
-    const int64_t n_tiles = p.n_tiles;
+    if (tid == 0) {
+        s_head = make_uint4(ld_cg32(&st->tau), ld_cg32(&st->tie_src), ld_cg32(&st->tie_row), 0u);
+        s_boundary = -1; s_running = 0ull;
+    }
+    __syncthreads();
+    const uint32_t tau = s_head.x, tie_src = s_head.y;
+    const unsigned long long need = ld_cg64(&st->need);
+
+    // what happens to the keys equal to tau, range by range: all go (ranges before the cut), none go (after it), or -- in the one
+    // range where the cut falls -- the first (need - running) in index order
+    if (tie_src != TIES_ALL) {
+        const uint32_t* cnt = tie_src == TIES_ROW ? p.cta_hist + (size_t)s_head.z * p.n_ranges : st->range_count;
+        unsigned long long carry = 0;
+        for (int c0 = 0; c0 < p.n_ranges; c0 += kT) {
+            const int r = c0 + tid;
+            const unsigned long long here = r < p.n_ranges ? ld_cg32(cnt + r) : 0u;
+            unsigned long long total;
+            const unsigned long long before = carry + block_excl_scan<kT>(here, s_scr, &total);
+            if (r < p.n_ranges) {
+                s_keep[r] = before >= need ? 1 : 0;
+                if (before < need && need < before + here) { s_boundary = r; s_running = before; }
+            }
+            carry += total;
+        }
+        __syncthreads();
+    }
+    const int boundary = s_boundary;
+    const bool all_go = tie_src == TIES_ALL;
 
     auto store_vec = [&](int64_t vec, const float* v) {
         if (kOutVecs == 1) {
@@ -608,128 +813,112 @@ __global__ void __launch_bounds__(kT) apply_kernel(const UParams p) {
         }
     };
 
-    if (!ranked) {
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // the last CTA walks the boundary range in order; the others (all of them when there is none) stream the remaining tiles
+    const int n_workers = max(1, (int)gridDim.x - (boundary >= 0 ? 1 : 0));
+    if (boundary >= 0 && blockIdx.x == gridDim.x - 1) {
+        unsigned long long running = s_running;
+        const int64_t t0 = (int64_t)boundary * p.tiles_per_range, t1 = min(p.n_tiles, t0 + p.tiles_per_range);
+        uint4 nraw[U];                                        // the next tile's vectors, requested one tile ahead
+        auto bfetch = [&](int64_t t) {
+            const int64_t base = t * kTileVecs;
+            const int r = (int)min((int64_t)kTileVecs, p.n_vec - base);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int li = tid + u * kT;
+                nraw[u] = (li < r) ? ld_stream(p.in + base + li) : make_uint4(0u, 0u, 0u, 0u);
+            }
+        };
+        if (t0 < t1) bfetch(t0);
+        for (int64_t tile = t0; tile < t1; ++tile) {
             const int64_t tile_base = tile * kTileVecs;
             const int rem = (int)min((int64_t)kTileVecs, p.n_vec - tile_base);
-            uint4 raw[U];
+            float v[U][V];
+            uint32_t tm[U];                                   // bit e: element e of vector u equals tau
+#pragma unroll
+            for (int u = 0; u < U; ++u) unpack_vec<DT>(nraw[u], v[u]);
+            if (tile + 1 < t1) bfetch(tile + 1);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int li = tid + u * kT;
-                raw[u] = (li < rem) ? ld_stream(p.in + tile_base + li) : make_uint4(0u, 0u, 0u, 0u);
+                if (MODE == MODE_QS) quantize_vec<DT, STOC>(v[u], p, tile_base + li);
+                tm[u] = 0u;
+#pragma unroll
+                for (int e = 0; e < V; ++e) tm[u] |= (li < rem && topk_key(v[u][e]) == tau) ? (1u << e) : 0u;
             }
+            // packed scan of the per-vector tie counts (field totals <= 256 * 8 < 65536); vector order inside the tile is u * kT + tid
+            uint32_t c01 = __popc(tm[0]) | (__popc(tm[1]) << 16), c23 = U == 4 ? (__popc(tm[U - 2]) | (__popc(tm[U - 1]) << 16)) : 0u;
+            uint32_t i01 = c01, i23 = c23;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t o01 = __shfl_up_sync(0xffffffffu, i01, off), o23 = __shfl_up_sync(0xffffffffu, i23, off);
+                if (lane >= off) { i01 += o01; i23 += o23; }
+            }
+            __syncthreads();                                  // s_w of the previous tile has been read
+            if (lane == 31) { s_w[0][warp] = i01; s_w[1][warp] = i23; }
+            __syncthreads();
+            uint32_t wb01 = 0u, wb23 = 0u, t01 = 0u, t23 = 0u;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {
+                const uint32_t a = s_w[0][w], bb = s_w[1][w];
+                wb01 += w < warp ? a : 0u; wb23 += w < warp ? bb : 0u; t01 += a; t23 += bb;
+            }
+            const uint32_t tot[4] = {t01 & 0xffffu, t01 >> 16, t23 & 0xffffu, t23 >> 16};
+            const uint32_t ex01 = wb01 + i01 - c01, ex23 = wb23 + i23 - c23;      // exclusive prefixes within each field
+            const uint32_t exu[4] = {ex01 & 0xffffu, ex01 >> 16, ex23 & 0xffffu, ex23 >> 16};
+            uint32_t before_u = 0u;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int li = tid + u * kT;
-                float v[V];
-                unpack_vec<DT>(raw[u], v);
-                if (MODE == MODE_QS) quantize_vec<DT, STOC>(v, p, tile_base + li);
+                unsigned long long rank = running + before_u + exu[u];
 #pragma unroll
-                for (int e = 0; e < V; ++e) v[e] = topk_key(v[e]) < lim ? 0.0f : v[e];
-                if (MODE == MODE_SQ) quantize_vec<DT, STOC>(v, p, tile_base + li);
-                if (li < rem) store_vec(tile_base + li, v);
+                for (int e = 0; e < V; ++e) {
+                    const uint32_t kk = topk_key(v[u][e]);
+                    bool drop = kk < tau;
+                    if (tm[u] & (1u << e)) { drop = rank < need; ++rank; }
+                    v[u][e] = drop ? 0.0f : v[u][e];
+                }
+                before_u += tot[u];
+                if (MODE == MODE_SQ) quantize_vec<DT, STOC>(v[u], p, tile_base + li);
+                if (li < rem) store_vec(tile_base + li, v[u]);
             }
+            running += before_u;
         }
-        return;
+        if (gridDim.x > 1) return;
     }
+    if ((int)blockIdx.x >= n_workers) return;
 
-    // ranked ties: tiles in index order, chained scan of the per-tile tie counts with decoupled look-back
-    while (true) {
-        if (tid == 0) s_tile = (int64_t)atomicAdd(&st->tile_counter, 1u);
-        __syncthreads();
-        const int64_t tile = s_tile;
-        if (tile >= n_tiles) break;
+    // streaming tiles: the next tile's vectors are requested before this tile's arithmetic starts
+    uint4 nxt[U];
+    auto fetch = [&](int64_t t) {
+        const int64_t base = t * kTileVecs;
+        const int r = (int)min((int64_t)kTileVecs, p.n_vec - base);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int li = tid + u * kT;
+            nxt[u] = (li < r) ? ld_stream(p.in + base + li) : make_uint4(0u, 0u, 0u, 0u);
+        }
+    };
+    if ((int64_t)blockIdx.x < p.n_tiles) fetch(blockIdx.x);
+    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += n_workers) {
         const int64_t tile_base = tile * kTileVecs;
         const int rem = (int)min((int64_t)kTileVecs, p.n_vec - tile_base);
-        float v[U][V];
-        uint32_t tm[U];                                       // bit e: element e of vector u equals tau
+        uint4 raw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) raw[u] = nxt[u];
+        if (tile + n_workers < p.n_tiles) fetch(tile + n_workers);
+        const int range = (int)(tile / p.tiles_per_range);
+        if (range == boundary) continue;
+        const uint32_t lim = tau + ((all_go || !s_keep[range]) ? 1u : 0u);        // drop key < lim (keys <= 0x7f800001: no overflow)
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int li = tid + u * kT;
-            const uint4 raw = (li < rem) ? ld_stream(p.in + tile_base + li) : make_uint4(0u, 0u, 0u, 0u);
-            unpack_vec<DT>(raw, v[u]);
-        }
+            float v[V];
+            unpack_vec<DT>(raw[u], v);
+            if (MODE == MODE_QS) quantize_vec<DT, STOC>(v, p, tile_base + li);
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int li = tid + u * kT;
-            if (MODE == MODE_QS) quantize_vec<DT, STOC>(v[u], p, tile_base + li);
-            tm[u] = 0u;
-#pragma unroll
-            for (int e = 0; e < V; ++e) tm[u] |= (li < rem && topk_key(v[u][e]) == tau) ? (1u << e) : 0u;
-        }
-        // packed scan of the four per-vector tie counts (field totals <= 256 * 8 < 65536); vector order inside the tile is u * kT + tid
-        uint32_t c01 = __popc(tm[0]) | (__popc(tm[1]) << 16), c23 = U == 4 ? (__popc(tm[U - 2]) | (__popc(tm[U - 1]) << 16)) : 0u;
-        uint32_t i01 = c01, i23 = c23;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const uint32_t o01 = __shfl_up_sync(0xffffffffu, i01, off), o23 = __shfl_up_sync(0xffffffffu, i23, off);
-            if (lane >= off) { i01 += o01; i23 += o23; }
-        }
-        if (lane == 31) { s_w[0][warp] = i01; s_w[1][warp] = i23; }
-        __syncthreads();
-        uint32_t wb01 = 0u, wb23 = 0u, t01 = 0u, t23 = 0u;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            const uint32_t a = s_w[0][w], b = s_w[1][w];
-            wb01 += w < warp ? a : 0u; wb23 += w < warp ? b : 0u; t01 += a; t23 += b;
-        }
-        const uint32_t tot[4] = {t01 & 0xffffu, t01 >> 16, t23 & 0xffffu, t23 >> 16};
-        const uint32_t tile_total = tot[0] + tot[1] + tot[2] + tot[3];
-        const uint32_t ex01 = wb01 + i01 - c01, ex23 = wb23 + i23 - c23;      // exclusive prefixes within each field
-        const uint32_t exu[4] = {ex01 & 0xffffu, ex01 >> 16, ex23 & 0xffffu, ex23 >> 16};
-        // look-back (warp 0)
-        if (warp == 0) {
-            unsigned long long excl = 0;
-            if (tile == 0) {
-                if (lane == 0) st_volatile64(p.tile_state + tile, (2ull << 62) | (unsigned long long)tile_total);
-            } else {
-                if (lane == 0) st_volatile64(p.tile_state + tile, (1ull << 62) | (unsigned long long)tile_total);
-                int64_t j = tile - 1;
-                while (true) {
-                    const int64_t idx = j - lane;
-                    const unsigned long long s = idx >= 0 ? ld_volatile64(p.tile_state + idx) : (2ull << 62);
-                    const uint32_t status = (uint32_t)(s >> 62);
-                    const uint32_t ready = __ballot_sync(0xffffffffu, status != 0u), pref = __ballot_sync(0xffffffffu, status == 2u);
-                    const unsigned long long val = s & ((1ull << 62) - 1ull);
-                    if (pref) {
-                        const int first = __ffs(pref) - 1;
-                        const uint32_t upto = first == 31 ? 0xffffffffu : ((2u << first) - 1u);
-                        if ((ready & upto) == upto) {
-                            unsigned long long part = lane <= first ? val : 0ull;
-#pragma unroll
-                            for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-                            excl += part;
-                            break;
-                        }
-                    } else if (ready == 0xffffffffu) {
-                        unsigned long long part = val;
-#pragma unroll
-                        for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-                        excl += part;
-                        j -= 32;
-                    }
-                }
-                if (lane == 0) st_volatile64(p.tile_state + tile, (2ull << 62) | (excl + (unsigned long long)tile_total));
-            }
-            if (lane == 0) s_excl = excl;
-        }
-        __syncthreads();
-        const unsigned long long tile_excl = s_excl;
-        uint32_t before_u = 0u;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int li = tid + u * kT;
-            unsigned long long rank = tile_excl + before_u + exu[u];
-#pragma unroll
-            for (int e = 0; e < V; ++e) {
-                const uint32_t kk = topk_key(v[u][e]);
-                bool drop = kk < tau;
-                if (tm[u] & (1u << e)) { drop = rank < need; ++rank; }
-                v[u][e] = drop ? 0.0f : v[u][e];
-            }
-            before_u += tot[u];
-            if (MODE == MODE_SQ) quantize_vec<DT, STOC>(v[u], p, tile_base + li);
-            if (li < rem) store_vec(tile_base + li, v[u]);
+            for (int e = 0; e < V; ++e) v[e] = topk_key(v[e]) < lim ? 0.0f : v[e];
+            if (MODE == MODE_SQ) quantize_vec<DT, STOC>(v, p, tile_base + li);
+            if (li < rem) store_vec(tile_base + li, v);
         }
     }
 }
@@ -738,78 +927,89 @@ template <class Kernel>
 static cudaError_t launch_one(Kernel kernel, int grid, int threads, size_t smem, cudaStream_t s, bool pdl, bool cooperative, const UParams& p) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    if (cooperative) { attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1; }
-    else { attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0; }
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, p);
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0; ++na;
+    if (cooperative) { attr[na].id = cudaLaunchAttributeCooperative; attr[na].val.cooperative = 1; ++na; }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
+    if (e != cudaSuccess && cooperative && pdl) {
+        // a driver that refuses a cooperative launch with programmatic serialization: plain stream order (the kernel's
+        // griddepcontrol.wait is then a no-op)
+        cudaGetLastError();
+        attr[0].val.programmaticStreamSerializationAllowed = 0;
+        e = cudaLaunchKernelEx(&cfg, kernel, p);
+    }
+    return e;
 }
 
-struct WsLayout { size_t state, tiles, cand, total; unsigned long long cap; };
-static WsLayout ws_layout(int64_t n, int dtype) {
-    const int V = dtype == BFP_DT_F32 ? 4 : 8;
-    const int64_t n_vec = (n + V - 1) / V;
+struct WsLayout { size_t state, rows, cand, total; unsigned long long cap; };
+static WsLayout ws_layout(int64_t n) {
     WsLayout w;
     w.state = (sizeof(FusedState) + 255) / 256 * 256;
-    w.tiles = (size_t)((n_vec + 511) / 512 * 8 + 255) / 256 * 256;
+    w.rows = (size_t)kWin * kMaxRanges * 4;                       // per-range counts of every window bin (only the used part is touched)
     w.cap = (unsigned long long)std::max<int64_t>(65536, n / 8);
-    w.cand = (size_t)(w.cap * 4 + 255) / 256 * 256;
-    w.total = w.state + w.tiles + w.cand;
+    w.cand = (size_t)(w.cap * 8 + 255) / 256 * 256;
+    w.total = w.state + w.rows + w.cand;
     return w;
 }
 
 template <int DT, int MODE, bool STOC>
 int run_fused(const UnstructuredArgs& a, cudaStream_t s) {
     constexpr int V = DType<DT>::kVec;
+    constexpr int U = TileCfg<DT>::kU;
     const int64_t n = a.n;
-    const WsLayout w = ws_layout(n, DT);
+    const WsLayout w = ws_layout(n);
+    const int sms = device_info().sm_count;
     UParams p = {};
     p.in = static_cast<const uint4*>(a.in);
     p.out = static_cast<uint4*>(a.out);
     p.n_vec = n / V;
-    p.n_tiles = (p.n_vec + kT * TileCfg<DT>::kU - 1) / (kT * TileCfg<DT>::kU);      // apply_kernel's tiles
+    p.n_tiles = (p.n_vec + kT * U - 1) / (kT * U);
     p.k = a.k; p.n = (unsigned long long)n;
     p.lanes_per_block = MODE == MODE_S_ONLY ? 1 : a.B / V;
     p.m = a.m; p.eps = a.eps; p.seed = a.seed; p.offset = a.offset;
     char* base = static_cast<char*>(a.workspace);
     p.st = reinterpret_cast<FusedState*>(base);
-    p.tile_state = reinterpret_cast<unsigned long long*>(base + w.state);
-    p.cand = reinterpret_cast<uint32_t*>(base + w.state + w.tiles);
+    p.cta_hist = reinterpret_cast<uint32_t*>(base + w.state);
+    p.cand = reinterpret_cast<uint2*>(base + w.state + w.rows);
     p.cand_cap = w.cap;
     p.force_fallback = tuning().unstructured_force_fallback;
-    const int sms = device_info().sm_count;
     const bool pdl = tuning().pdl != 0;
 
     auto k_sample = sample_kernel<DT, MODE, STOC>;
     auto k_a = pass_a_kernel<DT, MODE, STOC>;
     auto k_r = refine_kernel<DT, MODE, STOC>;
     auto k_ap = apply_kernel<DT, MODE, STOC>;
-    static const bool dbg = getenv("BFP_UNSTRUCTURED_TIMING") != nullptr;      // per-phase device times on stderr (tools only)
-    cudaEvent_t ev[5]; int nev = 0;
-    auto mark = [&] { if (dbg) { cudaEventCreate(&ev[nev]); cudaEventRecord(ev[nev], s); ++nev; } };
-    mark();
-    // per device, once per instantiation: the sample kernel's shared-memory opt-in and the resident CTAs per SM of the three grids
-    struct PerDevice { bool init = false; int occ_a = 0, occ_r = 0, occ_ap = 0; };
+    // per device, once per instantiation: the sample kernel's shared-memory opt-in and the resident CTAs per SM of the refine grid
+    struct PerDevice { bool init = false; int occ_r = 0, occ_a = 0, occ_ap = 0; };
     static PerDevice per_device[64];
     PerDevice& pd = per_device[std::max(0, std::min(63, device_info().device))];
     if (!pd.init) {
         cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072);
-        pd.occ_a = kernel_occupancy(k_a, kT); pd.occ_r = kernel_occupancy(k_r, kT); pd.occ_ap = kernel_occupancy(k_ap, kT);
+        pd.occ_r = kernel_occupancy(k_r, kT);
+        pd.occ_a = kernel_occupancy(k_a, kT);
+        pd.occ_ap = kernel_occupancy(k_ap, kT);
         pd.init = true;
     }
-    cudaError_t e = launch_one(k_sample, 1, kSampleThreads, 131072, s, pdl, false, p);
+    // contiguous ranges of whole tiles: one CTA of pass A each, all resident at once (a single wave)
+    const int64_t want = std::min<int64_t>(kMaxRanges, (int64_t)sms * pd.occ_a);
+    p.tiles_per_range = (int)std::max<int64_t>(1, (p.n_tiles + want - 1) / want);
+    p.n_ranges = (int)((p.n_tiles + p.tiles_per_range - 1) / p.tiles_per_range);
+    static const bool dbg = getenv("BFP_UNSTRUCTURED_TIMING") != nullptr;      // per-phase device times on stderr (tools only)
+    cudaEvent_t ev[5]; int nev = 0;
+    auto mark = [&] { if (dbg) { cudaEventCreate(&ev[nev]); cudaEventRecord(ev[nev], s); ++nev; } };
+    mark();
+    cudaError_t e = launch_one(k_sample, kSampleCtas, kSampleThreads, 131072, s, pdl, false, p);
     if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "unstructured sample kernel: %s", cudaGetErrorString(e));
     count_launch();
     mark();
-    constexpr int UA = TileCfg<DT>::kU;
-    const int64_t tiles_a = (p.n_vec + kT * UA - 1) / (kT * UA);
-    const int grid_a = (int)std::max<int64_t>(1, std::min<int64_t>(tiles_a, (int64_t)sms * pd.occ_a));
-    e = launch_one(k_a, grid_a, kT, 0, s, pdl, false, p);
+    e = launch_one(k_a, p.n_ranges, kT, 0, s, pdl, false, p);
     if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "unstructured pass A: %s", cudaGetErrorString(e));
     count_launch();
     mark();
-    const int grid_r = (int)std::max<int64_t>(1, std::min<int64_t>(tiles_a, (int64_t)sms * std::min(pd.occ_r, 4)));
-    e = launch_one(k_r, grid_r, kT, 0, s, false, true, p);
+    const int grid_r = (int)std::max<int64_t>(1, std::min<int64_t>(p.n_tiles, (int64_t)sms * std::min(pd.occ_r, 2)));
+    e = launch_one(k_r, grid_r, kT, 0, s, pdl, true, p);
     if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "unstructured refine kernel (cooperative launch): %s", cudaGetErrorString(e));
     count_launch();
     mark();
@@ -824,8 +1024,10 @@ int run_fused(const UnstructuredArgs& a, cudaStream_t s) {
         for (int i = 0; i + 1 < nev; ++i) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); fprintf(stderr, "%s %.1f us  ", names[i], ms * 1e3f); }
         FusedState h;
         cudaMemcpy(&h, p.st, offsetof(FusedState, win_hist), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "| valid %u window [%u, +%u] hot %d below %llu cand %llu bin %u need %llu ties %llu grids %d/%d/%d\n", h.valid, h.lo_bin, h.span, (int)h.hot_bin,
-                h.below, h.cand_count, h.bin, h.need, h.ties_total, grid_a, grid_r, grid_ap);
+        fprintf(stderr, "| sample clk: sampled %lld sync %lld slices %lld sync %lld ranks %lld rest %lld ", h.clk[1] - h.clk[0], h.clk[2] - h.clk[1], h.clk[3] - h.clk[2],
+                h.clk[4] - h.clk[3], h.clk[5] - h.clk[4], h.clk[6] - h.clk[5]);
+        fprintf(stderr, "| path %u bracket [%u, +%u] hot %08x below %llu listed %llu bin %u tau %08x need %llu ties %llu tie_src %u ranges %d x %d tiles, refine grid %d\n",
+                h.path, h.lo_bin, h.span, h.hot_key, h.below, h.cand_count, h.bin, h.tau, h.need, h.ties_total, h.tie_src, p.n_ranges, p.tiles_per_range, grid_r);
         for (int i = 0; i < nev; ++i) cudaEventDestroy(ev[i]);
     }
     return check_launch("fused unstructured sparsity kernels");
@@ -843,12 +1045,12 @@ int dispatch_mode(const UnstructuredArgs& a, cudaStream_t s) {
 }
 }  // namespace
 
-size_t unstructured_fused_workspace_bytes(int64_t n, int dtype) { return ws_layout(std::max<int64_t>(n, 0), dtype).total; }
+size_t unstructured_fused_workspace_bytes(int64_t n, int /*dtype*/) { return ws_layout(std::max<int64_t>(n, 0)).total; }
 
 // which calls the two-read pipeline takes; everything else composes bfp_unstructured_sparsify and bfp_quantize
 bool unstructured_fused_supported(const UnstructuredArgs& a) {
     const int V = a.dtype == BFP_DT_F32 ? 4 : 8;
-    if (a.n <= 0 || a.n % V) return false;
+    if (a.n <= 0 || a.n % V || a.n >= (int64_t(1) << 32)) return false;      // 32-bit counters per bin
     if (reinterpret_cast<uintptr_t>(a.in) % 16 || reinterpret_cast<uintptr_t>(a.out) % 16 || reinterpret_cast<uintptr_t>(a.workspace) % 16) return false;
     if (a.order == BFP_ORDER_SPARSIFY_ONLY) return true;
     const int B = a.B;

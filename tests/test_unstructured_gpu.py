@@ -244,3 +244,19 @@ def test_fused_unstructured_entry_point_and_live_reference(ops):
         if ref is not None:
             r = ref.float_to_bfp_blocked(w, **ref_args(ref, **cfg), identifier="w")
             assert torch.equal(y, r), first
+
+
+@pytest.mark.parametrize("dt", ["f32", "bf16", "f16"])
+def test_fused_unstructured_midsize_brackets_match_oracle(ops, oracle, dt):
+    """Tensors larger than the sample (so the bracket is a real estimate): window mode, list mode (a bracket straddling the zeros
+    of a ReLU output), duplicated values whose ties are cut by index, a cut that falls between two ranges."""
+    g = torch.Generator().manual_seed(21)
+    w = torch.randn(512, 1024, generator=g) * 0.02
+    dup = w.clone(); dup.view(-1)[::3] = dup.view(-1)[1::3][: dup.view(-1)[::3].numel()]          # plenty of exact ties
+    cases = [("randn", w), ("relu", torch.relu(w)), ("coarse", (torch.randn(512, 1024, generator=g) * 3).round()), ("dup", dup),
+             ("sparse90", torch.where(torch.rand(512, 1024, generator=g) < 0.9, torch.zeros(()), w))]
+    for (name, x32), (order, frac) in itertools.product(cases, (("s", 0.5), ("sq", 0.5), ("qs", 0.5), ("s", 0.93), ("sq", 0.25), ("qs", 0.75))):
+        x = x32.to(TORCH_DT[dt])
+        y = _run_fused(ops, x.cuda(), frac, order, 64, 7)
+        o = _oracle_compose(oracle, _np(x)[0], frac, order, 64, 7, dt)
+        assert _golden.mismatches(_np(y)[0], o, dt) == 0, (name, order, frac)
