@@ -248,6 +248,24 @@ int bfp_gemm_bf16_acc(const void* a_bf16, const void* b_bf16, float* out, int64_
 int bfp_gemm_bf16_sp_acc(const void* x_bf16, const void* w_comp, const void* w_meta, float* out, int64_t T, int64_t N, int64_t K,
                          void* stream);
 
+/* Block-scaled FP8-class variant of the BFP linear for narrow mantissas (HBFP4 / HBFP5: mant_bits <= 4, block_size a multiple
+ * of 32): tcgen05.mma.kind::mxf8f6f4.block_scale, twice the tensor-core rate of the bf16 kind.  The integer mantissa q (|q| <= 16)
+ * is exact in E4M3 and the block scale 2^(e-m) is exactly a UE8M0 byte, which the hardware applies per 32 elements of K before
+ * the fp32 accumulation: same result contract as bfp_gemm_bf16 (exact products, fp32 accumulation order differs).  Replaces the
+ * F.linear on fake-quantised tensors of bfp_ops.py:187-190.
+ *   bfp_mx_layout:      Kp = K rounded up to 128; sf_bytes of the scale array for rows grouped in tiles of tile_rows (128 for
+ *                       the activation operand; the GEMM's N tile, 128 or 256, for the weight).
+ *   bfp_mx_from_packed: int8 mantissas + fp32 block-major scales (bfp_quantize_pack output, same rows / K / block_size) ->
+ *                       vals uint8 [rows, Kp] (E4M3 bytes; caller zero-fills nothing: every byte is written) + sf (one 512-byte
+ *                       atom per 128 rows x 128 k in the order tcgen05.cp.32x128b.warpx4 moves it to TMEM, csrc/bfp_gemm_mx.cu).
+ *                       *violations (device uint32, caller-zeroed) counts 16-byte chunks holding a mantissa beyond +-16.
+ *   bfp_gemm_mx:        out[T,N] (fp32) = A . B^T + bias.  K is the logical K of both operands; N % 4 == 0; 16-byte aligned. */
+int bfp_mx_layout(int64_t rows, int64_t K, int tile_rows, int64_t* Kp, int64_t* sf_bytes);
+int bfp_mx_from_packed(const int8_t* mant, const float* scale_t, int64_t rows, int64_t K, int block_size, int tile_rows, void* vals,
+                       void* sf, uint32_t* violations, void* stream);
+int bfp_gemm_mx(const void* a_vals, const void* a_sf, const void* b_vals, const void* b_sf, int b_tile_rows, const float* bias,
+                float* out, int64_t T, int64_t N, int64_t K, void* stream);
+
 /* 2:4 structured-sparse variant of the BFP linear for weights pruned by _structured_N_M_sparsity with N=2, M=4
  * (bfp_ops.py:73-91; the reference then multiplies the zero-filled dense tensor, bfp_ops.py:187-190).  The pruned
  * exact-bf16 weight is stored compressed and the tensor core skips the zeros (tcgen05.mma.sp.kind::f16: 32 logical k per

@@ -135,6 +135,7 @@ int bfp_set_option(const char* name, int64_t value) {
     else if (!strcmp(name, "gemm_sp_tile") && (value == 0 || value == 240 || value == 256 || value == 480)) t.gemm_sp_tile = (int)value;
     else if (!strcmp(name, "gemm_sp_cta_group") && value >= 0 && value <= 2) t.gemm_sp_cta_group = (int)value;
     else if (!strcmp(name, "gemm_bf16_tile_n") && (value == 0 || value == 128 || value == 256)) t.gemm_bf16_tile_n = (int)value;
+    else if (!strcmp(name, "gemm_mx_variant") && value >= 0 && value <= 255) t.gemm_mx_variant = (int)value;
     else if (!strcmp(name, "unstructured_force_fallback") && (value == 0 || value == 1)) t.unstructured_force_fallback = (int)value;
     else return set_errorf(BFP_E_ARG, "unknown option or bad value: %s", name);
     return BFP_OK;
@@ -335,6 +336,28 @@ int bfp_gemm_bf16_sp_acc(const void* x_bf16, const void* w_comp, const void* w_m
     if (int rc = require_device()) return rc;
     void* outs[1] = {out};
     return gemm_bf16_sp_multi_device(x_bf16, w_comp, w_meta, nullptr, outs, 1, BFP_DT_F32, N, T, N, round_up(K, 8), static_cast<cudaStream_t>(stream), 1);
+}
+
+int bfp_mx_layout(int64_t rows, int64_t K, int tile_rows, int64_t* Kp, int64_t* sf_bytes) { return mx_layout(rows, K, tile_rows, Kp, sf_bytes); }
+
+int bfp_mx_from_packed(const int8_t* mant, const float* scale_t, int64_t rows, int64_t K, int block_size, int tile_rows, void* vals, void* sf,
+                       uint32_t* violations, void* stream) {
+    if (rows < 0 || K < 0 || block_size <= 0 || tile_rows < 1) return set_error(BFP_E_ARG, "bad argument");
+    if (rows * K > 0 && (!mant || !scale_t || !vals || !sf || !violations)) return set_error(BFP_E_ARG, "null pointer");
+    if (reinterpret_cast<uintptr_t>(mant) % 16 || reinterpret_cast<uintptr_t>(vals) % 16 || reinterpret_cast<uintptr_t>(sf) % 16)
+        return set_error(BFP_E_ALIGN, "mant, vals and sf must be 16-byte aligned");
+    if (int rc = require_device()) return rc;
+    return mx_from_packed_device(mant, scale_t, packed_rows_pad(rows), rows, K, block_size, tile_rows, static_cast<uint8_t*>(vals), static_cast<uint8_t*>(sf),
+                                 violations, static_cast<cudaStream_t>(stream));
+}
+
+int bfp_gemm_mx(const void* a_vals, const void* a_sf, const void* b_vals, const void* b_sf, int b_tile_rows, const float* bias, float* out, int64_t T,
+                int64_t N, int64_t K, void* stream) {
+    if (T < 0 || N < 0 || K < 0) return set_error(BFP_E_ARG, "negative shape");
+    if (T * N > 0 && (!a_vals || !a_sf || !b_vals || !b_sf || !out)) return set_error(BFP_E_ARG, "null pointer");
+    if (int rc = require_device()) return rc;
+    return gemm_mx_device(static_cast<const uint8_t*>(a_vals), static_cast<const uint8_t*>(a_sf), static_cast<const uint8_t*>(b_vals),
+                          static_cast<const uint8_t*>(b_sf), b_tile_rows, bias, out, T, N, round_up(K, 128), static_cast<cudaStream_t>(stream));
 }
 
 int bfp_sp_layout(int64_t rows, int64_t K, int64_t* Kc, int64_t* meta_bytes) { return sp_layout(rows, round_up(K, 8), Kc, meta_bytes); }

@@ -1,0 +1,428 @@
+// bfp_gemm_mx.cu -- the BFP linear for narrow mantissas (HBFP4 / HBFP5: mant_bits <= 4) on the block-scaled FP8-class tensor-core
+// path: tcgen05.mma.kind::mxf8f6f4.block_scale (sm_100a), twice the rate of kind::f16.
+//
+// Replaces the reference's dequantise-then-fp32-GEMM (bfp_ops.py:187-190).  A BFP value is q * 2^(e-m) with |q| <= 2^m - 1.  For
+// m <= 4 the integer q is exactly representable in E4M3 (integers up to 16), and the block scale 2^(e-m) is exactly a UE8M0 byte
+// (the biased exponent).  The hardware multiplies every 32-element group of K by the product of its two scales before the fp32
+// accumulation in TMEM, so for block sizes that are multiples of 32 the instruction computes exactly
+//     y[t,n] = sum_k (qa[t,k] 2^pa[t,k/B]) (qb[n,k] 2^pb[n,k/B])
+// with exact products and fp32 accumulation -- the same function as the exact-bf16 kind (bfp_gemm.cu), with half the operand bytes
+// and no CUDA-core rescale (which is what limits the int8 kind to 13 % of peak).
+//
+// Operand form ("mx", produced by bfp_mx_from_packed from the int8-mantissa pack of bfp_quantize_pack):
+//   vals  uint8 [rows, Kp]  E4M3 byte of q, Kp = K rounded up to 128 (zero filled)
+//   sf    uint8 [Kp / 128][row_tiles][atoms][512]  UE8M0 scale of (row, 32-group of K): one 512-byte ATOM per 128 rows and 128 k in
+//         the byte order tcgen05.cp.32x128b.warpx4 moves into four TMEM columns: byte 16 (r % 32) + 4 (r / 32) + g for row r of
+//         the atom and 32-group g of the slab (layout restated from the public CUTLASS headers: Sm1xxBlockScaledBasicChunk /
+//         UMMA::tmem_sf_frg).  Rows are grouped in tiles of `tile_rows` (128 for the A operand, the N tile for B), each tile
+//         padded to whole atoms, so a tile's scales for one K slab are one contiguous bulk copy.
+//
+// Kernel: the warp-specialised persistent structure of bfp_gemm_bf16_kernel (TMA producer warp, one MMA-issuing thread, TMEM
+// allocator warp, 8 epilogue warps, smem ring of 128-byte K slabs = 4 MMAs of K = 32).  Per slab the MMA thread first moves the
+// slab's scale atoms smem -> TMEM (tcgen05.cp, in order with the MMAs on the tensor pipe), then issues four MMAs whose scale
+// factor ids select the 32-group.  TMEM: accumulator(s) + 4 columns of A scales + 4 columns per 128 B rows.
+#include <cuda.h>
+#include <cstdio>
+
+#include <algorithm>
+
+#include "bfp_internal.h"
+#include "bfp_tc.cuh"
+
+namespace bfp {
+
+namespace gemm_mx {
+using namespace gemm;
+
+constexpr int BM = 128, BKB = 128;                     // rows of A per CTA, K bytes (= elements) per slab
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 128 + kEpiWarps * 32;         // 384
+constexpr int kTmemCols = 512;
+constexpr int kSmemBarriers = 1024;
+
+template <int TBN, int CG> struct Cfg {
+    static constexpr int kRowsB = TBN / CG;                                  // B rows staged by one CTA
+    static constexpr int kAtomsB = (TBN + 127) / 128;                        // scale atoms of the whole B tile (every CTA of a pair needs all)
+    static constexpr int kSfBytes = 512 + kAtomsB * 512;
+    static constexpr int kStageBytes = BM * BKB + kRowsB * BKB + 2048;       // operands + scale atoms (padded to keep 1024-byte alignment)
+    static constexpr int kStages = (200 * 1024 - 8 * 4096) / kStageBytes > 8 ? 8 : (200 * 1024 - 8 * 4096) / kStageBytes;
+    static constexpr int kBufs = 2 * TBN + 4 + 4 * kAtomsB <= kTmemCols ? 2 : 1;   // accumulator buffers that fit beside the scale columns
+    static constexpr int kSfCol = kBufs * TBN;                               // first scale column
+    static constexpr int kSmemStaging = 8 * 4096;
+    static constexpr int kSmemTotal = kStages * kStageBytes + kSmemStaging + kSmemBarriers + 1024;
+    // block-scaled instruction descriptor (cute InstrDescriptorBlockScaled): a/b format E4M3 (0), K-major, N >> 3 at bit 17,
+    // scale format UE8M0 (bit 23), M >> 4 at bit 24; b_sf_id at bits 4-5 and a_sf_id at bits 29-30 are added per MMA
+    static constexpr uint32_t kIdesc = ((uint32_t)(TBN >> 3) << 17) | (1u << 23) | ((uint32_t)((BM * CG) >> 4) << 24);
+    static constexpr int kColsPerThread = TBN / 2;                           // 8 epilogue warps: 4 lane quarters x 2 column halves
+    static_assert(kStageBytes % 1024 == 0, "stages must keep the 1024-byte alignment of SWIZZLE_128B tiles");
+    static_assert(kSfBytes <= 2048, "scale atoms must fit their slot");
+};
+
+struct Params {
+    const uint8_t* sf_a;        // [slabs][tiles_m * CG][512]
+    const uint8_t* sf_b;        // [slabs][tiles_n][atoms_b][512]
+    const float* bias;
+    float* out;
+    int out_dtype, out_tma;
+    int T, N;
+    int num_k_stages;           // Kp / 128
+    int tiles_m, tiles_n;       // tiles_m counts CG * 128 rows
+    int sf_a_tiles;             // row tiles (of 128) in the A scale array
+    int variant;                // debug knobs (bfp_set_option("gemm_mx_variant")): bit 0 = cp descriptor with LBO/SBO swapped
+};
+
+template <int CG>
+__device__ __forceinline__ void mma_mx(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t tmem_sfa, uint32_t tmem_sfb,
+                                       uint32_t accumulate) {
+    if constexpr (CG == 1)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %6, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%4], [%5], p;\n\t}"
+            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(tmem_sfa), "r"(tmem_sfb), "r"(accumulate) : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %6, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%4], [%5], p;\n\t}"
+            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(tmem_sfa), "r"(tmem_sfb), "r"(accumulate) : "memory");
+}
+// 32 rows x 16 bytes of shared memory -> four TMEM columns of lanes 0-31, replicated to the other three lane quarters
+template <int CG>
+__device__ __forceinline__ void tmem_cp_sf(uint32_t tmem_dst, uint64_t smem_desc) {
+    if constexpr (CG == 1) asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(tmem_dst), "l"(smem_desc) : "memory");
+    else asm volatile("tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;" ::"r"(tmem_dst), "l"(smem_desc) : "memory");
+}
+
+struct Barriers {
+    uint64_t full[8];
+    uint64_t empty[8];
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+template <int TBN, int CG>
+__global__ void __launch_bounds__(kThreads, 1)
+bfp_gemm_mx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   const __grid_constant__ CUtensorMap map_out, const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    using C = Cfg<TBN, CG>;
+    constexpr int kStages = C::kStages, kStageBytes = C::kStageBytes, kCols = C::kColsPerThread, kBufs = C::kBufs;
+    uint8_t* staging = smem + kStages * kStageBytes;
+    Barriers* bars = reinterpret_cast<Barriers*>(staging + C::kSmemStaging);
+    auto stage_a = [&](int s) { return smem + s * kStageBytes; };
+    auto stage_b = [&](int s) { return smem + s * kStageBytes + BM * BKB; };
+    auto stage_sf = [&](int s) { return smem + s * kStageBytes + BM * BKB + C::kRowsB * BKB; };      // A atom, then the B atoms
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();
+    const int unit = (int)blockIdx.x / CG, num_units = (int)gridDim.x / CG;
+    const int num_tiles = p.tiles_m * p.tiles_n;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], kEpiWarps * CG); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        if constexpr (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        }
+    }
+    tc_fence_before();
+    if constexpr (CG == 1) __syncthreads(); else cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            const uint64_t pol_keep = l2_policy_evict_last();
+            for (int tile = unit; tile < num_tiles; tile += num_units) {
+                const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
+                const int a_tile = tm * CG + (int)rank;                       // this CTA's 128 A rows
+                const int b_row = tn * TBN + (int)rank * C::kRowsB;           // this CTA's share of the B tile
+                for (int ks = 0; ks < p.num_k_stages; ++ks) {
+                    mbar_wait(&bars->empty[stage], phase ^ 1);
+                    // every CTA's bytes land on its OWN barrier for the scale atoms (each CTA needs them in its own smem) and --
+                    // for CG = 2 -- on the leader's barrier for the operands; the leader's MMA thread waits on both
+                    if (CG == 1) {
+                        mbar_expect_tx(&bars->full[stage], (uint32_t)(BM * BKB + C::kRowsB * BKB + C::kSfBytes));
+                        const uint32_t bar = smem_u32(&bars->full[stage]);
+                        tma_load_2d_to_hint<1>(stage_a(stage), &map_a, bar, ks * BKB, a_tile * BM, pol_keep);
+                        tma_load_2d_to_hint<1>(stage_b(stage), &map_b, bar, ks * BKB, b_row, pol_keep);
+                        bulk_load(stage_sf(stage), p.sf_a + ((size_t)ks * p.sf_a_tiles + a_tile) * 512, 512, &bars->full[stage]);
+                        bulk_load(stage_sf(stage) + 512, p.sf_b + ((size_t)ks * p.tiles_n + tn) * (C::kAtomsB * 512), C::kAtomsB * 512, &bars->full[stage]);
+                    }
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int buf = 0; uint32_t buf_phase[2] = {0, 0};
+            const uint32_t sf_col = tmem_base + (uint32_t)C::kSfCol;
+            for (int tile = unit; tile < num_tiles; tile += num_units) {
+                mbar_wait(&bars->tmem_empty[buf], buf_phase[buf] ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)buf * TBN;
+                for (int ks = 0; ks < p.num_k_stages; ++ks) {
+                    mbar_wait(&bars->full[stage], phase);
+                    tc_fence_after();
+                    // scale atoms of this slab: A -> columns sf_col .. +3, B atom j -> sf_col + 4 + 4 j .. (in order with the MMAs)
+                    const uint32_t sfs = smem_u32(stage_sf(stage));
+                    const uint32_t sbo = (p.variant & 1) ? 16u : 128u, lbo = (p.variant & 1) ? 128u : 16u;
+                    tmem_cp_sf<CG>(sf_col, make_smem_desc_k(sfs, 0, sbo, lbo));
+#pragma unroll
+                    for (int j = 0; j < C::kAtomsB; ++j) tmem_cp_sf<CG>(sf_col + 4 + 4 * j, make_smem_desc_k(sfs + 512 + 512 * j, 0, sbo, lbo));
+                    const uint64_t da = make_smem_desc(smem_u32(stage_a(stage)));
+                    const uint64_t db = make_smem_desc(smem_u32(stage_b(stage)));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {        // 32 elements = 32 bytes of K per MMA: +2 in 16-byte units; scale id = 32-group of the slab
+                        const uint32_t idesc = C::kIdesc | ((uint32_t)i << 4) | ((uint32_t)i << 29);
+                        mma_mx<CG>(d, da + (uint64_t)(i * 2), db + (uint64_t)(i * 2), idesc, sf_col, sf_col + 4, (ks | i) != 0);
+                    }
+                    commit<CG>(&bars->empty[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                commit<CG>(&bars->tmem_full[buf]);
+                buf_phase[buf] ^= 1;
+                if (kBufs == 2) buf ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        const int ew = warp - 4, q = warp & 3, half = ew >> 2;
+        int buf = 0; uint32_t buf_phase[2] = {0, 0};
+        const uint64_t pol = l2_policy_evict_first();
+        uint8_t* sbuf = staging + ew * 4096;
+        for (int tile = unit; tile < num_tiles; tile += num_units) {
+            const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
+            mbar_wait(&bars->tmem_full[buf], buf_phase[buf]);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TBN + half * kCols);
+            const int row0 = (tm * CG + (int)rank) * BM + q * 32;
+            const int n0 = tn * TBN + half * kCols;
+            if (kBufs == 1) {
+                // single accumulator: drain it into registers in one burst and hand it back before the stores
+                uint32_t r[kCols];
+#pragma unroll
+                for (int i = 0; i < kCols / 16; ++i) tmem_ld16(taddr + i * 16, r + i * 16);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (CG == 1) mbar_arrive(&bars->tmem_empty[buf]);
+                    else mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[buf]), 0));
+                }
+#pragma unroll
+                for (int c = 0; c < kCols / 32; ++c) {
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 o = make_float4(__uint_as_float(r[c * 32 + 4 * j]), __uint_as_float(r[c * 32 + 4 * j + 1]), __uint_as_float(r[c * 32 + 4 * j + 2]),
+                                               __uint_as_float(r[c * 32 + 4 * j + 3]));
+                        if (p.bias) {
+                            const int nb = n0 + c * 32 + 4 * j;
+                            if (nb < p.N) o.x += p.bias[nb];
+                            if (nb + 1 < p.N) o.y += p.bias[nb + 1];
+                            if (nb + 2 < p.N) o.z += p.bias[nb + 2];
+                            if (nb + 3 < p.N) o.w += p.bias[nb + 3];
+                        }
+                        *reinterpret_cast<float4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) { tma_store_2d_hint(&map_out, sbuf, n0 + c * 32, row0, pol); tma_store_commit(); }
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < kCols / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld16(taddr + c * 32, r);
+                    tmem_ld16(taddr + c * 32 + 16, r + 16);
+                    tmem_ld_wait();
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 o = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                        if (p.bias) {
+                            const int nb = n0 + c * 32 + 4 * j;
+                            if (nb < p.N) o.x += p.bias[nb];
+                            if (nb + 1 < p.N) o.y += p.bias[nb + 1];
+                            if (nb + 2 < p.N) o.z += p.bias[nb + 2];
+                            if (nb + 3 < p.N) o.w += p.bias[nb + 3];
+                        }
+                        *reinterpret_cast<float4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) { tma_store_2d_hint(&map_out, sbuf, n0 + c * 32, row0, pol); tma_store_commit(); }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (CG == 1) mbar_arrive(&bars->tmem_empty[buf]);
+                    else mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[buf]), 0));
+                }
+            }
+            buf_phase[buf] ^= 1;
+            if (kBufs == 2) buf ^= 1;
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    if constexpr (CG == 1) __syncthreads(); else cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+}
+
+// ---- operand conversion: int8 mantissas + fp32 block-major scales (bfp_quantize_pack) -> E4M3 bytes + UE8M0 scale atoms -----------
+__global__ void __launch_bounds__(256) mx_vals_kernel(const int8_t* __restrict__ mant, uint8_t* __restrict__ vals, int64_t rows, int64_t Kp_in, int64_t Kp_out,
+                                                      unsigned int* __restrict__ violations) {
+    // one thread per 16 output bytes
+    const int64_t chunks_per_row = Kp_out / 16;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * chunks_per_row) return;
+    const int64_t row = i / chunks_per_row, c = i - row * chunks_per_row;
+    uint4 w = make_uint4(0u, 0u, 0u, 0u);
+    if (c * 16 < Kp_in) w = *reinterpret_cast<const uint4*>(mant + row * Kp_in + c * 16);      // Kp_in is a multiple of 16
+    uint32_t in[4] = {w.x, w.y, w.z, w.w}, out[4];
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t o = 0u;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int q = (int)(int8_t)((in[j] >> (8 * b)) & 0xffu);
+            const uint32_t a = (uint32_t)(q < 0 ? -q : q);
+            bad |= a > 16u;
+            // E4M3 of the integer a in [1, 16]: exponent field 7 + floor(log2 a), mantissa = the three bits below the leading one
+            uint32_t e = 0u;
+            if (a) {
+                const int lg = 31 - __clz(a);
+                e = ((uint32_t)(lg + 7) << 3) | (((a << 3) >> lg) & 7u);
+            }
+            o |= (e | (q < 0 ? 0x80u : 0u)) << (8 * b);
+        }
+        out[j] = o;
+    }
+    if (bad) atomicAdd(violations, 1u);
+    *reinterpret_cast<uint4*>(vals + row * Kp_out + c * 16) = make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+// scale_t [nkb][ld_s] fp32 (2^p per BFP block, NaN = unrepresentable) -> atoms; one thread per (slab, tile, atom, row-in-atom)
+__global__ void __launch_bounds__(256) mx_sf_kernel(const float* __restrict__ scale_t, int64_t ld_s, uint8_t* __restrict__ sf, int64_t rows, int64_t K, int B,
+                                                    int tile_rows, int atoms, int64_t n_tiles, int64_t n_slabs) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = n_slabs * n_tiles * atoms * 128;
+    if (i >= total) return;
+    const int r = (int)(i & 127);
+    int64_t rest = i >> 7;
+    const int atom = (int)(rest % atoms); rest /= atoms;
+    const int64_t tile = rest % n_tiles, slab = rest / n_tiles;
+    const int in_tile = atom * 128 + r;
+    const int64_t row = tile * tile_rows + in_tile;
+    uint32_t word = 0u;
+    if (in_tile < tile_rows && row < rows) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int64_t k = slab * 128 + g * 32;
+            uint32_t byte = 0u;
+            if (k < K) byte = (__float_as_uint(scale_t[(k / B) * ld_s + row]) >> 23) & 0xffu;      // 2^p -> p + 127; NaN -> 0xff (NaN scale)
+            word |= byte << (8 * g);
+        }
+    }
+    uint8_t* atom_base = sf + (((slab * n_tiles + tile) * atoms + atom) * 512);
+    *reinterpret_cast<uint32_t*>(atom_base + 16 * (r & 31) + 4 * (r >> 5)) = word;
+}
+
+}  // namespace gemm_mx
+
+int mx_layout(int64_t rows, int64_t K, int tile_rows, int64_t* Kp, int64_t* sf_bytes) {
+    if (rows < 0 || K < 0 || tile_rows < 1) return set_error(BFP_E_ARG, "bad argument");
+    const int64_t kp = round_up(K, 128), atoms = (tile_rows + 127) / 128, tiles = (rows + tile_rows - 1) / tile_rows;
+    if (Kp) *Kp = kp;
+    if (sf_bytes) *sf_bytes = (kp / 128) * tiles * atoms * 512;
+    return BFP_OK;
+}
+
+int mx_from_packed_device(const int8_t* mant, const float* scale_t, int64_t ld_s, int64_t rows, int64_t K, int block_size, int tile_rows, uint8_t* vals,
+                          uint8_t* sf, unsigned int* violations, cudaStream_t st) {
+    using namespace gemm_mx;
+    if (rows == 0 || K == 0) return BFP_OK;
+    if (block_size % 32 || block_size <= 0) return set_error(BFP_E_UNSUPPORTED, "block-scaled operands need a block_size that is a multiple of 32 (one hardware scale per 32 elements)");
+    const int64_t kp_in = packed_kp(K), kp_out = round_up(K, 128);
+    const int64_t chunks = rows * (kp_out / 16);
+    mx_vals_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(mant, vals, rows, kp_in, kp_out, violations);
+    count_launch();
+    const int atoms = (tile_rows + 127) / 128;
+    const int64_t tiles = (rows + tile_rows - 1) / tile_rows, slabs = kp_out / 128;
+    const int64_t total = slabs * tiles * atoms * 128;
+    mx_sf_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(scale_t, ld_s, sf, rows, K, block_size, tile_rows, atoms, tiles, slabs);
+    count_launch();
+    return check_launch("mx operand conversion");
+}
+
+template <int TBN, int CG>
+static int launch_mx(const CUtensorMap& map_a, const CUtensorMap& map_b, const CUtensorMap& map_out, const gemm_mx::Params& p, int units, cudaStream_t st) {
+    using namespace gemm_mx;
+    using C = Cfg<TBN, CG>;
+    cudaError_t e = cudaFuncSetAttribute(bfp_gemm_mx_kernel<TBN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemTotal);
+    if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(units * CG)); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = C::kSmemTotal; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, bfp_gemm_mx_kernel<TBN, CG>, map_a, map_b, map_out, p);
+    if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaLaunchKernelEx(bfp_gemm_mx_kernel): %s", cudaGetErrorString(e));
+    return BFP_OK;
+}
+
+int gemm_mx_device(const uint8_t* a_vals, const uint8_t* a_sf, const uint8_t* b_vals, const uint8_t* b_sf, int b_tile_rows, const float* bias, float* out,
+                   int64_t T, int64_t N, int64_t Kp, cudaStream_t st) {
+    using namespace gemm_mx;
+    if (T == 0 || N == 0) return BFP_OK;
+    if (Kp % 128 != 0 || Kp <= 0) return set_error(BFP_E_ARG, "mx operand K must be a positive multiple of 128");
+    if (T > INT32_MAX || N > INT32_MAX || Kp > INT32_MAX) return set_error(BFP_E_ARG, "dimension too large");
+    if (reinterpret_cast<uintptr_t>(a_vals) % 16 || reinterpret_cast<uintptr_t>(b_vals) % 16 || reinterpret_cast<uintptr_t>(a_sf) % 16 ||
+        reinterpret_cast<uintptr_t>(b_sf) % 16 || reinterpret_cast<uintptr_t>(out) % 16 || (N * 4) % 16)
+        return set_error(BFP_E_ALIGN, "mx operands and the output must be 16-byte aligned (N a multiple of 4)");
+    if (b_tile_rows != 128 && b_tile_rows != 256) return set_error(BFP_E_UNSUPPORTED, "B scale atoms must be tiled by 128 or 256 rows");
+    Params p;
+    p.sf_a = a_sf; p.sf_b = b_sf; p.bias = bias; p.out = out; p.out_dtype = BFP_DT_F32; p.out_tma = 1;
+    p.T = (int)T; p.N = (int)N; p.num_k_stages = (int)(Kp / 128);
+    p.variant = tuning().gemm_mx_variant;
+    const int tbn = b_tile_rows, cg = 1;
+    p.tiles_m = (int)((T + BM * cg - 1) / (BM * cg));
+    p.tiles_n = (int)((N + tbn - 1) / tbn);
+    p.sf_a_tiles = (int)((T + 127) / 128);
+    CUtensorMap map_a, map_b, map_out;
+    if (int rc = make_map(&map_a, a_vals, T, Kp, BM)) return rc;
+    if (int rc = make_map(&map_b, b_vals, N, Kp, tbn / cg)) return rc;
+    if (int rc = make_map_out(&map_out, out, BFP_DT_F32, T, N, N * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    const int sms = std::max(2, device_info().sm_count);
+    const int units = (int)std::min<int64_t>((int64_t)p.tiles_m * p.tiles_n, sms / cg);
+    int rc;
+    if (tbn == 256) rc = launch_mx<256, 1>(map_a, map_b, map_out, p, units, st);
+    else rc = launch_mx<128, 1>(map_a, map_b, map_out, p, units, st);
+    if (rc) return rc;
+    count_launch();
+    return check_launch("bfp_gemm_mx_kernel");
+}
+
+}  // namespace bfp
