@@ -254,17 +254,25 @@ int bfp_gemm_bf16_sp_acc(const void* x_bf16, const void* w_comp, const void* w_m
  * the fp32 accumulation: same result contract as bfp_gemm_bf16 (exact products, fp32 accumulation order differs).  Replaces the
  * F.linear on fake-quantised tensors of bfp_ops.py:187-190.
  *   bfp_mx_layout:      Kp = K rounded up to 128; sf_bytes of the scale array for rows grouped in tiles of tile_rows (128 for
- *                       the activation operand; the GEMM's N tile, 128 or 256, for the weight).
+ *                       the activation operand; the GEMM's N tile -- 128, 240 or 256 -- for the weight).
  *   bfp_mx_from_packed: int8 mantissas + fp32 block-major scales (bfp_quantize_pack output, same rows / K / block_size) ->
- *                       vals uint8 [rows, Kp] (E4M3 bytes; caller zero-fills nothing: every byte is written) + sf (one 512-byte
- *                       atom per 128 rows x 128 k in the order tcgen05.cp.32x128b.warpx4 moves it to TMEM, csrc/bfp_gemm_mx.cu).
- *                       *violations (device uint32, caller-zeroed) counts 16-byte chunks holding a mantissa beyond +-16.
- *   bfp_gemm_mx:        out[T,N] (fp32) = A . B^T + bias.  K is the logical K of both operands; N % 4 == 0; 16-byte aligned. */
-int bfp_mx_layout(int64_t rows, int64_t K, int tile_rows, int64_t* Kp, int64_t* sf_bytes);
-int bfp_mx_from_packed(const int8_t* mant, const float* scale_t, int64_t rows, int64_t K, int block_size, int tile_rows, void* vals,
-                       void* sf, uint32_t* violations, void* stream);
-int bfp_gemm_mx(const void* a_vals, const void* a_sf, const void* b_vals, const void* b_sf, int b_tile_rows, const float* bias,
-                float* out, int64_t T, int64_t N, int64_t K, void* stream);
+ *                       vals uint8 [rows, Kp] (E4M3 bytes, every byte written) + sf (one 512-byte atom per 128 rows x 128 k in the
+ *                       order tcgen05.cp.32x128b.warpx4 moves it to TMEM, csrc/bfp_gemm_mx.cu).
+ *                       fold = 0: the general form -- integer mantissas, one scale per 32 elements (block_size % 32 == 0).
+ *                       fold = 1: the weight form -- the block exponents are folded into the E4M3 values relative to one reference
+ *                       exponent per row (row_ref: rows int32 of scratch), so the row has a single scale, the GEMM copies the B
+ *                       scales once per tile instead of once per K slab (a copy costs ~50 clk of the tensor pipe), and any
+ *                       block_size works.  Exact while every block exponent of a row is within ten octaves of its largest.
+ *                       *violations (device uint32, caller-zeroed) counts what the form cannot hold (mantissas beyond +-16; for
+ *                       fold = 1 rows whose exponent spread is too wide or that hold NaN-marked blocks): then use the other form
+ *                       or bfp_gemm_bf16.
+ *   bfp_gemm_mx:        out[T,N] (fp32) = A . B^T + bias.  A in the general form (tile_rows 128), B in either (b_folded).  K is
+ *                       the logical K of both operands; N % 4 == 0; 16-byte aligned buffers. */
+int bfp_mx_layout(int64_t rows, int64_t K, int tile_rows, int fold, int64_t* Kp, int64_t* sf_bytes);
+int bfp_mx_from_packed(const int8_t* mant, const float* scale_t, int64_t rows, int64_t K, int block_size, int tile_rows, int fold,
+                       void* vals, void* sf, int32_t* row_ref, uint32_t* violations, void* stream);
+int bfp_gemm_mx(const void* a_vals, const void* a_sf, const void* b_vals, const void* b_sf, int b_tile_rows, int b_folded,
+                const float* bias, float* out, int64_t T, int64_t N, int64_t K, void* stream);
 
 /* 2:4 structured-sparse variant of the BFP linear for weights pruned by _structured_N_M_sparsity with N=2, M=4
  * (bfp_ops.py:73-91; the reference then multiplies the zero-filled dense tensor, bfp_ops.py:187-190).  The pruned

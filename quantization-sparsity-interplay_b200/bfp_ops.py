@@ -460,46 +460,49 @@ def bfp_linear_packed(xp, wp, bias=None):
 
 class PackedMX:
     """Block-scaled FP8-class operand (include/bfp_b200.h bfp_mx_from_packed): E4M3 bytes of the mantissas + UE8M0 scale atoms."""
-    __slots__ = ("vals", "sf", "rows", "K", "tile_rows", "block_size", "mant_bits")
+    __slots__ = ("vals", "sf", "rows", "K", "tile_rows", "block_size", "mant_bits", "folded")
 
-    def __init__(self, vals, sf, rows, K, tile_rows, block_size, mant_bits):
+    def __init__(self, vals, sf, rows, K, tile_rows, block_size, mant_bits, folded):
         self.vals, self.sf, self.rows, self.K, self.tile_rows = vals, sf, rows, K, tile_rows
-        self.block_size, self.mant_bits = block_size, mant_bits
+        self.block_size, self.mant_bits, self.folded = block_size, mant_bits, folded
 
 
-def pack_bfp_mx(t, tile_rows=128, identifier='', philox=None, check=True, **bfp_args):
+def pack_bfp_mx(t, tile_rows=128, fold=False, identifier='', philox=None, check=True, **bfp_args):
     """float_to_bfp_blocked into the block-scaled operand form of bfp_gemm_mx: needs mant_bits <= 4 (the integer mantissa is exact
-    in E4M3) and a block_size that is a multiple of 32 (one hardware scale per 32 elements of K).  tile_rows: 128 for the
-    activation operand, the GEMM's N tile (128 or 256) for the weight."""
+    in E4M3).  General form (activations, tile_rows 128): block_size a multiple of 32 (one hardware scale per 32 elements of K).
+    fold=True (weights; tile_rows = the GEMM's N tile, 128 / 240 / 256): the block exponents ride in the E4M3 values and the row has
+    one scale -- any block size, exact while a row's block exponents span at most ten octaves.  Returns None (check=True) when the
+    tensor does not fit the requested form."""
     m, B = int(bfp_args['mant_bits']), int(bfp_args['block_size'])
-    if not (1 <= m <= 4) or B % 32:
-        raise ValueError("the block-scaled form needs mant_bits <= 4 and block_size % 32 == 0")
+    if not (1 <= m <= 4) or (not fold and B % 32):
+        raise ValueError("the block-scaled form needs mant_bits <= 4 and (general form) block_size % 32 == 0")
     pk = pack_bfp(t, identifier=identifier, philox=philox, **bfp_args)
     L = _lib.lib()
     kp, sfb = ctypes.c_int64(), ctypes.c_int64()
-    _lib.check(L.bfp_mx_layout(pk.rows, pk.K, int(tile_rows), ctypes.byref(kp), ctypes.byref(sfb)))
+    _lib.check(L.bfp_mx_layout(pk.rows, pk.K, int(tile_rows), int(bool(fold)), ctypes.byref(kp), ctypes.byref(sfb)))
     dev = pk.mant.device
     vals = torch.empty((pk.rows, kp.value), dtype=torch.uint8, device=dev)
     sf = torch.empty(max(sfb.value, 16), dtype=torch.uint8, device=dev)
     viol = torch.zeros(1, dtype=torch.int32, device=dev)
+    ref = torch.empty(max(pk.rows, 1), dtype=torch.int32, device=dev) if fold else None
     if pk.rows and pk.K:
         with _on(dev):
-            _lib.check(L.bfp_mx_from_packed(pk.mant.data_ptr(), pk.scale_t.data_ptr(), pk.rows, pk.K, B, int(tile_rows), vals.data_ptr(),
-                                            sf.data_ptr(), viol.data_ptr(), _stream()))
+            _lib.check(L.bfp_mx_from_packed(pk.mant.data_ptr(), pk.scale_t.data_ptr(), pk.rows, pk.K, B, int(tile_rows), int(bool(fold)),
+                                            vals.data_ptr(), sf.data_ptr(), ref.data_ptr() if fold else None, viol.data_ptr(), _stream()))
         if check and int(viol.item()):
-            raise ValueError("mantissas beyond +-16 cannot be block-scaled FP8 operands")
-    return PackedMX(vals, sf, pk.rows, pk.K, int(tile_rows), B, m)
+            return None
+    return PackedMX(vals, sf, pk.rows, pk.K, int(tile_rows), B, m, bool(fold))
 
 
 def bfp_linear_mx(xp, wp, bias=None, out_shape=None):
     """y = x w^T + bias on block-scaled operands (include/bfp_b200.h bfp_gemm_mx): tcgen05.mma.kind::mxf8f6f4.block_scale."""
-    assert xp.K == wp.K and xp.tile_rows == 128
+    assert xp.K == wp.K and xp.tile_rows == 128 and not xp.folded
     N = wp.rows
     out = torch.empty((xp.rows, N), dtype=torch.float32, device=xp.vals.device)
     b = bias.detach().to(dtype=torch.float32).contiguous() if bias is not None else None
     if out.numel():
         with _on(out.device):
-            _lib.check(_lib.lib().bfp_gemm_mx(xp.vals.data_ptr(), xp.sf.data_ptr(), wp.vals.data_ptr(), wp.sf.data_ptr(), wp.tile_rows,
+            _lib.check(_lib.lib().bfp_gemm_mx(xp.vals.data_ptr(), xp.sf.data_ptr(), wp.vals.data_ptr(), wp.sf.data_ptr(), wp.tile_rows, int(wp.folded),
                                               b.data_ptr() if b is not None else None, out.data_ptr(), xp.rows, N, xp.K, _stream()))
     return out if out_shape is None else out.view(out_shape)
 

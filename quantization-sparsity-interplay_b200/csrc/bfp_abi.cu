@@ -338,26 +338,26 @@ int bfp_gemm_bf16_sp_acc(const void* x_bf16, const void* w_comp, const void* w_m
     return gemm_bf16_sp_multi_device(x_bf16, w_comp, w_meta, nullptr, outs, 1, BFP_DT_F32, N, T, N, round_up(K, 8), static_cast<cudaStream_t>(stream), 1);
 }
 
-int bfp_mx_layout(int64_t rows, int64_t K, int tile_rows, int64_t* Kp, int64_t* sf_bytes) { return mx_layout(rows, K, tile_rows, Kp, sf_bytes); }
+int bfp_mx_layout(int64_t rows, int64_t K, int tile_rows, int fold, int64_t* Kp, int64_t* sf_bytes) { return mx_layout(rows, K, tile_rows, fold, Kp, sf_bytes); }
 
-int bfp_mx_from_packed(const int8_t* mant, const float* scale_t, int64_t rows, int64_t K, int block_size, int tile_rows, void* vals, void* sf,
-                       uint32_t* violations, void* stream) {
+int bfp_mx_from_packed(const int8_t* mant, const float* scale_t, int64_t rows, int64_t K, int block_size, int tile_rows, int fold, void* vals, void* sf,
+                       int32_t* row_ref, uint32_t* violations, void* stream) {
     if (rows < 0 || K < 0 || block_size <= 0 || tile_rows < 1) return set_error(BFP_E_ARG, "bad argument");
     if (rows * K > 0 && (!mant || !scale_t || !vals || !sf || !violations)) return set_error(BFP_E_ARG, "null pointer");
     if (reinterpret_cast<uintptr_t>(mant) % 16 || reinterpret_cast<uintptr_t>(vals) % 16 || reinterpret_cast<uintptr_t>(sf) % 16)
         return set_error(BFP_E_ALIGN, "mant, vals and sf must be 16-byte aligned");
     if (int rc = require_device()) return rc;
-    return mx_from_packed_device(mant, scale_t, packed_rows_pad(rows), rows, K, block_size, tile_rows, static_cast<uint8_t*>(vals), static_cast<uint8_t*>(sf),
-                                 violations, static_cast<cudaStream_t>(stream));
+    return mx_from_packed_device(mant, scale_t, packed_rows_pad(rows), rows, K, block_size, tile_rows, fold, static_cast<uint8_t*>(vals),
+                                 static_cast<uint8_t*>(sf), row_ref, violations, static_cast<cudaStream_t>(stream));
 }
 
-int bfp_gemm_mx(const void* a_vals, const void* a_sf, const void* b_vals, const void* b_sf, int b_tile_rows, const float* bias, float* out, int64_t T,
-                int64_t N, int64_t K, void* stream) {
+int bfp_gemm_mx(const void* a_vals, const void* a_sf, const void* b_vals, const void* b_sf, int b_tile_rows, int b_folded, const float* bias, float* out,
+                int64_t T, int64_t N, int64_t K, void* stream) {
     if (T < 0 || N < 0 || K < 0) return set_error(BFP_E_ARG, "negative shape");
     if (T * N > 0 && (!a_vals || !a_sf || !b_vals || !b_sf || !out)) return set_error(BFP_E_ARG, "null pointer");
     if (int rc = require_device()) return rc;
     return gemm_mx_device(static_cast<const uint8_t*>(a_vals), static_cast<const uint8_t*>(a_sf), static_cast<const uint8_t*>(b_vals),
-                          static_cast<const uint8_t*>(b_sf), b_tile_rows, bias, out, T, N, round_up(K, 128), static_cast<cudaStream_t>(stream));
+                          static_cast<const uint8_t*>(b_sf), b_tile_rows, b_folded, bias, out, T, N, round_up(K, 128), static_cast<cudaStream_t>(stream));
 }
 
 int bfp_sp_layout(int64_t rows, int64_t K, int64_t* Kc, int64_t* meta_bytes) { return sp_layout(rows, round_up(K, 8), Kc, meta_bytes); }

@@ -80,11 +80,11 @@ int gemm_bf16_sp_device(const void* x_bf16, const void* w_comp, const void* w_me
 int gemm_bf16_sp_multi_device(const void* x_bf16, const void* w_comp, const void* w_meta, const float* bias, void* const* out_ptrs, int n_out,
                               int out_dtype, int64_t ld_out, int64_t T, int64_t N, int64_t Kp, cudaStream_t st, int accumulate = 0);
 
-int mx_layout(int64_t rows, int64_t K, int tile_rows, int64_t* Kp, int64_t* sf_bytes);
-int mx_from_packed_device(const int8_t* mant, const float* scale_t, int64_t ld_s, int64_t rows, int64_t K, int block_size, int tile_rows, uint8_t* vals,
-                          uint8_t* sf, unsigned int* violations, cudaStream_t st);
-int gemm_mx_device(const uint8_t* a_vals, const uint8_t* a_sf, const uint8_t* b_vals, const uint8_t* b_sf, int b_tile_rows, const float* bias, float* out,
-                   int64_t T, int64_t N, int64_t Kp, cudaStream_t st);
+int mx_layout(int64_t rows, int64_t K, int tile_rows, int fold, int64_t* Kp, int64_t* sf_bytes);
+int mx_from_packed_device(const int8_t* mant, const float* scale_t, int64_t ld_s, int64_t rows, int64_t K, int block_size, int tile_rows, int fold,
+                          uint8_t* vals, uint8_t* sf, int* row_ref, unsigned int* violations, cudaStream_t st);
+int gemm_mx_device(const uint8_t* a_vals, const uint8_t* a_sf, const uint8_t* b_vals, const uint8_t* b_sf, int b_tile_rows, int b_folded, const float* bias,
+                   float* out, int64_t T, int64_t N, int64_t Kp, cudaStream_t st);
 
 size_t int_workspace_bytes(int64_t C);
 int int_quantize_device(const void* in, float* out, int64_t A, int64_t C, int64_t inner, int dtype, int bits, void* workspace, cudaStream_t s);

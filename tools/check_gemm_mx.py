@@ -15,23 +15,24 @@ def args(m, B):
 def rel(a, b):
     return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
 
-def one(T, N, K, m, B, tbn, variant, scale_spread=True):
+def one(T, N, K, m, B, tbn, variant, fold=False, scale_spread=True):
     _lib.check(L.bfp_set_option(b"gemm_mx_variant", variant))
     a = args(m, B)
     x = torch.randn(T, K, device="cuda")
     w = torch.randn(N, K, device="cuda") * 0.05
     if scale_spread:   # block exponents that differ along K and across rows, so a mis-indexed scale shows
         x = x * torch.exp2(torch.randint(-6, 7, (T, K // B), device="cuda").repeat_interleave(B, 1).float())
-        w = w * torch.exp2(torch.randint(-6, 7, (N, K // B), device="cuda").repeat_interleave(B, 1).float())
+        w = w * torch.exp2(torch.randint(-3 if fold else -6, 4 if fold else 7, (N, K // B), device="cuda").repeat_interleave(B, 1).float())
     xq = ops.float_to_bfp_blocked(x, **a, identifier="in")
     wq = ops.float_to_bfp_blocked(w, **a, identifier="w")
     ref = xq.double() @ wq.double().t()
     xp = ops.pack_bfp_mx(x, 128, identifier="in", **a)
-    wp = ops.pack_bfp_mx(w, tbn, identifier="w", **a)
+    wp = ops.pack_bfp_mx(w, tbn, fold=fold, identifier="w", **a)
+    assert wp is not None, "the weight did not fit the requested form"
     y = ops.bfp_linear_mx(xp, wp)
     torch.cuda.synchronize()
     r = rel(y, ref)
-    msg = f"T={T} N={N} K={K} m={m} B={B} tile_n={tbn} variant={variant}: rel err {r:.3e}"
+    msg = f"T={T} N={N} K={K} m={m} B={B} tile_n={tbn} variant={variant} fold={int(fold)}: rel err {r:.3e}"
     if r > 1e-5:
         # hypotheses: scales ignored; every MMA uses the slab's first scale; A / B scales swapped between 32-groups
         pk_x, pk_w = ops.pack_bfp(x, identifier="in", **a), ops.pack_bfp(w, identifier="w", **a)
@@ -56,19 +57,23 @@ if "bench" in sys.argv:
         a = args(3, 64)
         x, w = torch.randn(T, K, device="cuda"), torch.randn(N, K, device="cuda") * 0.05
         xp = ops.pack_bfp_mx(x, 128, identifier="in", **a)
-        for tbn in (256, 128):
-            wp = ops.pack_bfp_mx(w, tbn, identifier="w", **a)
+        for tbn, variant, fold in ((240, 0, True), (240, 0, False), (256, 0, True), (256, 0, False), (240, 2, True), (240, 6, True)):
+            _lib.check(L.bfp_set_option(b"gemm_mx_variant", variant))
+            wp = ops.pack_bfp_mx(w, tbn, fold=fold, identifier="w", **a)
             for _ in range(3): ops.bfp_linear_mx(xp, wp)
             torch.cuda.synchronize(); e0.record()
             for _ in range(20): ops.bfp_linear_mx(xp, wp)
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 20
-            xb, wb = ops.pack_bfp_bf16(x, identifier="in", **a), ops.pack_bfp_bf16(w, identifier="w", **a)
-            print(f"T={T} N={N} K={K} tile_n={tbn}: {ms * 1e3:.1f} us = {2 * T * N * K / ms / 1e9:.0f} TFLOP/s", flush=True)
+            print(f"T={T} N={N} K={K} tile_n={tbn} variant {variant} fold {int(fold)}: {ms * 1e3:.1f} us = {2 * T * N * K / ms / 1e9:.0f} TFLOP/s", flush=True)
+        _lib.check(L.bfp_set_option(b"gemm_mx_variant", 0))
 else:
     ok = True
-    for variant in (0, 1):
-        for (T, N, K, m, B, tbn) in ((128, 128, 128, 3, 32, 128), (128, 256, 128, 3, 32, 256), (128, 128, 512, 3, 32, 128), (256, 512, 1024, 3, 64, 256),
-                                     (200, 260, 640, 4, 32, 128), (4096, 4096, 4096, 3, 64, 256)):
-            ok = (one(T, N, K, m, B, tbn, variant) <= 1e-5) and ok
+    cases = ((128, 128, 128, 3, 32, 128), (128, 256, 128, 3, 32, 256), (256, 256, 128, 3, 32, 256), (128, 128, 512, 3, 32, 128), (256, 512, 1024, 3, 64, 256),
+             (200, 260, 640, 4, 32, 128), (300, 520, 640, 4, 32, 256), (300, 520, 640, 4, 32, 240), (256, 240, 256, 3, 32, 240), (4096, 4096, 4096, 3, 64, 256),
+             (4096, 4096, 4096, 3, 64, 240))
+    for variant, fold in ((0, False), (0, True), (1, False)):        # variant 0: CTA pairs where they apply, 1: single CTAs
+        for (T, N, K, m, B, tbn) in cases:
+            ok = (one(T, N, K, m, B, tbn, variant, fold) <= 1e-5) and ok
+    # folded weights take any block size (the activation side needs 32-multiples): HBFP4 weights in blocks of 16 against blocks of 32
     print("ALL OK" if ok else "MISMATCH")
