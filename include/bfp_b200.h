@@ -271,6 +271,12 @@ int bfp_gemm_bf16_sp_acc(const void* x_bf16, const void* w_comp, const void* w_m
 int bfp_mx_layout(int64_t rows, int64_t K, int tile_rows, int fold, int64_t* Kp, int64_t* sf_bytes);
 int bfp_mx_from_packed(const int8_t* mant, const float* scale_t, int64_t rows, int64_t K, int block_size, int tile_rows, int fold,
                        void* vals, void* sf, int32_t* row_ref, uint32_t* violations, void* stream);
+/* float_to_bfp_blocked (quantise only, nearest rounding; bfp_ops.py:46-59) of an activation tensor straight into the general mx form in
+ * one pass (vals [rows, K] + scale atoms of 128-row tiles).  Needs mant_bits in [1, 4], block_size 32 / 64 / 128, K a multiple of 128
+ * (fp32) / 256 (half), 16-byte aligned buffers: BFP_E_UNSUPPORTED otherwise (bfp_quantize_pack + bfp_mx_from_packed).  The caller
+ * zero-fills sf once when rows % 128 != 0 (the rows of the last tile that do not exist are never written). */
+int bfp_quantize_pack_mx(const void* in, void* vals, void* sf, int64_t rows, int64_t K, int in_dtype, int block_size, int mant_bits,
+                         float eps, void* stream);
 int bfp_gemm_mx(const void* a_vals, const void* a_sf, const void* b_vals, const void* b_sf, int b_tile_rows, int b_folded,
                 const float* bias, float* out, int64_t T, int64_t N, int64_t K, void* stream);
 

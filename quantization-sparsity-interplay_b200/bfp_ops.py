@@ -507,6 +507,54 @@ def bfp_linear_mx(xp, wp, bias=None, out_shape=None):
     return out if out_shape is None else out.view(out_shape)
 
 
+def pack_activation_mx(x, bfp_args):
+    """An activation tensor [..., K] in the general block-scaled form (tile_rows 128) for bfp_gemm_mx: one fused kernel
+    (bfp_quantize_pack_mx) when the configuration is quantise-only with nearest rounding and K is a multiple of 128 (fp32) / 256
+    (half); otherwise bfp_quantize_pack + bfp_mx_from_packed."""
+    B, m = int(bfp_args['block_size']), int(bfp_args['mant_bits'])
+    src = x.detach().contiguous()
+    K = src.shape[-1]
+    rows = src.numel() // K if K else 0
+    vec = 4 if src.dtype == torch.float32 else 8
+    fused = (bfp_args['in_sparsity'] != True and bfp_args['rounding_mode'] == rounding_modes.DETERM and B in (32, 64, 128)      # noqa: E712
+             and K % (32 * vec) == 0 and rows > 0 and src.data_ptr() % 16 == 0)
+    if not fused:
+        return pack_bfp_mx(src.view(rows, K), 128, identifier='in', check=False, **bfp_args)
+    L = _lib.lib()
+    sfb = ctypes.c_int64()
+    _lib.check(L.bfp_mx_layout(rows, K, 128, 0, None, ctypes.byref(sfb)))
+    vals = torch.empty((rows, K), dtype=torch.uint8, device=src.device)
+    sf = (torch.zeros if rows % 128 else torch.empty)(max(sfb.value, 16), dtype=torch.uint8, device=src.device)
+    with _on(src.device):
+        _lib.check(L.bfp_quantize_pack_mx(src.data_ptr(), vals.data_ptr(), sf.data_ptr(), rows, K, _DT[src.dtype], B, m, float(bfp_args['epsilon']),
+                                          _stream()))
+    return PackedMX(vals, sf, rows, K, 128, B, m, False)
+
+
+def _mx_eligible(x, w, bfp_args):
+    """HBFP4 / HBFP5 inference on the block-scaled FP8-class tensor-core path (csrc/bfp_gemm_mx.cu): mant_bits <= 4, activation
+    blocks that are multiples of 32, an output width the TMA store can take.  BFP_GEMM_KIND=sp|bf16|i8 opts out, =mx insists."""
+    want = os.environ.get("BFP_GEMM_KIND", "")
+    if want not in ("", "mx"):
+        return False
+    return (bfp_args['rounding_mode'] == rounding_modes.DETERM and 1 <= bfp_args['mant_bits'] <= 4 and bfp_args['block_size'] in (32, 64, 128)
+            and w.shape[0] % 4 == 0 and x.dim() >= 1 and x.shape[-1] == w.shape[1]
+            and not (bfp_args['in_sparsity'] == True and bfp_args['sparsity_mode'] == 'unstructured'))      # noqa: E712
+
+
+def _packed_activation_mx(x, bfp_args):
+    if os.environ.get("BFP_ACT_CACHE", "1") != "1" or torch.cuda.is_current_stream_capturing():
+        return pack_activation_mx(x, bfp_args)
+    key = ("mx", bfp_args['block_size'], bfp_args['mant_bits'], float(bfp_args['epsilon']), bfp_args['in_sparsity'] == True,   # noqa: E712
+           bfp_args['N'], bfp_args['M'], bfp_args['first'], bfp_args['sparsity_mode'], float(bfp_args['sparsity_frac']), _stream(x.device))
+    hit = _ACT_CACHE.get(x.device)
+    if hit is not None and hit[0] is x and hit[1] == x._version and hit[2] == key:
+        return hit[3]
+    xp = pack_activation_mx(x, bfp_args)
+    _ACT_CACHE[x.device] = (x, x._version, key, xp)
+    return xp
+
+
 def pack_bfp_bf16(t, identifier='', philox=None, **bfp_args):
     """float_to_bfp_blocked straight to a dequantised bf16 [rows, Kp] operand (Kp = K rounded up to 8).  Exact for
     mant_bits <= 8: q * 2^(e-m) has at most 8 significant bits.  Any block size."""
@@ -1115,13 +1163,16 @@ class BFPLinear(torch.nn.Linear):
                 packed = compress_2to4_bf16(pack_bfp_bf16(w.detach(), identifier='w', **self.bfp_args), check=self._cacheable())
             elif kind == 'sp_static':
                 packed = self._build_static_sparse_weight()
+            elif kind == 'mx':
+                # folded block-scaled form (None when a row's block exponents span more than the form holds: the caller moves on)
+                packed = pack_bfp_mx(w.detach(), 240 if w.shape[0] >= 240 else 128, fold=True, identifier='w', **self.bfp_args)
             else:
                 packed = (pack_bfp if kind == 'i8' else pack_bfp_bf16)(w.detach(), identifier='w', **self.bfp_args)
             hit = (key, packed)
             if self._cacheable():
                 self._packed_by_kind = {k: v for k, v in self._packed_by_kind.items() if v[0][1:] == key[1:]}   # drop stale kinds
                 self._packed_by_kind[kind] = hit
-        if kind != 'sp_static':
+        if kind != 'sp_static' and hit[1] is not None:
             self._packed_w = hit
         return hit[1]
 
@@ -1202,7 +1253,16 @@ class BFPLinear(torch.nn.Linear):
             if not determ or training:
                 kind = None             # training configurations the autograd Function does not cover keep the reference's structure
             y = None
-            if kind == 'i8':
+            if kind is not None and _mx_eligible(input, self.weight, self.bfp_args):
+                # HBFP4 / HBFP5: block-scaled FP8-class MMA (twice the bf16 rate); zeros of a pruned weight are just zeros here
+                wp = self._packed_weight('mx')
+                if wp is not None:
+                    y = bfp_linear_mx(_packed_activation_mx(input, self.bfp_args), wp, self.bias,
+                                      out_shape=tuple(input.shape[:-1]) + (self.out_features,))
+                    kind = 'mx'
+            if y is not None:
+                pass
+            elif kind == 'i8':
                 # inference fast path: pack activations on the fly, cached packed weight, tcgen05 int8 BFP GEMM
                 y = bfp_linear_packed(pack_bfp(input, identifier='in', **self.bfp_args), self._packed_weight(kind), self.bias)
             elif kind == 'sp':

@@ -351,6 +351,13 @@ int bfp_mx_from_packed(const int8_t* mant, const float* scale_t, int64_t rows, i
                                  static_cast<uint8_t*>(sf), row_ref, violations, static_cast<cudaStream_t>(stream));
 }
 
+int bfp_quantize_pack_mx(const void* in, void* vals, void* sf, int64_t rows, int64_t K, int in_dtype, int block_size, int mant_bits, float eps, void* stream) {
+    if (rows < 0 || K < 0 || in_dtype < 0 || in_dtype > 2 || block_size <= 0) return set_error(BFP_E_ARG, "bad argument");
+    if (rows * K > 0 && (!in || !vals || !sf)) return set_error(BFP_E_ARG, "null pointer");
+    if (int rc = require_device()) return rc;
+    return mx_pack_device(in, in_dtype, rows, K, block_size, mant_bits, eps, static_cast<uint8_t*>(vals), static_cast<uint8_t*>(sf), static_cast<cudaStream_t>(stream));
+}
+
 int bfp_gemm_mx(const void* a_vals, const void* a_sf, const void* b_vals, const void* b_sf, int b_tile_rows, int b_folded, const float* bias, float* out,
                 int64_t T, int64_t N, int64_t K, void* stream) {
     if (T < 0 || N < 0 || K < 0) return set_error(BFP_E_ARG, "negative shape");

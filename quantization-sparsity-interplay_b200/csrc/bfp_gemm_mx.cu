@@ -27,6 +27,7 @@
 #include <algorithm>
 
 #include "bfp_internal.h"
+#include "bfp_stream.cuh"
 #include "bfp_tc.cuh"
 
 namespace bfp {
@@ -383,6 +384,74 @@ __global__ void __launch_bounds__(256) mx_sf_kernel(const float* __restrict__ sc
     *reinterpret_cast<uint32_t*>(atom_base + 16 * (r & 31) + 4 * (r >> 5)) = word;
 }
 
+// ---- fused activation pack: float_to_bfp_blocked (quantise only, nearest rounding) straight into the general mx form -----------------
+// One pass: lane l of a warp owns one 128-bit vector (4 fp32 / 8 half values); a BFP block is 2^j adjacent lanes (block max by
+// butterfly, the quantiser arithmetic of bfp_common.cuh); a warp covers 128 (fp32) or 256 (half) consecutive k of one row, i.e. one
+// or two K slabs, and writes their E4M3 bytes (4 / 8 per lane, coalesced) and the row's four scale bytes per slab (one 32-bit store).
+// Blocks the packed form cannot represent (slow-path scales: NaN / Inf / denormal range) get the NaN scale 0xff like bfp_quantize_pack.
+template <int DT>
+__global__ void __launch_bounds__(256) mx_pack_kernel(const uint4* __restrict__ in, uint8_t* __restrict__ vals, uint8_t* __restrict__ sf, int64_t rows, int64_t K,
+                                                      int lanes_per_block, int m, float eps, int64_t n_tiles) {
+    using D = DType<DT>;
+    constexpr int V = D::kVec;
+    constexpr int kSlabsPerWarp = 32 * V / 128;             // 1 (fp32) or 2 (half)
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_per_row = K / (32 * V);
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t wi = gw; wi < rows * warps_per_row; wi += n_warps) {
+        const int64_t row = wi / warps_per_row, wk = wi - row * warps_per_row;
+        const int64_t vec = row * (K / V) + wk * 32 + lane;
+        float v[V];
+        unpack_vec<DT>(ld_stream(in + vec), v);
+        uint32_t amax = 0u;
+#pragma unroll
+        for (int i = 0; i < V; ++i) amax = max(amax, abs_bits(v[i]));
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1)
+            if (off < lanes_per_block) amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+        const BlockScale sc = make_scale<DT>(amax, m, eps);
+        uint32_t bytes[V / 4];
+        uint32_t sbyte = 0xffu;                               // NaN scale unless the block is on the exact path
+        if (sc.fast) {
+            sbyte = (uint32_t)(sc.p + 127);
+#pragma unroll
+            for (int w = 0; w < V / 4; ++w) {
+                uint32_t o = 0u;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const float t = v[4 * w + b];
+                    const float qf = fminf(fmaxf(rintf(t * sc.inv), -sc.vmax), sc.vmax);     // the integer mantissa (bfp_ops.py:40-44 on the grid)
+                    const int q = (int)qf;
+                    const uint32_t a = (uint32_t)(q < 0 ? -q : q);
+                    const uint32_t e = a ? e4m3_of(a, 0) : 0u;
+                    o |= (e | (q < 0 ? 0x80u : 0u)) << (8 * b);
+                }
+                bytes[w] = o;
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < V / 4; ++w) bytes[w] = 0u;
+        }
+        uint8_t* dst = vals + row * K + (wk * 32 + lane) * V;
+        if (V == 4) *reinterpret_cast<uint32_t*>(dst) = bytes[0];
+        else *reinterpret_cast<uint2*>(dst) = make_uint2(bytes[0], bytes[V == 8 ? 1 : 0]);
+        // scale bytes: 32-group g of slab s lives in lanes [(s * 128 + g * 32) / V, ...): gather the four bytes of a slab into lane 0 / 16
+#pragma unroll
+        for (int sl = 0; sl < kSlabsPerWarp; ++sl) {
+            uint32_t word = 0u;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) word |= __shfl_sync(0xffffffffu, sbyte, (sl * 128 + g * 32) / V) << (8 * g);
+            if (lane == 0) {
+                const int64_t slab = wk * kSlabsPerWarp + sl, tile = row >> 7;
+                const int r = (int)(row & 127);
+                *reinterpret_cast<uint32_t*>(sf + ((slab * n_tiles + tile) * 512) + 16 * (r & 31) + 4 * (r >> 5)) = word;
+            }
+        }
+    }
+}
+
 }  // namespace gemm_mx
 
 int mx_layout(int64_t rows, int64_t K, int tile_rows, int fold, int64_t* Kp, int64_t* sf_bytes) {
@@ -415,6 +484,41 @@ int mx_from_packed_device(const int8_t* mant, const float* scale_t, int64_t ld_s
     mx_sf_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(scale_t, ld_s, fold ? row_ref : nullptr, sf, rows, K, block_size, tile_rows, atoms, tiles, slabs);
     count_launch();
     return check_launch("mx operand conversion");
+}
+
+// float_to_bfp_blocked (quantise only) -> general mx form in one pass.  Needs nearest rounding, mant_bits in [1, 4], a power-of-two
+// block_size in {32, 64, 128}, K a multiple of 128 (fp32) / 256 (half) and 16-byte aligned buffers: BFP_E_UNSUPPORTED otherwise (pack
+// with bfp_quantize_pack and convert with bfp_mx_from_packed).  Rows beyond `rows` inside the last 128-row tile keep whatever the sf
+// buffer held: the caller zero-fills sf once when rows % 128 != 0.
+int mx_pack_device(const void* in, int dtype, int64_t rows, int64_t K, int block_size, int mant_bits, float eps, uint8_t* vals, uint8_t* sf, cudaStream_t st) {
+    using namespace gemm_mx;
+    if (rows == 0 || K == 0) return BFP_OK;
+    const int V = dtype == BFP_DT_F32 ? 4 : 8;
+    if (mant_bits < 1 || mant_bits > 4) return set_error(BFP_E_UNSUPPORTED, "the block-scaled form holds mant_bits in [1, 4]");
+    if ((block_size != 32 && block_size != 64 && block_size != 128) || K % (32 * V) || reinterpret_cast<uintptr_t>(in) % 16 ||
+        reinterpret_cast<uintptr_t>(vals) % 16 || reinterpret_cast<uintptr_t>(sf) % 16)
+        return set_error(BFP_E_UNSUPPORTED, "fused mx pack: block_size 32 / 64 / 128, K a multiple of 128 (fp32) or 256 (half), 16-byte aligned buffers");
+    if (dtype != BFP_DT_F32) ensure_exp_tables(st);          // this translation unit's copy of the half-precision exponent table
+    const int64_t n_tiles = (rows + 127) / 128;
+    const int64_t warps = rows * (K / (32 * V));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((warps + 7) / 8, (int64_t)device_info().sm_count * 8));
+    const uint4* src = static_cast<const uint4*>(in);
+    const int lpb = block_size / V;
+    int rc;
+    struct P { const uint4* in; uint8_t* vals; uint8_t* sf; int64_t rows, K; int lpb, m; float eps; int64_t n_tiles; };
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(256); cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = tuning().pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e;
+    if (dtype == BFP_DT_F32) e = cudaLaunchKernelEx(&cfg, mx_pack_kernel<BFP_DT_F32>, src, vals, sf, rows, K, lpb, mant_bits, eps, n_tiles);
+    else if (dtype == BFP_DT_F16) e = cudaLaunchKernelEx(&cfg, mx_pack_kernel<BFP_DT_F16>, src, vals, sf, rows, K, lpb, mant_bits, eps, n_tiles);
+    else e = cudaLaunchKernelEx(&cfg, mx_pack_kernel<BFP_DT_BF16>, src, vals, sf, rows, K, lpb, mant_bits, eps, n_tiles);
+    (void)rc;
+    if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaLaunchKernelEx(mx_pack_kernel): %s", cudaGetErrorString(e));
+    count_launch();
+    return check_launch("mx_pack_kernel");
 }
 
 template <int TBN, int CG>

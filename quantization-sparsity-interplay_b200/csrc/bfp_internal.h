@@ -83,6 +83,7 @@ int gemm_bf16_sp_multi_device(const void* x_bf16, const void* w_comp, const void
 int mx_layout(int64_t rows, int64_t K, int tile_rows, int fold, int64_t* Kp, int64_t* sf_bytes);
 int mx_from_packed_device(const int8_t* mant, const float* scale_t, int64_t ld_s, int64_t rows, int64_t K, int block_size, int tile_rows, int fold,
                           uint8_t* vals, uint8_t* sf, int* row_ref, unsigned int* violations, cudaStream_t st);
+int mx_pack_device(const void* in, int dtype, int64_t rows, int64_t K, int block_size, int mant_bits, float eps, uint8_t* vals, uint8_t* sf, cudaStream_t st);
 int gemm_mx_device(const uint8_t* a_vals, const uint8_t* a_sf, const uint8_t* b_vals, const uint8_t* b_sf, int b_tile_rows, int b_folded, const float* bias,
                    float* out, int64_t T, int64_t N, int64_t Kp, cudaStream_t st);
 

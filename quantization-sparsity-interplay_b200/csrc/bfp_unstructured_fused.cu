@@ -1061,6 +1061,7 @@ bool unstructured_fused_supported(const UnstructuredArgs& a) {
 
 int unstructured_fused_device(const UnstructuredArgs& a, cudaStream_t s) {
     if (a.k == 0 || a.k >= (unsigned long long)a.n) return set_error(BFP_E_ARG, "k must be in (0, numel)");
+    if (a.dtype != BFP_DT_F32 && a.order != BFP_ORDER_SPARSIFY_ONLY) ensure_exp_tables(s);    // this translation unit's copy of the half-precision exponent table
     switch (a.dtype) {
     case BFP_DT_F32: return dispatch_mode<BFP_DT_F32>(a, s);
     case BFP_DT_F16: return dispatch_mode<BFP_DT_F16>(a, s);

@@ -901,3 +901,107 @@ def test_trainable_bias_alone_gets_its_gradient(ops):
         assert y2.requires_grad
         y2.float().sum().backward()
         assert torch.allclose(b.grad.float(), torch.full((128,), 40.0 * 127 / 128, device="cuda"))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Block-scaled FP8-class kind (csrc/bfp_gemm_mx.cu): HBFP4 / HBFP5 on tcgen05.mma.kind::mxf8f6f4.block_scale
+# ---------------------------------------------------------------------------------------------------------------
+def _args(mant_bits=3, block_size=64, w_sparsity=False, first="s"):
+    from qsi_b200 import bfp_ops
+    return bfp_ops.unpack_bfp_args(dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=mant_bits,
+                                        block_size=block_size, w_sparsity=w_sparsity, N=2, M=4, first=first, sparsity_mode="structured", device="cuda"))
+
+
+def _mx_decode(p):
+    """PackedMX -> fp32 [rows, K]: E4M3 byte x 2^(scale byte - 127), restating the operand layout of include/bfp_b200.h."""
+    v = p.vals.cpu().numpy().astype(np.int64)
+    sign = np.where(v & 0x80, -1.0, 1.0)
+    e, mm = (v >> 3) & 15, v & 7
+    mag = np.where(e > 0, (1.0 + mm / 8.0) * np.exp2(e - 7.0), mm / 8.0 * 2.0 ** -6)
+    vals = (sign * mag)[:, : p.K]
+    sf = p.sf.cpu().numpy()
+    rows, K, tr = p.rows, p.K, p.tile_rows
+    atoms, n_tiles = (tr + 127) // 128, (rows + tr - 1) // tr
+    r = np.arange(rows)[:, None]
+    k = np.arange(K)[None, :]
+    tile, in_tile = r // tr, r % tr
+    atom, ra = in_tile // 128, in_tile % 128
+    slab, g = (0 * k if p.folded else k // 128), (k % 128) // 32
+    off = ((slab * n_tiles + tile) * atoms + atom) * 512 + 16 * (ra % 32) + 4 * (ra // 32) + g
+    scale = np.exp2(sf[off].astype(np.float64) - 127.0)
+    return (vals * scale).astype(np.float32)
+
+
+@pytest.mark.parametrize("m,B", [(3, 32), (3, 64), (4, 128)])
+def test_mx_pack_contract(ops, m, B):
+    """decode(pack_mx(x)) == float_to_bfp_blocked(x), for the general form, the folded (weight) form, the fused activation pack."""
+    g = torch.Generator(device="cuda").manual_seed(31)
+    a = _args(mant_bits=m, block_size=B, w_sparsity=False)
+    for rows, K in ((128, 256), (200, 640), (1, 128), (300, 1024)):
+        x = torch.randn(rows, K, device="cuda", generator=g) * torch.exp2(torch.randint(-4, 5, (rows, K // B), device="cuda", generator=g).repeat_interleave(B, 1).float())
+        ref = ops.float_to_bfp_blocked(x, **a, identifier="in").cpu().numpy()
+        for tile_rows, fold in ((128, False), (240, True), (256, True), (128, True)):
+            p = ops.pack_bfp_mx(x, tile_rows, fold=fold, identifier="in", **a)
+            assert p is not None
+            assert np.array_equal(_mx_decode(p), ref), (rows, K, tile_rows, fold)
+        if K % 128 == 0:
+            pf = ops.pack_activation_mx(x, a)
+            p2 = ops.pack_bfp_mx(x, 128, identifier="in", **a)
+            assert torch.equal(pf.vals, p2.vals)
+            assert np.array_equal(_mx_decode(pf), ref)
+    # half-precision activations through the fused pack
+    for dt in (torch.float16, torch.bfloat16):
+        x = (torch.randn(130, 512, device="cuda", generator=g) * 0.1).to(dt)
+        ref = ops.float_to_bfp_blocked(x, **a, identifier="in").float().cpu().numpy()
+        assert np.array_equal(_mx_decode(ops.pack_activation_mx(x, a)), ref), dt
+    # a weight whose block exponents span more than the folded form holds is refused (the general form still takes it)
+    w = torch.randn(64, 256, device="cuda", generator=g)
+    w[:, :B] *= 2.0 ** 20
+    assert ops.pack_bfp_mx(w, 128, fold=True, identifier="w", **a) is None
+    assert np.array_equal(_mx_decode(ops.pack_bfp_mx(w, 128, identifier="w", **a)), ops.float_to_bfp_blocked(w, **a, identifier="w").cpu().numpy())
+
+
+@pytest.mark.parametrize("T,N,K,m,B", [(128, 128, 128, 3, 32), (200, 260, 640, 4, 32), (300, 520, 1024, 3, 64), (1000, 1004, 512, 3, 128), (4096, 4096, 4096, 3, 64)])
+def test_mx_gemm_matches_oracle(ops, oracle, T, N, K, m, B):
+    g = torch.Generator(device="cuda").manual_seed(33)
+    a = _args(mant_bits=m, block_size=B, w_sparsity=False)
+    x = torch.randn(T, K, device="cuda", generator=g) * torch.exp2(torch.randint(-5, 6, (T, K // B), device="cuda", generator=g).repeat_interleave(B, 1).float())
+    w = torch.randn(N, K, device="cuda", generator=g) * 0.05 * torch.exp2(torch.randint(-3, 4, (N, K // B), device="cuda", generator=g).repeat_interleave(B, 1).float())
+    bias = torch.randn(N, device="cuda", generator=g)
+    xq, wq = ops.float_to_bfp_blocked(x, **a, identifier="in"), ops.float_to_bfp_blocked(w, **a, identifier="w")
+    ref = (xq.double() @ wq.double().t() + bias.double())
+    xp = ops.pack_activation_mx(x, a)
+    for tile_rows, fold in ((240, True), (256, True), (128, True), (240, False), (256, False), (128, False)):
+        wp = ops.pack_bfp_mx(w, tile_rows, fold=fold, identifier="w", **a)
+        y = ops.bfp_linear_mx(xp, wp, bias)
+        rel = float((y.double() - ref).norm() / ref.norm())
+        assert rel <= 1e-5, (tile_rows, fold, rel)                       # north_star tolerance; measured ~1e-7
+    if T <= 300:
+        o = oracle.linear(xq.cpu().numpy(), wq.cpu().numpy(), bias.cpu().numpy())
+        assert float(np.linalg.norm(y.cpu().numpy() - o) / np.linalg.norm(o)) <= 1e-5
+
+
+@pytest.mark.parametrize("w_sparse", [False, True])
+def test_bfplinear_hbfp4_takes_the_block_scaled_path(ops, oracle, w_sparse):
+    """HBFP4 modules run on the block-scaled MMA (folded weight cached, activation packed by the fused kernel) and give the oracle's
+    result; the bf16 kinds stay available through BFP_GEMM_KIND."""
+    import os
+    g = torch.Generator().manual_seed(35)
+    a = _args(mant_bits=3, block_size=64, w_sparsity=w_sparse)
+    lin = ops.BFPLinear(512, 384, bias=True, **a).cuda()
+    x = torch.randn(3, 50, 512, generator=g).cuda()
+    with torch.no_grad():
+        y = lin(x)
+    assert lin._packed_w[0][0] == "mx" and y.shape == (3, 50, 384)
+    xq, _ = oracle.bfp_quantize(x.cpu().numpy(), 64, 3)
+    wq, _ = oracle.float_to_bfp_blocked(lin.weight.detach().cpu().numpy(), 3, 64, "sq" if w_sparse else "q")
+    ref = oracle.linear(xq.reshape(-1, 512), wq, lin.bias.detach().cpu().numpy()).reshape(3, 50, 384)
+    assert float(np.linalg.norm(y.cpu().numpy() - ref) / np.linalg.norm(ref)) <= 1e-5
+    os.environ["BFP_GEMM_KIND"] = "bf16"
+    try:
+        with torch.no_grad():
+            y2 = lin(x)
+        assert lin._packed_w[0][0] in ("bf16", "sp")
+    finally:
+        os.environ.pop("BFP_GEMM_KIND")
+    assert float((y - y2).norm() / y2.norm()) <= 1e-6
