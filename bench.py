@@ -195,7 +195,7 @@ def run_reference_arm(a, rank, world):
         v, kind, cores, sample, dt = cpu_arm(budget, threads, workload)
         vals.append(v); secs.append(dt); info = (kind, cores, sample)
     value = sum(vals) / len(vals)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": a.gpus, "steps": a.steps,
+    line = {"impl": "reference", "device": "cpu (the reference's torch-CPU path on the host cores; no GPU is used by this arm)", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True,
             "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_for(world), "device": "host CPU cores (the reference arm of this tier is the reference's CPU path; no GPU is used)",
@@ -475,7 +475,8 @@ def leg_gemm(torch, dev, g, peaks):
         torch.cuda.synchronize()
         return g0.elapsed_time(g1) / iters
 
-    per_shape, calls, ops_total = [], {"sp": [], "bf16": [], "i8": [], "linear_fwd": []}, 0.0
+    margs = dict(gargs, mant_bits=3)                       # HBFP4: the block-scaled FP8-class kind (csrc/bfp_gemm_mx.cu)
+    per_shape, calls, ops_total = [], {"sp": [], "bf16": [], "i8": [], "linear_fwd": [], "mx_hbfp4": [], "linear_fwd_hbfp4": []}, 0.0
     ms_sum = {k: 0.0 for k in calls}
     keep = []
     for (T, Nn, Kk) in ((4096, 4096, 4096), (4096, 11008, 4096), (4096, 4096, 11008)):
@@ -485,7 +486,9 @@ def leg_gemm(torch, dev, g, peaks):
         xb, wb = bfp_ops.pack_bfp_bf16(xg, identifier="in", **gargs), bfp_ops.pack_bfp_bf16(wg, identifier="w", **gargs)
         ws = bfp_ops.compress_2to4_bf16(wb)
         og = torch.empty(T, Nn, device=dev)
-        keep.append((xg, xp, wp, xb, wb, ws, og))
+        xm = bfp_ops.pack_activation_mx(xg, margs)
+        wm = bfp_ops.pack_bfp_mx(wg, 240, fold=True, identifier="w", **margs)
+        keep.append((xg, xp, wp, xb, wb, ws, og, xm, wm))
         f = {
             "i8": (lambda xp=xp, wp=wp, og=og, T=T, Nn=Nn, Kk=Kk: _lib.check(L.bfp_gemm_i8(
                 xp.mant.data_ptr(), xp.scale_t.data_ptr(), wp.mant.data_ptr(), wp.scale_t.data_ptr(), None, og.data_ptr(), T, Nn, Kk, 64, stream))),
@@ -495,6 +498,10 @@ def leg_gemm(torch, dev, g, peaks):
                 xb.data_ptr(), ws.comp.data_ptr(), ws.meta.data_ptr(), None, og.data_ptr(), T, Nn, Kk, stream))),
             # the whole BFPLinear forward a caller sees: quantise x on the fly + contraction (weight pack cached)
             "linear_fwd": (lambda xg=xg, ws=ws: bfp_ops.bfp_linear_bf16_sp(bfp_ops.pack_bfp_bf16(xg, identifier="in", **gargs), ws)),
+            # HBFP4 (2:4 s->q weights, zeros kept): tcgen05.mma.kind::mxf8f6f4.block_scale on E4M3 mantissas + UE8M0 block scales
+            "mx_hbfp4": (lambda xm=xm, wm=wm, og=og, T=T, Nn=Nn, Kk=Kk: _lib.check(L.bfp_gemm_mx(
+                xm.vals.data_ptr(), xm.sf.data_ptr(), wm.vals.data_ptr(), wm.sf.data_ptr(), wm.tile_rows, 1, None, og.data_ptr(), T, Nn, Kk, stream))),
+            "linear_fwd_hbfp4": (lambda xg=xg, wm=wm: bfp_ops.bfp_linear_mx(bfp_ops.pack_activation_mx(xg, margs), wm)),
         }
         nops = 2.0 * T * Nn * Kk
         row = {"T": T, "N": Nn, "K": Kk}
@@ -508,7 +515,7 @@ def leg_gemm(torch, dev, g, peaks):
     burst = {k: ops_total / v / 1e9 for k, v in ms_sum.items()}
     # sustained: cycle the three shapes back to back for >= 2 s per kind (the power-limited steady state)
     sustained = {}
-    for k in ("sp", "bf16", "i8"):
+    for k in ("sp", "bf16", "i8", "mx_hbfp4"):
         cyc_ms = ms_sum[k]
         reps = max(3, int(2000.0 / max(cyc_ms, 1e-3)) + 1)
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -523,7 +530,7 @@ def leg_gemm(torch, dev, g, peaks):
     bf16_burst = peaks.get("bf16_tflops") or 1658.0
     bf16_sus = peaks.get("bf16_tflops_sustained") or 1391.6
     int_mm = 2988.0      # torch._int_mm 8192^3 on this pool's B200 (profiles/r01_probe_ref_gpu.log), the measured library int8 figure
-    sp_s, bf_s, i8_s = sustained["sp"]["tops"], sustained["bf16"]["tops"], sustained["i8"]["tops"]
+    sp_s, bf_s, i8_s, mx_s = sustained["sp"]["tops"], sustained["bf16"]["tops"], sustained["i8"]["tops"], sustained["mx_hbfp4"]["tops"]
     return {
         "tops": burst["sp"], "unit": "TOPS (2*T*N*K ops, dense-equivalent; the 2:4 kernel executes half)",
         "kernel": "bfp_gemm_bf16_sp_kernel (tcgen05.mma.sp.cta_group::2.kind::f16, 2:4-compressed exact-bf16 BFP weight)",
@@ -535,6 +542,10 @@ def leg_gemm(torch, dev, g, peaks):
                                  "frac_of_nominal_sparse_bf16_4500": sp_s / 4500.0, "frac_of_measured_int_mm_2988": sp_s / int_mm},
             "dense_bf16_kind": {"achieved": bf_s, "peak": bf16_sus, "frac": bf_s / bf16_sus,
                                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained", "burst_frac_of_bf16_burst_peak": burst["bf16"] / bf16_burst},
+            "mx_hbfp4_kind": {"achieved": mx_s, "peak": 2.0 * bf16_sus, "frac": mx_s / (2.0 * bf16_sus),
+                              "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops_sustained (the FP8-class kinds run at twice the bf16 rate)",
+                              "frac_of_nominal_fp8_4500": mx_s / 4500.0, "frac_of_measured_int_mm_2988": mx_s / int_mm,
+                              "kernel": "bfp_gemm_mx_kernel<240, 2> (tcgen05.mma.cta_group::2.kind::mxf8f6f4.block_scale, dense; mant_bits 3)"},
             "int8_kind": {"achieved": i8_s, "peak": int_mm, "frac": i8_s / int_mm, "peak_source": "measured torch._int_mm 8192^3 (cuBLASLt int8)",
                           "frac_of_nominal_int8_4500": i8_s / 4500.0,
                           "note": "kind::i8 MMA + per-block fp32 rescale on the CUDA cores: epilogue-bound by construction (DESIGN.md section 4); never the default kind"},

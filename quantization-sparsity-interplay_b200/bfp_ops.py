@@ -73,6 +73,10 @@ class _PhiloxState:
 
     @classmethod
     def next(cls):
+        if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+            # the (seed, offset) pair is baked into the kernel arguments: a replayed graph would reuse the same uniforms every step
+            raise RuntimeError("bfp_b200: stochastic rounding cannot be captured into a CUDA graph (its Philox offset advances on the host); "
+                               "capture with rounding_mode='determ' or run the stochastic calls eagerly")
         s = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
         if s != cls.seed:
             cls.seed, cls.calls = s, 0
