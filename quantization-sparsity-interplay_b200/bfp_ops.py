@@ -698,7 +698,7 @@ def _tensor_core_eligible(x, w, bfp_args):
     training = torch.is_grad_enabled() and (x.requires_grad or w.requires_grad)
     if training and os.environ.get("BFP_TRAIN_PATH", "tc") != "tc":
         return False
-    dtype_ok = x.dtype == w.dtype and (x.dtype == torch.float32 or (x.dtype in (torch.float16, torch.bfloat16) and not training))
+    dtype_ok = x.dtype == w.dtype and x.dtype in _DT          # half precision: fp32 accumulation, one rounding to the dtype (library HGEMM semantics)
     if bfp_args['rounding_mode'] != rounding_modes.DETERM and not training:
         # the stochastic quantiser promotes every operand to fp32: any mix of float dtypes is one case
         dtype_ok = x.dtype in _DT and w.dtype in _DT
@@ -940,10 +940,11 @@ class _BFPLinearTC(torch.autograd.Function):
         wb = cached_w if cached_w is not None else pack_bfp_bf16(w, identifier='w', **bfp_args)   # dense [N, Kp] or SparseBF16
         out_shape = tuple(x.shape[:-1]) + (N,)
         if isinstance(wb, SparseBF16):
-            y = bfp_linear_bf16_sp(xb, wb, bias, out_shape=out_shape)
+            y = bfp_linear_bf16_sp(xb, wb, bias, out_shape=out_shape, out_dtype=x.dtype)
         else:
-            y = bfp_linear_bf16(xb, wb, bias, out_shape=out_shape)
+            y = bfp_linear_bf16(xb, wb, bias, out_shape=out_shape, out_dtype=x.dtype)
         ctx.bfp_args, ctx.K, ctx.N, ctx.x_shape, ctx.has_bias = bfp_args, K, N, tuple(x.shape), bias is not None
+        ctx.x_dtype, ctx.w_dtype, ctx.b_dtype = x.dtype, w.dtype, (bias.dtype if bias is not None else None)
         ctx.wb_dense = wb if not isinstance(wb, SparseBF16) else dense_w      # tensor, or a callable that packs it on demand
         ctx.save_for_backward(xb)
         return y
@@ -953,20 +954,22 @@ class _BFPLinearTC(torch.autograd.Function):
         (xb,) = ctx.saved_tensors
         a, K, N = ctx.bfp_args, ctx.K, ctx.N
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        gq = pack_bfp_bf16(gy.reshape(-1, N).float(), identifier='grad', **a)  # [T, Np], blocked along N (bfp_ops.py:181)
+        # quantised in the gradient's own dtype (the half-precision block exponent differs from the fp32 one);
+        # with grad_sparsity the N:M mask of identifier='grad' is part of the same pack
+        gq = pack_bfp_bf16(gy.reshape(-1, N).contiguous(), identifier='grad', **a)  # [T, Np], blocked along N (bfp_ops.py:181)
         T, Np = gq.shape
         grad_x = grad_w = grad_b = None
         if need_x:
             wb = ctx.wb_dense() if callable(ctx.wb_dense) else ctx.wb_dense     # dgrad contracts over N: the dense form
             wbT = _transpose_pad(wb, N, K, Np)                                  # [K, Np]
-            grad_x = bfp_linear_bf16(gq, wbT).view(ctx.x_shape)
+            grad_x = bfp_linear_bf16(gq, wbT, out_dtype=ctx.x_dtype).view(ctx.x_shape)
         if need_w:
             Tp = -(-T // 8) * 8
             gqT = _transpose_pad(gq, T, N, Tp)                                  # [N, Tp]
             xbT = _transpose_pad(xb, T, K, Tp)                                  # [K, Tp]
-            grad_w = bfp_linear_bf16(gqT, xbT)                                  # [N, K]
+            grad_w = bfp_linear_bf16(gqT, xbT, out_dtype=ctx.w_dtype)           # [N, K]
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            grad_b = gq[:, :N].sum(0, dtype=torch.float32)
+            grad_b = gq[:, :N].sum(0, dtype=torch.float32).to(ctx.b_dtype)
         return grad_x, grad_w, grad_b, None, None, None
 
 
@@ -1242,8 +1245,10 @@ class BFPLinear(torch.nn.Linear):
                 if packed is not None:
                     return _int_tc_linear(input, packed, self.bias, self.bfp_args)
             kind = _tensor_core_kind(input, self.weight, self.bfp_args) if (determ or training) else None
-            if (training and kind is not None and self.bfp_args['mant_bits'] <= 8 and self.bfp_args['grad_sparsity'] != True   # noqa: E712
-                    and input.dtype == torch.float32 and self.weight.dtype == torch.float32):
+            if (training and kind is not None and self.bfp_args['mant_bits'] <= 8
+                    and (self.bfp_args['grad_sparsity'] != True or self.bfp_args['sparsity_mode'] == 'structured')   # noqa: E712
+                    and input.dtype == self.weight.dtype and input.dtype in _DT
+                    and (determ or input.dtype == torch.float32)):
                 # training: forward + dgrad + wgrad on the tensor cores.  Stochastic rounding re-quantises the weight on
                 # every forward like the reference (no cache), and keeps it dense for the backward contraction over N.
                 tkind = kind if kind in ('sp', 'bf16') else 'bf16'

@@ -644,22 +644,57 @@ def test_bfplinear_input_sparsity_on_tensor_cores(ops, mode, monkeypatch):
         assert float((got.double() - exact).norm() / exact.norm()) <= 1e-5
 
 
-def test_bfplinear_training_with_grad_sparsity_keeps_autograd(ops, monkeypatch):
-    """grad_sparsity is not covered by the tensor-core autograd Function: the module must fall back to the reference's
-    structure (and still produce gradients), never to the inference kernels."""
+def test_bfplinear_training_with_grad_sparsity_on_tensor_cores(ops, monkeypatch):
+    """grad_sparsity (bfp_ops.py:136-137): the N:M mask of the output gradient is part of the same pack as its quantisation, so
+    the tensor-core autograd Function covers it; gradients equal the reference's structure (fake-quant + torch autograd)."""
     kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=7, block_size=64,
               w_sparsity=True, grad_sparsity=True, N=2, M=4, first="s", sparsity_mode="structured", device="cuda")
     torch.manual_seed(2)
     lin = ops.BFPLinear(256, 128, bias=True, **dict(kw)).cuda()
     x = torch.randn(64, 256, device="cuda", requires_grad=True)
     y = lin(x)
-    assert y.requires_grad
+    assert y.requires_grad and y.grad_fn.name().startswith("_BFPLinearTC")
     y.square().sum().backward()
-    gx, gw = x.grad.clone(), lin.weight.grad.clone()
-    x.grad = None; lin.weight.grad = None
+    gx, gw, gb = x.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone()
+    x.grad = None; lin.weight.grad = None; lin.bias.grad = None
     monkeypatch.setenv("BFP_LINEAR_PATH", "fakequant")
-    lin(x).square().sum().backward()
-    assert torch.allclose(gx, x.grad, rtol=1e-5, atol=1e-6) and torch.allclose(gw, lin.weight.grad, rtol=1e-5, atol=1e-6)
+    monkeypatch.setenv("BFP_TRAIN_PATH", "fakequant")
+    y2 = lin(x)
+    assert not y2.grad_fn.name().startswith("_BFPLinearTC")
+    y2.square().sum().backward()
+    for a, b in ((gx, x.grad), (gw, lin.weight.grad), (gb, lin.bias.grad)):
+        assert ((a.double() - b.double()).norm() / b.double().norm()).item() <= 1e-5
+    # the gradient really was sparsified: half of every group of four output-gradient entries contributes nothing to grad_w's rows
+    assert (gx != 0).any()
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("w_sparse", [False, True])
+def test_bfplinear_half_precision_training_on_tensor_cores(ops, dt, w_sparse, monkeypatch):
+    """fp16 / bf16 modules (what run_llama.py loads) train on the tensor cores too: fp32 accumulation in TMEM, one rounding to the
+    dtype -- the semantics of the library HGEMM the reference's structure calls on the fake-quantised half tensors -- and the output
+    gradient quantised in its own dtype.  Against the fake-quant path through torch autograd, within a few ulps of the dtype."""
+    kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=7, block_size=64,
+              w_sparsity=w_sparse, N=2, M=4, first="s", sparsity_mode="structured", device="cuda")
+    torch.manual_seed(11)
+    lin = ops.BFPLinear(512, 256, bias=True, **dict(kw)).cuda().to(dt)
+    x0 = (torch.randn(4, 96, 512, device="cuda") * 0.5).to(dt)
+    gy = (torch.randn(4, 96, 256, device="cuda") * 0.1).to(dt)
+    res = {}
+    for path in ("tc", "fakequant"):
+        monkeypatch.setenv("BFP_TRAIN_PATH", path)
+        monkeypatch.setenv("BFP_LINEAR_PATH", "tc" if path == "tc" else "fakequant")
+        lin.zero_grad()
+        x = x0.clone().requires_grad_(True)
+        y = lin(x)
+        assert y.dtype == dt
+        y.backward(gy)
+        res[path] = (y.detach(), x.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone())
+        assert y.grad_fn.name().startswith("_BFPLinearTC") == (path == "tc")
+    tol = 4e-3 if dt == torch.float16 else 2e-2                          # a few ulps of the dtype (different accumulation orders round differently)
+    for g, r in zip(res["tc"], res["fakequant"]):
+        assert g.dtype == r.dtype
+        assert ((g.double() - r.double()).norm() / r.double().norm()).item() <= tol
 
 
 @pytest.mark.parametrize("shape", [(5, 200, 136, 72), (12, 512, 512, 64), (7, 300, 64, 512), (3, 1, 8, 8), (2, 1000, 520, 264)])
