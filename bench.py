@@ -21,6 +21,7 @@ the single-GPU result checked on rank 0) is reported as `column_parallel`.
             ncu child process (dram bytes of one launch) when ncu is available, else null
   quant_modes   the reference's real operating modes (stochastic rounding, fp16 / bf16 tensors) on the same shapes
   unstructured  global magnitude pruning fused with the quantiser (the other sparsity mode of the reference's scripts)
+  config3_llama13b_layer  BASELINE configs[2]: the seven BFPLinear forwards of a LLaMA-2-13B layer at 4096 tokens (HBFP8, HBFP4, reference)
   gemm      BFP GEMM TOPS at the LLaMA-7B shapes, burst and sustained (>= 2 s), with its own roofline block
   cpu_baseline  the CPU implementation (reference if baseline/_ref is present, else the oracle port) on a bounded sample
 """
@@ -452,6 +453,53 @@ def leg_unstructured(torch, dev, peak):
     return out
 
 
+def leg_config3(torch, dev):
+    """BASELINE.json configs[2]: LLaMA-2-13B BFP linear forward, 4096 tokens per step, on-the-fly BFP activations x 2:4-sparse BFP
+    weights: the seven BFPLinear forwards of one decoder layer through the public module API (activation quantise + GEMM, packed
+    weight cached), HBFP8 and HBFP4, and the unmodified reference's BFPLinear on the same GPU (one pass) when baseline/_ref is present."""
+    from qsi_b200 import bfp_ops, dist as qd2
+    from _refload import load_reference
+    shapes, T = qd2.LAYER_SHAPES["llama-13b"], 4096
+    flop = sum(2.0 * T * n * k for n, k in shapes)
+    g = torch.Generator(device=dev).manual_seed(13)
+    ws = [torch.randn(n, k, device=dev, generator=g) * 0.02 for n, k in shapes]
+    xs = {k: torch.randn(T, k, device=dev, generator=g) for k in sorted({k for _, k in shapes})}
+    out = {"model": "llama-13b", "tokens": T, "layer_shapes_N_K": [list(sh) for sh in shapes], "tflop_per_layer": flop / 1e12}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    keep = None
+    for tag, impl, m in (("hbfp8", bfp_ops, 7), ("hbfp4", bfp_ops, 3), ("reference_hbfp8_same_gpu", load_reference(), 7)):
+        if impl is None:
+            continue
+        kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=m, weight_mant_bits=15, block_size=64,
+                  w_sparsity=True, N=N_, M=M_, first="s", sparsity_mode="structured", sparsity_frac=0.5, device="cuda")
+        lins = []
+        for w in ws:
+            lin = impl.BFPLinear(w.shape[1], w.shape[0], bias=False, **dict(kw)).to(dev)
+            lin.weight = torch.nn.Parameter(w, requires_grad=False)
+            lins.append(lin)
+        ours = impl is bfp_ops
+        with torch.no_grad():
+            for _ in range(2 if ours else 1):
+                ys = [lin(xs[lin.in_features]) for lin in lins]
+            torch.cuda.synchronize()
+            iters = 10 if ours else 1
+            e0.record()
+            for _ in range(iters):
+                ys = [lin(xs[lin.in_features]) for lin in lins]
+            e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        out[tag] = {"ms_per_layer": ms, "tflops": flop / ms / 1e9}
+        if ours:
+            out[tag]["weight_kinds"] = sorted({lin._packed_w[0][0] for lin in lins})
+        if tag == "hbfp8":
+            keep = [y.clone() for y in ys]
+        elif tag.startswith("reference") and keep is not None:
+            out["hbfp8_max_rel_err_vs_reference"] = max(float((a_ - b_).norm() / b_.norm()) for a_, b_ in zip(keep, ys))
+            out["hbfp8_speedup_vs_reference_same_gpu"] = ms / out["hbfp8"]["ms_per_layer"]
+        del lins, ys
+    return out
+
+
 def leg_gemm(torch, dev, g, peaks):
     """Secondary metric of BASELINE.json: BFP GEMM TOPS at the LLaMA-7B shapes (T = 4096 tokens, HBFP8 B=64, 2:4 s->q weights):
     2:4-sparse exact-bf16 kind (what BFPLinear runs), dense exact-bf16 kind, int8 + per-block rescale kind; burst (10 launches)
@@ -714,6 +762,10 @@ def main():
                 extras["unstructured"] = leg_unstructured(torch, dev, peak)
             except Exception as e:
                 extras["unstructured"] = {"error": repr(e)[:300]}
+            try:
+                extras["config3_llama13b_layer"] = leg_config3(torch, dev)
+            except Exception as e:          # noqa: BLE001
+                extras["config3_llama13b_layer"] = {"error": repr(e)[:300]}
             try:
                 extras["gemm"] = leg_gemm(torch, dev, torch.Generator(device=dev).manual_seed(2000), peaks)
             except Exception as e:          # noqa: BLE001
