@@ -21,6 +21,7 @@ the single-GPU result checked on rank 0) is reported as `column_parallel`.
             ncu child process (dram bytes of one launch) when ncu is available, else null
   quant_modes   the reference's real operating modes (stochastic rounding, fp16 / bf16 tensors) on the same shapes
   unstructured  global magnitude pruning fused with the quantiser (the other sparsity mode of the reference's scripts)
+  models        BASELINE configs[0] / [3]: OPT-125M and ViT-B/16 drop-ins, logits vs the unmodified reference on the same GPU, both timed
   config3_llama13b_layer  BASELINE configs[2]: the seven BFPLinear forwards of a LLaMA-2-13B layer at 4096 tokens (HBFP8, HBFP4, reference)
   gemm      BFP GEMM TOPS at the LLaMA-7B shapes, burst and sustained (>= 2 s), with its own roofline block
   cpu_baseline  the CPU implementation (reference if baseline/_ref is present, else the oracle port) on a bounded sample
@@ -453,6 +454,52 @@ def leg_unstructured(torch, dev, peak):
     return out
 
 
+def leg_models(torch, dev):
+    """BASELINE.json configs[0] and configs[3] at the model level, on this GPU: stock `transformers` OPT-125M (8 x 512 tokens, HBFP8 + 2:4)
+    and ViT-B/16 (batch 256, BFP6 + 2:4), random init, every block nn.Linear swapped for BFPLinear (and the ViT patch embedding for
+    BFPConv2d) -- the substitution the reference's patched model files make (tools/model_dropin.py).  One forward each with this repo's
+    bfp_ops and with the unmodified reference's (baseline/_ref) on the same GPU: logits compared, both timed."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import model_dropin as md
+    from qsi_b200 import bfp_ops
+    from _refload import load_reference
+    ref = load_reference()
+    out = {}
+    for name, kind, m, seq in (("config1_opt125m_8x512_hbfp8_2to4", "opt", 7, 512), ("config4_vit_b16_b256_bfp6_2to4", "vit", 5, 0)):
+        kw = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=m, weight_mant_bits=15,
+                  block_size=64, w_sparsity=True, N=N_, M=M_, first="s", sparsity_mode="structured", sparsity_frac=0.5, device="cuda")
+        row, logits = {}, {}
+        for tag, impl in (("ours", bfp_ops), ("reference_same_gpu", ref)):
+            if impl is None:
+                continue
+            model, cfg = md.build(kind, 0)
+            n = md.swap(model, impl, kw, md.OPT_TARGETS if kind == "opt" else None)
+            model = model.to(dev)
+            g = torch.Generator().manual_seed(1)
+            inp = (dict(input_ids=torch.randint(0, cfg.vocab_size, (8, seq), generator=g).to(dev)) if kind == "opt"
+                   else dict(pixel_values=torch.randn(256, 3, 224, 224, generator=g).to(dev)))
+            ours = impl is bfp_ops
+            with torch.no_grad():
+                for _ in range(3 if ours else 1):
+                    y = model(**inp).logits
+                torch.cuda.synchronize()
+                iters = 5 if ours else 2
+                t0 = time.perf_counter()
+                for _ in range(iters):
+                    y = model(**inp).logits
+                torch.cuda.synchronize()
+                dt = (time.perf_counter() - t0) / iters
+            logits[tag] = y.float()
+            row[tag] = {"forward_ms": dt * 1e3, "swapped_modules": n}
+            del model
+        if "reference_same_gpu" in logits:
+            d = logits["ours"] - logits["reference_same_gpu"]
+            row["logits_rel_err_vs_reference"] = float(d.norm() / logits["reference_same_gpu"].norm())
+            row["speedup_vs_reference_same_gpu"] = row["reference_same_gpu"]["forward_ms"] / row["ours"]["forward_ms"]
+        out[name] = row
+    return out
+
+
 def leg_config3(torch, dev):
     """BASELINE.json configs[2]: LLaMA-2-13B BFP linear forward, 4096 tokens per step, on-the-fly BFP activations x 2:4-sparse BFP
     weights: the seven BFPLinear forwards of one decoder layer through the public module API (activation quantise + GEMM, packed
@@ -762,6 +809,10 @@ def main():
                 extras["unstructured"] = leg_unstructured(torch, dev, peak)
             except Exception as e:
                 extras["unstructured"] = {"error": repr(e)[:300]}
+            try:
+                extras["models"] = leg_models(torch, dev)
+            except Exception as e:          # noqa: BLE001
+                extras["models"] = {"error": repr(e)[:300]}
             try:
                 extras["config3_llama13b_layer"] = leg_config3(torch, dev)
             except Exception as e:          # noqa: BLE001

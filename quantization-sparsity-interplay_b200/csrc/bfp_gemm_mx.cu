@@ -67,7 +67,7 @@ struct Params {
     int tiles_m, tiles_n;       // tiles_m counts CG * 128 rows
     int sf_a_tiles;             // row tiles (of 128) in the A scale array
     int b_folded;               // 1 = the B operand carries its block exponents in its E4M3 values and has ONE scale per row (atoms of one slab)
-    int debug;                  // timing experiments (wrong results): bit 1 = no operand loads, bit 2 = no scale copies, bit 3 = no scale loads
+    int debug;                  // timing experiments (wrong results): bit 1 = no operand loads, bit 2 = no scale copies, bit 3 = no scale loads, bit 4 = no B tile loads, bit 5 = every slab loads k = 0
 };
 
 template <int CG>
@@ -154,10 +154,12 @@ bfp_gemm_mx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     // With a folded B operand (one scale per row, p.b_folded) the B atoms are loaded with the tile's first slab only.
                     const bool load_sfa = !(p.debug & 8);
                     const bool load_sfb = (!p.b_folded || ks == 0) && !(p.debug & 8);
-                    if (rank == 0) mbar_expect_tx(&bars->full[stage], (uint32_t)CG * (uint32_t)(BM * BKB + C::kRowsB * BKB + (load_sfa ? 512 : 0) + (load_sfb ? C::kAtomsB * 512 : 0)));
+                    const bool load_b = !(p.debug & 16);                                   // timing experiments: no B tile / always the first slab
+                    const int kc = (p.debug & 32) ? 0 : ks * BKB;
+                    if (rank == 0) mbar_expect_tx(&bars->full[stage], (uint32_t)CG * (uint32_t)(BM * BKB + (load_b ? C::kRowsB * BKB : 0) + (load_sfa ? 512 : 0) + (load_sfb ? C::kAtomsB * 512 : 0)));
                     const uint32_t bar = CG == 1 ? smem_u32(&bars->full[stage]) : mapa_u32(smem_u32(&bars->full[stage]), 0);
-                    tma_load_2d_to_hint<CG>(stage_a(stage), &map_a, bar, ks * BKB, a_tile * BM, pol_keep);
-                    tma_load_2d_to_hint<CG>(stage_b(stage), &map_b, bar, ks * BKB, b_row, pol_keep);
+                    tma_load_2d_to_hint<CG>(stage_a(stage), &map_a, bar, kc, a_tile * BM, pol_keep);
+                    if (load_b) tma_load_2d_to_hint<CG>(stage_b(stage), &map_b, bar, kc, b_row, pol_keep);
                     if (load_sfa) tma_load_2d_to<CG>(stage_sf(stage), &map_sfa, bar, 0, (ks * p.sf_a_tiles + a_tile) * 2);
                     if (load_sfb) tma_load_2d_to<CG>(stage_sf(stage) + 512, &map_sfb, bar, 0, ((p.b_folded ? 0 : ks * p.tiles_n) + tn) * (C::kAtomsB * 2));
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -554,7 +556,7 @@ int gemm_mx_device(const uint8_t* a_vals, const uint8_t* a_sf, const uint8_t* b_
     p.bias = bias; p.out = out; p.out_dtype = BFP_DT_F32; p.out_tma = 1;
     p.T = (int)T; p.N = (int)N; p.num_k_stages = (int)(Kp / 128);
     p.b_folded = b_folded ? 1 : 0;
-    p.debug = tuning().gemm_mx_variant & 14;
+    p.debug = tuning().gemm_mx_variant & 62;
     // CTA pairs (cta_group::2: each CTA stages its 128 A rows and HALF of the B tile) for the 240- and 256-wide tiles whenever there is
     // more than one 128-row strip; bfp_set_option("gemm_mx_variant", 1) forces single CTAs on the 256-wide tile
     const int tbn = b_tile_rows;

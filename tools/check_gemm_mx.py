@@ -57,7 +57,7 @@ if "bench" in sys.argv:
         a = args(3, 64)
         x, w = torch.randn(T, K, device="cuda"), torch.randn(N, K, device="cuda") * 0.05
         xp = ops.pack_bfp_mx(x, 128, identifier="in", **a)
-        for tbn, variant, fold in ((240, 0, True), (240, 8, True), (240, 4, True), (240, 12, True), (240, 2, True), (240, 6, True)):
+        for tbn, variant, fold in ((240, 0, True), (240, 12, True), (240, 12 + 16, True), (240, 12 + 32, True), (240, 6, True)):
             _lib.check(L.bfp_set_option(b"gemm_mx_variant", variant))
             wp = ops.pack_bfp_mx(w, tbn, fold=fold, identifier="w", **a)
             for _ in range(3): ops.bfp_linear_mx(xp, wp)
