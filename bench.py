@@ -40,6 +40,13 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "BFP+N:M quantize GB/s (% HBM peak); BFP GEMM TOPS at LLaMA-7B shapes"
+_REAL_STDOUT = None            # the process's original stdout once main() has redirected fd 1 to stderr
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 SHAPES = [(4096, 4096), (4096, 11008)]
 MANTS = [3, 5, 7]
 BLOCKS = [16, 32, 64]
@@ -204,7 +211,7 @@ def run_reference_arm(a, rank, world):
             "cpu_baseline": {"value": value, "unit": "GB/s", "cores": info[1], "kind": info[0], "sample": info[2]},
             "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -734,6 +741,13 @@ def main():
     ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--cpu-baseline-child", action="store_true", help=argparse.SUPPRESS)
     a = ap.parse_args()
+    global _REAL_STDOUT
+    if not (a.traffic_child or a.cpu_baseline_child):
+        # stdout carries exactly ONE line, the JSON record: everything else that writes to fd 1 (NCCL's version banner, library chatter)
+        # is sent to stderr for the duration of the run
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
     if a.traffic_child:
         return traffic_child()
     if a.cpu_baseline_child:
@@ -907,7 +921,7 @@ def main():
         "clocks": clocks,
     }
     line.update(extras)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 if __name__ == "__main__":

@@ -66,7 +66,8 @@ struct FusedState {
     uint32_t lo_bin, span;                 // bracket = bins [lo_bin, lo_bin + span] of the 16 leading key bits
     uint32_t hot_key;                      // a round key holding > 1/64 of the sample: counted in registers, never queued (kNoKey: none)
     uint32_t path;                         // PATH_*; pass A / refine downgrade it to PATH_TENSOR when the two-read path does not hold
-    unsigned int done_a, pad0;
+    unsigned int done_a, done_r;
+    uint32_t flag_r, pad0;                 // refine: set by the CTA that finished the selection
     unsigned long long below;              // keys below the bracket
     unsigned long long cand_count;         // listed keys (may exceed the capacity: then path = PATH_TENSOR)
     unsigned long long hot_total;          // list mode: keys equal to hot_key
@@ -80,11 +81,13 @@ struct FusedState {
     uint32_t prefix_value, prefix_mask;    // radix select state
     unsigned long long fb_need;
     long long clk[8];                      // sample kernel phase timestamps (BFP_UNSTRUCTURED_TIMING)
-    uint32_t win_hist[kWin];
+    alignas(16) uint32_t win_hist[kWin];   // (the histograms are read with 128-bit loads)
     uint32_t fb_hist[3][kFbBins];
     uint32_t range_count[kMaxRanges];
     uint32_t low_hist[kLowBins];
 };
+static_assert(offsetof(FusedState, win_hist) % 16 == 0 && offsetof(FusedState, fb_hist) % 16 == 0 && offsetof(FusedState, low_hist) % 16 == 0 &&
+              offsetof(FusedState, range_count) % 16 == 0, "histograms are read with 128-bit loads");
 constexpr size_t kStateHeaderWords = offsetof(FusedState, fb_hist) / 4;    // zeroed by the sample kernel (the rest by pass A)
 
 struct UParams {
@@ -272,23 +275,25 @@ __global__ void __cluster_dims__(kSampleCtas, 1, 1) __launch_bounds__(kSampleThr
     pdl_wait();
     using D = DType<DT>;
     constexpr int V = D::kVec;
-    constexpr int kOwn = 65536 / kSampleCtas;                // bins per CTA
-    constexpr int kPer = kOwn / kSampleThreads;              // bins per thread
+    constexpr int kCoarse = 1024, kFinePer = 65536 / kCoarse;      // coarse bin = 64 fine bins; thread t of a CTA owns coarse bin t
+    static_assert(kCoarse == kSampleThreads, "one coarse bin per thread");
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned int rank = cluster.block_rank();
-    extern __shared__ unsigned int s_h[];                    // 65536 16-bit counters, two per word (this CTA's share of the sample)
+    extern __shared__ unsigned int s_h[];                    // 65536 16-bit counters, two per word: this CTA's share of the sample
+    __shared__ unsigned int s_coarse[kCoarse];               // this CTA's coarse histogram (read by CTA 0 through distributed shared memory)
     __shared__ unsigned long long s_scr[32];
-    __shared__ unsigned long long s_tot[kSampleCtas];        // sample keys per owner CTA (every CTA holds a copy)
-    __shared__ uint32_t s_lohi[2];                           // CTA 0's copy is the one that counts
-    __shared__ unsigned long long s_best, s_best_all[kSampleCtas], s_mass_all[kSampleCtas];   // CTA 0 collects the others'
+    __shared__ unsigned int s_fine[2][kFinePer];             // CTA 0: merged fine counts of the two coarse bins that hold the rank bracket
+    __shared__ uint32_t s_cb[2];                             // CTA 0: those coarse bins ...
+    __shared__ unsigned long long s_cb_before[2];            // ... and the sample keys before them
+    __shared__ unsigned long long s_best;
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < 32768; i += kSampleThreads) s_h[i] = 0u;
     if (rank == 0) {
         uint32_t* w = reinterpret_cast<uint32_t*>(p.st);
         for (int i = tid; i < (int)kStateHeaderWords; i += kSampleThreads) w[i] = 0u;
     }
-    if (tid == 0) { s_lohi[0] = 0u; s_lohi[1] = 65535u; s_best = 0ull; }
-    cluster.sync();
+    if (tid == 0) { s_cb[0] = 0u; s_cb[1] = kCoarse - 1; s_cb_before[0] = 0ull; s_cb_before[1] = 0ull; s_best = 0ull; }
+    __syncthreads();
     long long clk[8];
     auto stamp = [&](int i) { if (rank == 0 && tid == 0) clk[i] = clock64(); };
     stamp(0);
@@ -315,106 +320,110 @@ __global__ void __cluster_dims__(kSampleCtas, 1, 1) __launch_bounds__(kSampleThr
         if (MODE == MODE_QS) quantize_vec<DT, STOC>(v, p, vec);
 #pragma unroll
         for (int e = 0; e < V; ++e) {
-            const uint32_t bin = topk_key(v[e]) >> 15;
-            // two rounds of leader aggregation (massive ties: zeros, quantised values), then plain atomics
-            bool todo = active;
-#pragma unroll 1
-            for (int r = 0; r < 2; ++r) {
-                const uint32_t act = __ballot_sync(0xffffffffu, todo);
-                if (act == 0u) break;
-                const int leader = __ffs(act) - 1;
-                const uint32_t lb = __shfl_sync(0xffffffffu, bin, leader);
-                const bool same = todo && bin == lb;
-                const uint32_t mm = __ballot_sync(0xffffffffu, same);
-                if (lane == leader) atomicAdd(&s_h[lb >> 1], (unsigned int)__popc(mm) << (16 * (lb & 1u)));
-                todo = todo && !same;
-            }
-            if (todo) atomicAdd(&s_h[bin >> 1], 1u << (16 * (bin & 1u)));
+            // one shared-memory atomic per distinct bin of the warp (massive ties -- zeros, quantised values -- would otherwise serialise)
+            const uint32_t bin = active ? (topk_key(v[e]) >> 15) : 0xffffffffu;
+            const uint32_t same = __match_any_sync(0xffffffffu, bin);
+            if (active && lane == __ffs(same) - 1) atomicAdd(&s_h[bin >> 1], (unsigned int)__popc(same) << (16 * (bin & 1u)));
         }
     }
+    __syncthreads();
     stamp(1);
+    {   // this CTA's coarse histogram: thread t sums its 64 fine counters (32 words, rotated start: bank = lane)
+        unsigned int c = 0;
+        for (int i = 0; i < 32; ++i) { const unsigned int w = s_h[tid * 32 + ((i + lane) & 31)]; c += (w & 0xffffu) + (w >> 16); }
+        s_coarse[tid] = c;
+    }
     cluster.sync();
     stamp(2);
-
-    // thread t owns bins [kPer t, kPer t + kPer) of this CTA's slice: one 128-bit read from each of the eight tables
-    static_assert(kPer == 8, "eight 16-bit counters = one uint4");
-    unsigned int c[kPer];
-    unsigned long long mine = 0;
+    if (rank == 0) {
+        // merged coarse histogram (one remote word per CTA and thread), its scan, and the coarse bins of the two bracket ranks
+        unsigned long long mine = 0;
 #pragma unroll
-    for (int i = 0; i < kPer; ++i) c[i] = 0u;
-#pragma unroll
-    for (int r = 0; r < kSampleCtas; ++r) {
-        const uint4 w = *reinterpret_cast<const uint4*>(cluster.map_shared_rank(s_h, r) + (rank * kOwn + tid * kPer) / 2);
-        c[0] += w.x & 0xffffu; c[1] += w.x >> 16; c[2] += w.y & 0xffffu; c[3] += w.y >> 16;
-        c[4] += w.z & 0xffffu; c[5] += w.z >> 16; c[6] += w.w & 0xffffu; c[7] += w.w >> 16;
-    }
-#pragma unroll
-    for (int i = 0; i < kPer; ++i) mine += c[i];
-    unsigned long long own_total;
-    const unsigned long long before_cta = block_excl_scan<kSampleThreads>(mine, s_scr, &own_total);
-    if (tid < kSampleCtas) cluster.map_shared_rank(s_tot, tid)[rank] = own_total;
-    stamp(3);
-    cluster.sync();
-    stamp(4);
-    unsigned long long before = before_cta, total = 0;
-#pragma unroll
-    for (int r = 0; r < kSampleCtas; ++r) { const unsigned long long t = s_tot[r]; before += (unsigned int)r < rank ? t : 0ull; total += t; }
-    // rank bracket of the k-th smallest key inside the sorted sample
-    const unsigned long long S = (unsigned long long)S_v * V;     // == total
-    long long r_lo, r_hi;
-    if ((unsigned long long)S_v == (unsigned long long)p.n_vec) {
-        r_lo = r_hi = (long long)p.k - 1;                    // the sample is the tensor
-    } else {
-        const float q = (float)p.k / (float)p.n;
-        const float mean = q * (float)S;
-        const float sd = sqrtf((float)S * q * (1.0f - q) * (MODE == MODE_QS ? 4.0f : 1.0f));   // design effect: a block shares its scale
-        r_lo = (long long)floorf(mean - 5.5f * sd) - 2;
-        r_hi = (long long)ceilf(mean + 5.5f * sd) + 2;
-    }
-    for (int which = 0; which < 2; ++which) {
-        const long long r = which ? r_hi : r_lo;
-        if (r >= 0 && (unsigned long long)r < total && before <= (unsigned long long)r && (unsigned long long)r < before + mine) {
-            unsigned long long acc = before;
-            bool found = false;
-#pragma unroll
-            for (int i = 0; i < kPer; ++i) {
-                if (!found && (unsigned long long)r < acc + c[i]) { cluster.map_shared_rank(s_lohi, 0)[which] = rank * kOwn + tid * kPer + i; found = true; }
-                acc += c[i];
+        for (int r = 0; r < kSampleCtas; ++r) mine += cluster.map_shared_rank(s_coarse, r)[tid];
+        unsigned long long total;
+        const unsigned long long before = block_excl_scan<kSampleThreads>(mine, s_scr, &total);
+        const unsigned long long S = (unsigned long long)S_v * V;     // == total
+        long long r_lo, r_hi;
+        if ((unsigned long long)S_v == (unsigned long long)p.n_vec) {
+            r_lo = r_hi = (long long)p.k - 1;                // the sample is the tensor
+        } else {
+            const float q = (float)p.k / (float)p.n;
+            const float mean = q * (float)S;
+            const float sd = sqrtf((float)S * q * (1.0f - q) * (MODE == MODE_QS ? 4.0f : 1.0f));   // design effect: a block shares its scale
+            r_lo = (long long)floorf(mean - 5.5f * sd) - 2;
+            r_hi = (long long)ceilf(mean + 5.5f * sd) + 2;
+        }
+        const bool lo_open = r_lo < 0, hi_open = r_hi >= (long long)total;     // the bracket reaches the bottom / the top of the key range
+        for (int which = 0; which < 2; ++which) {
+            const long long r = which ? r_hi : r_lo;
+            if (r >= 0 && (unsigned long long)r < total && before <= (unsigned long long)r && (unsigned long long)r < before + mine) {
+                s_cb[which] = (uint32_t)tid; s_cb_before[which] = before;
             }
         }
-    }
-    cluster.sync();
-    stamp(5);
-    const uint32_t lo = cluster.map_shared_rank(s_lohi, 0)[0], hi = max(cluster.map_shared_rank(s_lohi, 0)[1], lo), span = hi - lo;
-    // the most populated bracket bin of the sample, and the sample mass of the bracket
-    unsigned long long in_bracket = 0, best = 0;
+        __syncthreads();
+        // merged fine counts of those two coarse bins
+        if (tid < 2 * kFinePer) {
+            const int which = tid / kFinePer, f = tid % kFinePer;
+            const uint32_t b = s_cb[which] * kFinePer + f;
+            unsigned int c = 0;
 #pragma unroll
-    for (int i = 0; i < kPer; ++i) {
-        const uint32_t b = rank * kOwn + tid * kPer + i;
-        const unsigned int cc = c[i];
-        if (b >= lo && b <= hi) { in_bracket += cc; best = max(best, ((unsigned long long)cc << 32) | b); }
+            for (int r = 0; r < kSampleCtas; ++r) { const unsigned int w = cluster.map_shared_rank(s_h, r)[b >> 1]; c += (b & 1u) ? (w >> 16) : (w & 0xffffu); }
+            s_fine[which][f] = c;
+        }
+        __syncthreads();
+        stamp(3);
+        // hot bin: a fine bin holding more than 1/64 of the sample can only live in a coarse bin that does; those (at most 64) are merged too
+        const bool heavy = mine * 64ull > S;
+        __shared__ int s_nheavy, s_heavy_list[64];
+        if (tid == 0) s_nheavy = 0;
+        __syncthreads();
+        if (heavy) { const int i = atomicAdd(&s_nheavy, 1); if (i < 64) s_heavy_list[i] = tid; }
+        __syncthreads();
+        const int nheavy = min(s_nheavy, 64);
+        for (int i0 = 0; i0 < nheavy; i0 += kSampleThreads / kFinePer) {       // sixteen heavy coarse bins per round, 64 threads each
+            const int i = i0 + tid / kFinePer;
+            if (i < nheavy) {
+                const uint32_t b = (uint32_t)s_heavy_list[i] * kFinePer + (uint32_t)(tid % kFinePer);
+                unsigned int c = 0;
+#pragma unroll
+                for (int r = 0; r < kSampleCtas; ++r) { const unsigned int w = cluster.map_shared_rank(s_h, r)[b >> 1]; c += (b & 1u) ? (w >> 16) : (w & 0xffffu); }
+                if ((unsigned long long)c * 64ull > S) atomicMax(&s_best, ((unsigned long long)c << 32) | b);
+            }
+        }
+        __syncthreads();
+        stamp(4);
+        if (tid == 0) {
+            // the fine bins of the two ranks
+            uint32_t lo = 0u, hi = 65535u;
+            if (!lo_open) {
+                unsigned long long acc = s_cb_before[0];
+                for (int f = 0; f < kFinePer; ++f) { if ((unsigned long long)r_lo < acc + s_fine[0][f]) { lo = s_cb[0] * kFinePer + f; break; } acc += s_fine[0][f]; }
+            }
+            if (!hi_open) {
+                unsigned long long acc = s_cb_before[1];
+                for (int f = 0; f < kFinePer; ++f) { if ((unsigned long long)r_hi < acc + s_fine[1][f]) { hi = s_cb[1] * kFinePer + f; break; } acc += s_fine[1][f]; }
+            }
+            hi = max(hi, lo);
+            const uint32_t span = hi - lo;
+            // sample mass of the bracket: an upper estimate from the rank bracket itself (ranks r_lo .. r_hi plus the two edge bins)
+            const unsigned long long mass = (unsigned long long)((hi_open ? (long long)total - 1 : r_hi) - (lo_open ? 0 : r_lo) + 1)
+                                            + s_fine[0][lo % kFinePer] + s_fine[1][hi % kFinePer];
+            FusedState* st = p.st;
+            st->lo_bin = lo; st->span = span;
+            const unsigned long long bst = s_best;
+            const uint32_t hot_bin = (uint32_t)(bst & 0xffffffffu);
+            const bool hot = (bst >> 32) != 0ull && hot_bin >= lo && hot_bin <= hi;
+            st->hot_key = hot ? (hot_bin << 15) : kNoKey;
+            uint32_t path = span < (uint32_t)kWin ? PATH_WINDOW : PATH_LIST;
+            // list mode lists everything in the bracket but the hot key: only worth it (and only fits) when that is a small share
+            if (path == PATH_LIST && (mass > (hot ? (bst >> 32) : 0ull) ? mass - (hot ? (bst >> 32) : 0ull) : 0ull) * 12ull > S) path = PATH_TENSOR;
+            if (p.force_fallback) path = PATH_TENSOR;
+            st->path = path;
+            stamp(5);
+            for (int i = 0; i < 6; ++i) st->clk[i] = clk[i];
+        }
     }
-    if (best >> 32) atomicMax(&s_best, best);
-    const unsigned long long mass = block_sum<kSampleThreads>(in_bracket, s_scr);
-    if (tid == 0) { cluster.map_shared_rank(s_best_all, 0)[rank] = s_best; cluster.map_shared_rank(s_mass_all, 0)[rank] = mass; }
-    cluster.sync();
-    if (rank == 0 && tid == 0) {
-        unsigned long long bst = 0, m = 0;
-        for (int r = 0; r < kSampleCtas; ++r) { bst = max(bst, s_best_all[r]); m += s_mass_all[r]; }
-        const unsigned long long best_c = bst >> 32;
-        FusedState* st = p.st;
-        st->lo_bin = lo; st->span = span;
-        const bool hot = best_c * 64ull > S;
-        st->hot_key = hot ? ((uint32_t)(bst & 0xffffffffu) << 15) : kNoKey;
-        uint32_t path = span < (uint32_t)kWin ? PATH_WINDOW : PATH_LIST;
-        // list mode lists everything in the bracket but the hot key: only worth it (and only fits) when that is a small share
-        if (path == PATH_LIST && (m - (hot ? best_c : 0ull)) * 12ull > S) path = PATH_TENSOR;
-        if (p.force_fallback) path = PATH_TENSOR;
-        st->path = path;
-        stamp(6);
-        for (int i = 0; i < 7; ++i) st->clk[i] = clk[i];
-    }
-    // (the last remote accesses -- the writes into CTA 0's arrays -- precede the barrier above: no CTA's memory is addressed after it)
+    cluster.sync();                                          // CTA 0 reads the other CTAs' shared memory until here
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -671,9 +680,15 @@ __global__ void __launch_bounds__(kT) refine_kernel(const UParams p) {
         for_each_listed([&](uint32_t kk, uint32_t) { if ((kk >> 15) == bin) { atomicAdd(&st->low_hist[kk & 0x7fffu], 1u); ++impure; } });
         const unsigned long long i_sum = block_sum<kT>(impure, s_scr);
         if (tid == 0 && i_sum) atomicAdd(&st->impure_in_bin, i_sum);
+        // the last CTA to arrive selects; the others wait for its flag (every CTA of a cooperative launch is resident, so waiting is
+        // safe) -- one grid-wide barrier less than two grid.sync()
+        __shared__ int s_last;
         __threadfence();
-        grid.sync();
-        if (blockIdx.x == 0) {
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(&st->done_r, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
             const unsigned long long cnt = ld_cg64(&st->cnt_bin), imp = ld_cg64(&st->impure_in_bin), need_bin = ld_cg64(&st->need_bin);
             const unsigned long long pure = cnt > imp ? cnt - imp : 0ull;        // keys of the bin with zero trailing bits
             const SelectResult r = block_select<kT, kLowBins / kT>(st->low_hist, kLowBins, need_bin, 0u, pure, s_scr, &s_res);
@@ -685,10 +700,14 @@ __global__ void __launch_bounds__(kT) refine_kernel(const UParams p) {
                 st->ties_total = r.count;
                 st->tie_src = need == r.count ? TIES_ALL : (r.bin == 0u ? TIES_ROW : TIES_COUNTED);
                 st->tie_row = bin - ld_cg32(&st->lo_bin);
+                __threadfence();
+                *reinterpret_cast<volatile uint32_t*>(&st->flag_r) = 1u;
             }
-            __threadfence();
+            __syncthreads();
+        } else {
+            if (tid == 0) { while (*reinterpret_cast<volatile uint32_t*>(&st->flag_r) == 0u) { } __threadfence(); }
+            __syncthreads();
         }
-        grid.sync();
         if (ld_cg32(&st->tie_src) == TIES_COUNTED) count_listed_ties(ld_cg32(&st->tau));
         return;
     }
@@ -1024,8 +1043,8 @@ int run_fused(const UnstructuredArgs& a, cudaStream_t s) {
         for (int i = 0; i + 1 < nev; ++i) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); fprintf(stderr, "%s %.1f us  ", names[i], ms * 1e3f); }
         FusedState h;
         cudaMemcpy(&h, p.st, offsetof(FusedState, win_hist), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "| sample clk: sampled %lld sync %lld slices %lld sync %lld ranks %lld rest %lld ", h.clk[1] - h.clk[0], h.clk[2] - h.clk[1], h.clk[3] - h.clk[2],
-                h.clk[4] - h.clk[3], h.clk[5] - h.clk[4], h.clk[6] - h.clk[5]);
+        fprintf(stderr, "| sample clk: sampled %lld coarse+sync %lld merge %lld hot %lld rest %lld ", h.clk[1] - h.clk[0], h.clk[2] - h.clk[1], h.clk[3] - h.clk[2],
+                h.clk[4] - h.clk[3], h.clk[5] - h.clk[4]);
         fprintf(stderr, "| path %u bracket [%u, +%u] hot %08x below %llu listed %llu bin %u tau %08x need %llu ties %llu tie_src %u ranges %d x %d tiles, refine grid %d\n",
                 h.path, h.lo_bin, h.span, h.hot_key, h.below, h.cand_count, h.bin, h.tau, h.need, h.ties_total, h.tie_src, p.n_ranges, p.tiles_per_range, grid_r);
         for (int i = 0; i < nev; ++i) cudaEventDestroy(ev[i]);
