@@ -280,6 +280,35 @@ int bfp_quantize_pack_mx(const void* in, void* vals, void* sf, int64_t rows, int
 int bfp_gemm_mx(const void* a_vals, const void* a_sf, const void* b_vals, const void* b_sf, int b_tile_rows, int b_folded,
                 const float* bias, float* out, int64_t T, int64_t N, int64_t K, void* stream);
 
+/* ---- MX (OCP Microscaling) formats: the arithmetic behind the reference's mx_layers.py -----------------------------------------
+ * /root/reference/src/transformers/bfp/mx_layers.py:23-109 wraps mx.Linear / mx.Conv2d / mx.matmul of microsoft/microxcaling (not
+ * vendored, not pinned: parity unpinned -- restated from the library's published emulation and the OCP MX v1.0 specification,
+ * oracle/mx_oracle.py).  Element formats: formats.py:24-33 (the enum values below are the reference's ElemFormat values),
+ * parameters formats.py:86-123.  Every rounding is the library's 'nearest' = half away from zero.
+ *   bfp_bfloat_round:     quantize_elemwise_op for bfloatX (mx/elemwise_ops.py _quantize_bfloat): out = rb(in), or with a bias row
+ *                         (fp32 [ncols], n % ncols == 0) the bias step of mx/linear.py: out = rb(rb(in) + rb(bias[col])).
+ *   bfp_ocp_mx_quantize:  rb (bfloat, 0 = none) then quantize_mx_op along the last dim: zero-padded blocks of block_size (0 = the whole
+ *                         row), shared scale 2^se with se = clamp(floor(log2 max|x|) - emax_elem, +-(2^(scale_bits-1) - 1)), elements
+ *                         rounded to elem_format with saturation.  out_kind 0: fake-quantised tensor in the input dtype [rows, K];
+ *                         out_kind 1: exact bf16 operand [rows, ld_out] for bfp_gemm_bf16 / bfp_compress_2to4_bf16 (every MX value
+ *                         has <= 8 significant bits; columns K .. ld_out-1 are the caller's zero fill).
+ *   bfp_ocp_mx_pack:      the same quantiser straight into the operand form of tcgen05.mma.kind::mxf8f6f4.block_scale (bfp_gemm_mx):
+ *                         vals = E4M3 byte of every element, sf = the blocks' UE8M0 scale bytes in atoms of tile_rows-row tiles
+ *                         (bfp_mx_layout, fold = 0).  Formats whose values are E4M3 numbers (fp8_e4m3, fp6_*, fp4_e2m1, int4, int2),
+ *                         block_size 32 / 64 / 128, K % 128 == 0 (fp32) / 256 (half), scale_bits 8; else BFP_E_UNSUPPORTED (use
+ *                         out_kind 1).  A NaN / Inf block gets the NaN scale 0xff, as the emulation makes the whole block NaN.
+ *   bfp_gemm_mx_round:    bfp_gemm_mx whose epilogue applies the output steps of mx/linear.py: out = rb(acc), then with a bias
+ *                         out = rb(out + rb(bias)) (bfloat 0 = plain bfp_gemm_mx). */
+enum { BFP_MX_INT8 = 1, BFP_MX_INT4 = 2, BFP_MX_INT2 = 3, BFP_MX_FP8_E5M2 = 4, BFP_MX_FP8_E4M3 = 5, BFP_MX_FP6_E3M2 = 6,
+       BFP_MX_FP6_E2M3 = 7, BFP_MX_FP4_E2M1 = 8 };
+int bfp_bfloat_round(const void* in, void* out, const float* bias, int64_t n, int64_t ncols, int dtype, int bfloat, void* stream);
+int bfp_ocp_mx_quantize(const void* in, void* out, int64_t rows, int64_t K, int in_dtype, int out_kind, int64_t ld_out, int block_size,
+                        int elem_format, int scale_bits, int bfloat, int flush_fp32_subnorms, void* stream);
+int bfp_ocp_mx_pack(const void* in, void* vals, void* sf, int64_t rows, int64_t K, int in_dtype, int tile_rows, int block_size,
+                    int elem_format, int scale_bits, int bfloat, int flush_fp32_subnorms, void* stream);
+int bfp_gemm_mx_round(const void* a_vals, const void* a_sf, const void* b_vals, const void* b_sf, int b_tile_rows, int b_folded,
+                      const float* bias, float* out, int64_t T, int64_t N, int64_t K, int bfloat, void* stream);
+
 /* 2:4 structured-sparse variant of the BFP linear for weights pruned by _structured_N_M_sparsity with N=2, M=4
  * (bfp_ops.py:73-91; the reference then multiplies the zero-filled dense tensor, bfp_ops.py:187-190).  The pruned
  * exact-bf16 weight is stored compressed and the tensor core skips the zeros (tcgen05.mma.sp.kind::f16: 32 logical k per

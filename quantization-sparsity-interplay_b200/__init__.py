@@ -5,6 +5,7 @@ Layout:
   csrc/            hand-written CUDA kernels + the C ABI (include/bfp_b200.h) -> libbfp_b200.so
   _lib.py          ctypes binding of the C ABI (no torch types cross the boundary)
   bfp_ops.py       host-side mirror of the reference module: same names, arguments and error behaviour
+  mx_layers.py     host-side mirror of the reference's mx_layers.py (MXLinear / MXConv2d / MXMatmul over the MX formats)
   dist.py          multi-GPU partitioning of the compression pass / column-parallel linear
 
 There is no CPU fallback and no dependency on oracle/: every compute entry point fails loudly when the CUDA library or
@@ -12,7 +13,7 @@ a B200 is missing.
 """
 from . import _lib  # noqa: F401
 
-__all__ = ["_lib", "bfp_ops", "install_as_reference_module"]
+__all__ = ["_lib", "bfp_ops", "mx_layers", "install_as_reference_module"]
 
 
 def install_as_reference_module():
@@ -20,7 +21,7 @@ def install_as_reference_module():
     ViT model files import (modeling_opt.py:42, modeling_llama.py:65, modeling_vit.py:41)."""
     import sys
     import types
-    from . import bfp_ops
+    from . import bfp_ops, mx_layers
     pkg = sys.modules.get("transformers.bfp")
     if pkg is None:
         pkg = types.ModuleType("transformers.bfp")
@@ -28,4 +29,6 @@ def install_as_reference_module():
         sys.modules["transformers.bfp"] = pkg
     pkg.bfp_ops = bfp_ops
     sys.modules["transformers.bfp.bfp_ops"] = bfp_ops
+    pkg.mx_layers = mx_layers                       # modeling_opt.py:44, modeling_llama.py:67, modeling_vit.py:43
+    sys.modules["transformers.bfp.mx_layers"] = mx_layers
     return bfp_ops

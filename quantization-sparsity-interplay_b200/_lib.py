@@ -53,6 +53,10 @@ SIGNATURES = {
     "bfp_mx_from_packed": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "bfp_quantize_pack_mx": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp]),
     "bfp_gemm_mx": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "bfp_bfloat_round": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),
+    "bfp_ocp_mx_quantize": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "bfp_ocp_mx_pack": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "bfp_gemm_mx_round": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _i64, _i64, _i32, _vp]),
     "bfp_unstructured_quantize_workspace_bytes": (ctypes.c_size_t, [_i64, _i32]),
     "bfp_unstructured_quantize": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _u64, _i32, _i32, _i32, _f32, _i32, _u64, _u64, _vp,
                                          ctypes.c_size_t, _vp]),

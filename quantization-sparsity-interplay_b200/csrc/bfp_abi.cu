@@ -367,6 +367,43 @@ int bfp_gemm_mx(const void* a_vals, const void* a_sf, const void* b_vals, const 
                           static_cast<const uint8_t*>(b_sf), b_tile_rows, b_folded, bias, out, T, N, round_up(K, 128), static_cast<cudaStream_t>(stream));
 }
 
+int bfp_bfloat_round(const void* in, void* out, const float* bias, int64_t n, int64_t ncols, int dtype, int bfloat, void* stream) {
+    if (n < 0 || dtype < 0 || dtype > 2) return set_error(BFP_E_ARG, "bad argument");
+    if (n > 0 && (!in || !out)) return set_error(BFP_E_ARG, "null pointer");
+    if (bias && (ncols <= 0 || n % ncols)) return set_error(BFP_E_ARG, "bias: n must be a multiple of ncols");
+    if (int rc = require_device()) return rc;
+    return bfloat_round_device(in, out, bias, n, ncols, dtype, bfloat, static_cast<cudaStream_t>(stream));
+}
+
+int bfp_ocp_mx_quantize(const void* in, void* out, int64_t rows, int64_t K, int in_dtype, int out_kind, int64_t ld_out, int block_size, int elem_format,
+                        int scale_bits, int bfloat, int flush_fp32_subnorms, void* stream) {
+    if (rows < 0 || K < 0 || in_dtype < 0 || in_dtype > 2 || block_size < 0 || out_kind < 0 || out_kind > 1) return set_error(BFP_E_ARG, "bad argument");
+    if (rows * K > 0 && (!in || !out)) return set_error(BFP_E_ARG, "null pointer");
+    if (int rc = require_device()) return rc;
+    return ocp_mx_quantize_device(in, out, rows, K, in_dtype, out_kind, ld_out, block_size, elem_format, scale_bits, bfloat, flush_fp32_subnorms,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+int bfp_ocp_mx_pack(const void* in, void* vals, void* sf, int64_t rows, int64_t K, int in_dtype, int tile_rows, int block_size, int elem_format, int scale_bits,
+                    int bfloat, int flush_fp32_subnorms, void* stream) {
+    if (rows < 0 || K < 0 || in_dtype < 0 || in_dtype > 2 || block_size <= 0) return set_error(BFP_E_ARG, "bad argument");
+    if (rows * K > 0 && (!in || !vals || !sf)) return set_error(BFP_E_ARG, "null pointer");
+    if (int rc = require_device()) return rc;
+    return ocp_mx_pack_device(in, static_cast<uint8_t*>(vals), static_cast<uint8_t*>(sf), rows, K, in_dtype, tile_rows, block_size, elem_format, scale_bits,
+                              bfloat, flush_fp32_subnorms, static_cast<cudaStream_t>(stream));
+}
+
+int bfp_gemm_mx_round(const void* a_vals, const void* a_sf, const void* b_vals, const void* b_sf, int b_tile_rows, int b_folded, const float* bias, float* out,
+                      int64_t T, int64_t N, int64_t K, int bfloat, void* stream) {
+    if (T < 0 || N < 0 || K < 0) return set_error(BFP_E_ARG, "negative shape");
+    if (bfloat != 0 && (bfloat < 10 || bfloat > 32)) return set_error(BFP_E_ARG, "bfloat must be 0 or in [10, 32]");
+    if (T * N > 0 && (!a_vals || !a_sf || !b_vals || !b_sf || !out)) return set_error(BFP_E_ARG, "null pointer");
+    if (int rc = require_device()) return rc;
+    return gemm_mx_device(static_cast<const uint8_t*>(a_vals), static_cast<const uint8_t*>(a_sf), static_cast<const uint8_t*>(b_vals),
+                          static_cast<const uint8_t*>(b_sf), b_tile_rows, b_folded, bias, out, T, N, round_up(K, 128), static_cast<cudaStream_t>(stream),
+                          bfloat == 32 ? 0 : bfloat);
+}
+
 int bfp_sp_layout(int64_t rows, int64_t K, int64_t* Kc, int64_t* meta_bytes) { return sp_layout(rows, round_up(K, 8), Kc, meta_bytes); }
 
 int bfp_compress_2to4_bf16(const void* w_bf16, int64_t rows, int64_t K, void* w_comp, void* w_meta, uint32_t* violations, void* stream) {

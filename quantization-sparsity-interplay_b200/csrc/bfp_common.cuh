@@ -61,6 +61,19 @@ __device__ __forceinline__ uint32_t topk_key(float x) { return min(abs_bits(x), 
 __device__ __forceinline__ float t_max(float a, float b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
 __device__ __forceinline__ float t_min(float a, float b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }
 
+// bfloatX rounding of one fp32 value (mx/elemwise_ops.py _quantize_bfloat, round 'nearest', subnormals kept, overflow -> Inf): on the
+// bit pattern of |x| the library's floor(|x| 2^(bits-2-pe) + 0.5) is "add half of the dropped field, clear it" -- the carry into the
+// exponent is the rounding up to the next binade, 0x7f800000 is the overflow to Inf, and the subnormal range is linear in the bits.
+__device__ __forceinline__ float round_bfloat(float x, int bfloat) {
+    if (bfloat <= 0 || bfloat >= 32) return x;
+    const uint32_t b = __float_as_uint(x), a = b & 0x7fffffffu;
+    if (a >= 0x7f800000u) return x;                                   // Inf / NaN pass through
+    const int drop = 32 - bfloat;
+    const uint32_t r = (a + (1u << (drop - 1))) & ~((1u << drop) - 1u);
+    if (r == 0u) return a == 0u ? 0.0f : __uint_as_float(b & 0x80000000u);   // sign(0) = 0 -> +0.0; a rounded-away negative keeps -0.0
+    return __uint_as_float(r | (b & 0x80000000u));
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011), counter = (elt/4 lo, elt/4 hi, offset lo, offset hi), key = seed.
 // ---------------------------------------------------------------------------------------------------------------

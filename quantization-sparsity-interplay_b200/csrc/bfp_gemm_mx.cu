@@ -67,6 +67,7 @@ struct Params {
     int tiles_m, tiles_n;       // tiles_m counts CG * 128 rows
     int sf_a_tiles;             // row tiles (of 128) in the A scale array
     int b_folded;               // 1 = the B operand carries its block exponents in its E4M3 values and has ONE scale per row (atoms of one slab)
+    int out_bfloat;             // MX linear (mx/linear.py): 0 = plain; else out = rb(acc), with a bias rb(rb(acc) + rb(bias)), rb = bfloatX half-away rounding
     int debug;                  // timing experiments (wrong results): bit 1 = no operand loads, bit 2 = no scale copies, bit 3 = no scale loads, bit 4 = no B tile loads, bit 5 = every slab loads k = 0
 };
 
@@ -243,12 +244,14 @@ bfp_gemm_mx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     for (int j = 0; j < 4; ++j) {
                         float4 o = make_float4(__uint_as_float(r[c * 16 + 4 * j]), __uint_as_float(r[c * 16 + 4 * j + 1]), __uint_as_float(r[c * 16 + 4 * j + 2]),
                                                __uint_as_float(r[c * 16 + 4 * j + 3]));
+                        if (p.out_bfloat) { o.x = round_bfloat(o.x, p.out_bfloat); o.y = round_bfloat(o.y, p.out_bfloat); o.z = round_bfloat(o.z, p.out_bfloat); o.w = round_bfloat(o.w, p.out_bfloat); }
                         if (p.bias) {
                             const int nb = n0 + c * 16 + 4 * j;
-                            if (nb < p.N) o.x += p.bias[nb];
-                            if (nb + 1 < p.N) o.y += p.bias[nb + 1];
-                            if (nb + 2 < p.N) o.z += p.bias[nb + 2];
-                            if (nb + 3 < p.N) o.w += p.bias[nb + 3];
+                            const int rbb = p.out_bfloat;        // round_bfloat(x, 0) is the identity
+                            if (nb < p.N) o.x = round_bfloat(o.x + round_bfloat(p.bias[nb], rbb), rbb);
+                            if (nb + 1 < p.N) o.y = round_bfloat(o.y + round_bfloat(p.bias[nb + 1], rbb), rbb);
+                            if (nb + 2 < p.N) o.z = round_bfloat(o.z + round_bfloat(p.bias[nb + 2], rbb), rbb);
+                            if (nb + 3 < p.N) o.w = round_bfloat(o.w + round_bfloat(p.bias[nb + 3], rbb), rbb);
                         }
                         *reinterpret_cast<float4*>(sbuf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = o;      // SWIZZLE_64B: chunk ^ (row / 2 % 4)
                     }
@@ -543,7 +546,7 @@ static int launch_mx(const CUtensorMap& map_a, const CUtensorMap& map_b, const C
 }
 
 int gemm_mx_device(const uint8_t* a_vals, const uint8_t* a_sf, const uint8_t* b_vals, const uint8_t* b_sf, int b_tile_rows, int b_folded, const float* bias,
-                   float* out, int64_t T, int64_t N, int64_t Kp, cudaStream_t st) {
+                   float* out, int64_t T, int64_t N, int64_t Kp, cudaStream_t st, int out_bfloat) {
     using namespace gemm_mx;
     if (T == 0 || N == 0) return BFP_OK;
     if (Kp % 128 != 0 || Kp <= 0) return set_error(BFP_E_ARG, "mx operand K must be a positive multiple of 128");
@@ -556,6 +559,7 @@ int gemm_mx_device(const uint8_t* a_vals, const uint8_t* a_sf, const uint8_t* b_
     p.bias = bias; p.out = out; p.out_dtype = BFP_DT_F32; p.out_tma = 1;
     p.T = (int)T; p.N = (int)N; p.num_k_stages = (int)(Kp / 128);
     p.b_folded = b_folded ? 1 : 0;
+    p.out_bfloat = out_bfloat;
     p.debug = tuning().gemm_mx_variant & 62;
     // CTA pairs (cta_group::2: each CTA stages its 128 A rows and HALF of the B tile) for the 240- and 256-wide tiles whenever there is
     // more than one 128-row strip; bfp_set_option("gemm_mx_variant", 1) forces single CTAs on the 256-wide tile

@@ -85,7 +85,13 @@ int mx_from_packed_device(const int8_t* mant, const float* scale_t, int64_t ld_s
                           uint8_t* vals, uint8_t* sf, int* row_ref, unsigned int* violations, cudaStream_t st);
 int mx_pack_device(const void* in, int dtype, int64_t rows, int64_t K, int block_size, int mant_bits, float eps, uint8_t* vals, uint8_t* sf, cudaStream_t st);
 int gemm_mx_device(const uint8_t* a_vals, const uint8_t* a_sf, const uint8_t* b_vals, const uint8_t* b_sf, int b_tile_rows, int b_folded, const float* bias,
-                   float* out, int64_t T, int64_t N, int64_t Kp, cudaStream_t st);
+                   float* out, int64_t T, int64_t N, int64_t Kp, cudaStream_t st, int out_bfloat = 0);
+// MX (OCP Microscaling) formats, bfp_ocp_mx.cu
+int ocp_mx_quantize_device(const void* in, void* out, int64_t rows, int64_t K, int dtype, int out_kind, int64_t ld_out, int block_size, int elem_format,
+                           int scale_bits, int bfloat, int flush, cudaStream_t st);
+int ocp_mx_pack_device(const void* in, uint8_t* vals, uint8_t* sf, int64_t rows, int64_t K, int dtype, int tile_rows, int block_size, int elem_format,
+                       int scale_bits, int bfloat, int flush, cudaStream_t st);
+int bfloat_round_device(const void* in, void* out, const float* bias, int64_t n, int64_t ncols, int dtype, int bfloat, cudaStream_t st);
 
 size_t int_workspace_bytes(int64_t C);
 int int_quantize_device(const void* in, float* out, int64_t A, int64_t C, int64_t inner, int dtype, int bits, void* workspace, cudaStream_t s);
