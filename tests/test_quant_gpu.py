@@ -425,3 +425,76 @@ def test_padded_row_mode_equals_generic_path(dt, shape, B, sparse):
                                                              outs[1].view(torch.int16 if outs[1].element_size() == 2 else torch.int32)), (first, rmode)
         if packs:
             assert torch.equal(packs[0].view(torch.int16), packs[1].view(torch.int16)), (first, "pack")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Row f3: the optimiser wrappers (bfp_optim.py:8-64, bfp_optim_lstm.py:12-95) -- sgd_update selects the wide mantissa
+# ---------------------------------------------------------------------------------------------------------------
+def _optim_args(**kw):
+    base = dict(num_format="bfp", sparsity_num_format="bfp", rounding_mode="determ", epsilon=1e-8, mant_bits=7, weight_mant_bits=15,
+                block_size=64, device="cuda")
+    base.update(kw)
+    return base
+
+
+def test_bfp_optim_wrapper_keeps_wide_and_narrow_weights(oracle):
+    import qsi_b200  # noqa: F401
+    from qsi_b200 import bfp_optim
+    torch.manual_seed(0)
+    p = torch.nn.Parameter(torch.randn(32, 256, device="cuda") * 0.1)
+    p0 = p.detach().cpu().numpy().copy()
+    opt = bfp_optim.get_bfp_optim(torch.optim.SGD, "SGD")([p], lr=0.1, **_optim_args())
+    assert type(opt).__name__ == "BFPSGD" and bfp_optim.get_bfp_optim(torch.optim.SGD, "SGD") is type(opt)
+    g1 = torch.randn_like(p)
+    p.grad = g1.clone()
+    opt.step()
+    # first step: the weight is constrained to the wide format, updated in fp32, then stored wide (shadow) and narrow (p)
+    def plain_sgd(start, g):                                  # the wrapped optimiser's own fp32 update from `start`
+        r = torch.nn.Parameter(torch.from_numpy(start).cuda())
+        r.grad = g.clone()
+        torch.optim.SGD([r], lr=0.1).step()
+        return r.detach().cpu().numpy()
+    w0, _ = oracle.bfp_quantize(p0, 64, 15)
+    upd = plain_sgd(w0, g1)
+    wide, _ = oracle.bfp_quantize(upd, 64, 15)
+    narrow, _ = oracle.bfp_quantize(upd, 64, 7)
+    assert np.array_equal(opt.state[p]["shadow_p"].cpu().numpy().view(np.uint32), wide.view(np.uint32))
+    assert np.array_equal(p.detach().cpu().numpy().view(np.uint32), narrow.view(np.uint32))
+    # second step starts from the wide copy, not from the narrow weights the model sees
+    g2 = torch.randn_like(p)
+    p.grad = g2.clone()
+    opt.step()
+    upd2 = plain_sgd(wide, g2)
+    wide2, _ = oracle.bfp_quantize(upd2, 64, 15)
+    narrow2, _ = oracle.bfp_quantize(upd2, 64, 7)
+    assert np.array_equal(opt.state[p]["shadow_p"].cpu().numpy().view(np.uint32), wide2.view(np.uint32))
+    assert np.array_equal(p.detach().cpu().numpy().view(np.uint32), narrow2.view(np.uint32))
+    # num_format fp32: the wrapped optimiser, untouched
+    q = torch.nn.Parameter(torch.ones(4, 64, device="cuda"))
+    o2 = bfp_optim.get_bfp_optim(torch.optim.SGD, "SGD")([q], lr=0.5, num_format="fp32")
+    q.grad = torch.ones_like(q)
+    o2.step()
+    assert torch.equal(q.detach(), torch.full_like(q, 0.5)) and "shadow_p" not in o2.state[q]
+
+
+def test_bfp_adam_constrains_the_update_to_the_wide_format(oracle):
+    import qsi_b200  # noqa: F401
+    from qsi_b200 import bfp_optim
+    torch.manual_seed(1)
+    p = torch.nn.Parameter(torch.randn(16, 128, device="cuda"))
+    r = torch.nn.Parameter(p.detach().clone())
+    opt = bfp_optim.BFPAdam([p], lr=1e-2, bfp_args=_optim_args())
+    ref = torch.optim.Adam([r], lr=1e-2)
+    for _ in range(3):
+        g = torch.randn_like(p)
+        p.grad, r.grad = g.clone(), g.clone()
+        before = p.detach().clone()
+        opt.step()
+        # one plain Adam step from the same point, then the wide-mantissa constraint
+        r.data.copy_(before)
+        ref.step()
+        want, _ = oracle.bfp_quantize(r.detach().cpu().numpy(), 64, 15)
+        got = p.detach().cpu().numpy()
+        assert np.abs(got - want).max() <= 2.0 ** -14 * np.abs(want).max()      # same grid; the two Adam formulations differ by an fp32 ulp
+        q, _ = oracle.bfp_quantize(got, 64, 15)
+        assert np.array_equal(q.view(np.uint32), got.view(np.uint32))           # the result is on the wide BFP grid
