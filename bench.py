@@ -461,6 +461,64 @@ def leg_unstructured(torch, dev, peak):
     return out
 
 
+def leg_mx_formats(torch, dev, peak):
+    """SURVEY section 8 row f4 (last item): the MX formats behind the reference's mx_layers.py.  The fused quantiser against the HBM
+    roofline (fake-quant and the block-scaled operand form) and MXLinear forwards at the LLaMA-7B shapes (4096 tokens) on the tensor
+    cores: fp8_e4m3 / fp4_e2m1 on tcgen05.mma.kind::mxf8f6f4.block_scale (an MX block IS the hardware's block), int8 on the bf16 kinds."""
+    from qsi_b200 import mx_layers as mx
+    g = torch.Generator(device=dev).manual_seed(31)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, iters=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    out = {"block": 32, "bfloat": 16, "scale_bits": 8, "quantiser": [], "linear": []}
+    shape = (4096, 11008)
+    bufs = [torch.randn(*shape, device=dev, generator=g) for _ in range(4)]
+    n = shape[0] * shape[1]
+    for fmt in ("fp8_e4m3", "int8"):
+        i = [0]
+
+        def fq():
+            i[0] += 1
+            return mx._mx_quantize_last(bufs[i[0] % 4], mx.ELEM_FORMATS[fmt], 32, 8, 16, False)
+        us = timed(fq) * 1e3
+        out["quantiser"].append({"shape": list(shape), "dtype": "f32", "format": fmt, "out": "fake-quant", "bytes_per_element": 8, "us": us,
+                                 "GBps": n * 8 / us / 1e3, "frac_of_hbm_peak": n * 8 / us / 1e3 / peak})
+    sp = mx.finalize_mx_specs(mx.apply_mx_specs(dict(block_size=32, bfloat=16, scale_bits=8, w_elem_format="fp8_e4m3", a_elem_format="fp8_e4m3")))
+    i = [0]
+
+    def pk():
+        i[0] += 1
+        return mx._pack_block_scaled(bufs[i[0] % 4], mx.ELEM_FORMATS["fp8_e4m3"], 128, sp, 16)
+    us = timed(pk) * 1e3
+    bpe = 4 + 1 + 1.0 / 32
+    out["quantiser"].append({"shape": list(shape), "dtype": "f32", "format": "fp8_e4m3", "out": "E4M3 bytes + UE8M0 scale atoms", "bytes_per_element": bpe,
+                             "us": us, "GBps": n * bpe / us / 1e3, "frac_of_hbm_peak": n * bpe / us / 1e3 / peak})
+    del bufs
+    T = 4096
+    for fmt in ("fp8_e4m3", "fp4_e2m1", "int8"):
+        ms_sum, ops = 0.0, 0.0
+        for (N, K) in ((4096, 4096), (11008, 4096), (4096, 11008)):
+            x = torch.randn(T, K, device=dev, generator=g)
+            lin = mx.MXLinear(K, N, bias=False, mx_specs=dict(block_size=32, bfloat=16, scale_bits=8, w_elem_format=fmt, a_elem_format=fmt)).to(dev).eval()
+            with torch.no_grad():
+                ms_sum += timed(lambda: lin(x))
+            ops += 2.0 * T * N * K
+            del lin, x
+        out["linear"].append({"format": fmt, "tokens": T, "shapes": "llama-7b", "ms_three_forwards": ms_sum, "tflops": ops / ms_sum / 1e9,
+                              "includes": "activation quantise + pack, GEMM, bfloat output rounding (weight pack cached)",
+                              "kind": "tcgen05.mma.kind::mxf8f6f4.block_scale" if fmt != "int8" else "tcgen05.mma.kind::f16 on exact-bf16 MX values"})
+    return out
+
+
 def leg_models(torch, dev):
     """BASELINE.json configs[0] and configs[3] at the model level, on this GPU: stock `transformers` OPT-125M (8 x 512 tokens, HBFP8 + 2:4)
     and ViT-B/16 (batch 256, BFP6 + 2:4), random init, every block nn.Linear swapped for BFPLinear (and the ViT patch embedding for
@@ -824,6 +882,10 @@ def main():
             except Exception as e:
                 extras["unstructured"] = {"error": repr(e)[:300]}
             try:
+                extras["mx_formats"] = leg_mx_formats(torch, dev, peak)
+            except Exception as e:          # noqa: BLE001
+                extras["mx_formats"] = {"error": repr(e)[:300]}
+            try:
                 extras["models"] = leg_models(torch, dev)
             except Exception as e:          # noqa: BLE001
                 extras["models"] = {"error": repr(e)[:300]}
@@ -866,7 +928,7 @@ def main():
         return last
 
     y = None
-    for _ in range(8 if world == 1 else 3):                # warm-up: staging buffers + torch's pinned-host block cache.  The result is
+    for _ in range(8 if world == 1 else 6):                # warm-up: staging buffers + torch's pinned-host block cache.  The result is
         y = e2e_step()                                     # HELD exactly as in the timed loop: holding one output alive needs one more
                                                            # cached pinned block (a one-time ~0.3 s cudaHostAlloc that round 1 timed)
     torch.cuda.synchronize()

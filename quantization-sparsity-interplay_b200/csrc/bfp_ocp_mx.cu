@@ -113,47 +113,128 @@ __device__ __forceinline__ uint32_t e4m3_byte(float v) {
 
 enum { kOutFake = 0, kOutBf16 = 1, kOutPacked = 2 };
 
+// n / d for a launch-invariant divisor (Granlund & Montgomery 1994, figure 4.1): q = (t + ((n - t) >> sh1)) >> sh2, t = mulhi(m, n)
+struct FastDiv { uint32_t m, sh1, sh2; };
+static FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;                                        // ceil(log2 d)
+    f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    f.sh1 = l < 1 ? l : 1; f.sh2 = l > 0 ? l - 1 : 0;
+    return f;
+}
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& f) {
+    const uint32_t t = __umulhi(f.m, n);
+    return (t + ((n - t) >> f.sh1)) >> f.sh2;
+}
+
+// Per-launch constants of the fast path (functions of the format only).
+struct Fast {
+    uint32_t bf_half, bf_mask;      // bfloat rounding on the bit pattern of |x|: (a + half) & mask  (identity: 0, ~0)
+    int pe_min_b;                   // min_exp + 127
+    int up_c;                       // 254 + mbits - 2: 2^(mbits-2-pe) has the bits (up_c - (pe + 127)) << 23
+    float up_int, down_int;         // integer formats: 2^(mbits-2), 2^(2-mbits)
+    float max_norm;
+    int emax, scale_emax;
+    int e4m3_sub;                   // packed: the format has values below 2^-6 (fp8_e4m3 only): E4M3 subnormal bytes
+    FastDiv vec_per_row;
+};
+
+// One vector of a block whose shared exponent needs the literal evaluation (zero / subnormal / Inf / NaN maximum, a maximum within
+// 128 ulp below a power of two, a scale at the end of the E8M0 range): rare, out of line, everything by value (no local memory on
+// the caller's fast path).  lo / hi = the bfloat-rounded values; returns the quantised elements (sign applied), 2^se and its byte.
+struct GeneralOut { uint4 lo, hi; float scale; uint32_t sbyte; };
+template <int V>
+__device__ __noinline__ GeneralOut mx_vec_general(uint4 lo, uint4 hi, uint32_t amax, const Params p) {
+    const Shared sh = shared_exponent(amax, p);
+    const float inv = pow2i(-sh.se);
+    uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+        w[i] = sh.nan ? 0x7fc00000u : __float_as_uint(quantize_element(sh.zero ? 0.0f : __uint_as_float(w[i]) * inv, p));
+    GeneralOut o;
+    o.lo = make_uint4(w[0], w[1], w[2], w[3]); o.hi = make_uint4(w[4], w[5], w[6], w[7]);
+    o.scale = sh.nan ? __uint_as_float(0x7fc00000u) : pow2i(sh.se);
+    o.sbyte = sh.nan ? 0xffu : (uint32_t)(sh.se + 127);
+    return o;
+}
+
 // Stream kernel: K % block == 0, block a power-of-two multiple of the 128-bit vector, so the tensor is a flat sequence of vectors and
 // a block is 2^j adjacent lanes (block max by butterfly).  Persistent grid, kStreamUnroll independent 128-bit loads per thread.
-//   OUT = kOutFake: out has the input dtype;  kOutBf16: bf16 [rows, ld_out];  kOutPacked (block 32 / 64 / 128, K % 128 == 0, a warp
+//   OUT = kOutFake: out has the input dtype;  kOutBf16: bf16 [rows, K];  kOutPacked (block 32 / 64 / 128, K % 128 == 0, a warp
 //   covers whole 128-element slabs of one row): E4M3 bytes + one UE8M0 byte per (row, 32 elements) in scale atoms.
-template <int DT, int OUT>
-__global__ void __launch_bounds__(kStreamThreads) mx_stream_kernel(const Params p) {
+//   FLOATFMT: the element format has exponent bits (private exponent per element) / is a fixed-point grid.
+// Fast path per block (all but ~1e-5 of them): finite, normal maximum not within 128 ulp below a power of two, scale strictly inside
+// the E8M0 range -- then se comes from the exponent field and every step is the literal fp32 operation of the emulation with the
+// powers of two built from exponent bits (a multiplication by 2^-e is the same correctly rounded quotient as the division by 2^e).
+template <int DT, int OUT, bool FLOATFMT>
+__global__ void __launch_bounds__(kStreamThreads) mx_stream_kernel(const Params p, const Fast f) {
     using D = DType<DT>;
     constexpr int V = D::kVec;
     constexpr int kTileVecs = kStreamThreads * kStreamUnroll;
     const int64_t n_tiles = (p.n_vec + kTileVecs - 1) / kTileVecs;
     const uint4* in = static_cast<const uint4*>(p.in);
     const int lane = threadIdx.x & 31;
-    const int64_t vec_per_row = p.K / V;
+    (void)lane;
     pdl_launch_dependents();
     pdl_wait();
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t base = tile * kTileVecs;
+        const int rem = (int)min((int64_t)kTileVecs, p.n_vec - base);
         uint4 raw[kStreamUnroll];
 #pragma unroll
         for (int u = 0; u < kStreamUnroll; ++u) {
-            const int64_t vi = base + (int)threadIdx.x + u * kStreamThreads;
-            raw[u] = vi < p.n_vec ? ld_stream(in + vi) : make_uint4(0u, 0u, 0u, 0u);
+            const int li = (int)threadIdx.x + u * kStreamThreads;
+            raw[u] = li < rem ? ld_stream(in + base + li) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
         for (int u = 0; u < kStreamUnroll; ++u) {
-            const int64_t vi = base + (int)threadIdx.x + u * kStreamThreads;
+            const int li = (int)threadIdx.x + u * kStreamThreads;
             float v[V];
             unpack_vec<DT>(raw[u], v);
+            uint32_t r[V], sgn[V];
             uint32_t amax = 0u;
 #pragma unroll
-            for (int i = 0; i < V; ++i) { v[i] = round_bfloat(v[i], p.bfloat); amax = max(amax, __float_as_uint(v[i]) & 0x7fffffffu); }
+            for (int i = 0; i < V; ++i) {
+                const uint32_t b = __float_as_uint(v[i]), a = b & 0x7fffffffu;
+                const uint32_t rr = (a + f.bf_half) & f.bf_mask;                   // bfloat rounding, half away from zero
+                r[i] = a >= 0x7f800000u ? a : rr;                                  // Inf / NaN pass through
+                sgn[i] = r[i] ? (b & 0x80000000u) : 0u;                            // sign(+-0) = 0: zeros come out +0.0
+                amax = max(amax, r[i]);
+            }
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1)
                 if (off < p.lanes_per_block) amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, off));
-            const Shared sh = shared_exponent(amax, p);
-            const float scale = pow2i(sh.se), inv = pow2i(-sh.se);
-            float q[V];                                                // elements before the multiplication by 2^se
+            const int se = (int)(amax >> 23) - 127 - f.emax;
+            const bool fast = amax >= 0x00800000u && amax < 0x7f800000u && (amax & 0x7fffffu) < 0x7fff80u && se > -f.scale_emax && se < f.scale_emax;
+            float q[V], scale;
+            uint32_t sbyte;
+            if (fast) {
+                const float inv = __uint_as_float((uint32_t)(127 - se) << 23);
+                scale = __uint_as_float((uint32_t)(127 + se) << 23);
+                sbyte = (uint32_t)(se + 127);
 #pragma unroll
-            for (int i = 0; i < V; ++i) {
-                const float a = sh.zero ? 0.0f : v[i] * inv;           // = v / 2^se: the same correctly rounded quotient
-                q[i] = quantize_element(a, p);
+                for (int i = 0; i < V; ++i) {
+                    const float ap = __uint_as_float(r[i]) * inv;                  // |x| / 2^se
+                    float y;
+                    if (FLOATFMT) {
+                        const int pe_b = max((int)(__float_as_uint(ap) >> 23), f.pe_min_b);
+                        const uint32_t up = (uint32_t)(f.up_c - pe_b) << 23;
+                        y = floorf(__fadd_rn(ap * __uint_as_float(up), 0.5f)) * __uint_as_float(0x7f000000u - up);
+                    } else {
+                        y = floorf(__fadd_rn(ap * f.up_int, 0.5f)) * f.down_int;
+                    }
+                    q[i] = fminf(y, f.max_norm);
+                }
+            } else {
+                uint32_t vb[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vb[i] = i < V ? (r[i < V ? i : 0] | (__float_as_uint(v[i < V ? i : 0]) & 0x80000000u)) : 0u;
+                const GeneralOut g = mx_vec_general<V>(make_uint4(vb[0], vb[1], vb[2], vb[3]), make_uint4(vb[4], vb[5], vb[6], vb[7]), amax, p);
+                const uint32_t gw[8] = {g.lo.x, g.lo.y, g.lo.z, g.lo.w, g.hi.x, g.hi.y, g.hi.z, g.hi.w};
+                scale = g.scale; sbyte = g.sbyte;
+#pragma unroll
+                for (int i = 0; i < V; ++i) { sgn[i] = gw[i] & 0x80000000u; q[i] = __uint_as_float(gw[i] & 0x7fffffffu); }     // quantize_element already applied sign(.)
             }
             if (OUT == kOutPacked) {
                 uint32_t bytes[V / 4];
@@ -161,38 +242,41 @@ __global__ void __launch_bounds__(kStreamThreads) mx_stream_kernel(const Params 
                 for (int w = 0; w < V / 4; ++w) {
                     uint32_t o = 0u;
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) o |= (sh.nan ? 0u : e4m3_byte(q[4 * w + b])) << (8 * b);
+                    for (int b = 0; b < 4; ++b) {
+                        const float y = q[4 * w + b];
+                        uint32_t nb = max(__float_as_uint(y) >> 20, 960u) - 960u;                 // normal E4M3: (e + 7) << 3 | m3; 0 for y = 0
+                        if (f.e4m3_sub) {
+                            const uint32_t sub = (__float_as_uint(y + 0.015625f) >> 20) - 968u;   // y < 2^-6: m = y / 2^-9 rides in the mantissa of y + 2^-6
+                            nb = y < 0.015625f ? sub : nb;
+                        }
+                        o |= ((nb & 0x7fu) | (sgn[4 * w + b] >> 24)) << (8 * b);
+                    }
                     bytes[w] = o;
                 }
-                const uint32_t sbyte = sh.nan ? 0xffu : (uint32_t)(sh.se + 127);
-                const bool live = vi < p.n_vec;
-                const int64_t vi_c = live ? vi : 0;
-                const int64_t row = vi_c / vec_per_row, col = (vi_c - row * vec_per_row) * V;
+                const bool live = li < rem;
+                const uint32_t vi = (uint32_t)(base + li);
                 if (live) {
-                    uint8_t* dst = static_cast<uint8_t*>(p.out) + row * p.ld_out + col;
+                    uint8_t* dst = static_cast<uint8_t*>(p.out) + (int64_t)vi * V;
                     if (V == 4) *reinterpret_cast<uint32_t*>(dst) = bytes[0];
                     else *reinterpret_cast<uint2*>(dst) = make_uint2(bytes[0], bytes[V == 8 ? 1 : 0]);
                 }
-                // scale bytes: a warp covers 32 V consecutive elements of one row (K % (32 V) == 0) = 32 V / 128 slabs of four 32-groups;
-                // the first lane of each slab gathers its four bytes and writes one word of the row's atom
-                constexpr int kLanesPerSlab = 128 / V, kLanesPerGroup = 32 / V;
-                uint32_t word = 0u;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) word |= __shfl_sync(0xffffffffu, sbyte, (lane / kLanesPerSlab) * kLanesPerSlab + g * kLanesPerGroup) << (8 * g);
-                if (live && (lane % kLanesPerSlab) == 0) {
-                    const int64_t slab = col >> 7, rt = row / p.tile_rows;
-                    const int rr = (int)(row - rt * p.tile_rows), r = rr & 127;
-                    *reinterpret_cast<uint32_t*>(p.sf + (((slab * p.n_row_tiles + rt) * p.atoms + (rr >> 7)) * 512) + 16 * (r & 31) + 4 * (r >> 5)) = word;
+                // scale bytes: the first lane of every 32-element group stores the group's byte (a block is a whole number of groups)
+                constexpr int kLanesPerGroup = 32 / V;
+                if (live && (lane % kLanesPerGroup) == 0) {
+                    const uint32_t row = fastdiv(vi, f.vec_per_row);
+                    const uint32_t col = (vi - row * (uint32_t)(p.K / V)) * V;
+                    const uint32_t slab = col >> 7, g = (col >> 5) & 3u, rt = row / (uint32_t)p.tile_rows;
+                    const uint32_t rr = row - rt * (uint32_t)p.tile_rows, ra = rr & 127u;
+                    p.sf[(((int64_t)slab * p.n_row_tiles + rt) * p.atoms + (rr >> 7)) * 512 + 16 * (ra & 31u) + 4 * (ra >> 5) + g] = (uint8_t)sbyte;
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < V; ++i) q[i] = sh.nan ? __uint_as_float(0x7fc00000u) : q[i] * scale;
-                if (vi < p.n_vec) {
+                for (int i = 0; i < V; ++i) q[i] = __uint_as_float(__float_as_uint(q[i] * scale) | sgn[i]);
+                if (li < rem) {
                     if (OUT == kOutFake) {
-                        st_stream(static_cast<uint4*>(p.out) + vi, pack_vec<DT>(q));
+                        st_stream(static_cast<uint4*>(p.out) + base + li, pack_vec<DT>(q));
                     } else {
-                        const int64_t row = vi / vec_per_row, col = (vi - row * vec_per_row) * V;
-                        __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + row * p.ld_out + col;
+                        __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + (base + li) * V;
                         if (V == 8) {
                             st_stream(reinterpret_cast<uint4*>(dst), pack_vec<BFP_DT_BF16>(q));
                         } else {
@@ -254,18 +338,49 @@ static int fill_params(ocp::Params& p, int elem_format, int scale_bits, int bflo
     return BFP_OK;
 }
 
+template <int DT, int OUT>
+static int launch_stream(const ocp::Params& p, const ocp::Fast& f, int64_t n_tiles, cudaStream_t st) {
+    using namespace ocp;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(kStreamThreads); cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = tuning().pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e;
+    if (p.ebits > 0) {
+        cfg.gridDim = dim3((unsigned)stream_grid(kernel_occupancy(mx_stream_kernel<DT, OUT, true>, kStreamThreads), n_tiles));
+        e = cudaLaunchKernelEx(&cfg, mx_stream_kernel<DT, OUT, true>, p, f);
+    } else {
+        cfg.gridDim = dim3((unsigned)stream_grid(kernel_occupancy(mx_stream_kernel<DT, OUT, false>, kStreamThreads), n_tiles));
+        e = cudaLaunchKernelEx(&cfg, mx_stream_kernel<DT, OUT, false>, p, f);
+    }
+    if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaLaunchKernelEx(mx_stream_kernel): %s", cudaGetErrorString(e));
+    return BFP_OK;
+}
+
 template <int OUT>
 static int launch_mx_quant(ocp::Params& p, int dtype, bool stream_ok, cudaStream_t st) {
     using namespace ocp;
-    if (stream_ok) {
-        const int V = dtype == BFP_DT_F32 ? 4 : 8;
+    const int V = dtype == BFP_DT_F32 ? 4 : 8;
+    if (stream_ok && p.rows * p.K / V < (int64_t)UINT32_MAX) {
         p.n_vec = p.rows * p.K / V;
         p.lanes_per_block = p.block / V;
+        Fast f = {};
+        const int drop = 32 - p.bfloat;
+        f.bf_half = (p.bfloat > 0 && p.bfloat < 32) ? (1u << (drop - 1)) : 0u;
+        f.bf_mask = (p.bfloat > 0 && p.bfloat < 32) ? ~((1u << drop) - 1u) : 0xffffffffu;
+        f.pe_min_b = p.min_exp + 127;
+        f.up_c = 254 + p.mbits - 2;
+        f.up_int = (float)(1 << (p.mbits - 2)); f.down_int = 1.0f / (float)(1 << (p.mbits - 2));
+        f.max_norm = p.max_norm; f.emax = p.emax; f.scale_emax = p.scale_emax;
+        f.e4m3_sub = (p.ebits == 4 && p.mbits == 5) ? 1 : 0;
+        f.vec_per_row = make_fastdiv((uint32_t)(p.K / V));
         const int64_t n_tiles = (p.n_vec + kStreamThreads * kStreamUnroll - 1) / (kStreamThreads * kStreamUnroll);
         int rc;
-        if (dtype == BFP_DT_F32) rc = launch_pdl(mx_stream_kernel<BFP_DT_F32, OUT>, stream_grid(kernel_occupancy(mx_stream_kernel<BFP_DT_F32, OUT>, kStreamThreads), n_tiles), kStreamThreads, st, p);
-        else if (dtype == BFP_DT_F16) rc = launch_pdl(mx_stream_kernel<BFP_DT_F16, OUT>, stream_grid(kernel_occupancy(mx_stream_kernel<BFP_DT_F16, OUT>, kStreamThreads), n_tiles), kStreamThreads, st, p);
-        else rc = launch_pdl(mx_stream_kernel<BFP_DT_BF16, OUT>, stream_grid(kernel_occupancy(mx_stream_kernel<BFP_DT_BF16, OUT>, kStreamThreads), n_tiles), kStreamThreads, st, p);
+        if (dtype == BFP_DT_F32) rc = launch_stream<BFP_DT_F32, OUT>(p, f, n_tiles, st);
+        else if (dtype == BFP_DT_F16) rc = launch_stream<BFP_DT_F16, OUT>(p, f, n_tiles, st);
+        else rc = launch_stream<BFP_DT_BF16, OUT>(p, f, n_tiles, st);
         if (rc) return rc;
         count_launch();
         return check_launch("mx_stream_kernel");
@@ -299,7 +414,7 @@ int ocp_mx_quantize_device(const void* in, void* out, int64_t rows, int64_t K, i
     if (out_kind == 0) { p.ld_out = K; return launch_mx_quant<ocp::kOutFake>(p, dtype, stream_ok, st); }
     p.ld_out = ld_out;
     if (ld_out < K || ld_out % 8) return set_error(BFP_E_ARG, "bf16 operand: ld_out >= K and a multiple of 8");
-    return launch_mx_quant<ocp::kOutBf16>(p, dtype, stream_ok && (ld_out * 2) % 16 == 0, st);
+    return launch_mx_quant<ocp::kOutBf16>(p, dtype, stream_ok && ld_out == K, st);
 }
 
 int ocp_mx_pack_device(const void* in, uint8_t* vals, uint8_t* sf, int64_t rows, int64_t K, int dtype, int tile_rows, int block_size, int elem_format,
