@@ -80,7 +80,9 @@ class _PhiloxState:
         s = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
         if s != cls.seed:
             cls.seed, cls.calls = s, 0
-        off = cls.calls
+        # ranks of one job draw from disjoint streams: the rank rides in the top bits of the 64-bit offset (sharded weights and
+        # replicated activations then never share uniforms across GPUs)
+        off = cls.calls | (int(os.environ.get("RANK", "0")) & 0xFFFF) << 48
         cls.calls += 1
         return s, off
 

@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(256) mx_sf_kernel(const float* __restrict__ sc
 // Blocks the packed form cannot represent (slow-path scales: NaN / Inf / denormal range) get the NaN scale 0xff like bfp_quantize_pack.
 template <int DT>
 __global__ void __launch_bounds__(256) mx_pack_kernel(const uint4* __restrict__ in, uint8_t* __restrict__ vals, uint8_t* __restrict__ sf, int64_t rows, int64_t K,
-                                                      int lanes_per_block, int m, float eps, int64_t n_tiles) {
+                                                      int lanes_per_block, int m, float eps, int64_t n_tiles, FastDiv wpr_div) {
     using D = DType<DT>;
     constexpr int V = D::kVec;
     constexpr int kSlabsPerWarp = 32 * V / 128;             // 1 (fp32) or 2 (half)
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(256) mx_pack_kernel(const uint4* __restrict__ 
     const int64_t warps_per_row = K / (32 * V);
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t wi = gw; wi < rows * warps_per_row; wi += n_warps) {
-        const int64_t row = wi / warps_per_row, wk = wi - row * warps_per_row;
+        const int64_t row = (int64_t)fastdiv((uint32_t)wi, wpr_div), wk = wi - row * warps_per_row;       // wi < 2^32 (checked by the host)
         const int64_t vec = row * (K / V) + wk * 32 + lane;
         float v[V];
         unpack_vec<DT>(ld_stream(in + vec), v);
@@ -429,10 +429,11 @@ __global__ void __launch_bounds__(256) mx_pack_kernel(const uint4* __restrict__ 
                 for (int b = 0; b < 4; ++b) {
                     const float t = v[4 * w + b];
                     const float qf = fminf(fmaxf(rintf(t * sc.inv), -sc.vmax), sc.vmax);     // the integer mantissa (bfp_ops.py:40-44 on the grid)
-                    const int q = (int)qf;
-                    const uint32_t a = (uint32_t)(q < 0 ? -q : q);
-                    const uint32_t e = a ? e4m3_of(a, 0) : 0u;
-                    o |= (e | (q < 0 ? 0x80u : 0u)) << (8 * b);
+                    // E4M3 byte of an integer |q| <= 15 held as a float: (e + 7) << 3 | m3 = the float's exponent and top mantissa bits
+                    // rebased (127 - 7) << 3 = 960; zero (either sign) -> 0
+                    const uint32_t qb = __float_as_uint(qf), ab = qb & 0x7fffffffu;
+                    const uint32_t nb = max(ab >> 20, 960u) - 960u;
+                    o |= (nb | (ab ? (qb >> 24) & 0x80u : 0u)) << (8 * b);
                 }
                 bytes[w] = o;
             }
@@ -518,9 +519,11 @@ int mx_pack_device(const void* in, int dtype, int64_t rows, int64_t K, int block
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = tuning().pdl ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaError_t e;
-    if (dtype == BFP_DT_F32) e = cudaLaunchKernelEx(&cfg, mx_pack_kernel<BFP_DT_F32>, src, vals, sf, rows, K, lpb, mant_bits, eps, n_tiles);
-    else if (dtype == BFP_DT_F16) e = cudaLaunchKernelEx(&cfg, mx_pack_kernel<BFP_DT_F16>, src, vals, sf, rows, K, lpb, mant_bits, eps, n_tiles);
-    else e = cudaLaunchKernelEx(&cfg, mx_pack_kernel<BFP_DT_BF16>, src, vals, sf, rows, K, lpb, mant_bits, eps, n_tiles);
+    if (warps >= (int64_t)UINT32_MAX) return set_error(BFP_E_UNSUPPORTED, "fused mx pack: tensor too large (use bfp_quantize_pack + bfp_mx_from_packed)");
+    const FastDiv wpr = make_fastdiv((uint32_t)(K / (32 * V)));
+    if (dtype == BFP_DT_F32) e = cudaLaunchKernelEx(&cfg, mx_pack_kernel<BFP_DT_F32>, src, vals, sf, rows, K, lpb, mant_bits, eps, n_tiles, wpr);
+    else if (dtype == BFP_DT_F16) e = cudaLaunchKernelEx(&cfg, mx_pack_kernel<BFP_DT_F16>, src, vals, sf, rows, K, lpb, mant_bits, eps, n_tiles, wpr);
+    else e = cudaLaunchKernelEx(&cfg, mx_pack_kernel<BFP_DT_BF16>, src, vals, sf, rows, K, lpb, mant_bits, eps, n_tiles, wpr);
     (void)rc;
     if (e != cudaSuccess) return set_errorf(BFP_E_CUDA, "cudaLaunchKernelEx(mx_pack_kernel): %s", cudaGetErrorString(e));
     count_launch();

@@ -113,21 +113,6 @@ __device__ __forceinline__ uint32_t e4m3_byte(float v) {
 
 enum { kOutFake = 0, kOutBf16 = 1, kOutPacked = 2 };
 
-// n / d for a launch-invariant divisor (Granlund & Montgomery 1994, figure 4.1): q = (t + ((n - t) >> sh1)) >> sh2, t = mulhi(m, n)
-struct FastDiv { uint32_t m, sh1, sh2; };
-static FastDiv make_fastdiv(uint32_t d) {
-    FastDiv f;
-    uint32_t l = 0;
-    while ((1ull << l) < d) ++l;                                        // ceil(log2 d)
-    f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
-    f.sh1 = l < 1 ? l : 1; f.sh2 = l > 0 ? l - 1 : 0;
-    return f;
-}
-__device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& f) {
-    const uint32_t t = __umulhi(f.m, n);
-    return (t + ((n - t) >> f.sh1)) >> f.sh2;
-}
-
 // Per-launch constants of the fast path (functions of the format only).
 struct Fast {
     uint32_t bf_half, bf_mask;      // bfloat rounding on the bit pattern of |x|: (a + half) & mask  (identity: 0, ~0)
@@ -137,7 +122,8 @@ struct Fast {
     float max_norm;
     int emax, scale_emax;
     int e4m3_sub;                   // packed: the format has values below 2^-6 (fp8_e4m3 only): E4M3 subnormal bytes
-    FastDiv vec_per_row;
+    FastDiv vec_per_row, tile_rows;
+    uint32_t slab_stride;           // packed: bytes between the atoms of consecutive K slabs = n_row_tiles * atoms * 512
 };
 
 // One vector of a block whose shared exponent needs the literal evaluation (zero / subnormal / Inf / NaN maximum, a maximum within
@@ -175,7 +161,6 @@ __global__ void __launch_bounds__(kStreamThreads) mx_stream_kernel(const Params 
     const int64_t n_tiles = (p.n_vec + kTileVecs - 1) / kTileVecs;
     const uint4* in = static_cast<const uint4*>(p.in);
     const int lane = threadIdx.x & 31;
-    (void)lane;
     pdl_launch_dependents();
     pdl_wait();
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -186,6 +171,18 @@ __global__ void __launch_bounds__(kStreamThreads) mx_stream_kernel(const Params 
         for (int u = 0; u < kStreamUnroll; ++u) {
             const int li = (int)threadIdx.x + u * kStreamThreads;
             raw[u] = li < rem ? ld_stream(in + base + li) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        uint32_t sf_off = 0u;
+        if (OUT == kOutPacked) {
+            // byte offset of (row, first slab, group 0) of the 32 V elements this warp covers in step (lane % kStreamUnroll): all lanes of
+            // a warp share it, so lane u works it out for step u and the steps fetch it with one shuffle instead of every lane
+            // repeating the address arithmetic for every vector
+            static_assert(kStreamUnroll <= 32, "one lane per unroll step");
+            const uint32_t vw = (uint32_t)base + (threadIdx.x & ~31u) + (uint32_t)(lane % kStreamUnroll) * kStreamThreads;
+            const uint32_t row = fastdiv(vw, f.vec_per_row);
+            const uint32_t slab = ((vw - row * (uint32_t)(p.K / V)) * V) >> 7;
+            const uint32_t rt = fastdiv(row, f.tile_rows), rr = row - rt * (uint32_t)p.tile_rows, ra = rr & 127u;
+            sf_off = slab * f.slab_stride + (rt * (uint32_t)p.atoms + (rr >> 7)) * 512u + 16u * (ra & 31u) + 4u * (ra >> 5);
         }
 #pragma unroll
         for (int u = 0; u < kStreamUnroll; ++u) {
@@ -249,7 +246,7 @@ __global__ void __launch_bounds__(kStreamThreads) mx_stream_kernel(const Params 
                             const uint32_t sub = (__float_as_uint(y + 0.015625f) >> 20) - 968u;   // y < 2^-6: m = y / 2^-9 rides in the mantissa of y + 2^-6
                             nb = y < 0.015625f ? sub : nb;
                         }
-                        o |= ((nb & 0x7fu) | (sgn[4 * w + b] >> 24)) << (8 * b);
+                        o |= (nb | (sgn[4 * w + b] >> 24)) << (8 * b);                           // nb <= 0x7e (448)
                     }
                     bytes[w] = o;
                 }
@@ -260,15 +257,12 @@ __global__ void __launch_bounds__(kStreamThreads) mx_stream_kernel(const Params 
                     if (V == 4) *reinterpret_cast<uint32_t*>(dst) = bytes[0];
                     else *reinterpret_cast<uint2*>(dst) = make_uint2(bytes[0], bytes[V == 8 ? 1 : 0]);
                 }
-                // scale bytes: the first lane of every 32-element group stores the group's byte (a block is a whole number of groups)
-                constexpr int kLanesPerGroup = 32 / V;
-                if (live && (lane % kLanesPerGroup) == 0) {
-                    const uint32_t row = fastdiv(vi, f.vec_per_row);
-                    const uint32_t col = (vi - row * (uint32_t)(p.K / V)) * V;
-                    const uint32_t slab = col >> 7, g = (col >> 5) & 3u, rt = row / (uint32_t)p.tile_rows;
-                    const uint32_t rr = row - rt * (uint32_t)p.tile_rows, ra = rr & 127u;
-                    p.sf[(((int64_t)slab * p.n_row_tiles + rt) * p.atoms + (rr >> 7)) * 512 + 16 * (ra & 31u) + 4 * (ra >> 5) + g] = (uint8_t)sbyte;
-                }
+                // scale bytes: the first lane of every 32-element group stores the group's byte at the warp's atom address (computed
+                // once per tile by lane u for step u, see sf_off) + its slab (16-bit inputs: a warp spans two) + its group
+                constexpr int kLanesPerGroup = 32 / V, kLanesPerSlab = 128 / V;
+                const uint32_t off = __shfl_sync(0xffffffffu, sf_off, u);
+                if (live && (lane % kLanesPerGroup) == 0)
+                    p.sf[off + (uint32_t)(lane / kLanesPerSlab) * f.slab_stride + (uint32_t)((lane % kLanesPerSlab) / kLanesPerGroup)] = (uint8_t)sbyte;
             } else {
 #pragma unroll
                 for (int i = 0; i < V; ++i) q[i] = __uint_as_float(__float_as_uint(q[i] * scale) | sgn[i]);
@@ -376,6 +370,12 @@ static int launch_mx_quant(ocp::Params& p, int dtype, bool stream_ok, cudaStream
         f.max_norm = p.max_norm; f.emax = p.emax; f.scale_emax = p.scale_emax;
         f.e4m3_sub = (p.ebits == 4 && p.mbits == 5) ? 1 : 0;
         f.vec_per_row = make_fastdiv((uint32_t)(p.K / V));
+        if (OUT == kOutPacked) {
+            f.tile_rows = make_fastdiv((uint32_t)p.tile_rows);
+            const int64_t stride = p.n_row_tiles * p.atoms * 512;
+            if (stride * (p.K / 128) >= (int64_t)UINT32_MAX) return set_error(BFP_E_UNSUPPORTED, "MX block-scaled pack: scale array beyond 4 GB");
+            f.slab_stride = (uint32_t)stride;
+        }
         const int64_t n_tiles = (p.n_vec + kStreamThreads * kStreamUnroll - 1) / (kStreamThreads * kStreamUnroll);
         int rc;
         if (dtype == BFP_DT_F32) rc = launch_stream<BFP_DT_F32, OUT>(p, f, n_tiles, st);

@@ -29,6 +29,22 @@ inline int launch_pdl(Kernel kernel, int grid, int threads, cudaStream_t st, con
     return BFP_OK;
 }
 
+// n / d for a launch-invariant divisor (Granlund & Montgomery 1994, figure 4.1): q = (t + ((n - t) >> sh1)) >> sh2, t = mulhi(m, n)
+struct FastDiv { uint32_t m, sh1, sh2; };
+inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;                                        // ceil(log2 d)
+    f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    f.sh1 = l < 1 ? l : 1; f.sh2 = l > 0 ? l - 1 : 0;
+    return f;
+}
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& f) {
+    const uint32_t t = __umulhi(f.m, n);
+    return (t + ((n - t) >> f.sh1)) >> f.sh2;
+}
+
+
 // ---------------------------------------------------------------------------------------------------------------
 // 128-bit streaming loads / stores
 // ---------------------------------------------------------------------------------------------------------------
