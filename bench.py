@@ -970,7 +970,7 @@ def main():
         "data": "synthetic", "config": cfg, "config_detail": cfg_detail,
         "hbm_peak_pct": 100.0 * (value / world) / peak,
         "roofline": {"bound": "hbm", "kernel": "quant_stream_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "frac": achieved / peak, "frac_of_nominal_hbm3e_8000": achieved / 8000.0, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": bytes_launch},
         "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": int(e2e_bytes // 2), "d2h_bytes_per_step": int(e2e_bytes // 2),
                 "steps": e2e_steps, "api": "bfp_ops.float_to_bfp_blocked(pinned CPU tensor) -> bfp_quantize_host", "sample": e2e_sample,

@@ -184,19 +184,32 @@ def _weight_tile(N):
 
 
 class _PackedWeightCache:
-    """Packed form of a module's weight, rebuilt when the parameter object, its version or its storage changes (and never reused
-    while the module trains: in-place optimiser writes through .data do not bump the version)."""
+    """Packed forms of a module's weight, with the protocol of BFPLinear's cache (bfp_ops.BFPLinear._packed_weight): keyed on the
+    parameter's storage, version, shape and dtype; never served while the module trains with a trainable weight (in-place optimiser
+    writes through `.data` do not bump the version); dropped by `invalidate()` -- the modules call it from `_apply` / `load_state_dict`
+    and expose it as `invalidate_packed()` for callers that rewrite the weight through `.data` in eval mode.  BFP_WEIGHT_CACHE=0
+    disables caching; =verify adds a checksum of the whole weight to the key (one extra read and a host sync per forward)."""
 
     def __init__(self):
-        self.key, self.value = None, None
+        self.entries = {}
+
+    def invalidate(self):
+        self.entries = {}
 
     def get(self, module, w, kind, build):
-        key = (kind, id(w), w._version, w.data_ptr(), tuple(w.shape), w.dtype)
-        if module.training or w.requires_grad and torch.is_grad_enabled():
+        import os
+        mode = os.environ.get("BFP_WEIGHT_CACHE", "1")
+        if mode == "0" or (module is not None and module.training and w.requires_grad):
             return build()
-        if self.key != key:
-            self.key, self.value = key, build()
-        return self.value
+        key = (w.data_ptr(), w._version, tuple(w.shape), w.dtype, w.device)
+        if mode == "verify":
+            key = key + (int(w.detach().view(torch.int16 if w.element_size() == 2 else torch.int32).sum(dtype=torch.int64).item()),)
+        hit = self.entries.get(kind)
+        if hit is None or hit[0] != key:
+            self.entries = {k: v for k, v in self.entries.items() if v[0] == key}          # a changed weight drops every stale form
+            hit = (key, build())
+            self.entries[kind] = hit
+        return hit[1]
 
 
 def mx_linear_forward(x, w, bias, mx_specs, cache=None, module=None, prefer_sparse=False):
@@ -330,6 +343,19 @@ class MXLinear(torch.nn.Linear):
         self.sparsity, self.device, self.sparsity_mode, self.sparsity_frac, self.N, self.M = sparsity, device, sparsity_mode, sparsity_frac, N, M
         self.sparsity_init = False
         self._packed = _PackedWeightCache()
+
+    def invalidate_packed(self):
+        """Drops the cached packed weight (call after modifying the weight through `.data` outside training)."""
+        self._packed.invalidate()
+
+    def _apply(self, fn, *args, **kwargs):
+        if "_packed" in self.__dict__:
+            self._packed.invalidate()
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._packed.invalidate()
+        return super()._load_from_state_dict(*args, **kwargs)
 
     def forward(self, inputs):
         _sparsify_weight_once(self)

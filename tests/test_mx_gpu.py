@@ -256,6 +256,34 @@ def test_mxlinear_prunes_its_weight_once_like_the_reference(mx, O, fmt, mode):
     _layer_close(y.cpu().numpy(), want)
 
 
+def test_mxlinear_packed_weight_cache_follows_the_weight(mx, O):
+    torch.manual_seed(5)
+    fmt = "fp8_e4m3"
+    lin = mx.MXLinear(256, 128, bias=False, mx_specs=dict(SPEC, w_elem_format=fmt, a_elem_format=fmt)).cuda().eval()
+    x = torch.from_numpy(_data(21, (32, 256))).cuda()
+
+    def check():
+        with torch.no_grad():
+            y = lin(x)
+        want, _, _ = O.mx_linear(x.cpu().numpy(), lin.weight.detach().cpu().numpy(), None, fmt, fmt, 32, 16, 8)
+        _layer_close(y.cpu().numpy(), want)
+    check()
+    assert len(lin._packed.entries) == 1
+    with torch.no_grad():
+        lin.weight.mul_(0.37)                       # in-place through autograd's view of the tensor: the version moves
+    check()
+    lin.weight.data.mul_(1.7)                       # through .data: the version does NOT move -- the documented protocol is invalidate_packed()
+    lin.invalidate_packed()
+    check()
+    lin.load_state_dict({"weight": torch.randn(128, 256)})          # hooks drop the cache
+    check()
+    lin.train()                                     # a training module with a trainable weight never serves a cached form
+    lin.weight.data.mul_(0.5)
+    check()
+    lin.eval().half().float()                       # _apply (dtype / device moves) drops it too
+    check()
+
+
 def test_mxlinear_without_specs_is_a_plain_linear(mx):
     lin = mx.MXLinear(64, 32, mx_specs=None).cuda()
     x = torch.randn(5, 64, device="cuda")

@@ -165,3 +165,33 @@ def test_specs_helpers_match_reference_specs_py():
         L.apply_mx_specs({"not_a_spec": 1})
     with pytest.raises(KeyError):
         ref.apply_mx_specs({"not_a_spec": 1})
+
+
+def test_mx_layers_host_logic_without_a_gpu():
+    """The host mirror on a CPU-only machine: modules without MX specs are plain torch layers; anything that would need the CUDA
+    library refuses loudly (no CPU fallback, no route through the oracle)."""
+    import qsi_b200  # noqa: F401
+    from qsi_b200 import mx_layers as L
+    lin = L.MXLinear(16, 8, mx_specs=None, sparsity=False)
+    x = torch.randn(3, 16)
+    assert lin.mx_none and torch.equal(lin(x), torch.nn.functional.linear(x, lin.weight, lin.bias))
+    conv = L.MXConv2d(3, 4, kernel_size=2, mx_specs={})
+    assert conv.mx_none and conv(torch.randn(1, 3, 4, 4)).shape == (1, 4, 3, 3)
+    assert torch.equal(L.MXMatmul(x, x.t()), x @ x.t())
+    spec = dict(w_elem_format="fp8_e4m3", a_elem_format="fp8_e4m3", block_size=32, bfloat=16, scale_bits=8)
+    q = L.MXLinear(64, 8, mx_specs=spec)
+    assert not q.mx_none and q.mx_specs["w_elem_format_bp"] == "fp8_e4m3"
+    if not torch.cuda.is_available():
+        with pytest.raises(ValueError, match="CUDA"):
+            q(torch.randn(2, 64))
+        with pytest.raises(ValueError, match="CUDA"):
+            L.quantize_mx_op(torch.randn(2, 64), q.mx_specs, "fp8_e4m3", axes=[-1])
+    assert L._format_id("fp4") == L._format_id("FP4_E2M1") == 8 and L._format_id(None) is None
+    assert L._block_scaled_ok(5, 8, q.mx_specs, 4096, torch.float32, torch.float32, 4096)
+    assert not L._block_scaled_ok(5, 1, q.mx_specs, 4096, torch.float32, torch.float32, 4096)          # int8 is not an E4M3 subset
+    assert not L._block_scaled_ok(5, 5, dict(q.mx_specs, block_size=16), 4096, torch.float32, torch.float32, 4096)
+    assert not L._block_scaled_ok(5, 5, q.mx_specs, 4224, torch.bfloat16, torch.bfloat16, 4096)        # 16-bit inputs need K % 256 == 0
+    with pytest.raises(NotImplementedError):
+        L._need_nearest("floor")
+    with pytest.raises(ValueError):
+        L._bfloat_of(dict(q.mx_specs, bfloat=8))
