@@ -71,10 +71,8 @@ __device__ __forceinline__ void process_vec(const uint4& raw, const StreamParams
 #pragma unroll
             for (int i = 0; i < V; ++i) amax = max(amax, abs_bits(v[i]));
         }
-        // butterfly over the lanes that share this block; every lane of the warp executes every shuffle
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1)
-            if (off < p.lanes_per_block) amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+        // maximum over the lanes that share this block; every lane of the warp takes part
+        amax = block_max_u32(amax, p.lanes_per_block, block_lane_mask(p.lanes_per_block));
         const BlockScale sc = make_scale<DT>(amax, p.m, p.eps);
         float un[STOC ? V : 1];
         if (STOC) {
@@ -224,7 +222,17 @@ __device__ __forceinline__ void process_tile(const uint4* raw, const StreamParam
         }
     }
     if (kQuant) {
-        // butterfly over the lanes that share a block; every lane of the warp executes every shuffle
+        // maximum over the lanes that share a block; every lane of the warp takes part
+#ifdef BFP_REDUX_MAX
+        {
+            const uint32_t bmask = block_lane_mask(p.lanes_per_block);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (kHalf) amax[u] = max(amax[u] & 0xffffu, amax[u] >> 16);       // one 16-bit key per lane before the reduction
+                amax[u] = block_max_u32(amax[u], p.lanes_per_block, bmask);
+            }
+        }
+#else
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             if (off < p.lanes_per_block) {
@@ -235,6 +243,7 @@ __device__ __forceinline__ void process_tile(const uint4* raw, const StreamParam
                 }
             }
         }
+#endif
         const SimpleConsts<DT, STOC> sk(p.m);
         const int m = p.m;
 #pragma unroll
@@ -512,6 +521,47 @@ __global__ void __launch_bounds__(kStreamThreads, StreamOcc<DT, STOC>::kMinCtas)
                 nxt[u] = (li < rem) ? ld_stream(p.in + base + li) : make_uint4(0u, 0u, 0u, 0u);
             }
         };
+#ifdef BFP_STOC_PINGPONG
+        // two named register buffers alternate between "being processed" and "being fetched", so the hand-over needs no copies
+        // (the single-buffer form moves 16 registers per tile)
+        uint4 alt[kStreamUnroll];
+        auto fetch_to = [&](uint4* dst, int64_t t) {
+            const int64_t base = t * kTileVecs;
+            const int rem = (int)min((int64_t)kTileVecs, p.n_vec - base);
+#pragma unroll
+            for (int u = 0; u < kStreamUnroll; ++u) {
+                const int li = (int)threadIdx.x + u * kStreamThreads;
+                dst[u] = (li < rem) ? ld_stream(p.in + base + li) : make_uint4(0u, 0u, 0u, 0u);
+            }
+        };
+        auto run = [&](const uint4* raw, int64_t tile) {
+            const int64_t tile_base = tile * kTileVecs;
+            const int rem = (int)min((int64_t)kTileVecs, p.n_vec - tile_base);
+            int64_t vidx[kStreamUnroll];
+#pragma unroll
+            for (int u = 0; u < kStreamUnroll; ++u) vidx[u] = tile_base + (int)threadIdx.x + u * kStreamThreads;
+            process_vectors<DT, ORDER, M, KD, TIE, STOC>(raw, p, vidx, [&](int u, const uint4* o) {
+                const int li = (int)threadIdx.x + u * kStreamThreads;
+                if (li < rem) {
+                    uint4* dst = p.out + (tile_base + li) * kOutVecs;
+                    st_stream(dst, o[0]);
+                    if (kOutVecs == 2) st_stream(dst + 1, o[kOutVecs - 1]);
+                }
+            });
+        };
+        int64_t tile = blockIdx.x;
+        if (tile < n_tiles) fetch_to(nxt, tile);
+        while (tile < n_tiles) {
+            const int64_t t1 = tile + gridDim.x;
+            if (t1 < n_tiles) fetch_to(alt, t1);
+            run(nxt, tile);
+            if (t1 >= n_tiles) break;
+            const int64_t t2 = t1 + gridDim.x;
+            if (t2 < n_tiles) fetch_to(nxt, t2);
+            run(alt, t1);
+            tile = t2;
+        }
+#else
         if ((int64_t)blockIdx.x < n_tiles) fetch(blockIdx.x);
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int64_t tile_base = tile * kTileVecs;
@@ -530,6 +580,7 @@ __global__ void __launch_bounds__(kStreamThreads, StreamOcc<DT, STOC>::kMinCtas)
                 }
             });
         }
+#endif
         return;
     }
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {

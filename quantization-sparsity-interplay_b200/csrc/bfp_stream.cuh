@@ -29,6 +29,26 @@ inline int launch_pdl(Kernel kernel, int grid, int threads, cudaStream_t st, con
     return BFP_OK;
 }
 
+// Block maximum of unsigned keys over the 2^j adjacent lanes that share a BFP / MX block.  Default: xor butterfly (j shuffle + max
+// pairs).  -DBFP_REDUX_MAX: one redux.sync.max.u32 per value with the block's lanes as member mask (every lane of the warp executes
+// it; the groups of a warp reduce independently).
+__device__ __forceinline__ uint32_t block_lane_mask(int lanes_per_block) {
+    const uint32_t lane = threadIdx.x & 31u;
+    return lanes_per_block >= 32 ? 0xffffffffu : (((1u << lanes_per_block) - 1u) << (lane & ~(uint32_t)(lanes_per_block - 1)));
+}
+__device__ __forceinline__ uint32_t block_max_u32(uint32_t v, int lanes_per_block, uint32_t mask) {
+#ifdef BFP_REDUX_MAX
+    (void)lanes_per_block;
+    return __reduce_max_sync(mask, v);
+#else
+    (void)mask;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1)
+        if (off < lanes_per_block) v = max(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+#endif
+}
+
 // n / d for a launch-invariant divisor (Granlund & Montgomery 1994, figure 4.1): q = (t + ((n - t) >> sh1)) >> sh2, t = mulhi(m, n)
 struct FastDiv { uint32_t m, sh1, sh2; };
 inline FastDiv make_fastdiv(uint32_t d) {

@@ -280,43 +280,59 @@ def _try_compress(wb):
         return wb
 
 
+def _mx_operand(t2d, axis, fmt, sp):
+    """Exact-bf16 GEMM operand of the MX quantisation of a 2-D tensor along `axis`: [other dim, Kp] with the quantised axis last
+    (K-major, zero padded to a multiple of 8) -- for axis 0 the transposed contiguous copy the quantiser needs anyway IS the operand."""
+    src = (t2d.detach().t() if axis == 0 else t2d.detach()).contiguous()
+    return _mx_quantize_last(src, fmt, sp["block_size"], sp["scale_bits"], 0, sp["mx_flush_fp32_subnorms"], out_kind=1)
+
+
+def _round_inplace(y, sp):
+    b = _bfloat_of(sp)
+    if b and y.numel():
+        with _on(y.device):
+            _lib.check(_lib.lib().bfp_bfloat_round(y.data_ptr(), y.data_ptr(), None, y.numel(), 0, _DT[y.dtype], b, _stream()))
+    return y
+
+
 class _MXLinearFunction(torch.autograd.Function):
-    """Training path (mx/linear.py LinearFunction forward + backward with quantize_backprop): MX fake-quantisation by the CUDA
-    quantiser along the axes the library uses, contractions by the library GEMM (the tensor-core kinds serve inference)."""
+    """Training path (mx/linear.py LinearFunction forward + backward with quantize_backprop).  The forward is the inference forward;
+    the backward quantises along the axes the library uses -- weight gradient: both factors along the token dim; input gradient: the
+    weight along out_features, the output gradient along its last dim -- straight into exact-bf16 operands, and both contractions
+    run on the tcgen05 bf16 kind (fp32 accumulation), followed by the library's bfloat rounding of each gradient."""
 
     @staticmethod
     def forward(ctx, x, w, bias, mx_specs):
-        bf_in, bf_w = quantize_elemwise_op(x, mx_specs), quantize_elemwise_op(w, mx_specs)
         ctx.has_bias, ctx.mx_specs = bias is not None, mx_specs
-        ctx.save_for_backward(*((bf_in, bf_w) if mx_specs["quantize_backprop"] else (x, w)))
-        q_in = quantize_mx_op(bf_in, mx_specs, mx_specs["a_elem_format"], axes=[-1])
-        q_w = quantize_mx_op(bf_w, mx_specs, mx_specs["w_elem_format"], axes=[-1])
-        y = quantize_elemwise_op(F.linear(q_in, q_w), mx_specs)
-        if bias is not None:
-            y = quantize_elemwise_op(y + quantize_elemwise_op(bias, mx_specs).to(y.dtype), mx_specs)
-        return y
+        if mx_specs["quantize_backprop"]:
+            ctx.save_for_backward(quantize_elemwise_op(x, mx_specs), quantize_elemwise_op(w, mx_specs))
+        else:
+            ctx.save_for_backward(x, w)
+        return mx_linear_forward(x, w, bias, mx_specs)
 
     @staticmethod
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
         sp = ctx.mx_specs if ctx.mx_specs["quantize_backprop"] else None
         out_dim, in_dim = w.shape
-        gy = quantize_elemwise_op(gy, sp)
-        if sp is None:
-            gx = gy @ w
-            gw = gy.reshape(-1, out_dim).t() @ x.reshape(-1, in_dim)
-        else:
-            # weight gradient: both factors blocked along the token dim (the contraction of gy^T x)
-            qx = quantize_mx_op(x.reshape(-1, in_dim), sp, sp["a_elem_format_bp_ex"], axes=[0])
-            qg = quantize_mx_op(gy.reshape(-1, out_dim), sp, sp["a_elem_format_bp_ex"], axes=[0])
+        gy = quantize_elemwise_op(gy.contiguous(), sp)
+        g2, x2 = gy.reshape(-1, out_dim), x.reshape(-1, in_dim)
+        f_ex = _format_id(sp["a_elem_format_bp_ex"]) if sp is not None else None
+        f_w, f_os = (_format_id(sp["w_elem_format_bp"]), _format_id(sp["a_elem_format_bp_os"])) if sp is not None else (None, None)
+        if sp is None or f_ex is None or f_w is None or f_os is None or not (g2.dtype == x2.dtype == w.dtype == torch.float32):
+            # no element format for some operand (or half-precision modules): the library's own structure on fake-quantised tensors
+            qx = quantize_mx_op(x2, sp, sp["a_elem_format_bp_ex"], axes=[0]) if sp is not None else x2
+            qg = quantize_mx_op(g2, sp, sp["a_elem_format_bp_ex"], axes=[0]) if sp is not None else g2
             gw = quantize_elemwise_op(qg.t() @ qx, sp)
-            # input gradient: weight blocked along out_features, output gradient along its last dim
-            qw = quantize_mx_op(w, sp, sp["w_elem_format_bp"], axes=[0])
-            qo = quantize_mx_op(gy, sp, sp["a_elem_format_bp_os"], axes=[-1])
+            qw = quantize_mx_op(w, sp, sp["w_elem_format_bp"], axes=[0]) if sp is not None else w
+            qo = quantize_mx_op(gy, sp, sp["a_elem_format_bp_os"], axes=[-1]) if sp is not None else gy
             gx = quantize_elemwise_op(qo @ qw, sp)
+        else:
+            gw = _round_inplace(bfp_linear_bf16(_mx_operand(g2, 0, f_ex, sp), _mx_operand(x2, 0, f_ex, sp)), sp)                 # [out, in]
+            gx = _round_inplace(bfp_linear_bf16(_mx_operand(g2, 1, f_os, sp), _mx_operand(w, 0, f_w, sp)), sp).view(gy.shape[:-1] + (in_dim,))
         gb = None
         if ctx.has_bias:
-            gb = quantize_elemwise_op(gy.reshape(-1, out_dim).sum(0), sp)
+            gb = quantize_elemwise_op(g2.sum(0), sp)
         return gx, gw, gb, None
 
 
