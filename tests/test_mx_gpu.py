@@ -352,3 +352,67 @@ def test_unsupported_options_raise(mx):
         mx.quantize_elemwise_op(torch.ones(4, device="cuda"), mx.finalize_mx_specs(mx.apply_mx_specs(dict(bfloat=8))))
     with pytest.raises(ValueError):
         mx.quantize_mx_op(torch.ones(4, 32), mx.finalize_mx_specs(mx.apply_mx_specs(dict(SPEC))), "fp8_e4m3", axes=[-1])       # CPU tensor: no fallback
+
+
+class _EmulatedMXLinear(torch.nn.Linear):
+    """mx.Linear written with the torch ops the library's emulation uses (the reference's MXLinear minus the import it cannot satisfy
+    here): bfloat16 rounding half away from zero, MX along the contraction dim, fp32 F.linear, rounding, bias, rounding."""
+
+    def __init__(self, src, fmt, block, O):
+        super().__init__(src.in_features, src.out_features, bias=src.bias is not None)
+        self.weight, self.bias, self.fmt, self.block, self.O = src.weight, src.bias, fmt, block, O
+
+    @staticmethod
+    def rb(t):
+        return ((t.contiguous().view(torch.int32) + 0x8000) & ~0xFFFF).view(torch.float32)
+
+    def forward(self, x):
+        K = x.shape[-1]
+        qx = _torch_quantize_mx(self.rb(x).view(-1, K), self.fmt, self.block, self.O).view(x.shape)
+        qw = _torch_quantize_mx(self.rb(self.weight.detach()), self.fmt, self.block, self.O)
+        y = self.rb(torch.nn.functional.linear(qx, qw))
+        return self.rb(y + self.rb(self.bias.detach())) if self.bias is not None else y
+
+
+def test_opt_model_with_mxlinear_matches_the_emulated_library(mx, O):
+    """Model level: stock OPT (OPTConfig() widths, 2 layers, 4 x 256 tokens) with the six block linears of every layer swapped for
+    MXLinear (fp8_e4m3, block 32, bfloat16, 2:4-pruned weights) -- the substitution modeling_opt.py:165-169,328-330 makes -- against
+    the same model with the emulation written in torch ops.  Individual outputs differ only where the fp32 summation order crosses a
+    bfloat16 rounding boundary, so the logits agree to a small multiple of the bfloat16 step."""
+    import transformers
+    fmt, block = "fp8_e4m3", 32
+    targets = ("q_proj", "k_proj", "v_proj", "out_proj", "fc1", "fc2")
+
+    def build(make):
+        torch.manual_seed(0)
+        cfg = transformers.OPTConfig()
+        cfg.num_hidden_layers = 2
+        model = transformers.OPTForCausalLM(cfg).eval()
+        n = 0
+        for parent in list(model.modules()):
+            for name, ch in list(parent.named_children()):
+                if isinstance(ch, torch.nn.Linear) and name in targets:
+                    setattr(parent, name, make(ch))
+                    n += 1
+        return model.cuda(), cfg, n
+
+    def ours(ch):
+        new = mx.MXLinear(ch.in_features, ch.out_features, bias=ch.bias is not None, mx_specs=dict(SPEC, w_elem_format=fmt, a_elem_format=fmt),
+                          sparsity=True, device="cuda", sparsity_mode="structured", N=2, M=4)
+        new.weight, new.bias = ch.weight, ch.bias
+        return new.eval()
+
+    m1, cfg, n1 = build(ours)
+    ids = torch.randint(0, cfg.vocab_size, (4, 256), generator=torch.Generator().manual_seed(1)).cuda()
+    with torch.no_grad():
+        y1 = m1(input_ids=ids).logits.float()
+    pruned = {k: v.detach().clone() for k, v in m1.state_dict().items()}          # the weights after MXLinear's one-time 2:4 pruning
+    del m1
+    m2, _, n2 = build(lambda ch: _EmulatedMXLinear(ch, fmt, block, O))
+    m2.load_state_dict(pruned)
+    with torch.no_grad():
+        y2 = m2(input_ids=ids).logits.float()
+    assert n1 == n2 == 12
+    rel = float((y1 - y2).norm() / y2.norm())
+    print(f"MX OPT drop-in: logits rel. difference vs the emulated library {rel:.3e}")
+    assert rel < 1e-3                     # measured 8.9e-5 on B200
