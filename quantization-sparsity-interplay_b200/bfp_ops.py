@@ -21,6 +21,7 @@ Semantics kept from the reference (line numbers refer to the reference file):
 import ctypes
 import math
 import os
+import weakref
 
 import torch
 import torch.nn.functional as F
@@ -554,10 +555,10 @@ def _packed_activation_mx(x, bfp_args):
     key = ("mx", bfp_args['block_size'], bfp_args['mant_bits'], float(bfp_args['epsilon']), bfp_args['in_sparsity'] == True,   # noqa: E712
            bfp_args['N'], bfp_args['M'], bfp_args['first'], bfp_args['sparsity_mode'], float(bfp_args['sparsity_frac']), _stream(x.device))
     hit = _ACT_CACHE.get(x.device)
-    if hit is not None and hit[0] is x and hit[1] == x._version and hit[2] == key:
+    if hit is not None and hit[0]() is x and hit[1] == x._version and hit[2] == key:
         return hit[3]
     xp = pack_activation_mx(x, bfp_args)
-    _ACT_CACHE[x.device] = (x, x._version, key, xp)
+    _act_cache_put(x, key, xp)
     return xp
 
 
@@ -1097,6 +1098,19 @@ class BFPConv2d(torch.nn.Conv2d):
 _ACT_CACHE = {}
 
 
+def _act_cache_put(x, key, packed):
+    """One entry per device: the packed form of the LAST activation, so sibling projections (q / k / v, gate / up) quantise their
+    shared input once.  The activation itself is held weakly -- the cache never keeps a tensor alive -- and the entry (with its
+    packed copy) goes when the activation does."""
+    dev = x.device
+
+    def gone(ref, dev=dev):
+        hit = _ACT_CACHE.get(dev)
+        if hit is not None and hit[0] is ref:
+            del _ACT_CACHE[dev]
+    _ACT_CACHE[dev] = (weakref.ref(x, gone), x._version, key, packed)
+
+
 def _packed_activation(x, bfp_args):
     if os.environ.get("BFP_ACT_CACHE", "1") != "1" or torch.cuda.is_current_stream_capturing():
         return pack_bfp_bf16(x, identifier='in', **bfp_args)
@@ -1104,10 +1118,10 @@ def _packed_activation(x, bfp_args):
            bfp_args['N'], bfp_args['M'], bfp_args['first'], bfp_args['sparsity_mode'], float(bfp_args['sparsity_frac']),
            _stream(x.device))                                                         # same stream: the entry is ordered before its reuse
     hit = _ACT_CACHE.get(x.device)
-    if hit is not None and hit[0] is x and hit[1] == x._version and hit[2] == key:
+    if hit is not None and hit[0]() is x and hit[1] == x._version and hit[2] == key:
         return hit[3]
     xb = pack_bfp_bf16(x, identifier='in', **bfp_args)
-    _ACT_CACHE[x.device] = (x, x._version, key, xb)
+    _act_cache_put(x, key, xb)
     return xb
 
 
