@@ -17,10 +17,18 @@ from .bfp_ops import float_to_bfp_blocked, float_to_bfp_tiled, unpack_bfp_args
 _bfp_optims = {}
 
 
+def _trainable(optimizer):
+    """(param, state) of every parameter that has a gradient this step."""
+    for group in optimizer.param_groups:
+        for p in group['params']:
+            if p.grad is not None:
+                yield p, optimizer.state[p]
+
+
 def _gen_bfp_optim(optim, name):
     class BFPOptim(optim):
-        """bfp_optim.py:10-58: the wrapped optimiser's fp32 update on the WIDE weights (kept in state['shadow_p']), then both BFP
-        copies of the result: wide -> shadow_p, narrow -> p.data."""
+        """bfp_optim.py:10-58.  Two BFP copies of every weight: the WIDE one (state['shadow_p'], `weight_mant_bits`) is what the
+        wrapped optimiser updates in fp32; the NARROW one (`mant_bits`) is what p.data holds between steps."""
 
         def __init__(self, *args, **kwargs):
             self.bfp_args = unpack_bfp_args(kwargs)
@@ -32,28 +40,22 @@ def _gen_bfp_optim(optim, name):
             self._bfp_modules = [m for m in modules if hasattr(m, "invalidate_packed")]
             return self
 
+        def _wide(self, t):
+            return float_to_bfp_tiled(t, sgd_update=True, **self.bfp_args)
+
         def step(self, *args, **kwargs):
             if self.bfp_args['num_format'] == 'fp32':
                 return super().step(*args, **kwargs)
-            for group in self.param_groups:
-                for p in group['params']:
-                    if p.grad is None:
-                        continue
-                    state = self.state[p]
-                    if 'shadow_p' not in state:
-                        p.data.copy_(float_to_bfp_tiled(p.data, sgd_update=True, **self.bfp_args))
-                    else:
-                        p.data.copy_(state['shadow_p'])
+            # the update starts from the wide weights (first step: the constrained initial weights)
+            for p, state in _trainable(self):
+                p.data.copy_(state['shadow_p'] if 'shadow_p' in state else self._wide(p.data))
             loss = super().step(*args, **kwargs)
-            for group in self.param_groups:
-                for p in group['params']:
-                    if p.grad is None:
-                        continue
-                    state = self.state[p]
-                    if 'shadow_p' not in state:
-                        state['shadow_p'] = torch.zeros_like(p.data)
-                    state['shadow_p'].copy_(float_to_bfp_tiled(p.data, sgd_update=True, **self.bfp_args))
-                    p.data.copy_(float_to_bfp_tiled(p.data, **self.bfp_args))
+            # keep the wide result for the next step, hand the narrow one to the model
+            for p, state in _trainable(self):
+                if 'shadow_p' not in state:
+                    state['shadow_p'] = torch.zeros_like(p.data)
+                state['shadow_p'].copy_(self._wide(p.data))
+                p.data.copy_(float_to_bfp_tiled(p.data, **self.bfp_args))
             for m in self._bfp_modules:
                 m.invalidate_packed()
             return loss
@@ -63,19 +65,30 @@ def _gen_bfp_optim(optim, name):
 
 
 def get_bfp_optim(optim, name):
-    """bfp_optim.py:60-64"""
-    if name not in _bfp_optims:
-        _bfp_optims[name] = _gen_bfp_optim(optim, name)
-    return _bfp_optims[name]
+    """bfp_optim.py:60-64: one wrapper class per name."""
+    cls = _bfp_optims.get(name)
+    if cls is None:
+        cls = _bfp_optims[name] = _gen_bfp_optim(optim, name)
+    return cls
 
 
 class BFPAdam(torch.optim.Adam):
-    """bfp_optim_lstm.py:12-95: Adam whose updated weight is constrained to the wide BFP format after every step.  The reference
-    reads its BFP arguments from bfp_config.yaml (bfp_util.get_bfp_args); here they are passed in (`bfp_args`, the same dict)."""
+    """bfp_optim_lstm.py:12-95: Adam (the formulation of that file: eps added to sqrt(v) before the bias corrections are folded into
+    the step size) whose updated weight is constrained to the wide BFP format after every step.  The reference reads its BFP arguments
+    from bfp_config.yaml (bfp_util.get_bfp_args); here they are passed in (`bfp_args`, the same dict)."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, bfp_args=None):
         self.bfp_args = unpack_bfp_args(dict(bfp_args or {}))
         super().__init__(params, lr, betas, eps, weight_decay, amsgrad)
+
+    def _moments(self, p, group):
+        state = self.state[p]
+        if not state:
+            state['step'] = 0
+            for k in ('exp_avg', 'exp_avg_sq') + (('max_exp_avg_sq',) if group['amsgrad'] else ()):
+                state[k] = torch.zeros_like(p.data)
+        state['step'] += 1
+        return state
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -83,38 +96,29 @@ class BFPAdam(torch.optim.Adam):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        fmt = self.bfp_args['num_format']
+        if fmt not in ('fp32', 'bfp'):
+            raise NotImplementedError('NumFormat not implemented')
         for group in self.param_groups:
+            b1, b2 = group['betas']
             for p in group['params']:
                 if p.grad is None:
                     continue
-                grad = p.grad.data
-                if grad.is_sparse:
+                g = p.grad.data
+                if g.is_sparse:
                     raise RuntimeError('Adam does not support sparse gradients, please consider SparseAdam instead')
-                amsgrad = group['amsgrad']
-                state = self.state[p]
-                if len(state) == 0:
-                    state['step'] = 0
-                    state['exp_avg'] = torch.zeros_like(p.data)
-                    state['exp_avg_sq'] = torch.zeros_like(p.data)
-                    if amsgrad:
-                        state['max_exp_avg_sq'] = torch.zeros_like(p.data)
-                exp_avg, exp_avg_sq = state['exp_avg'], state['exp_avg_sq']
-                beta1, beta2 = group['betas']
-                state['step'] += 1
+                state = self._moments(p, group)
                 if group['weight_decay'] != 0:
-                    grad = grad.add(p.data, alpha=group['weight_decay'])
-                exp_avg.mul_(beta1).add_(grad, alpha=1 - beta1)
-                exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
-                if amsgrad:
-                    torch.max(state['max_exp_avg_sq'], exp_avg_sq, out=state['max_exp_avg_sq'])
-                    denom = state['max_exp_avg_sq'].sqrt().add_(group['eps'])
-                else:
-                    denom = exp_avg_sq.sqrt().add_(group['eps'])
-                step_size = group['lr'] * math.sqrt(1 - beta2 ** state['step']) / (1 - beta1 ** state['step'])
-                if self.bfp_args['num_format'] == 'fp32':
-                    p.data.addcdiv_(exp_avg, denom, value=-step_size)
-                elif self.bfp_args['num_format'] == 'bfp':
-                    p.data.copy_(float_to_bfp_blocked(p.data.addcdiv_(exp_avg, denom, value=-step_size), sgd_update=True, **self.bfp_args))
-                else:
-                    raise NotImplementedError('NumFormat not implemented')
+                    g = g.add(p.data, alpha=group['weight_decay'])
+                m, v = state['exp_avg'], state['exp_avg_sq']
+                m.mul_(b1).add_(g, alpha=1 - b1)
+                v.mul_(b2).addcmul_(g, g, value=1 - b2)
+                if group['amsgrad']:
+                    torch.max(state['max_exp_avg_sq'], v, out=state['max_exp_avg_sq'])
+                    v = state['max_exp_avg_sq']
+                denom = v.sqrt().add_(group['eps'])
+                t = state['step']
+                p.data.addcdiv_(m, denom, value=-group['lr'] * math.sqrt(1 - b2 ** t) / (1 - b1 ** t))
+                if fmt == 'bfp':
+                    p.data.copy_(float_to_bfp_blocked(p.data, sgd_update=True, **self.bfp_args))
         return loss
