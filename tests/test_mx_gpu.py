@@ -284,6 +284,20 @@ def test_mxlinear_packed_weight_cache_follows_the_weight(mx, O):
     check()
 
 
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("fmt", ["fp8_e4m3", "int8"])
+def test_mxlinear_half_precision_modules(mx, O, dt, fmt):
+    """fp16 / bf16 modules (what run_llama.py loads): computed in fp32, rounded once to the module's dtype."""
+    torch.manual_seed(6)
+    lin = mx.MXLinear(512, 256, bias=True, mx_specs=dict(SPEC, w_elem_format=fmt, a_elem_format=fmt)).cuda().to(dt).eval()
+    x = torch.from_numpy(_data(22, (40, 512))).cuda().to(dt)
+    with torch.no_grad():
+        y = lin(x)
+    assert y.dtype == dt and y.shape == (40, 256)
+    want, _, _ = O.mx_linear(x.float().cpu().numpy(), lin.weight.detach().float().cpu().numpy(), lin.bias.detach().float().cpu().numpy(), fmt, fmt, 32, 16, 8)
+    _layer_close(y.float().cpu().numpy(), torch.from_numpy(want).to(dt).float().numpy())
+
+
 def test_mxlinear_without_specs_is_a_plain_linear(mx):
     lin = mx.MXLinear(64, 32, mx_specs=None).cuda()
     x = torch.randn(5, 64, device="cuda")
