@@ -18,7 +18,7 @@ import torch.nn.functional as F
 
 from . import _lib
 from .bfp_ops import (_DT, _on, _stream, _structured_N_M_sparsity, _unstructured_sparsity, SparseBF16, PackedMX, bfp_linear_bf16,
-                      bfp_linear_bf16_sp, compress_2to4_bf16)
+                      bfp_linear_bf16_sp, compress_2to4_bf16, _is_patch_embedding)
 
 # formats.py:24-33 (ElemFormat values) -- the ids of include/bfp_b200.h BFP_MX_*
 ELEM_FORMATS = {"int8": 1, "int4": 2, "int2": 3, "fp8_e5m2": 4, "fp8_e4m3": 5, "fp6_e3m2": 6, "fp6_e2m3": 7, "fp4": 8, "fp4_e2m1": 8}
@@ -386,7 +386,8 @@ class MXLinear(torch.nn.Linear):
 class MXConv2d(torch.nn.Conv2d):
     """mx_layers.py:59-99 over mx/convolution.py ConvFunction.forward: bfloat rounding, MX along the CHANNEL axis of input and weight
     (axes=[1]), the convolution on the quantised tensors, bfloat rounding, bias, bfloat rounding.  The quantiser is one fused CUDA pass
-    per tensor over a channels-last view; the convolution itself is the library's (exact: MX values fit TF32)."""
+    per tensor over a channels-last view; patch embeddings (kernel == stride: ViT) run as im2col-by-permutation + a tcgen05 GEMM, any
+    other convolution is the library's on the quantised tensors (exact: MX values fit TF32)."""
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True, mx_specs=None, name=None,
                  sparsity=False, device=None, sparsity_mode="structured", sparsity_frac=0.0, N=0, M=0):
@@ -412,7 +413,22 @@ class MXConv2d(torch.nn.Conv2d):
                 return quantize_elemwise_op(cl, sp).permute(0, 3, 1, 2)
             return _mx_quantize_last(cl, fmt, sp["block_size"], sp["scale_bits"], bfloat, sp["mx_flush_fp32_subnorms"]).permute(0, 3, 1, 2)
 
-        y = F.conv2d(q(inputs, sp["a_elem_format"]), q(self.weight, sp["w_elem_format"]), None, self.stride, self.padding, self.dilation, self.groups)
+        xq, wq = q(inputs, sp["a_elem_format"]), q(self.weight, sp["w_elem_format"])
+        O, C, kh, kw = self.weight.shape
+        if (self.groups == 1 and _is_patch_embedding(inputs, self.weight, self.stride, self.padding, self.dilation) and (C * kh * kw) % 8 == 0
+                and inputs.dtype == torch.float32 and self.weight.dtype == torch.float32 and not (torch.is_grad_enabled() and (inputs.requires_grad or self.weight.requires_grad))):
+            # patch embedding (kernel == stride, the ViT case): the windows tile the image, so im2col is ONE permuting copy of the quantised
+            # input (exact in bf16: <= 8 significant bits) and the convolution is a tcgen05 GEMM; the result is a channels-last view
+            B, _, H, W = inputs.shape
+            Ho, Wo = H // kh, W // kw
+            a = xq.reshape(B, C, Ho, kh, Wo, kw).permute(0, 2, 4, 1, 3, 5).reshape(B * Ho * Wo, C * kh * kw).to(torch.bfloat16)
+            y = bfp_linear_bf16(a, wq.reshape(O, C * kh * kw).to(torch.bfloat16), None)                      # [B * L, O] fp32
+            b32 = self.bias.detach().to(torch.float32).contiguous() if self.bias is not None else None
+            with _on(y.device):
+                _lib.check(_lib.lib().bfp_bfloat_round(y.data_ptr(), y.data_ptr(), b32.data_ptr() if b32 is not None else None, y.numel(), O, _lib.DT_F32,
+                                                       bfloat, _stream()))
+            return y.view(B, Ho, Wo, O).permute(0, 3, 1, 2)
+        y = F.conv2d(xq, wq, None, self.stride, self.padding, self.dilation, self.groups)
         y = quantize_elemwise_op(y, sp)
         if self.bias is not None:
             y = quantize_elemwise_op(y + quantize_elemwise_op(self.bias, sp).view(1, -1, 1, 1), sp)
