@@ -195,3 +195,48 @@ def test_mx_layers_host_logic_without_a_gpu():
         L._need_nearest("floor")
     with pytest.raises(ValueError):
         L._bfloat_of(dict(q.mx_specs, bfloat=8))
+
+
+def test_packed_weight_cache_protocol_on_cpu(monkeypatch):
+    """The cache of the MX modules (the BFPLinear protocol): keyed on storage / version, bypassed while a module trains with a
+    trainable weight, dropped by invalidate(), switched off or checksummed by BFP_WEIGHT_CACHE."""
+    import qsi_b200  # noqa: F401
+    from qsi_b200 import mx_layers as L
+    lin = torch.nn.Linear(8, 4).eval()
+    cache, builds = L._PackedWeightCache(), []
+
+    def build():
+        builds.append(1)
+        return len(builds)
+    assert cache.get(lin, lin.weight, "bs", build) == 1 and cache.get(lin, lin.weight, "bs", build) == 1          # hit
+    assert cache.get(lin, lin.weight, "bf16", build) == 2 and len(cache.entries) == 2                             # second kind, same weight
+    with torch.no_grad():
+        lin.weight.mul_(2.0)                                                                                       # version moves: every form goes
+    assert cache.get(lin, lin.weight, "bs", build) == 3 and len(cache.entries) == 1
+    lin.weight.data.mul_(2.0)                                                                                      # .data write: version does not move ...
+    assert cache.get(lin, lin.weight, "bs", build) == 3
+    cache.invalidate()                                                                                             # ... the documented protocol
+    assert cache.get(lin, lin.weight, "bs", build) == 4
+    lin.train()                                                                                                    # training + trainable weight: never cached
+    assert cache.get(lin, lin.weight, "bs", build) == 5 and cache.get(lin, lin.weight, "bs", build) == 6
+    lin.eval()
+    monkeypatch.setenv("BFP_WEIGHT_CACHE", "verify")
+    assert cache.get(lin, lin.weight, "bs", build) == 7 and cache.get(lin, lin.weight, "bs", build) == 7
+    lin.weight.data.mul_(2.0)                                                                                      # the checksum sees a .data write
+    assert cache.get(lin, lin.weight, "bs", build) == 8
+    monkeypatch.setenv("BFP_WEIGHT_CACHE", "0")
+    assert cache.get(lin, lin.weight, "bs", build) == 9 and cache.get(lin, lin.weight, "bs", build) == 10
+
+
+def test_philox_offsets_are_disjoint_across_ranks(monkeypatch):
+    import qsi_b200  # noqa: F401
+    from qsi_b200 import bfp_ops as B
+    B._PhiloxState.seed = None
+    monkeypatch.setenv("RANK", "0")
+    s0, o0 = B._PhiloxState.next()
+    _, o0b = B._PhiloxState.next()
+    monkeypatch.setenv("RANK", "3")
+    s3, o3 = B._PhiloxState.next()
+    assert s0 == s3 == (torch.initial_seed() & 0xFFFFFFFFFFFFFFFF)
+    assert o0b == o0 + 1 and (o3 >> 48) == 3 and (o0 >> 48) == 0 and (o3 & ((1 << 48) - 1)) == 2
+    B._PhiloxState.seed = None
