@@ -240,3 +240,19 @@ def test_philox_offsets_are_disjoint_across_ranks(monkeypatch):
     assert s0 == s3 == (torch.initial_seed() & 0xFFFFFFFFFFFFFFFF)
     assert o0b == o0 + 1 and (o3 >> 48) == 3 and (o0 >> 48) == 0 and (o3 & ((1 << 48) - 1)) == 2
     B._PhiloxState.seed = None
+
+
+@pytest.mark.parametrize("fmt", FORMATS)
+def test_numpy_oracle_equals_the_torch_op_sequence(fmt):
+    """Two independent restatements of the library's _quantize_mx -- numpy (the oracle) and the torch op sequence the library itself
+    runs (tests/test_mx_gpu._torch_quantize_mx, evaluated here by torch-CPU; the GPU suite evaluates it with torch-CUDA against the
+    kernel) -- agree bit for bit, signed zeros included."""
+    import test_mx_gpu as G
+    for seed, scale in ((0, 1.0), (1, 1e-3), (2, 300.0)):
+        x = _data(30 + seed, (48, 256), scale)
+        x.flat[3::101] = 0.0
+        x.flat[5::103] = -0.0
+        x[0, :32] = 0.0
+        want = M.quantize_mx(x, fmt, 32)
+        got = G._torch_quantize_mx(torch.from_numpy(x.copy()), fmt, 32, M).numpy()
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (fmt, seed)
