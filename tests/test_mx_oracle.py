@@ -256,3 +256,20 @@ def test_numpy_oracle_equals_the_torch_op_sequence(fmt):
         want = M.quantize_mx(x, fmt, 32)
         got = G._torch_quantize_mx(torch.from_numpy(x.copy()), fmt, 32, M).numpy()
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (fmt, seed)
+
+
+def test_tables_match_the_recorded_reference_outputs():
+    """tests/golden/mx_reference_tables.json (made by tests/golden/make_mx_golden.py from the reference's formats.py / specs.py):
+    the oracle's format table and this package's spec helpers reproduce what the reference tree itself pins of the MX path."""
+    import json
+    import qsi_b200  # noqa: F401
+    from qsi_b200 import mx_layers as L
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mx_reference_tables.json")))
+    for name, r in g["formats"].items():
+        assert M.FORMATS[name] == (r["ebits"], r["mbits"], r["emax"], r["max_norm"]), name
+        assert M.FORMAT_IDS[name] == r["id"] == L.ELEM_FORMATS[name], name
+    for case in g["specs"]:
+        out = L.finalize_mx_specs(L.apply_mx_specs(dict(case["given"]) if case["given"] is not None else None))
+        assert (out is None) == (case["finalized"] is None), case["given"]
+        if out is not None:
+            assert dict(out) == case["finalized"], case["given"]
